@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bit-exact: record lists (guide, FLAG, contig, pos, NM) must be identical, in the same order."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import GLEN, make_case, revcomp_codes, write_fasta, write_guides
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "read_mapping_build")
+
+
+def oracle_rows(ascii_bytes, offsets, guides, k, pam=None):
+    from oracle import oracle as O
+    r = O.map_guides(O.text_codes(ascii_bytes), offsets, guides, k, pam=pam)
+    return r.rows()
+
+
+def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True):
+    import varscot_b200 as V
+    text = V.PackedText.from_ascii(ascii_bytes, offsets)
+    parts = []
+    nw = text.n_words
+    bounds = [nw * i // shards for i in range(shards + 1)]
+    for i in range(shards):
+        if bounds[i + 1] <= bounds[i]:
+            continue
+        with V.ScanContext(0) as ctx:
+            ctx.upload(text.words, bounds[i], bounds[i + 1] - bounds[i])
+            hits, _ = ctx.scan(guides, k, pam=pam, cap=1 << 12)
+            parts.append(hits.copy())
+    hits = np.concatenate(parts) if parts else np.zeros(0, V.HIT_DT)
+    rec, _ = V.resolve_hits(hits, offsets)
+    rows = []
+    for r in rec:
+        md = V.md_string(text, int(offsets[r["contig"]]) + int(r["pos"]), guides[r["guide"]], (int(r["flag"]) >> 4) & 1) if with_md else ""
+        rows.append((int(r["guide"]), int(r["flag"]), int(r["contig"]), int(r["pos"]), int(r["mm"]), md))
+    return rows
+
+
+def assert_same(case, shards=1):
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, case.k, case.pam)
+    got = gpu_rows(case.ascii, case.offsets, case.guides, case.k, case.pam, shards=shards)
+    assert len(got) == len(exp), f"{len(got)} GPU records vs {len(exp)} oracle records"
+    assert got == exp
+    return len(exp)
+
+
+@pytest.mark.parametrize("k", list(range(9)))
+def test_all_k(k):
+    case = make_case(seed=100 + k, contig_lens=[20000, 45, 3000, 0, 23, 46, 10000], n_guides=5, k=k)
+    n = assert_same(case)
+    assert n > 0
+
+
+@pytest.mark.parametrize("pam", [None, "AG", "TT", "CC", "GG"])
+def test_extra_pam(pam):
+    case = make_case(seed=7, contig_lens=[30000, 5000], n_guides=4, k=4, pam=pam, guide_pam=(pam or "GG"))
+    assert_same(case)
+
+
+def test_many_guides_chunking():
+    # > 512 guides exercises several constant-memory pattern chunks per strand
+    case = make_case(seed=11, contig_lens=[40000], n_guides=1100, k=3, plant=False)
+    rng = np.random.default_rng(5)
+    codes = np.frombuffer(case.ascii, dtype=np.uint8).copy()
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for g in (0, 511, 512, 513, 1023, 1024, 1099):
+        p = int(rng.integers(0, 40000 - GLEN))
+        w = case.guides[g].copy()
+        if g % 2:
+            w = revcomp_codes(w)
+        codes[p:p + GLEN] = lut[w]
+    case.ascii = bytes(codes)
+    n = assert_same(case)
+    assert n >= 7
+
+
+def test_edge_contigs():
+    """L < 23, L == 23, last-window rule R4 both ways, first window, N at every offset."""
+    rng = np.random.default_rng(3)
+    g = rng.integers(0, 4, GLEN).astype(np.uint8); g[21:] = 2
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    contigs = []
+    k = 4
+    # exact-length contigs: perfect, H2 <= K and H2 > K variants (K = 2)
+    for mm_pos in ([], [0, 1, 2], [12, 13], [12, 13, 14], [0, 12, 13, 14], [11, 15, 20], [3, 4, 5, 6]):
+        for strand in (0, 1):
+            w = g.copy()
+            for p in mm_pos:
+                w[p] = (w[p] + 1) % 4
+            w[21:] = 2
+            if strand:
+                w = revcomp_codes(w)
+            contigs.append(lut[w])
+            contigs.append(np.concatenate([lut[rng.integers(0, 4, 22)], lut[w]]))          # site is the LAST window of a 45-mer
+            contigs.append(np.concatenate([lut[w], lut[rng.integers(0, 4, 22)]]))          # site is the FIRST window
+    contigs.append(lut[g[:22]])                                                             # too short
+    contigs.append(np.zeros(0, np.uint8))                                                   # empty
+    for i in range(GLEN):                                                                   # N at each offset
+        w = lut[g].copy(); w[i] = ord("N")
+        contigs.append(np.concatenate([lut[rng.integers(0, 4, 5)], w, lut[rng.integers(0, 4, 5)]]))
+    lens = [len(c) for c in contigs]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    asc = bytes(np.concatenate(contigs))
+    guides = g.reshape(1, GLEN)
+    exp = oracle_rows(asc, off, guides, k)
+    got = gpu_rows(asc, off, guides, k)
+    assert got == exp
+    assert len(exp) >= 10
+
+
+def test_contig_swarm_over_65536():
+    """SNP-genome shape: > 65536 contigs of 45 bp; records ordered by (id mod 65536, pos, id >> 16)."""
+    rng = np.random.default_rng(9)
+    nct = 70000
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    codes = rng.integers(0, 4, (nct, 45)).astype(np.uint8)
+    guides = rng.integers(0, 4, (3, GLEN)).astype(np.uint8); guides[:, 21:] = 2
+    for c in list(range(0, nct, 997)) + [5, 65536 + 5, 69999]:
+        gi = c % 3
+        w = guides[gi].copy()
+        w[int(rng.integers(0, 20))] ^= 1
+        if c % 2:
+            w = revcomp_codes(w)
+        p = [0, 22, 7][c % 3]
+        codes[c, p:p + GLEN] = w
+    # identical (id mod 65536, pos) for contigs 5 and 65541, same guide and strand
+    codes[65536 + 5] = codes[5]
+    asc = bytes(lut[codes.reshape(-1)])
+    off = (np.arange(nct + 1) * 45).astype(np.uint64)
+    exp = oracle_rows(asc, off, guides, 4)
+    got = gpu_rows(asc, off, guides, 4)
+    assert got == exp
+    import varscot_b200 as V
+    text = V.PackedText.from_ascii(asc, off)
+    with V.ScanContext(0) as ctx:
+        ctx.upload(text.words)
+        hits, _ = ctx.scan(guides, 4)
+    _, coll = V.resolve_hits(hits, off)
+    assert coll >= 1
+
+
+@pytest.mark.parametrize("shards", [2, 3, 7])
+def test_sharded_text_equals_whole(shards):
+    case = make_case(seed=21, contig_lens=[50000, 45, 45, 45, 20000], n_guides=8, k=6)
+    assert_same(case, shards=shards)
+
+
+def test_hit_buffer_overflow_and_fetch():
+    import varscot_b200 as V
+    case = make_case(seed=33, contig_lens=[200000], n_guides=16, k=8, plant=False)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    with V.ScanContext(0) as ctx:
+        ctx.upload(text.words)
+        small, _ = ctx.scan(case.guides, 8, cap=4)          # forces VS_ERR_OVERFLOW + vs_scan_fetch
+        big, _ = ctx.scan(case.guides, 8, cap=1 << 20)
+    assert len(small) == len(big) > 4
+    a, _ = V.resolve_hits(small, case.offsets)
+    b, _ = V.resolve_hits(big, case.offsets)
+    assert a.tolist() == b.tolist()
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 8)
+    assert [(x[0], x[3], x[1], x[2], x[4]) for x in a.tolist()] == [e[:5] for e in exp]
+
+
+def test_repeat_scan_is_deterministic_after_resolve():
+    import varscot_b200 as V
+    case = make_case(seed=40, contig_lens=[100000], n_guides=10, k=6)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    with V.ScanContext(0) as ctx:
+        ctx.upload(text.words)
+        r = []
+        for _ in range(3):
+            hits, _ = ctx.scan(case.guides, 6)
+            r.append(V.resolve_hits(hits, case.offsets)[0].tolist())
+    assert r[0] == r[1] == r[2]
+
+
+def test_cli_sam_byte_identical_to_oracle_cli(tmp_path):
+    """The drop-in executables against the oracle executable: same argv, byte-identical SAM."""
+    case = make_case(seed=55, contig_lens=[80000, 45, 45, 0, 30000], n_guides=7, k=5, pam="AG")
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "guides.fa")
+    names = ["chr1 some description", "chr1_100_REF", "chr1_100_ALT_122_A_C", "empty", "chr2"]
+    write_fasta(gfa, names, case.ascii, case.offsets)
+    ids = [f"guide{i}" for i in range(7)]
+    gs = list(case.guide_strs)
+    gs[3] = gs[3][:5] + "N" + gs[3][6:]          # N in a guide becomes A (R5)
+    gs[4] = gs[4].lower()
+    write_guides(rfa, ids, gs)
+    idx = str(tmp_path / "idx" / "genome")
+    os.makedirs(os.path.dirname(idx))
+    r = subprocess.run([os.path.join(BIN, "bidir_index"), "-G", gfa, "-I", idx], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Number of sequences: 5" in r.stdout and "Index created successfully" in r.stdout
+    for style in ("seqan", "samtools"):
+        out, ref = str(tmp_path / f"out_{style}.sam"), str(tmp_path / f"ref_{style}.sam")
+        r = subprocess.run([os.path.join(BIN, "bidir_mapping"), "-G", gfa, "-I", idx, "-R", rfa, "-M", "5", "-T", "2", "-P", "AG",
+                            "-O", out, "--md-style", style], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Reads loaded (total: 7)." in r.stdout and "Index loaded." in r.stdout
+        o = subprocess.run([os.path.join(ROOT, "oracle", "oracle_bidir_mapping"), "-G", gfa, "-R", rfa, "-M", "5", "-P", "AG", "-O", ref,
+                            "--md-style", style], capture_output=True, text=True)
+        assert o.returncode == 0, o.stderr
+        a, b = open(out, "rb").read(), open(ref, "rb").read()
+        assert len(b) > 0
+        assert a == b
+    # without a cached index the mapper packs the FASTA itself
+    out2 = str(tmp_path / "out2.sam")
+    r = subprocess.run([os.path.join(BIN, "bidir_mapping"), "-G", gfa, "-I", str(tmp_path / "nonexistent"), "-R", rfa, "-M", "5", "-P", "AG",
+                        "-O", out2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out2, "rb").read() == open(str(tmp_path / "out_seqan.sam"), "rb").read()
+
+
+def test_config1_shape_50mbp():
+    """BASELINE config 1 shape: one 50 Mbp contig with N runs + a 20k-contig SNP swarm, 10 guides, k <= 4."""
+    rng = np.random.default_rng(1)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    n = 50_000_000
+    asc = lut[rng.integers(0, 4, n).astype(np.uint8)]
+    for s in (0, n // 2, n - 10000):
+        asc[s:s + 10000] = ord("N")
+    guides = rng.integers(0, 4, (10, GLEN)).astype(np.uint8); guides[:, 21:] = 2
+    for g in range(10):
+        for j in range(12):
+            w = guides[g].copy()
+            nm = j % 6
+            if nm:
+                idx = rng.choice(GLEN, nm, replace=False); w[idx] = (w[idx] + 1) % 4
+            if j % 2:
+                w = revcomp_codes(w)
+            p = int(rng.integers(20000, n - 20000))
+            asc[p:p + GLEN] = lut[w]
+    # SNP swarm: 10k SNVs -> REF + ALT 45-mers cut from the genome
+    pos = np.sort(rng.integers(30000, n - 30000, 10000))
+    swarm = []
+    for p in pos:
+        ref = asc[p - 22:p + 23].copy(); alt = ref.copy()
+        alt[22] = lut[(int(np.where(lut == (alt[22] if alt[22] != ord("N") else ord("A")))[0][0]) + 1) % 4]
+        swarm += [ref, alt]
+    asc_all = np.concatenate([asc] + swarm)
+    lens = [n] + [45] * len(swarm)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    exp = oracle_rows(bytes(asc_all), off, guides, 4)
+    got = gpu_rows(bytes(asc_all), off, guides, 4)
+    assert got == exp
+    assert len(exp) >= 60

@@ -1,0 +1,341 @@
+// varscot_b200/csrc/vs_cli.cpp — the two executables of the read_mapping stage as library calls.
+//
+//   vs_bidir_index_main   mirrors VARSCOT_pipeline/read_mapping/bidir_index.cpp:10-52
+//                         (-G/--genome fa|fasta|fastq, -I/--index prefix; stdout lines :42,:49)
+//   vs_bidir_mapping_main mirrors VARSCOT_pipeline/read_mapping/bidir_mapping.cpp:190-312
+//                         (-G -I -R -M -T -O -P; range check :234-238; stdout lines :265,:269;
+//                          exit codes :219-220,:237,:301-305; header-less SAM :298-309)
+// The argv contract is what VARSCOT_pipeline/VARSCOT:296-314 passes.  The "index" written at the
+// -I prefix is the bit-sliced packed text (<prefix>.vsidx), not an FM index.
+#include "vs_internal.h"
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+// ---- FASTA ----------------------------------------------------------------------------------
+// SeqAn readRecord semantics as used by the reference: id = the whole header line after '>'
+// (bidir_mapping.cpp:272-280), sequence = every non-whitespace character up to the next header.
+struct FastaSink {
+    std::function<void(const std::string &)> header;
+    std::function<void(const char *, size_t)> seq;
+    std::function<void()> end_record;
+};
+
+bool read_fasta(const std::string &path, const FastaSink &sink, std::string &err)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { err = "cannot open " + path; return false; }
+    std::vector<char> buf(8u << 20);
+    std::string hdr;
+    bool in_header = false, at_line_start = true, have_record = false;
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        size_t i = 0;
+        while (i < got) {
+            if (in_header) {
+                const char *nl = (const char *)memchr(buf.data() + i, '\n', got - i);
+                size_t e = nl ? (size_t)(nl - buf.data()) : got;
+                hdr.append(buf.data() + i, e - i);
+                i = e;
+                if (nl) {
+                    while (!hdr.empty() && (hdr.back() == '\r' || hdr.back() == '\n')) hdr.pop_back();
+                    sink.header(hdr);
+                    hdr.clear();
+                    in_header = false; at_line_start = true; have_record = true;
+                    ++i;
+                }
+                continue;
+            }
+            if (at_line_start && buf[i] == '>') {
+                if (have_record) sink.end_record();
+                in_header = true; ++i;
+                continue;
+            }
+            const char *nl = (const char *)memchr(buf.data() + i, '\n', got - i);
+            size_t e = nl ? (size_t)(nl - buf.data()) : got;
+            if (have_record && e > i) sink.seq(buf.data() + i, e - i);
+            at_line_start = nl != nullptr;
+            i = nl ? e + 1 : e;
+        }
+    }
+    fclose(f);
+    if (in_header) { sink.header(hdr); have_record = true; }
+    if (have_record) sink.end_record();
+    return true;
+}
+
+struct PackedText {
+    vs_packer *packer = nullptr;
+    vs_word *loaded_words = nullptr;
+    uint64_t *loaded_off = nullptr;
+    const vs_word *words = nullptr;
+    const uint64_t *off = nullptr;
+    uint64_t n_bases = 0;
+    uint32_t n_contigs = 0;
+    std::vector<std::string> names;
+    ~PackedText() { vs_packer_free(packer); vs_free(loaded_words); vs_free(loaded_off); }
+};
+
+bool pack_fasta(const std::string &path, PackedText &t, bool want_names, std::string &err)
+{
+    t.packer = vs_packer_new();
+    if (!t.packer) { err = "out of memory"; return false; }
+    int rc = VS_OK;
+    FastaSink sink;
+    sink.header = [&](const std::string &h) { if (want_names) t.names.push_back(h); };
+    sink.seq = [&](const char *s, size_t n) { if (rc == VS_OK) rc = vs_packer_append(t.packer, s, n); };
+    sink.end_record = [&]() { if (rc == VS_OK) rc = vs_packer_end_contig(t.packer); };
+    if (!read_fasta(path, sink, err)) return false;
+    if (rc != VS_OK) { err = "packing failed (out of memory?)"; return false; }
+    t.words = vs_packer_words(t.packer);
+    t.off = vs_packer_offsets(t.packer);
+    t.n_bases = vs_packer_num_bases(t.packer);
+    t.n_contigs = vs_packer_num_contigs(t.packer);
+    return true;
+}
+
+bool read_names(const std::string &path, std::vector<std::string> &names, std::string &err)
+{
+    FastaSink sink;
+    sink.header = [&](const std::string &h) { names.push_back(h); };
+    sink.seq = [](const char *, size_t) {};
+    sink.end_record = []() {};
+    return read_fasta(path, sink, err);
+}
+
+// ---- argument parsing (SeqAn ArgumentParser look-alike) ----------------------------------------
+struct Opt {
+    char s; const char *l; bool required; bool has_value; std::string value; bool seen = false;
+    std::vector<std::string> exts;   // valid file extensions (setValidValues)
+};
+
+bool has_ext(const std::string &path, const std::vector<std::string> &exts)
+{
+    if (exts.empty()) return true;
+    std::string low = path;
+    std::transform(low.begin(), low.end(), low.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    for (const auto &e : exts) {
+        std::string suf = "." + e;
+        if (low.size() >= suf.size() && low.compare(low.size() - suf.size(), suf.size(), suf) == 0) return true;
+    }
+    return false;
+}
+
+// returns 0 ok, 1 parse error, 2 help/version shown
+int parse_args(const char *prog, int argc, char **argv, std::vector<Opt> &opts, const char *desc)
+{
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "-h" || a == "--help") {
+            printf("%s\n\n%s\n\nOPTIONS\n", prog, desc);
+            for (auto &o : opts) printf("    -%c, --%s%s%s\n", o.s, o.l, o.has_value ? " ARG" : "", o.required ? " (required)" : "");
+            return 2;
+        }
+        if (a == "--version") { printf("%s version: varscot-b200 0.1\n", prog); return 2; }
+        Opt *hit = nullptr;
+        std::string inline_val; bool has_inline = false;
+        if (a.size() >= 3 && a[0] == '-' && a[1] == '-') {
+            std::string name = a.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) { inline_val = name.substr(eq + 1); name = name.substr(0, eq); has_inline = true; }
+            for (auto &o : opts) if (name == o.l) hit = &o;
+        } else if (a.size() == 2 && a[0] == '-') {
+            for (auto &o : opts) if (a[1] == o.s) hit = &o;
+        }
+        if (!hit) { fprintf(stderr, "%s: illegal option -- %s\n", prog, a.c_str()); return 1; }
+        if (hit->has_value) {
+            if (has_inline) hit->value = inline_val;
+            else if (i + 1 < argc) hit->value = argv[++i];
+            else { fprintf(stderr, "%s: option requires an argument -- %s\n", prog, a.c_str()); return 1; }
+        }
+        hit->seen = true;
+    }
+    for (auto &o : opts) {
+        if (o.required && !o.seen) { fprintf(stderr, "%s: option -%c/--%s is required but was not set\n", prog, o.s, o.l); return 1; }
+        if (o.seen && !has_ext(o.value, o.exts)) {
+            fprintf(stderr, "%s: the given path '%s' does not have a valid file extension for -%c/--%s\n", prog, o.value.c_str(), o.s, o.l);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+bool parse_int(const std::string &s, long &v)
+{
+    if (s.empty()) return false;
+    char *end = nullptr;
+    v = strtol(s.c_str(), &end, 10);
+    return end && *end == 0;
+}
+
+Opt *find_opt(std::vector<Opt> &opts, char s) { for (auto &o : opts) if (o.s == s) return &o; return nullptr; }
+
+std::vector<int> choose_devices(uint64_t n_bases)
+{
+    // Several mapper processes run concurrently (VARSCOT:321-322 runs two, parallel.py:17 up to 48 pipelines):
+    // small texts stay on ONE device picked by pid so processes spread out; big texts are sharded.
+    int n = vs_device_count();
+    std::vector<int> d;
+    if (n <= 0) return d;
+    if (const char *e = getenv("VARSCOT_DEVICE")) { int i = atoi(e); if (i >= 0 && i < n) { d.push_back(i); return d; } }
+    int want = (int)std::min<uint64_t>((uint64_t)n, std::max<uint64_t>(1, n_bases / (512ull << 20)));
+    if (const char *e = getenv("VARSCOT_GPUS")) { int g = atoi(e); if (g >= 1) want = std::min(g, n); }
+    int first = (int)((unsigned)getpid() % (unsigned)n);
+    for (int i = 0; i < want; ++i) d.push_back((first + i) % n);
+    return d;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int vs_bidir_index_main(int argc, char **argv)
+{
+    const char *prog = "bidir_index";
+    std::vector<Opt> opts = {
+        {'G', "genome", true, true, "", false, {"fa", "fasta", "fastq"}},
+        {'I', "index", true, true, "", false, {}},
+    };
+    int pr = parse_args(prog, argc, argv, opts,
+                        "VARSCOT - Index Creation (B200 build): packs a multi-sequence FASTA (Dna5: A, C, G, T, N) into the "
+                        "bit-sliced text the GPU scan reads. At most 4 giga bases in total.");
+    if (pr == 2) return 0;
+    if (pr == 1) return 1;
+    std::string genome = find_opt(opts, 'G')->value, index = find_opt(opts, 'I')->value;
+    if (has_ext(genome, {"fastq"})) { fprintf(stderr, "%s: FASTQ input is not supported by this build; convert to FASTA\n", prog); return 1; }
+    PackedText t;
+    std::string err;
+    if (!pack_fasta(genome, t, false, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+    if (t.n_bases > (1ull << 32)) { fprintf(stderr, "%s: the FASTA file may not contain more than 4 giga bases in total\n", prog); return 1; }
+    printf("Number of sequences: %u\n", t.n_contigs);
+    fflush(stdout);
+    if (vs_text_save(index.c_str(), t.words, t.n_bases, t.off, t.n_contigs) != VS_OK) {
+        fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr));
+        return 1;
+    }
+    printf("Index created successfully\n");
+    return 0;
+}
+
+extern "C" int vs_bidir_mapping_main(int argc, char **argv)
+{
+    const char *prog = "bidir_mapping";
+    std::vector<Opt> opts = {
+        {'G', "genome", true, true, "", false, {"fa", "fasta"}},
+        {'I', "index", true, true, "", false, {}},
+        {'R', "reads", true, true, "", false, {"fa", "fasta"}},
+        {'M', "mismatches", true, true, "", false, {}},
+        {'T', "threads", false, true, "1", false, {}},
+        {'O', "output", false, true, "", false, {"sam", "bam"}},
+        {'P', "pam", false, true, "", false, {}},
+        {'S', "md-style", false, true, "seqan", false, {}},     // extension: seqan | samtools
+    };
+    int pr = parse_args(prog, argc, argv, opts,
+                        "Read mapper for CRISPR-Cas9 off-targets (B200 build). Only supports Dna4 reads (everything else than ACGT "
+                        "will be converted to A). All reads must have the same length (23).");
+    if (pr == 2) return 0;
+    if (pr == 1) return 1;
+    long mism = 0, threads = 1;
+    if (!parse_int(find_opt(opts, 'M')->value, mism)) { fprintf(stderr, "%s: the given value '%s' for -M is not an integer\n", prog, find_opt(opts, 'M')->value.c_str()); return 1; }
+    if (!parse_int(find_opt(opts, 'T')->value, threads)) { fprintf(stderr, "%s: the given value for -T is not an integer\n", prog); return 1; }
+    if (mism < 0 || mism > 8) { fprintf(stderr, "Error: Maximum number of mismatches must lie between 0 and 8.\n"); return 1; }
+    std::string genome = find_opt(opts, 'G')->value, index = find_opt(opts, 'I')->value, reads = find_opt(opts, 'R')->value;
+    std::string output = find_opt(opts, 'O')->value, pam = find_opt(opts, 'P')->value, mdst = find_opt(opts, 'S')->value;
+    int md_style = mdst == "samtools" ? VS_MD_SAMTOOLS : VS_MD_SEQAN;
+
+    // additional PAM (bidir_mapping.cpp:240-247): a Dna5String compared with the 2-base window end, so only a
+    // two-letter ACGT string can ever match anything
+    int extra_pam = -1;
+    if (!pam.empty()) {
+        auto code = [](char c) { switch (std::toupper((unsigned char)c)) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': case 'U': return 3; default: return 4; } };
+        if (pam.size() == 2 && code(pam[0]) < 4 && code(pam[1]) < 4) extra_pam = 4 * code(pam[0]) + code(pam[1]);
+        else fprintf(stderr, "%s: warning: additional PAM '%s' can never match a 2-base window without N; ignored\n", prog, pam.c_str());
+    }
+
+    // reads: StringSet<DnaString> (bidir_mapping.cpp:256,263-264): non-ACGT -> A
+    std::vector<std::string> ids;
+    std::vector<uint8_t> guides;
+    {
+        std::string cur, err;
+        FastaSink sink;
+        sink.header = [&](const std::string &h) { ids.push_back(h); cur.clear(); };
+        sink.seq = [&](const char *s, size_t n) { for (size_t i = 0; i < n; ++i) if (!isspace((unsigned char)s[i])) cur.push_back(s[i]); };
+        bool bad = false;
+        sink.end_record = [&]() {
+            if (cur.size() != VS_GLEN) { bad = true; return; }
+            for (char c : cur) {
+                uint8_t v;
+                switch (std::toupper((unsigned char)c)) { case 'C': v = 1; break; case 'G': v = 2; break; case 'T': case 'U': v = 3; break; default: v = 0; }
+                guides.push_back(v);
+            }
+        };
+        if (!read_fasta(reads, sink, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+        if (bad) { fprintf(stderr, "%s: all reads must be %d nt long (guide + PAM)\n", prog, VS_GLEN); return 1; }
+    }
+    printf("Reads loaded (total: %zu).\n", ids.size());
+    fflush(stdout);
+
+    // "index": the packed text cached by bidir_index at the -I prefix; if it is absent or unreadable, pack -G now
+    PackedText t;
+    std::string err;
+    bool from_cache = vs_text_load(index.c_str(), &t.loaded_words, &t.n_bases, &t.loaded_off, &t.n_contigs) == VS_OK;
+    if (from_cache) {
+        t.words = t.loaded_words; t.off = t.loaded_off;
+        // contig ids from the genome FASTA, sequences discarded (bidir_mapping.cpp:272-280)
+        if (!read_names(genome, t.names, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+        if (t.names.size() != t.n_contigs) {
+            fprintf(stderr, "%s: index %s.vsidx has %u sequences but %s has %zu; re-run bidir_index\n", prog, index.c_str(), t.n_contigs, genome.c_str(), t.names.size());
+            return 1;
+        }
+    } else {
+        fprintf(stderr, "%s: note: no packed text at %s.vsidx (%s); packing %s now\n", prog, index.c_str(), vs_last_error(nullptr), genome.c_str());
+        if (!pack_fasta(genome, t, true, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+    }
+    if (t.n_bases > (1ull << 32)) { fprintf(stderr, "%s: text exceeds 4 giga bases\n", prog); return 1; }
+    printf("Index loaded.\n");
+    fflush(stdout);
+
+    // output is opened only after all work in the reference (bidir_mapping.cpp:298-305); failing early is equivalent for the caller
+    FILE *out = fopen(output.c_str(), "wb");
+    if (!out) { fprintf(stderr, "ERROR: Could not open output path.\n"); return 1; }
+
+    std::vector<vs_hit> hits;
+    const uint32_t n_guides = (uint32_t)ids.size();
+    if (n_guides && t.n_bases) {
+        std::vector<int> devices = choose_devices(t.n_bases);
+        if (devices.empty()) { fprintf(stderr, "%s: no usable CUDA device: %s (this build has no CPU path)\n", prog, vs_last_error(nullptr)); fclose(out); return 1; }
+        vs_scan_stats st;
+        int rc = vs::scan_text_sharded(t.words, (t.n_bases + 31) >> 5, devices, guides.data(), n_guides, (int)mism, extra_pam, hits, &st, err);
+        if (rc != VS_OK) { fprintf(stderr, "%s: scan failed: %s\n", prog, err.c_str()); fclose(out); return 1; }
+        if (getenv("VARSCOT_VERBOSE"))
+            fprintf(stderr, "%s: %zu device(s), %.3f ms scan (count %.3f, extract %.3f, score %.3f), %llu candidates, %llu hits\n", prog,
+                    devices.size(), st.total_ms, st.count_ms, st.extract_ms, st.score_ms,
+                    (unsigned long long)(st.n_cand_fwd + st.n_cand_rev), (unsigned long long)st.n_hits);
+    }
+    std::vector<vs_record> rec(hits.size());
+    uint64_t coll = 0;
+    if (!hits.empty() && vs_resolve_hits(hits.data(), hits.size(), t.off, t.n_contigs, rec.data(), &coll) != VS_OK) {
+        fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr)); fclose(out); return 1;
+    }
+    if (coll) fprintf(stderr, "%s: note: %llu records share a (contig id mod 65536, position) key; the reference's uint16 map key would have kept one of each\n", prog, (unsigned long long)coll);
+    std::string line;
+    std::vector<char> buf(1 << 16);
+    for (const vs_record &r : rec) {
+        char md[64];
+        const uint8_t *g = guides.data() + (size_t)r.guide * VS_GLEN;
+        vs_md_string(t.words, t.off[r.contig] + r.pos, g, (r.flag >> 4) & 1, md_style, md);
+        const std::string &qn = ids[r.guide], &rn = t.names[r.contig];
+        if (buf.size() < qn.size() + rn.size() + 256) buf.resize(qn.size() + rn.size() + 256);
+        int n = vs_format_sam(&r, qn.c_str(), rn.c_str(), g, md, buf.data(), buf.size());
+        if (n < 0 || fwrite(buf.data(), 1, (size_t)n, out) != (size_t)n) { fprintf(stderr, "%s: write error\n", prog); fclose(out); return 1; }
+    }
+    if (fclose(out) != 0) { fprintf(stderr, "%s: write error\n", prog); return 1; }
+    return 0;
+}

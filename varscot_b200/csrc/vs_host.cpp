@@ -1,0 +1,382 @@
+// varscot_b200/csrc/vs_host.cpp — host half of the C ABI in include/varscot_scan.h:
+// text packer (the B200 analogue of bidir_index.cpp:36-47), packed-text cache, hit resolution
+// (std::map order + primary/secondary flags of bidir_mapping.cpp:154,164-187), MD/SAM formatting
+// (:111-123, :177-187) and text sharding across devices.  No search arithmetic lives here: hits
+// come only from the CUDA kernels (vs_device.cu); nothing in this file can substitute for them.
+#include "vs_internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// alphabet: SeqAn Dna5 for the text (R6): A,C,G,T(U) case-insensitive -> 0..3, everything else N (4);
+// whitespace is not sequence.  SKIP = 255.
+namespace {
+struct Lut {
+    uint8_t t[256];
+    Lut()
+    {
+        for (int i = 0; i < 256; ++i) t[i] = 4;
+        t[(int)'A'] = t[(int)'a'] = 0; t[(int)'C'] = t[(int)'c'] = 1; t[(int)'G'] = t[(int)'g'] = 2;
+        t[(int)'T'] = t[(int)'t'] = 3; t[(int)'U'] = t[(int)'u'] = 3;
+        t[(int)' '] = t[(int)'\t'] = t[(int)'\n'] = t[(int)'\r'] = t[(int)'\v'] = t[(int)'\f'] = 255;
+    }
+};
+const Lut g_lut;
+}  // namespace
+
+struct vs_packer {
+    std::vector<vs_word> words;
+    std::vector<uint64_t> off{0};
+    uint64_t n = 0;
+    bool finalized = false;
+};
+
+extern "C" vs_packer *vs_packer_new(void) { return new (std::nothrow) vs_packer(); }
+extern "C" void vs_packer_free(vs_packer *p) { delete p; }
+
+extern "C" int vs_packer_append(vs_packer *p, const char *chars, size_t len)
+{
+    if (!p || (!chars && len)) return VS_ERR_ARG;
+    if (p->finalized) { vs_set_last_error("vs_packer_append: packer already finalized"); return VS_ERR_ARG; }
+    uint64_t need = ((p->n + len + 31) >> 5) + 1;
+    if (p->words.size() < need) {
+        try { p->words.resize(std::max<uint64_t>(need, p->words.size() * 2), vs_word{0, 0, 0, 0}); }
+        catch (...) { return VS_ERR_NOMEM; }
+    }
+    vs_word *W = p->words.data();
+    uint64_t n = p->n;
+    for (size_t i = 0; i < len; ++i) {
+        uint8_t c = g_lut.t[(uint8_t)chars[i]];
+        if (c == 255) continue;
+        vs_word &w = W[n >> 5];
+        uint32_t bit = 1u << (n & 31);
+        if (c & 2) w.hi |= bit;
+        if (c & 1) w.lo |= bit;
+        if (c & 4) w.nm |= bit;
+        ++n;
+    }
+    p->n = n;
+    return VS_OK;
+}
+
+extern "C" int vs_packer_end_contig(vs_packer *p)
+{
+    if (!p || p->finalized) return VS_ERR_ARG;
+    if (p->n > p->off.back()) {
+        uint64_t last = p->n - 1;
+        p->words[last >> 5].em |= 1u << (last & 31);
+    }
+    p->off.push_back(p->n);
+    return VS_OK;
+}
+
+extern "C" uint64_t vs_packer_num_bases(const vs_packer *p) { return p ? p->n : 0; }
+extern "C" uint32_t vs_packer_num_contigs(const vs_packer *p) { return p ? (uint32_t)(p->off.size() - 1) : 0; }
+extern "C" uint64_t vs_packer_num_words(const vs_packer *p) { return p ? (p->n + 31) >> 5 : 0; }
+
+extern "C" const vs_word *vs_packer_words(vs_packer *p)
+{
+    if (!p) return nullptr;
+    uint64_t nw = (p->n + 31) >> 5;
+    p->words.resize(nw + 1, vs_word{0, 0, 0, 0});
+    if (p->n & 31) p->words[nw - 1].nm |= ~0u << (p->n & 31);   // padding past the end is N
+    p->words[nw] = vs_word{0u, 0u, ~0u, 0u};
+    p->finalized = true;
+    return p->words.data();
+}
+extern "C" const uint64_t *vs_packer_offsets(vs_packer *p) { return p ? p->off.data() : nullptr; }
+
+extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs, vs_word *out)
+{
+    if (!out || (!ascii && n_bases) || (!contig_off && n_contigs)) return VS_ERR_ARG;
+    if (n_contigs && (contig_off[0] != 0 || contig_off[n_contigs] != n_bases)) {
+        vs_set_last_error("vs_pack_text: offsets must start at 0 and end at n_bases");
+        return VS_ERR_ARG;
+    }
+    uint64_t nw = (n_bases + 31) >> 5;
+    memset(out, 0, (nw + 1) * sizeof(vs_word));
+    for (uint64_t i = 0; i < n_bases; ++i) {
+        uint8_t c = g_lut.t[(uint8_t)ascii[i]];
+        if (c == 255) c = 4;              // whitespace inside a pre-split text is just a non-base
+        vs_word &w = out[i >> 5];
+        uint32_t bit = 1u << (i & 31);
+        if (c & 2) w.hi |= bit;
+        if (c & 1) w.lo |= bit;
+        if (c & 4) w.nm |= bit;
+    }
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+        if (contig_off[c + 1] < contig_off[c]) { vs_set_last_error("vs_pack_text: offsets must be non-decreasing"); return VS_ERR_ARG; }
+        if (contig_off[c + 1] > contig_off[c]) {
+            uint64_t last = contig_off[c + 1] - 1;
+            out[last >> 5].em |= 1u << (last & 31);
+        }
+    }
+    if (n_bases & 31) out[nw - 1].nm |= ~0u << (n_bases & 31);
+    out[nw] = vs_word{0u, 0u, ~0u, 0u};
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed-text cache: <prefix>.vsidx
+namespace {
+struct IdxHeader {
+    char magic[8];
+    uint64_t n_bases;
+    uint32_t n_contigs;
+    uint32_t reserved;
+};
+const char IDX_MAGIC[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '1'};
+}  // namespace
+
+extern "C" int vs_text_save(const char *prefix, const vs_word *words, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs)
+{
+    if (!prefix || !words || !contig_off) return VS_ERR_ARG;
+    std::string path = std::string(prefix) + ".vsidx";
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) { vs_set_last_error(("cannot open " + path + " for writing").c_str()); return VS_ERR_IO; }
+    IdxHeader h;
+    memcpy(h.magic, IDX_MAGIC, 8);
+    h.n_bases = n_bases; h.n_contigs = n_contigs; h.reserved = 0;
+    uint64_t nw = ((n_bases + 31) >> 5) + 1;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 &&
+              fwrite(contig_off, sizeof(uint64_t), (size_t)n_contigs + 1, f) == (size_t)n_contigs + 1 &&
+              fwrite(words, sizeof(vs_word), nw, f) == nw;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { vs_set_last_error(("short write to " + path).c_str()); return VS_ERR_IO; }
+    return VS_OK;
+}
+
+extern "C" int vs_text_load(const char *prefix, vs_word **words, uint64_t *n_bases, uint64_t **contig_off, uint32_t *n_contigs)
+{
+    if (!prefix || !words || !n_bases || !contig_off || !n_contigs) return VS_ERR_ARG;
+    *words = nullptr; *contig_off = nullptr;
+    std::string path = std::string(prefix) + ".vsidx";
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { vs_set_last_error(("cannot open " + path).c_str()); return VS_ERR_IO; }
+    IdxHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, IDX_MAGIC, 8) != 0) {
+        fclose(f); vs_set_last_error((path + " is not a VSIDX001 packed text").c_str()); return VS_ERR_IO;
+    }
+    uint64_t nw = ((h.n_bases + 31) >> 5) + 1;
+    uint64_t *off = (uint64_t *)malloc(((size_t)h.n_contigs + 1) * sizeof(uint64_t));
+    vs_word *w = (vs_word *)malloc(nw * sizeof(vs_word));
+    if (!off || !w) { free(off); free(w); fclose(f); return VS_ERR_NOMEM; }
+    bool ok = fread(off, sizeof(uint64_t), (size_t)h.n_contigs + 1, f) == (size_t)h.n_contigs + 1 &&
+              fread(w, sizeof(vs_word), nw, f) == nw;
+    fclose(f);
+    if (!ok || off[h.n_contigs] != h.n_bases) { free(off); free(w); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
+    *words = w; *contig_off = off; *n_bases = h.n_bases; *n_contigs = h.n_contigs;
+    return VS_OK;
+}
+
+extern "C" void vs_free(void *p) { free(p); }
+
+// ------------------------------------------------------------------------------------------------
+// hit resolution
+namespace {
+struct SortRec {
+    uint64_t k1;   // guide << 17 | strand << 16 | (contig & 0xFFFF)
+    uint64_t k2;   // pos << 32 | (contig >> 16) << 8 | mm
+    uint32_t contig;
+};
+inline bool operator<(const SortRec &a, const SortRec &b) { return a.k1 != b.k1 ? a.k1 < b.k1 : a.k2 < b.k2; }
+}  // namespace
+
+extern "C" int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
+                               vs_record *out, uint64_t *key16_collisions)
+{
+    if ((n && (!hits || !out)) || !contig_off || n_contigs == 0) return n ? VS_ERR_ARG : VS_OK;
+    if (key16_collisions) *key16_collisions = 0;
+    std::vector<SortRec> v;
+    try { v.resize(n); } catch (...) { return VS_ERR_NOMEM; }
+    const uint64_t *ob = contig_off, *oe = contig_off + n_contigs + 1;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t gp = hits[i].pos;
+        // last contig c with off[c] <= gp (empty contigs share an offset; the non-empty one is the last)
+        const uint64_t *it = std::upper_bound(ob, oe, gp);
+        if (it == ob || it == oe) { vs_set_last_error("vs_resolve_hits: hit position outside the text"); return VS_ERR_ARG; }
+        uint32_t c = (uint32_t)(it - ob - 1);
+        uint32_t pos = (uint32_t)(gp - contig_off[c]);
+        uint32_t info = hits[i].info;
+        uint64_t guide = info >> 8, strand = (info >> 7) & 1, mm = info & 0xF;
+        v[i].k1 = (guide << 17) | (strand << 16) | (c & 0xFFFFu);
+        v[i].k2 = ((uint64_t)pos << 32) | ((uint64_t)(c >> 16) << 8) | mm;
+        v[i].contig = c;
+    }
+    std::sort(v.begin(), v.end());
+    // running-best emission per (guide, strand) pass, bidir_mapping.cpp:164-187
+    uint64_t w = 0, coll = 0;
+    uint64_t i = 0;
+    auto emit = [&](const SortRec &r, uint16_t secondary) {
+        vs_record &o = out[w++];
+        o.guide = (uint32_t)(r.k1 >> 17);
+        o.contig = r.contig;
+        o.pos = (uint32_t)(r.k2 >> 32);
+        o.mm = (uint8_t)(r.k2 & 0xF);
+        o.flag = (uint16_t)(secondary | (((r.k1 >> 16) & 1) ? 16 : 0));
+        o.pad = 0;
+    };
+    while (i < n) {
+        uint64_t j = i + 1;
+        const uint64_t pass = v[i].k1 >> 16;
+        while (j < n && (v[j].k1 >> 16) == pass) ++j;
+        uint64_t best = i;
+        for (uint64_t t = i + 1; t < j; ++t) {
+            if (v[t].k1 == v[t - 1].k1 && (v[t].k2 >> 32) == (v[t - 1].k2 >> 32)) ++coll;   // same (id16, pos): uint16 key collision
+            if ((v[t].k2 & 0xF) >= (v[best].k2 & 0xF)) emit(v[t], 256);
+            else { emit(v[best], 256); best = t; }
+        }
+        emit(v[best], 0);
+        i = j;
+    }
+    if (key16_collisions) *key16_collisions = coll;
+    return VS_OK;
+}
+
+static inline int base_at(const vs_word *words, uint64_t p)
+{
+    const vs_word &w = words[p >> 5];
+    uint32_t b = (uint32_t)(p & 31);
+    if ((w.nm >> b) & 1) return 4;
+    return (int)(((w.hi >> b) & 1) << 1 | ((w.lo >> b) & 1));
+}
+
+extern "C" int vs_md_string(const vs_word *words, uint64_t gpos, const uint8_t *guide, int strand, int md_style, char *out)
+{
+    if (!words || !guide || !out) return VS_ERR_ARG;
+    static const char L[5] = {'A', 'C', 'G', 'T', 'N'};
+    int n = 0, run = 0;
+    bool in_match = false, any = false;
+    for (int i = 0; i < VS_GLEN; ++i) {
+        int g = strand ? 3 - guide[VS_GLEN - 1 - i] : guide[i];   // pattern of the pass, genome-forward orientation
+        int t = base_at(words, gpos + i);
+        if (t == g) { ++run; in_match = true; any = true; continue; }
+        // mismatch column: genome character (row 0 of the Align at bidir_mapping.cpp:117)
+        if (md_style == VS_MD_SAMTOOLS) n += sprintf(out + n, "%d", run);
+        else if (in_match) n += sprintf(out + n, "%d", run);
+        out[n++] = L[t];
+        run = 0; in_match = false; any = true;
+    }
+    if (md_style == VS_MD_SAMTOOLS || in_match) n += sprintf(out + n, "%d", run);
+    (void)any;
+    out[n] = 0;
+    return VS_OK;
+}
+
+extern "C" int vs_format_sam(const vs_record *r, const char *qname, const char *rname, const uint8_t *guide,
+                             const char *md, char *buf, size_t buflen)
+{
+    if (!r || !qname || !rname || !guide || !md || !buf) return -1;
+    static const char L[4] = {'A', 'C', 'G', 'T'};
+    char seq[VS_GLEN + 1];
+    for (int i = 0; i < VS_GLEN; ++i) seq[i] = L[guide[i] & 3];   // SEQ is always the original guide, bidir_mapping.cpp:106-108
+    seq[VS_GLEN] = 0;
+    int n = snprintf(buf, buflen, "%s\t%u\t%s\t%u\t255\t23M\t*\t0\t0\t%s\tIIIIIIIIIIIIIIIIIIIIIII\tNM:i:%u\tMD:Z:%s\n",
+                     qname, (unsigned)r->flag, rname, r->pos + 1u, seq, (unsigned)r->mm, md);
+    if (n < 0 || (size_t)n >= buflen) return -1;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharding across devices: contiguous word ranges, no collective, hits concatenated on the host
+namespace vs {
+
+std::vector<uint64_t> shard_bounds(uint64_t n_words, int n)
+{
+    if (n < 1) n = 1;
+    std::vector<uint64_t> b((size_t)n + 1, 0);
+    const uint64_t tile = 256;   // keep shard starts tile-aligned
+    uint64_t tiles = (n_words + tile - 1) / tile;
+    for (int i = 0; i <= n; ++i) {
+        uint64_t t = tiles * (uint64_t)i / (uint64_t)n;
+        b[(size_t)i] = std::min(n_words, t * tile);
+    }
+    b[(size_t)n] = n_words;
+    return b;
+}
+
+int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<int> &devices_in,
+                      const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                      std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err)
+{
+    std::vector<int> devices = devices_in;
+    if (devices.empty()) devices.push_back(0);
+    const int nd = (int)devices.size();
+    std::vector<uint64_t> b = shard_bounds(n_words, nd);
+    std::vector<std::vector<vs_hit>> part((size_t)nd);
+    std::vector<int> rc((size_t)nd, VS_OK);
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<vs_scan_stats> st((size_t)nd);
+    auto work = [&](int i) {
+        vs_ctx *ctx = nullptr;
+        memset(&st[(size_t)i], 0, sizeof(vs_scan_stats));
+        uint64_t w0 = b[(size_t)i], w1 = b[(size_t)i + 1];
+        if (w1 <= w0) return;
+        int r = vs_ctx_create(devices[(size_t)i], &ctx);
+        if (r == VS_OK) r = vs_text_upload(ctx, words + w0, w1 - w0, w0 * 32);
+        if (r == VS_OK) {
+            uint64_t n = 0;
+            std::vector<vs_hit> &h = part[(size_t)i];
+            h.resize(1u << 16);
+            r = vs_scan(ctx, guides, n_guides, k, extra_pam, h.data(), h.size(), &n, &st[(size_t)i]);
+            if (r == VS_ERR_OVERFLOW) {
+                h.resize(n);
+                r = vs_scan_fetch(ctx, h.data(), h.size(), &n);
+            }
+            if (r == VS_OK) h.resize(n);
+        }
+        if (r != VS_OK) errs[(size_t)i] = vs_last_error(ctx);
+        rc[(size_t)i] = r;
+        vs_ctx_destroy(ctx);
+    };
+    if (nd == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; ++i) th.emplace_back(work, i);
+        for (auto &t : th) t.join();
+    }
+    hits.clear();
+    if (agg) memset(agg, 0, sizeof(*agg));
+    for (int i = 0; i < nd; ++i) {
+        if (rc[(size_t)i] != VS_OK) { err = "device " + std::to_string(devices[(size_t)i]) + ": " + errs[(size_t)i]; return rc[(size_t)i]; }
+        hits.insert(hits.end(), part[(size_t)i].begin(), part[(size_t)i].end());
+        if (agg) {
+            const vs_scan_stats &s = st[(size_t)i];
+            agg->count_ms = std::max(agg->count_ms, s.count_ms); agg->extract_ms = std::max(agg->extract_ms, s.extract_ms);
+            agg->score_ms = std::max(agg->score_ms, s.score_ms); agg->total_ms = std::max(agg->total_ms, s.total_ms);
+            agg->n_cand_fwd += s.n_cand_fwd; agg->n_cand_rev += s.n_cand_rev;
+            agg->n_blocks_fwd += s.n_blocks_fwd; agg->n_blocks_rev += s.n_blocks_rev;
+            agg->n_hits += s.n_hits; agg->launches += s.launches; agg->score_launches += s.score_launches;
+        }
+    }
+    return VS_OK;
+}
+
+}  // namespace vs
+
+extern "C" int vs_map_packed(const vs_word *words, uint64_t n_bases, const uint8_t *guides, uint32_t n_guides,
+                             int k, int extra_pam, const int *devices, int n_devices,
+                             vs_hit **hits, uint64_t *n_hits, vs_scan_stats *stats)
+{
+    if (!hits || !n_hits || (!words && n_bases)) return VS_ERR_ARG;
+    *hits = nullptr; *n_hits = 0;
+    std::vector<int> dev;
+    for (int i = 0; i < n_devices && devices; ++i) dev.push_back(devices[i]);
+    std::vector<vs_hit> h;
+    std::string err;
+    int rc = vs::scan_text_sharded(words, (n_bases + 31) >> 5, dev, guides, n_guides, k, extra_pam, h, stats, err);
+    if (rc != VS_OK) { vs_set_last_error(err.c_str()); return rc; }
+    if (!h.empty()) {
+        vs_hit *o = (vs_hit *)malloc(h.size() * sizeof(vs_hit));
+        if (!o) return VS_ERR_NOMEM;
+        memcpy(o, h.data(), h.size() * sizeof(vs_hit));
+        *hits = o;
+    }
+    *n_hits = h.size();
+    return VS_OK;
+}

@@ -1,0 +1,20 @@
+// varscot_b200/csrc/vs_internal.h — helpers shared by the host and device halves of libvarscot_scan.
+#pragma once
+#include "../../include/varscot_scan.h"
+#include <string>
+#include <vector>
+
+void vs_set_last_error(const char *msg);
+
+namespace vs {
+
+// Scan a packed text on one or several devices (text sharded by word ranges, one host thread and one
+// context per device, no collective) and return all hits, unordered.  devices empty -> device 0.
+int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<int> &devices,
+                      const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                      std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err);
+
+// Split [0, n_words) into n contiguous shards of (almost) equal size, tile-aligned.
+std::vector<uint64_t> shard_bounds(uint64_t n_words, int n);
+
+}  // namespace vs
