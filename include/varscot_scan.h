@@ -122,6 +122,10 @@ int vs_map_packed(const vs_word *words, uint64_t n_bases, const uint8_t *guides,
                   int k, int extra_pam, const int *devices, int n_devices,
                   vs_hit **hits, uint64_t *n_hits, vs_scan_stats *stats);
 
+/* Shard plan used by vs_map_packed and by one-process-per-GPU callers: out[0..n] are word indices, shard i owns the
+ * window starts of words [out[i], out[i+1]) and reads one halo word after them.  Tile-aligned, balanced. */
+int vs_shard_bounds(uint64_t n_words, int n_shards, uint64_t *out);
+
 /* ---- host-side resolution ------------------------------------------------------------------- */
 typedef struct {
     uint32_t guide;

@@ -249,3 +249,20 @@ def test_config1_shape_50mbp():
     got = gpu_rows(bytes(asc_all), off, guides, 4)
     assert got == exp
     assert len(exp) >= 60
+
+
+def test_candidate_store_regrow_and_dense_hits():
+    """Low-complexity text: every window is a forward candidate (8x the sized-for density) and every one is a hit."""
+    import varscot_b200 as V
+    n = 1_200_000
+    asc = b"G" * n
+    off = np.array([0, n], dtype=np.uint64)
+    guides = np.full((1, GLEN), 2, dtype=np.uint8)
+    text = V.PackedText.from_ascii(asc, off)
+    with V.ScanContext(0) as ctx:
+        ctx.upload(text.words)
+        hits, st = ctx.scan(guides, 0, cap=16)
+    assert st.n_cand_fwd == n - 22 and st.n_cand_rev == 0
+    assert len(hits) == n - 22
+    assert np.array_equal(np.sort(hits["pos"]), np.arange(n - 22, dtype=np.uint32))
+    assert (hits["info"] == 0).all()

@@ -1,0 +1,226 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol, the packer,
+the packed-text cache, hit resolution (order + flags) and MD/SAM formatting agree with the oracle, the two
+executables keep the reference's argv contract and exit codes, and nothing in the product reaches the oracle."""
+import glob
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import varscot_b200 as V
+from varscot_b200 import _lib
+from oracle import oracle as O
+from tests.util import GLEN, make_case, write_fasta, write_guides
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "read_mapping_build")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "varscot_scan.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+
+
+def test_library_contains_sm100a_kernels():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_never_touches_the_oracle():
+    srcs = glob.glob(os.path.join(ROOT, "varscot_b200", "**", "*.*"), recursive=True) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    for f in srcs:
+        if f.endswith((".so", ".pyc")):
+            continue
+        txt = open(f, errors="ignore").read()
+        assert "vo_" not in txt and "libvo_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_no_device_fails_loudly():
+    if V.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(V.VarscotError) as e:
+        V.ScanContext(0)
+    assert e.value.code == _lib.VS_ERR_NODEVICE
+
+
+def test_pack_text_matches_numpy():
+    rng = np.random.default_rng(0)
+    lens = [100, 0, 37, 64, 5, 1, 31, 32, 33]
+    asc = bytes(rng.choice(np.frombuffer(b"ACGTNacgtnRYuU*-", dtype=np.uint8), sum(lens)))
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    t = V.PackedText.from_ascii(asc, off)
+    codes = O.text_codes(asc)
+    n = len(codes)
+    bits = lambda f: np.unpackbits(np.ascontiguousarray(t.words[f]).view(np.uint8), bitorder="little")
+    assert (bits("nm")[:n] == (codes == 4)).all()
+    assert ((bits("hi")[:n] * 2 + bits("lo")[:n])[codes < 4] == codes[codes < 4]).all()
+    assert (bits("hi")[:n][codes == 4] == 0).all() and (bits("lo")[:n][codes == 4] == 0).all()
+    ends = np.zeros(n, np.uint8)
+    ends[[int(b) - 1 for a, b in zip(off[:-1], off[1:]) if b > a]] = 1
+    assert (bits("em")[:n] == ends).all()
+    assert (bits("nm")[n:] == 1).all()                     # padding and the pad word read as N
+    assert len(t.words) == (n + 31) // 32 + 1
+
+
+def test_streaming_packer_and_fasta_quirks(tmp_path):
+    case = make_case(3, [1000, 0, 45, 70, 71, 23], 1, 4)
+    p = str(tmp_path / "g.fa")
+    names = ["chr1 with description", "empty", "c_45", "c70", "c71", "c23"]
+    write_fasta(p, names, case.ascii, case.offsets, width=70)
+    a = V.PackedText.from_fasta(p)
+    b = V.PackedText.from_ascii(case.ascii, case.offsets)
+    assert a.n_bases == b.n_bases and a.offsets.tolist() == b.offsets.tolist() and a.names == names
+    assert a.words.tobytes() == b.words.tobytes()
+    # CRLF line ends, blank lines, no trailing newline, leading junk before the first header
+    raw = open(p, "rb").read().replace(b"\n", b"\r\n")
+    raw = b"junk line\r\n" + raw.rstrip(b"\r\n").replace(b">c70", b"\r\n>c70")
+    p2 = str(tmp_path / "g2.fa")
+    open(p2, "wb").write(raw)
+    assert subprocess.run([os.path.join(BIN, "bidir_index"), "-G", p2, "-I", str(tmp_path / "i2")], capture_output=True).returncode == 0
+    c = V.PackedText.load(str(tmp_path / "i2"))
+    assert c.n_bases == b.n_bases and c.offsets.tolist() == b.offsets.tolist()
+    assert c.words.tobytes() == b.words.tobytes()
+
+
+def test_text_cache_roundtrip_and_errors(tmp_path):
+    case = make_case(4, [500, 45, 45], 1, 4)
+    t = V.PackedText.from_ascii(case.ascii, case.offsets)
+    t.save(str(tmp_path / "idx"))
+    u = V.PackedText.load(str(tmp_path / "idx"))
+    assert u.n_bases == t.n_bases and u.offsets.tolist() == t.offsets.tolist() and u.words.tobytes() == t.words.tobytes()
+    with pytest.raises(V.VarscotError):
+        V.PackedText.load(str(tmp_path / "missing"))
+    open(str(tmp_path / "bad.vsidx"), "wb").write(b"not an index")
+    with pytest.raises(V.VarscotError):
+        V.PackedText.load(str(tmp_path / "bad"))
+
+
+def _oracle_hits(case, k, pam=None):
+    r = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, pam=pam)
+    hits = np.zeros(len(r), dtype=V.HIT_DT)
+    hits["pos"] = (case.offsets[r.contig] + r.pos).astype(np.uint32)
+    hits["info"] = (r.guide.astype(np.uint32) << 8) | (((r.flag & 16) >> 4).astype(np.uint32) << 7) | r.mm
+    return r, hits
+
+
+@pytest.mark.parametrize("seed,k", [(1, 4), (2, 6), (3, 8), (4, 0)])
+def test_resolve_hits_reproduces_oracle_order_flags_md_sam(seed, k):
+    """Feed the oracle's hits, shuffled, through the product's host pipeline: order, FLAG, MD and SAM must match."""
+    case = make_case(seed, [40000, 45, 45, 0, 23, 9000], 6, k)
+    r, hits = _oracle_hits(case, k)
+    assert len(r) > 5
+    rng = np.random.default_rng(seed)
+    rec, coll = V.resolve_hits(hits[rng.permutation(len(hits))], case.offsets)
+    assert coll == 0
+    assert [(int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"])) for x in rec] == [x[:5] for x in r.rows()]
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    import ctypes as C
+    for style in (V.MD_SEQAN, V.MD_SAMTOOLS):
+        ro = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, md_style=style)
+        for i, x in enumerate(rec):
+            md = V.md_string(text, int(case.offsets[x["contig"]]) + int(x["pos"]), case.guides[x["guide"]], (int(x["flag"]) >> 4) & 1, style)
+            assert md == ro.md[i]
+            if style == V.MD_SEQAN and i < 20:
+                line = V.format_sam(x, f"g{x['guide']}", case.names[x["contig"]], case.guides[x["guide"]], md)
+                buf = C.create_string_buffer(512)
+                orec = O._Rec(int(ro.guide[i]), int(ro.contig[i]), int(ro.pos[i]), int(ro.flag[i]), int(ro.mm[i]), 0, ro.md[i].encode())
+                n = O.lib().vo_format_sam(C.byref(orec), f"g{x['guide']}".encode(), case.names[x["contig"]].encode(),
+                                          case.guides[x["guide"]].ctypes.data, buf, 512)
+                assert line == buf.raw[:n].decode()
+                assert len(line.rstrip("\n").split("\t")) == 13
+
+
+def test_resolve_hits_wide_key_order_and_collision_count():
+    nct = 65536 + 3
+    off = (np.arange(nct + 1) * 45).astype(np.uint64)
+    hits = np.zeros(4, dtype=V.HIT_DT)
+    # same guide/strand: contigs 2, 65538 (same id16, same pos), 1, 65537 (same id16, different pos)
+    hits["pos"] = [2 * 45 + 5, 65538 * 45 + 5, 1 * 45 + 7, 65537 * 45 + 3]
+    hits["info"] = [(0 << 8) | 2, (0 << 8) | 1, (0 << 8) | 3, (0 << 8) | 3]
+    rec, coll = V.resolve_hits(hits, off)
+    assert coll == 1
+    # key order: (id16=1,pos=3,c=65537) (1,7,c=1) (2,5,c=2) (2,5,c=65538); running best -> emission
+    key = [(65537, 3), (1, 3), (2, 2), (65538, 1)]
+    exp = []
+    best = 0
+    for i in range(1, 4):
+        if key[i][1] >= key[best][1]:
+            exp.append((key[i][0], 256))
+        else:
+            exp.append((key[best][0], 256)); best = i
+    exp.append((key[best][0], 0))
+    assert [(int(x["contig"]), int(x["flag"])) for x in rec] == exp
+
+
+def test_golden_rows_roundtrip_through_host_pipeline():
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "case_*.json"))):
+        d = json.load(open(path))
+        off = np.array(d["offsets"], dtype=np.uint64)
+        hits = np.zeros(len(d["rows"]), dtype=V.HIT_DT)
+        for i, (g, flag, c, pos, mm, md) in enumerate(d["rows"]):
+            hits[i] = (int(off[c]) + pos, (g << 8) | (((flag >> 4) & 1) << 7) | mm)
+        rec, _ = V.resolve_hits(hits[::-1].copy(), off)
+        text = V.PackedText.from_ascii(d["ascii"].encode(), off)
+        guides = V.guide_codes(d["guides"])
+        got = [[int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"]),
+                V.md_string(text, int(off[x["contig"]]) + int(x["pos"]), guides[x["guide"]], (int(x["flag"]) >> 4) & 1)] for x in rec]
+        assert got == d["rows"]
+
+
+def test_shard_bounds_cover_text_once():
+    for nw, n in ((0, 1), (1, 1), (255, 2), (256, 2), (1000, 3), (100000, 8), (110987654, 8)):
+        b = V.shard_bounds(nw, n)
+        assert b[0] == 0 and b[-1] == nw and (np.diff(b.astype(np.int64)) >= 0).all()
+        assert all(int(x) % 256 == 0 for x in b[1:-1])
+        if nw > 256 * n * 8:
+            sizes = np.diff(b.astype(np.int64))
+            assert sizes.max() - sizes.min() <= 512
+
+
+def run_cli(prog, *args):
+    return subprocess.run([os.path.join(BIN, prog), *map(str, args)], capture_output=True, text=True)
+
+
+def test_cli_contract_exit_codes(tmp_path):
+    case = make_case(9, [2000], 2, 4)
+    g, r = str(tmp_path / "g.fa"), str(tmp_path / "r.fa")
+    write_fasta(g, ["chr1"], case.ascii, case.offsets)
+    write_guides(r, ["a", "b"], case.guide_strs)
+    # bidir_index: stdout lines of bidir_index.cpp:42,49
+    x = run_cli("bidir_index", "-G", g, "-I", tmp_path / "idx")
+    assert x.returncode == 0 and x.stdout == "Number of sequences: 1\nIndex created successfully\n"
+    assert os.path.exists(tmp_path / "idx.vsidx")
+    assert run_cli("bidir_index", "--genome", g, "--index", tmp_path / "idx2").returncode == 0
+    assert run_cli("bidir_index", "-G", g).returncode == 1                                  # missing required -I
+    assert run_cli("bidir_index", "-G", tmp_path / "g.txt", "-I", tmp_path / "i").returncode == 1   # extension validation
+    assert run_cli("bidir_index", "-G", tmp_path / "nope.fa", "-I", tmp_path / "i").returncode == 1
+    assert run_cli("bidir_index", "-h").returncode == 0
+    # bidir_mapping: parse errors -> 1 (bidir_mapping.cpp:219-220), k outside 0..8 -> 1 with the reference's message (:234-238)
+    base = ["-G", g, "-I", tmp_path / "idx", "-R", r, "-O", tmp_path / "o.sam"]
+    x = run_cli("bidir_mapping", *base, "-M", 9)
+    assert x.returncode == 1 and "Maximum number of mismatches must lie between 0 and 8" in x.stderr
+    assert run_cli("bidir_mapping", *base, "-M", -1).returncode == 1
+    assert run_cli("bidir_mapping", *base).returncode == 1                                   # -M required
+    assert run_cli("bidir_mapping", *base, "-M", "x").returncode == 1
+    assert run_cli("bidir_mapping", "-G", g, "-I", tmp_path / "idx", "-R", r, "-M", 4, "-O", tmp_path / "o.txt").returncode == 1
+    assert run_cli("bidir_mapping", *base, "-M", 4, "--bogus").returncode == 1
+    assert run_cli("bidir_mapping", "--help").returncode == 0
+    x = run_cli("bidir_mapping", "-G", g, "-I", tmp_path / "idx", "-R", r, "-M", 4, "-O", tmp_path / "nodir" / "o.sam")
+    assert x.returncode == 1 and "Could not open output path" in x.stderr
+    # wrong guide length is refused
+    write_guides(str(tmp_path / "bad.fa"), ["a"], ["ACGT"])
+    assert run_cli("bidir_mapping", "-G", g, "-I", tmp_path / "idx", "-R", tmp_path / "bad.fa", "-M", 4, "-O", tmp_path / "o.sam").returncode == 1
+    if V.device_count() == 0:
+        x = run_cli("bidir_mapping", *base, "-M", 4)
+        assert x.returncode == 1 and "no usable CUDA device" in x.stderr and "Reads loaded (total: 2)." in x.stdout

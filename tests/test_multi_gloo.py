@@ -1,0 +1,69 @@
+"""N > 1 host logic on CPU: two gloo ranks each own one shard of the packed text (vs_shard_bounds), produce the hits
+of their own window starts (here with the oracle standing in for the device, reading the same halo the device reads),
+gather them on rank 0 and resolve; the merged records must equal the unpartitioned result.  No data-path collective
+exists in the product; gloo only carries the test's gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import varscot_b200 as V
+    from oracle import oracle as O
+    from tests.util import make_case
+    case = make_case(77, [30000, 45, 45, 45, 8211, 0, 23, 9000], 6, 6)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    codes = O.text_codes(case.ascii)
+    b = V.shard_bounds(text.n_words, world)
+    s0, s1 = int(b[rank]) * 32, min(int(b[rank + 1]) * 32, text.n_bases)
+    hits = np.zeros(0, dtype=V.HIT_DT)
+    if s1 > s0:
+        # the shard reads its owned words plus a halo; one extra base keeps owned windows away from the artificial end
+        e = min(text.n_bases, s1 + 23)
+        off = np.concatenate([[0], case.offsets[(case.offsets > s0) & (case.offsets < e)].astype(np.int64) - s0, [e - s0]]).astype(np.uint64)
+        r = O.map_guides(codes[s0:e], off, case.guides, case.k)
+        gpos = off[r.contig].astype(np.int64) + r.pos.astype(np.int64) + s0
+        own = gpos < s1
+        hits = np.zeros(int(own.sum()), dtype=V.HIT_DT)
+        hits["pos"] = gpos[own]
+        hits["info"] = (r.guide[own].astype(np.uint32) << 8) | (((r.flag[own] & 16) >> 4).astype(np.uint32) << 7) | r.mm[own]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, hits.tobytes())
+    t = torch.tensor([float(len(hits))])
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        allh = np.concatenate([np.frombuffer(x, dtype=V.HIT_DT) for x in gathered])
+        assert len(allh) == int(t.item())
+        rec, _ = V.resolve_hits(allh, case.offsets)
+        whole = O.map_guides(codes, case.offsets, case.guides, case.k)
+        got = [(int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"])) for x in rec]
+        q.put((got == [x[:5] for x in whole.rows()], len(got), [len(np.frombuffer(x, dtype=V.HIT_DT)) for x in gathered]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_hits_merge_to_unpartitioned_result(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, n, per = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and n > 10
+    assert sum(1 for x in per if x > 0) >= 2        # more than one rank contributed hits

@@ -46,7 +46,7 @@ EXPORTS = [
     "vs_packer_num_contigs", "vs_packer_num_words", "vs_packer_words", "vs_packer_offsets", "vs_pack_text",
     "vs_text_save", "vs_text_load", "vs_free", "vs_device_count", "vs_ctx_create", "vs_ctx_destroy",
     "vs_last_error", "vs_text_upload", "vs_host_alloc", "vs_host_free", "vs_scan", "vs_scan_fetch",
-    "vs_map_packed", "vs_resolve_hits", "vs_md_string", "vs_format_sam", "vs_bidir_index_main",
+    "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_md_string", "vs_format_sam", "vs_bidir_index_main",
     "vs_bidir_mapping_main", "vs_measure_int_peaks",
 ]
 
@@ -86,6 +86,7 @@ def lib():
     L.vs_scan.argtypes = [vp, vp, u32, i32, i32, vp, u64, C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_scan_fetch.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.vs_map_packed.argtypes = [vp, u64, vp, u32, i32, i32, vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(ScanStats)]
+    L.vs_shard_bounds.argtypes = [u64, i32, vp]
     L.vs_resolve_hits.argtypes = [vp, u64, vp, u32, vp, C.POINTER(u64)]
     L.vs_md_string.argtypes = [vp, u64, vp, i32, i32, C.c_char_p]
     L.vs_format_sam.argtypes = [C.POINTER(Record), C.c_char_p, C.c_char_p, vp, C.c_char_p, C.c_char_p, C.c_size_t]

@@ -1,5 +1,5 @@
 // varscot_b200/csrc/vs_device.cu — device half of the C ABI in include/varscot_scan.h:
-// context, packed-text upload, the scan (count -> prefix -> extract -> score) and the integer-pipe
+// context, packed-text upload, the scan (extract -> score) and the integer-pipe
 // microbenchmarks.  Replaces the index-resident search loop of bidir_mapping.cpp:268,285-295.
 // There is NO CPU fallback: every entry point fails with VS_ERR_CUDA / VS_ERR_NODEVICE when no
 // sm_100 device is usable.
@@ -21,9 +21,6 @@ struct vs_ctx {
     // text
     vs_word *d_words = nullptr;
     uint64_t words_cap = 0, n_words = 0, global_base = 0;
-    // per-tile tables
-    uint32_t *d_tiles = nullptr;        // 4 arrays of tiles_cap: nblk_f, nblk_r, off_f, off_r
-    uint64_t tiles_cap = 0;
     // counters: [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev, [4] hits
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
     // candidate stores
@@ -119,7 +116,6 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_words);
-    cudaFree(ctx->d_tiles);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]); }
@@ -152,13 +148,6 @@ extern "C" int vs_text_upload(vs_ctx *ctx, const vs_word *words, uint64_t n_word
     if (n_words) CK(cudaMemcpyAsync(ctx->d_words, words, (n_words + 1) * sizeof(vs_word), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_words = n_words;
     ctx->global_base = global_base;
-    uint64_t n_tiles = (n_words + TILE_WORDS - 1) / TILE_WORDS;
-    if (n_tiles > ctx->tiles_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_tiles); ctx->d_tiles = nullptr; ctx->tiles_cap = 0;
-        CK(cudaMalloc(&ctx->d_tiles, 4 * n_tiles * sizeof(uint32_t)));
-        ctx->tiles_cap = n_tiles;
-    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->err.clear();
     return VS_OK;
@@ -217,7 +206,6 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
     PamParams pp;
     make_pam(extra_pam, pp);
     const uint32_t n_tiles = (uint32_t)((ctx->n_words + TILE_WORDS - 1) / TILE_WORDS);
-    uint32_t *nblk_f = ctx->d_tiles, *nblk_r = nblk_f + ctx->tiles_cap, *off_f = nblk_r + ctx->tiles_cap, *off_r = off_f + ctx->tiles_cap;
 
     // pattern tables: byte offset of the selected mismatch plane per position, per strand pass
     const uint32_t n_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
@@ -232,33 +220,38 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
             }
         }
 
-    CK(cudaEventRecord(ctx->ev[0], st));
-    CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned long long), st));
-    k_count<<<n_tiles, TILE_THREADS, 0, st>>>(ctx->d_words, ctx->n_words, pp, nblk_f, nblk_r, ctx->d_cnt);
-    k_scan<<<1, 1024, 0, st>>>(nblk_f, nblk_r, n_tiles, off_f, off_r, ctx->d_cnt + 2);
-    S.launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[1], st));
-    CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    S.n_cand_fwd = ctx->h_cnt[0]; S.n_cand_rev = ctx->h_cnt[1];
-    S.n_blocks_fwd = ctx->h_cnt[2]; S.n_blocks_rev = ctx->h_cnt[3];
-    const uint64_t nb[2] = {S.n_blocks_fwd, S.n_blocks_rev};
-    for (int s = 0; s < 2; ++s) {
-        if (nb[s] > ctx->blocks_cap[s]) {
-            cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
-            ctx->d_planes[s] = ctx->d_pos[s] = nullptr; ctx->blocks_cap[s] = 0;
-            uint64_t cap = nb[s] + nb[s] / 16 + 64;
-            CK(cudaMalloc(&ctx->d_planes[s], cap * BLK_WORDS * sizeof(uint32_t)));
-            CK(cudaMalloc(&ctx->d_pos[s], cap * 32 * sizeof(uint32_t)));
-            ctx->blocks_cap[s] = cap;
-        }
+    // candidate stores: sized for the expected PAM density, regrown (and the extraction repeated) on overflow
+    auto ensure_blocks = [&](int s, uint64_t need) -> int {
+        if (need <= ctx->blocks_cap[s]) return VS_OK;
+        cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
+        ctx->d_planes[s] = ctx->d_pos[s] = nullptr; ctx->blocks_cap[s] = 0;
+        CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
+        ctx->blocks_cap[s] = need;
+        return VS_OK;
+    };
+    {
+        uint64_t est = (uint64_t)((double)ctx->n_words * pp.n / 16.0 * 1.15) + n_tiles + 1024;
+        for (int s = 0; s < 2; ++s)
+            if (ctx->blocks_cap[s] == 0) { int r = ensure_blocks(s, est); if (r != VS_OK) return r; }
     }
-    CK(cudaEventRecord(ctx->ev[2], st));
-    k_extract<<<n_tiles, TILE_THREADS, 0, st>>>(ctx->d_words, ctx->n_words, ctx->global_base, pp, off_f, off_r, nblk_f, nblk_r,
-                                                ctx->d_planes[0], ctx->d_pos[0], ctx->d_planes[1], ctx->d_pos[1]);
-    S.launches += 1;
-    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[0], st));
+    uint64_t nb[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned long long), st));
+        k_extract<<<n_tiles, TILE_THREADS, 0, st>>>(ctx->d_words, ctx->n_words, ctx->global_base, pp,
+                                                    ctx->d_planes[0], ctx->d_pos[0], ctx->blocks_cap[0],
+                                                    ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap[1], ctx->d_cnt);
+        S.launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        S.n_cand_fwd = ctx->h_cnt[0]; S.n_cand_rev = ctx->h_cnt[1];
+        nb[0] = S.n_blocks_fwd = ctx->h_cnt[2]; nb[1] = S.n_blocks_rev = ctx->h_cnt[3];
+        if (nb[0] <= ctx->blocks_cap[0] && nb[1] <= ctx->blocks_cap[1]) break;
+        if (attempt == 1) return fail(ctx, VS_ERR_CUDA, "vs_scan: candidate store overflow after regrow");
+        for (int s = 0; s < 2; ++s) { int r = ensure_blocks(s, nb[s] + nb[s] / 32 + 64); if (r != VS_OK) return r; }
+    }
     CK(cudaEventRecord(ctx->ev[3], st));
 
     if (!ctx->d_hits) {
@@ -304,8 +297,8 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
     if (out && ncopy) CK(cudaMemcpyAsync(out, ctx->d_hits, ncopy * sizeof(vs_hit), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaEventElapsedTime(&S.count_ms, ctx->ev[0], ctx->ev[1]));
-    CK(cudaEventElapsedTime(&S.extract_ms, ctx->ev[2], ctx->ev[3]));
+    S.count_ms = 0.f;     // the separate count pass is gone: k_extract claims block ranges with atomics
+    CK(cudaEventElapsedTime(&S.extract_ms, ctx->ev[0], ctx->ev[3]));
     CK(cudaEventElapsedTime(&S.score_ms, ctx->ev[3], ctx->ev[4]));
     CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[0], ctx->ev[5]));
     if (stats) *stats = S;

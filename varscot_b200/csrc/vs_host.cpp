@@ -380,3 +380,11 @@ extern "C" int vs_map_packed(const vs_word *words, uint64_t n_bases, const uint8
     *n_hits = h.size();
     return VS_OK;
 }
+
+extern "C" int vs_shard_bounds(uint64_t n_words, int n_shards, uint64_t *out)
+{
+    if (!out || n_shards < 1) return VS_ERR_ARG;
+    std::vector<uint64_t> b = vs::shard_bounds(n_words, n_shards);
+    for (int i = 0; i <= n_shards; ++i) out[i] = b[(size_t)i];
+    return VS_OK;
+}

@@ -5,10 +5,10 @@
 // delegate (:34-127) — restated as a dense, PAM-first Hamming scan (rules R1-R4 of SURVEY.md 8a).
 //
 // Pipeline per scan (all on one stream):
-//   k_count    : per tile of 8192 window starts, count PAM-valid / N-free / in-contig windows per strand
-//   k_scan     : exclusive prefix sum of per-tile block counts (deterministic candidate layout)
-//   k_extract  : compact the candidates of each strand into blocks of 32, bit-sliced ACROSS candidates:
-//                48 words per block = {hi_i, lo_i} for i < 23, last-window mask, valid mask; + 32 positions
+//   k_extract  : per tile of 8192 window starts, find the PAM-valid / N-free / in-contig windows of each strand
+//                (bit-parallel), compact them into blocks of 32 candidates and store each block bit-sliced
+//                ACROSS candidates (per-thread 32x32 register transposes): 48 words per block =
+//                hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; + 32 positions
 //   k_score<K> : one thread per candidate block; expands the 46 planes into 92 "mismatch if guide base is b"
 //                planes in shared memory, then for every guide: 23 LDS (plane selected by the guide base,
 //                offset warp-uniform from constant memory) + 36 LOP3 carry-save adder + 2 LOP3 threshold.
@@ -80,88 +80,45 @@ __device__ __forceinline__ void cand_masks(const vs_word &a, const vs_word &b, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_count: per tile, number of 32-candidate blocks per strand.
-__global__ void __launch_bounds__(TILE_THREADS)
-k_count(const vs_word *__restrict__ W, uint64_t n_words, PamParams pp,
-        uint32_t *__restrict__ nblk_f, uint32_t *__restrict__ nblk_r, unsigned long long *__restrict__ ncand)
+// 32 x 32 bit-matrix transpose in registers (LSB-first): out[i] bit c = in[c] bit i.
+// 5 butterfly stages x 16 swaps; ptxas drops the swaps that only feed unused outputs.
+__host__ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
 {
-    __shared__ uint32_t sf[TILE_THREADS / 32], sr[TILE_THREADS / 32];
-    uint64_t w = (uint64_t)blockIdx.x * TILE_WORDS + threadIdx.x;
-    uint32_t fwd = 0, rev = 0, last;
-    if (w < n_words) {
-        vs_word a = W[w], b = W[w + 1];
-        cand_masks(a, b, pp, fwd, rev, last);
-    }
-    uint32_t cf = __popc(fwd), cr = __popc(rev);
+    uint32_t m = 0x0000FFFFu;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { cf += __shfl_xor_sync(0xffffffffu, cf, o); cr += __shfl_xor_sync(0xffffffffu, cr, o); }
-    if ((threadIdx.x & 31) == 0) { sf[threadIdx.x >> 5] = cf; sr[threadIdx.x >> 5] = cr; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tf = 0, tr = 0;
+    for (int j = 16; j; j >>= 1, m ^= m << j) {
 #pragma unroll
-        for (int i = 0; i < TILE_THREADS / 32; ++i) { tf += sf[i]; tr += sr[i]; }
-        nblk_f[blockIdx.x] = (tf + 31) >> 5;
-        nblk_r[blockIdx.x] = (tr + 31) >> 5;
-        if (tf) atomicAdd(&ncand[0], (unsigned long long)tf);
-        if (tr) atomicAdd(&ncand[1], (unsigned long long)tr);
-    }
-}
-
-// k_scan: single-CTA exclusive prefix sum over the per-tile block counts of both strands.
-__global__ void __launch_bounds__(1024)
-k_scan(const uint32_t *__restrict__ nf, const uint32_t *__restrict__ nr, uint32_t n_tiles,
-       uint32_t *__restrict__ off_f, uint32_t *__restrict__ off_r, unsigned long long *__restrict__ totals)
-{
-    __shared__ uint32_t wf[32], wr[32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t per = (n_tiles + 1023u) / 1024u;
-    uint32_t beg = (uint32_t)tid * per, end = beg + per;
-    if (beg > n_tiles) beg = n_tiles;
-    if (end > n_tiles) end = n_tiles;
-    uint32_t sf = 0, sr = 0;
-    for (uint32_t i = beg; i < end; ++i) { sf += nf[i]; sr += nr[i]; }
-    uint32_t xf = sf, xr = sr;     // inclusive warp scan
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t a = __shfl_up_sync(0xffffffffu, xf, o), b = __shfl_up_sync(0xffffffffu, xr, o);
-        if (lane >= o) { xf += a; xr += b; }
-    }
-    if (lane == 31) { wf[wid] = xf; wr[wid] = xr; }
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t a = wf[lane], b = wr[lane];
-        uint32_t ia = a, ib = b;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t p = __shfl_up_sync(0xffffffffu, ia, o), q = __shfl_up_sync(0xffffffffu, ib, o);
-            if (lane >= o) { ia += p; ib += q; }
+        for (int k = 0; k < 32; k = ((k | j) + 1) & ~j) {
+            uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
+            a[k | j] ^= t;
+            a[k] ^= t << j;
         }
-        wf[lane] = ia - a; wr[lane] = ib - b;     // exclusive warp offsets
-        if (lane == 31) { totals[0] = ia; totals[1] = ib; }
-    }
-    __syncthreads();
-    uint32_t of = wf[wid] + xf - sf, orr = wr[wid] + xr - sr;
-    for (uint32_t i = beg; i < end; ++i) {
-        off_f[i] = of; off_r[i] = orr;
-        of += nf[i]; orr += nr[i];
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_extract: compact candidates, transpose 32 windows into bit-sliced planes, write blocks.
-// Queue entry (uint16): local start (13 bits) | last-window flag << 15.
+constexpr int Q_STRIDE = 33;                                   // halfwords per queued block: odd stride -> conflict-free reads
+constexpr int Q_CAP    = (TILE_STARTS / 32) * Q_STRIDE;
+
+// k_extract: one CTA per tile of 8192 window starts.
+//   phase 1 (all threads, bit-parallel over 32 starts each): candidate masks, CTA-wide prefix sum, queue the
+//            candidates of each strand in shared memory as (local start | last << 15);
+//   phase 2 (one THREAD per 32-candidate block): gather the 23-base windows from the staged planes, transpose
+//            32 x 23 bits twice in registers, write 48 plane words + 32 positions.
+// Block ranges are claimed with one atomicAdd per strand per tile on cnt[2], cnt[3] (layout order is not
+// deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written and the host,
+// which reads the counters back, grows the stores and launches again.
+// Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask.
 __global__ void __launch_bounds__(TILE_THREADS)
 k_extract(const vs_word *__restrict__ W, uint64_t n_words, uint64_t global_base, PamParams pp,
-          const uint32_t *__restrict__ off_f, const uint32_t *__restrict__ off_r,
-          const uint32_t *__restrict__ nblk_f, const uint32_t *__restrict__ nblk_r,
-          uint32_t *__restrict__ planes_f, uint32_t *__restrict__ pos_f,
-          uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r)
+          uint32_t *__restrict__ planes_f, uint32_t *__restrict__ pos_f, uint64_t cap_f,
+          uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r, uint64_t cap_r,
+          unsigned long long *__restrict__ cnt)
 {
-    __shared__ uint32_t s_hi[TILE_WORDS + 1], s_lo[TILE_WORDS + 1];
-    __shared__ uint16_t q[2][TILE_STARTS];
+    __shared__ uint2 s_hl[TILE_WORDS + 1];
+    __shared__ uint16_t q[2][Q_CAP];
     __shared__ uint32_t wsum[2][TILE_THREADS / 32];
     __shared__ uint32_t tot[2];
+    __shared__ unsigned long long base[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS;
     const uint64_t w = w0 + tid;
@@ -170,12 +127,12 @@ k_extract(const vs_word *__restrict__ W, uint64_t n_words, uint64_t global_base,
         vs_word a = {0u, 0u, ~0u, 0u}, b = {0u, 0u, ~0u, 0u};
         if (w <= n_words) a = W[w];          // w == n_words is the halo / pad word, always readable
         if (w < n_words) b = W[w + 1];
-        s_hi[tid] = a.hi; s_lo[tid] = a.lo;
-        if (tid == TILE_THREADS - 1) { s_hi[TILE_WORDS] = b.hi; s_lo[TILE_WORDS] = b.lo; }
+        s_hl[tid] = make_uint2(a.hi, a.lo);
+        if (tid == TILE_THREADS - 1) s_hl[TILE_WORDS] = make_uint2(b.hi, b.lo);
         if (w < n_words) cand_masks(a, b, pp, fwd, rev, last);
     }
-    // block-wide exclusive scan of the per-thread candidate counts
-    uint32_t cf = __popc(fwd), cr = __popc(rev);
+    // CTA-wide exclusive scan of the per-thread candidate counts
+    const uint32_t cf = __popc(fwd), cr = __popc(rev);
     uint32_t xf = cf, xr = cr;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -190,51 +147,88 @@ k_extract(const vs_word *__restrict__ W, uint64_t n_words, uint64_t global_base,
         uint32_t a = wsum[0][i], b = wsum[1][i];
         if (i < wid) { bf += a; br += b; }
     }
-    if (tid == TILE_THREADS - 1) { tot[0] = bf + xf; tot[1] = br + xr; }
-    uint32_t of = bf + xf - cf, orr = br + xr - cr;
+    if (tid == TILE_THREADS - 1) {
+        const uint32_t nf_ = bf + xf, nr_ = br + xr;
+        tot[0] = nf_; tot[1] = nr_;
+        // claim block ranges; candidate totals are for the statistics only
+        base[0] = atomicAdd(&cnt[2], (unsigned long long)((nf_ + 31) >> 5));
+        base[1] = atomicAdd(&cnt[3], (unsigned long long)((nr_ + 31) >> 5));
+        if (nf_) atomicAdd(&cnt[0], (unsigned long long)nf_);
+        if (nr_) atomicAdd(&cnt[1], (unsigned long long)nr_);
+    }
     {
+        uint32_t of = bf + xf - cf, orr = br + xr - cr;
         uint32_t m = fwd;
-        while (m) { int b = __ffs(m) - 1; m &= m - 1; q[0][of++] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15)); }
+        while (m) {
+            int b = __ffs(m) - 1; m &= m - 1;
+            q[0][(of >> 5) * Q_STRIDE + (of & 31)] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15));
+            ++of;
+        }
         m = rev;
-        while (m) { int b = __ffs(m) - 1; m &= m - 1; q[1][orr++] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15)); }
+        while (m) {
+            int b = __ffs(m) - 1; m &= m - 1;
+            q[1][(orr >> 5) * Q_STRIDE + (orr & 31)] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15));
+            ++orr;
+        }
     }
     __syncthreads();
     const uint32_t nf = tot[0], nr = tot[1];
-    const uint32_t nbf = nblk_f[blockIdx.x], nbr = nblk_r[blockIdx.x];   // == ceil(nf/32), ceil(nr/32)
-    const uint64_t gbase = global_base + w0 * 32;
-    for (uint32_t j = wid; j < nbf + nbr; j += TILE_THREADS / 32) {
+    const uint32_t nbf = (nf + 31) >> 5, nbr = (nr + 31) >> 5;
+    const uint32_t gbase = (uint32_t)(global_base + w0 * 32);
+    for (uint32_t j = tid; j < nbf + nbr; j += TILE_THREADS) {
         const int s = j >= nbf;
         const uint32_t jj = s ? j - nbf : j;
         const uint32_t n = s ? nr : nf;
-        const uint32_t idx = jj * 32 + lane;
-        const bool valid = idx < n;
-        uint32_t hiw = 0, low = 0, lst = 0, lp = 0;
-        if (valid) {
-            uint32_t e = q[s][idx];
-            lst = e >> 15; lp = e & 0x1FFFu;
-            uint32_t wi = lp >> 5, o = lp & 31;
-            hiw = __funnelshift_r(s_hi[wi], s_hi[wi + 1], o) & 0x7FFFFFu;
-            low = __funnelshift_r(s_lo[wi], s_lo[wi + 1], o) & 0x7FFFFFu;
-        }
-        uint32_t m0 = 0, m1 = 0;   // lane l keeps block word l (m0) and word 32 + l (m1, l < 16)
-#pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) {
-            uint32_t ph = __ballot_sync(0xffffffffu, (hiw >> i) & 1u);
-            uint32_t pl = __ballot_sync(0xffffffffu, (low >> i) & 1u);
-            const int wh = 2 * i, wl = 2 * i + 1;
-            if (wh < 32) { if (lane == wh) m0 = ph; } else { if (lane == wh - 32) m1 = ph; }
-            if (wl < 32) { if (lane == wl) m0 = pl; } else { if (lane == wl - 32) m1 = pl; }
-        }
-        uint32_t pla = __ballot_sync(0xffffffffu, lst);
-        uint32_t pva = __ballot_sync(0xffffffffu, valid);
-        if (lane == BLK_LAST - 32) m1 = pla;
-        if (lane == BLK_VALID - 32) m1 = pva;
-        const uint64_t blk = (uint64_t)(s ? off_r[blockIdx.x] : off_f[blockIdx.x]) + jj;
+        const uint64_t blk = base[s] + jj;
+        if (blk >= (s ? cap_r : cap_f)) continue;          // overflow: host regrows and relaunches
+        const uint32_t cntc = min(32u, n - jj * 32);
+        const uint16_t *qq = &q[s][jj * Q_STRIDE];
         uint32_t *pl_out = (s ? planes_r : planes_f) + blk * BLK_WORDS;
-        uint32_t *ps_out = (s ? pos_r : pos_f) + blk * 32;
-        pl_out[lane] = m0;
-        if (lane < 16) pl_out[32 + lane] = m1;
-        ps_out[lane] = valid ? (uint32_t)(gbase + lp) : 0xFFFFFFFFu;
+        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
+        uint32_t a[32];
+        uint32_t lastw = 0;
+        // hi planes (+ positions, last mask)
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            uint32_t pp4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c4 * 4 + u;
+                uint32_t hw = 0, ps = 0xFFFFFFFFu;
+                if ((uint32_t)c < cntc) {
+                    const uint32_t e = qq[c];
+                    const uint32_t lp = e & 0x1FFFu, wi = lp >> 5, o = lp & 31;
+                    hw = __funnelshift_r(s_hl[wi].x, s_hl[wi + 1].x, o) & 0x7FFFFFu;
+                    lastw |= (e >> 15) << c;
+                    ps = gbase + lp;
+                }
+                a[c] = hw; pp4[u] = ps;
+            }
+            ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
+        }
+        transpose32(a);
+        uint32_t carry = a[20], carry1 = a[21], carry2 = a[22];   // words 20..22 are stored with the first lo planes
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            reinterpret_cast<uint4 *>(pl_out)[i] = make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+        // lo planes
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            uint32_t lw = 0;
+            if ((uint32_t)c < cntc) {
+                const uint32_t lp = qq[c] & 0x1FFFu, wi = lp >> 5, o = lp & 31;
+                lw = __funnelshift_r(s_hl[wi].y, s_hl[wi + 1].y, o) & 0x7FFFFFu;
+            }
+            a[c] = lw;
+        }
+        transpose32(a);
+        // words 20..47: hi_20, hi_21, hi_22, lo_0 .. lo_22, last, valid
+        reinterpret_cast<uint4 *>(pl_out)[5] = make_uint4(carry, carry1, carry2, a[0]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            reinterpret_cast<uint4 *>(pl_out)[6 + i] = make_uint4(a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], a[4 * i + 4]);
+        const uint32_t validw = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
+        reinterpret_cast<uint4 *>(pl_out)[11] = make_uint4(a[21], a[22], lastw, validw);
     }
 }
 
@@ -285,7 +279,7 @@ k_score(ScoreArgs a)
         const uint32_t inv = ~v[BLK_VALID];
 #pragma unroll
         for (int i = 0; i < VS_GLEN; ++i) {
-            const uint32_t h = v[2 * i], l = v[2 * i + 1];
+            const uint32_t h = v[i], l = v[VS_GLEN + i];
             const uint32_t x = (i < 9) ? inv : 0u;     // 9 forced mismatches keep invalid lanes above any k <= 8
             my[(4 * i + 0) * SCORE_THREADS] = (h | l) | x;      // mismatch if guide base is A (00)
             my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | x;     // C (01)

@@ -201,6 +201,13 @@ def map_packed(text: PackedText, guides: np.ndarray, k: int, pam=None, devices=N
     return hits, st
 
 
+def shard_bounds(n_words: int, n_shards: int) -> np.ndarray:
+    """vs_shard_bounds: word ranges owned by each of n_shards ranks / devices."""
+    out = np.zeros(n_shards + 1, dtype=np.uint64)
+    check(_lib.lib().vs_shard_bounds(n_words, n_shards, out.ctypes.data))
+    return out
+
+
 def resolve_hits(hits: np.ndarray, offsets: np.ndarray):
     """vs_resolve_hits: reference emission order + flags. Returns (records, key16_collisions)."""
     L = _lib.lib()
