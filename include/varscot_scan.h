@@ -9,10 +9,11 @@
  *
  * Entry point                      replaces (reference file:line)
  * -------------------------------  -----------------------------------------------------------------
- * vs_packer_* / vs_pack_text       bidir_index.cpp:36-47  readRecords -> Dna5 StringSet -> indexCreate
+ * vs_packer_* / vs_pack_text /     bidir_index.cpp:36-47  readRecords -> Dna5 StringSet -> indexCreate
+ * vs_masks_from_planes / _sparse
  * vs_text_save / vs_text_load      bidir_index.cpp:47 save(index, path); bidir_mapping.cpp:268 open(index, path)
  * vs_ctx_create / vs_text_upload   bidir_mapping.cpp:268  index resident in RAM -> packed text resident in HBM
- * vs_scan                          bidir_mapping.cpp:285-295 omp-parallel loop over guides calling
+ * vs_scan / vs_scan_text           bidir_mapping.cpp:285-295 omp-parallel loop over guides calling
  *                                  searchAndVerifyEntireRead -> searchAndVerify (:31-148, :150-188):
  *                                  seed search + verify delegate, for both strands
  * vs_resolve_hits                  bidir_mapping.cpp:154,164-187  std::map order + primary/secondary flags
@@ -43,37 +44,56 @@ enum {
 };
 
 /* ---- packed text ---------------------------------------------------------------------------
- * The text (all contigs concatenated, "ConcatDirect" as bidir_index.cpp:12) is stored bit-sliced,
- * 32 bases per word, base j of a word in bit j:
- *   hi, lo : the two bits of the Dna code (A=00, C=01, G=10, T=11)
- *   nm     : 1 where the base is N (anything outside ACGT/U, R6) or padding past the end
- *   em     : 1 where the base is the LAST base of a contig
- * n_words = ceil(n_bases/32); the array always carries ONE extra pad word (nm = all ones) so that
- * word[i+1] is readable for every owned word i.
+ * The text (all contigs concatenated, "ConcatDirect" as bidir_index.cpp:12) is stored bit-sliced, 32 bases per
+ * word, base j of a word in bit j, as a structure of arrays:
+ *   bases[w] = {hi, lo}  the two bits of the Dna code (A=00, C=01, G=10, T=11); N and padding are 00
+ *   masks[w] = {iv, lw}  per WINDOW START p = 32 w + j:
+ *                iv: the 23-base window at p is not scannable — it contains an N (anything outside ACGT/U, R6),
+ *                    runs over the end of its contig, or runs past the end of the text (R1, R3)
+ *                lw: the window ends exactly on the last base of its contig (R4: bidir_mapping.cpp:51 lets only
+ *                    the second-half seed reach it)
+ * n_words = ceil(n_bases/32).  bases carries ONE extra all-zero pad word (bases[n_words]) so that word w+1 is
+ * readable for every w < n_words; masks has n_words entries.  `sparse` optionally lists the non-zero mask words
+ * in ascending word order: uploads then move only those over PCIe.
  */
-typedef struct { uint32_t hi, lo, nm, em; } vs_word;
+typedef struct { uint32_t hi, lo; } vs_bases;
+typedef struct { uint32_t iv, lw; } vs_masks;
+typedef struct { uint32_t word, iv, lw; } vs_mask_entry;
+
+typedef struct {
+    uint64_t n_bases;
+    uint64_t n_words;
+    uint32_t n_contigs;
+    uint32_t reserved;
+    const uint64_t      *contig_off;   /* n_contigs + 1 */
+    const vs_bases      *bases;        /* n_words + 1 */
+    const vs_masks      *masks;        /* n_words */
+    const vs_mask_entry *sparse;       /* n_sparse entries, or NULL */
+    uint64_t n_sparse;
+} vs_text_view;
 
 typedef struct vs_packer vs_packer;
 vs_packer *vs_packer_new(void);
 void       vs_packer_free(vs_packer *p);
-/* append raw sequence characters (no newlines needed to be stripped: whitespace is skipped) */
+/* append raw sequence characters (whitespace, incl. newlines, is skipped) */
 int        vs_packer_append(vs_packer *p, const char *chars, size_t n);
 /* close the current contig (contigs of length 0 are kept: they occupy an id, SeqAn StringSet semantics) */
 int        vs_packer_end_contig(vs_packer *p);
-uint64_t   vs_packer_num_bases(const vs_packer *p);
-uint32_t   vs_packer_num_contigs(const vs_packer *p);
-uint64_t   vs_packer_num_words(const vs_packer *p);           /* without the pad word */
-/* pointers stay valid until the packer is freed or appended to; words has num_words+1 entries, offsets n_contigs+1 */
-const vs_word  *vs_packer_words(vs_packer *p);
-const uint64_t *vs_packer_offsets(vs_packer *p);
+/* finish: computes the window masks and their sparse form; the view's pointers stay valid until vs_packer_free */
+int        vs_packer_finish(vs_packer *p, vs_text_view *out);
 
-/* one-shot: ASCII text of all contigs concatenated + n_contigs+1 offsets -> out_words[ceil(n/32)+1] */
-int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs, vs_word *out_words);
+/* one-shot: ASCII text of all contigs concatenated + n_contigs+1 offsets -> bases[ceil(n/32)+1], masks[ceil(n/32)] */
+int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
+                 vs_bases *out_bases, vs_masks *out_masks);
+/* window masks from an N plane and a contig-end plane (both n_words + 1 words, the extra word is read as padding) */
+int vs_masks_from_planes(const uint32_t *nm, const uint32_t *em, uint64_t n_words, vs_masks *out);
+/* sparse form of a mask array: malloc'd list of the non-zero words (release with vs_free) */
+int vs_masks_sparse(const vs_masks *masks, uint64_t n_words, vs_mask_entry **out, uint64_t *n_out);
 
-/* packed-text cache at the -I prefix (files <prefix>.vsidx) */
-int vs_text_save(const char *prefix, const vs_word *words, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs);
-/* loads into malloc'd buffers the caller frees with vs_free */
-int vs_text_load(const char *prefix, vs_word **words, uint64_t *n_bases, uint64_t **contig_off, uint32_t *n_contigs);
+/* packed-text cache at the -I prefix (file <prefix>.vsidx) */
+int vs_text_save(const char *prefix, const vs_text_view *text);
+/* loads into ONE malloc'd buffer (returned in *owner, release with vs_free) that the view points into */
+int vs_text_load(const char *prefix, vs_text_view *out, void **owner);
 void vs_free(void *p);
 
 /* ---- device context ------------------------------------------------------------------------- */
@@ -83,11 +103,12 @@ int  vs_device_count(void);                     /* >= 0, or -VS_ERR_* */
 int  vs_ctx_create(int device, vs_ctx **ctx);   /* one context per device per host thread */
 void vs_ctx_destroy(vs_ctx *ctx);
 const char *vs_last_error(const vs_ctx *ctx);   /* ctx may be NULL: last error of the calling thread */
+/* words per pipeline chunk (default 4 Mi words = 128 Mi bases); tests shrink it to cross chunk borders */
+int  vs_ctx_set_chunk_words(vs_ctx *ctx, uint64_t chunk_words);
 
-/* Upload words [0, n_words) of a shard; words[n_words] must be readable (next word of the text, or the
- * pad word).  Window START positions in [0, 32*n_words) are owned by this context; hit positions are
- * reported as global_base + local start.  pinned != 0 promises `words` is page-locked. */
-int vs_text_upload(vs_ctx *ctx, const vs_word *words, uint64_t n_words, uint64_t global_base);
+/* Make words [first_word, first_word + n_words) of the text resident on the device (+ one halo word of bases).
+ * Window STARTS in those words are owned by this context; hit positions are global (32 * first_word + local). */
+int vs_text_upload(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words);
 
 /* page-locked host memory for fast uploads / hit downloads */
 void *vs_host_alloc(size_t bytes);
@@ -99,26 +120,34 @@ typedef struct {
 } vs_hit;
 
 typedef struct {
-    float    count_ms, extract_ms, score_ms, total_ms;   /* CUDA-event times on the context's stream */
+    float    upload_ms, extract_ms, score_ms, total_ms;  /* CUDA-event times; extract/score are sums over chunks */
     uint64_t n_cand_fwd, n_cand_rev;                      /* PAM-valid, N-free windows per strand */
     uint64_t n_blocks_fwd, n_blocks_rev;                  /* 32-candidate blocks scored per strand */
     uint64_t n_hits;
+    uint64_t h2d_bytes, d2h_bytes;                        /* bytes this call moved over PCIe */
     uint32_t launches;                                    /* kernels launched by this call */
     uint32_t score_launches;
+    uint32_t n_chunks;
+    uint32_t redo_chunks;                                 /* chunks redone because a candidate store overflowed */
 } vs_scan_stats;
 
-/* Scan the uploaded text for every window within k mismatches of each guide, both strands (rules R1-R4,
+/* Scan the RESIDENT text for every window within k mismatches of each guide, both strands (rules R1-R4,
  * SURVEY.md section 8a).  guides: n_guides x 23 Dna codes (0..3).  extra_pam: -1 or 4*x+y for -P XY.
  * Hits arrive UNORDERED.  If more than out_cap hits exist returns VS_ERR_OVERFLOW with *n_hits = needed;
  * the hits stay on the device and vs_scan_fetch() retrieves them without rescanning. */
 int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
             vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats);
+/* Same, reading the text from HOST memory: the upload of chunk i+1 overlaps the scan of chunk i (the text is
+ * resident afterwards).  This is the end-to-end call the executables use. */
+int vs_scan_text(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words,
+                 const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                 vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats);
 int vs_scan_fetch(vs_ctx *ctx, vs_hit *out, uint64_t out_cap, uint64_t *n_hits);
 
 /* Convenience used by the executables and bindings: shard a packed text by word ranges over the given
  * devices (devices == NULL or n_devices == 0 -> device 0; one host thread + one context per device, no
  * collective), scan, and return all hits unordered in a malloc'd array (release with vs_free). */
-int vs_map_packed(const vs_word *words, uint64_t n_bases, const uint8_t *guides, uint32_t n_guides,
+int vs_map_packed(const vs_text_view *text, const uint8_t *guides, uint32_t n_guides,
                   int k, int extra_pam, const int *devices, int n_devices,
                   vs_hit **hits, uint64_t *n_hits, vs_scan_stats *stats);
 
@@ -145,7 +174,7 @@ int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, 
 #define VS_MD_SEQAN 0
 #define VS_MD_SAMTOOLS 1
 /* MD:Z value for the window at global position gpos against guide (codes) on the given strand. out >= 64 bytes. */
-int vs_md_string(const vs_word *words, uint64_t gpos, const uint8_t *guide, int strand, int md_style, char *out);
+int vs_md_string(const vs_bases *bases, uint64_t gpos, const uint8_t *guide, int strand, int md_style, char *out);
 /* one 13-column SAM line (R9) incl. '\n'; returns the length written (excluding NUL), or -1 if buflen is too small */
 int vs_format_sam(const vs_record *r, const char *qname, const char *rname, const uint8_t *guide,
                   const char *md, char *buf, size_t buflen);

@@ -20,7 +20,7 @@ def oracle_rows(ascii_bytes, offsets, guides, k, pam=None):
     return r.rows()
 
 
-def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True):
+def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True, chunk_words=None, streamed=False, use_sparse=True):
     import varscot_b200 as V
     text = V.PackedText.from_ascii(ascii_bytes, offsets)
     parts = []
@@ -30,8 +30,14 @@ def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True):
         if bounds[i + 1] <= bounds[i]:
             continue
         with V.ScanContext(0) as ctx:
-            ctx.upload(text.words, bounds[i], bounds[i + 1] - bounds[i])
-            hits, _ = ctx.scan(guides, k, pam=pam, cap=1 << 12)
+            if chunk_words:
+                ctx.set_chunk_words(chunk_words)
+            if streamed:
+                hits, _ = ctx.scan_text(text, guides, k, pam=pam, first_word=bounds[i], n_words=bounds[i + 1] - bounds[i], cap=1 << 12,
+                                        use_sparse=use_sparse)
+            else:
+                ctx.upload(text, bounds[i], bounds[i + 1] - bounds[i], use_sparse=use_sparse)
+                hits, _ = ctx.scan(guides, k, pam=pam, cap=1 << 12)
             parts.append(hits.copy())
     hits = np.concatenate(parts) if parts else np.zeros(0, V.HIT_DT)
     rec, _ = V.resolve_hits(hits, offsets)
@@ -42,9 +48,9 @@ def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True):
     return rows
 
 
-def assert_same(case, shards=1):
+def assert_same(case, shards=1, **kw):
     exp = oracle_rows(case.ascii, case.offsets, case.guides, case.k, case.pam)
-    got = gpu_rows(case.ascii, case.offsets, case.guides, case.k, case.pam, shards=shards)
+    got = gpu_rows(case.ascii, case.offsets, case.guides, case.k, case.pam, shards=shards, **kw)
     assert len(got) == len(exp), f"{len(got)} GPU records vs {len(exp)} oracle records"
     assert got == exp
     return len(exp)
@@ -139,7 +145,7 @@ def test_contig_swarm_over_65536():
     import varscot_b200 as V
     text = V.PackedText.from_ascii(asc, off)
     with V.ScanContext(0) as ctx:
-        ctx.upload(text.words)
+        ctx.upload(text)
         hits, _ = ctx.scan(guides, 4)
     _, coll = V.resolve_hits(hits, off)
     assert coll >= 1
@@ -151,12 +157,37 @@ def test_sharded_text_equals_whole(shards):
     assert_same(case, shards=shards)
 
 
+@pytest.mark.parametrize("chunk_words,streamed,use_sparse", [(64, False, True), (64, True, True), (1000, True, False), (7, True, True),
+                                                             (256, False, False), (1 << 22, True, True)])
+def test_chunked_and_streamed_scan(chunk_words, streamed, use_sparse):
+    """Pipeline chunks smaller than the text: chunk borders (halo word), per-chunk counters, dense and sparse mask upload."""
+    case = make_case(seed=61, contig_lens=[70000, 45, 45, 45, 0, 23, 40000], n_guides=9, k=6, pam="AG")
+    assert_same(case, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse)
+    assert_same(case, shards=3, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse)
+
+
+def test_streamed_scan_leaves_text_resident():
+    import varscot_b200 as V
+    case = make_case(seed=62, contig_lens=[90000, 30000], n_guides=5, k=5)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets).pin()
+    with V.ScanContext(0) as ctx:
+        ctx.set_chunk_words(512)
+        a, st = ctx.scan_text(text, case.guides, 5)
+        assert st.n_chunks > 1 and st.h2d_bytes > text.n_words * 8
+        b, st2 = ctx.scan(case.guides, 5)
+        assert st2.h2d_bytes < 100000
+    ra, _ = V.resolve_hits(a, case.offsets)
+    rb, _ = V.resolve_hits(b, case.offsets)
+    assert ra.tolist() == rb.tolist() and len(ra) > 0
+    text.unpin()
+
+
 def test_hit_buffer_overflow_and_fetch():
     import varscot_b200 as V
     case = make_case(seed=33, contig_lens=[200000], n_guides=16, k=8, plant=False)
     text = V.PackedText.from_ascii(case.ascii, case.offsets)
     with V.ScanContext(0) as ctx:
-        ctx.upload(text.words)
+        ctx.upload(text)
         small, _ = ctx.scan(case.guides, 8, cap=4)          # forces VS_ERR_OVERFLOW + vs_scan_fetch
         big, _ = ctx.scan(case.guides, 8, cap=1 << 20)
     assert len(small) == len(big) > 4
@@ -172,7 +203,7 @@ def test_repeat_scan_is_deterministic_after_resolve():
     case = make_case(seed=40, contig_lens=[100000], n_guides=10, k=6)
     text = V.PackedText.from_ascii(case.ascii, case.offsets)
     with V.ScanContext(0) as ctx:
-        ctx.upload(text.words)
+        ctx.upload(text)
         r = []
         for _ in range(3):
             hits, _ = ctx.scan(case.guides, 6)
@@ -260,8 +291,10 @@ def test_candidate_store_regrow_and_dense_hits():
     guides = np.full((1, GLEN), 2, dtype=np.uint8)
     text = V.PackedText.from_ascii(asc, off)
     with V.ScanContext(0) as ctx:
-        ctx.upload(text.words)
+        ctx.set_chunk_words(8192)
+        ctx.upload(text)
         hits, st = ctx.scan(guides, 0, cap=16)
+    assert st.redo_chunks > 0
     assert st.n_cand_fwd == n - 22 and st.n_cand_rev == 0
     assert len(hits) == n - 22
     assert np.array_equal(np.sort(hits["pos"]), np.arange(n - 22, dtype=np.uint32))

@@ -54,23 +54,39 @@ def test_no_device_fails_loudly():
     assert e.value.code == _lib.VS_ERR_NODEVICE
 
 
+def _expected_masks(codes, off):
+    """Brute-force window masks from Dna5 codes and contig offsets."""
+    n = len(codes)
+    nw = (n + 31) // 32
+    iv = np.ones(nw * 32, np.uint8)
+    lw = np.zeros(nw * 32, np.uint8)
+    for c in range(len(off) - 1):
+        s, e = int(off[c]), int(off[c + 1])
+        for p in range(s, e - 22):
+            if (codes[p:p + 23] < 4).all():
+                iv[p] = 0
+                lw[p] = 1 if p + 23 == e else 0
+    return np.packbits(iv, bitorder="little").view("<u4"), np.packbits(lw, bitorder="little").view("<u4")
+
+
 def test_pack_text_matches_numpy():
     rng = np.random.default_rng(0)
-    lens = [100, 0, 37, 64, 5, 1, 31, 32, 33]
-    asc = bytes(rng.choice(np.frombuffer(b"ACGTNacgtnRYuU*-", dtype=np.uint8), sum(lens)))
+    lens = [100, 0, 37, 64, 5, 1, 31, 32, 33, 23, 22, 45]
+    asc = bytes(rng.choice(np.frombuffer(b"ACGTACGTACGTACGTNacgtnRYuU*-", dtype=np.uint8), sum(lens)))
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     t = V.PackedText.from_ascii(asc, off)
     codes = O.text_codes(asc)
     n = len(codes)
-    bits = lambda f: np.unpackbits(np.ascontiguousarray(t.words[f]).view(np.uint8), bitorder="little")
-    assert (bits("nm")[:n] == (codes == 4)).all()
-    assert ((bits("hi")[:n] * 2 + bits("lo")[:n])[codes < 4] == codes[codes < 4]).all()
-    assert (bits("hi")[:n][codes == 4] == 0).all() and (bits("lo")[:n][codes == 4] == 0).all()
-    ends = np.zeros(n, np.uint8)
-    ends[[int(b) - 1 for a, b in zip(off[:-1], off[1:]) if b > a]] = 1
-    assert (bits("em")[:n] == ends).all()
-    assert (bits("nm")[n:] == 1).all()                     # padding and the pad word read as N
-    assert len(t.words) == (n + 31) // 32 + 1
+    bits = lambda a: np.unpackbits(np.ascontiguousarray(a).view(np.uint8), bitorder="little")
+    hi, lo = bits(t.bases["hi"]), bits(t.bases["lo"])
+    assert ((hi[:n] * 2 + lo[:n])[codes < 4] == codes[codes < 4]).all()
+    assert (hi[:n][codes == 4] == 0).all() and (lo[:n][codes == 4] == 0).all()
+    assert (hi[n:] == 0).all() and (lo[n:] == 0).all()          # padding and the pad word are zero
+    assert len(t.bases) == (n + 31) // 32 + 1 and len(t.masks) == (n + 31) // 32
+    eiv, elw = _expected_masks(codes, off)
+    assert (t.masks["iv"] == eiv).all() and (t.masks["lw"] == elw).all()
+    nz = np.flatnonzero((t.masks["iv"] | t.masks["lw"]) != 0)
+    assert t.sparse["word"].tolist() == nz.tolist() and (t.sparse["iv"] == t.masks["iv"][nz]).all() and (t.sparse["lw"] == t.masks["lw"][nz]).all()
 
 
 def test_streaming_packer_and_fasta_quirks(tmp_path):
@@ -81,7 +97,7 @@ def test_streaming_packer_and_fasta_quirks(tmp_path):
     a = V.PackedText.from_fasta(p)
     b = V.PackedText.from_ascii(case.ascii, case.offsets)
     assert a.n_bases == b.n_bases and a.offsets.tolist() == b.offsets.tolist() and a.names == names
-    assert a.words.tobytes() == b.words.tobytes()
+    assert a.bases.tobytes() == b.bases.tobytes() and a.masks.tobytes() == b.masks.tobytes() and a.sparse.tobytes() == b.sparse.tobytes()
     # CRLF line ends, blank lines, no trailing newline, leading junk before the first header
     raw = open(p, "rb").read().replace(b"\n", b"\r\n")
     raw = b"junk line\r\n" + raw.rstrip(b"\r\n").replace(b">c70", b"\r\n>c70")
@@ -90,7 +106,7 @@ def test_streaming_packer_and_fasta_quirks(tmp_path):
     assert subprocess.run([os.path.join(BIN, "bidir_index"), "-G", p2, "-I", str(tmp_path / "i2")], capture_output=True).returncode == 0
     c = V.PackedText.load(str(tmp_path / "i2"))
     assert c.n_bases == b.n_bases and c.offsets.tolist() == b.offsets.tolist()
-    assert c.words.tobytes() == b.words.tobytes()
+    assert c.bases.tobytes() == b.bases.tobytes() and c.masks.tobytes() == b.masks.tobytes() and c.sparse.tobytes() == b.sparse.tobytes()
 
 
 def test_text_cache_roundtrip_and_errors(tmp_path):
@@ -98,7 +114,8 @@ def test_text_cache_roundtrip_and_errors(tmp_path):
     t = V.PackedText.from_ascii(case.ascii, case.offsets)
     t.save(str(tmp_path / "idx"))
     u = V.PackedText.load(str(tmp_path / "idx"))
-    assert u.n_bases == t.n_bases and u.offsets.tolist() == t.offsets.tolist() and u.words.tobytes() == t.words.tobytes()
+    assert u.n_bases == t.n_bases and u.offsets.tolist() == t.offsets.tolist() and u.bases.tobytes() == t.bases.tobytes()
+    assert u.masks.tobytes() == t.masks.tobytes() and u.sparse.tobytes() == t.sparse.tobytes()
     with pytest.raises(V.VarscotError):
         V.PackedText.load(str(tmp_path / "missing"))
     open(str(tmp_path / "bad.vsidx"), "wb").write(b"not an index")

@@ -31,23 +31,29 @@ class Record(C.Structure):
 
 
 class ScanStats(C.Structure):
-    _fields_ = [("count_ms", C.c_float), ("extract_ms", C.c_float), ("score_ms", C.c_float), ("total_ms", C.c_float),
+    _fields_ = [("upload_ms", C.c_float), ("extract_ms", C.c_float), ("score_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_cand_fwd", C.c_uint64), ("n_cand_rev", C.c_uint64),
                 ("n_blocks_fwd", C.c_uint64), ("n_blocks_rev", C.c_uint64),
-                ("n_hits", C.c_uint64), ("launches", C.c_uint32), ("score_launches", C.c_uint32)]
+                ("n_hits", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("launches", C.c_uint32), ("score_launches", C.c_uint32), ("n_chunks", C.c_uint32), ("redo_chunks", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class TextView(C.Structure):
+    _fields_ = [("n_bases", C.c_uint64), ("n_words", C.c_uint64), ("n_contigs", C.c_uint32), ("reserved", C.c_uint32),
+                ("contig_off", C.c_void_p), ("bases", C.c_void_p), ("masks", C.c_void_p), ("sparse", C.c_void_p),
+                ("n_sparse", C.c_uint64)]
+
+
 # every symbol include/varscot_scan.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_num_bases",
-    "vs_packer_num_contigs", "vs_packer_num_words", "vs_packer_words", "vs_packer_offsets", "vs_pack_text",
-    "vs_text_save", "vs_text_load", "vs_free", "vs_device_count", "vs_ctx_create", "vs_ctx_destroy",
-    "vs_last_error", "vs_text_upload", "vs_host_alloc", "vs_host_free", "vs_scan", "vs_scan_fetch",
-    "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_md_string", "vs_format_sam", "vs_bidir_index_main",
-    "vs_bidir_mapping_main", "vs_measure_int_peaks",
+    "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_finish", "vs_pack_text",
+    "vs_masks_from_planes", "vs_masks_sparse", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
+    "vs_ctx_create", "vs_ctx_destroy", "vs_last_error", "vs_ctx_set_chunk_words", "vs_text_upload", "vs_host_alloc",
+    "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits",
+    "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_measure_int_peaks",
 ]
 
 _lib = None
@@ -67,25 +73,25 @@ def lib():
     L.vs_packer_free.argtypes = [vp]
     L.vs_packer_append.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.vs_packer_end_contig.argtypes = [vp]
-    L.vs_packer_num_bases.restype = u64; L.vs_packer_num_bases.argtypes = [vp]
-    L.vs_packer_num_contigs.restype = u32; L.vs_packer_num_contigs.argtypes = [vp]
-    L.vs_packer_num_words.restype = u64; L.vs_packer_num_words.argtypes = [vp]
-    L.vs_packer_words.restype = vp; L.vs_packer_words.argtypes = [vp]
-    L.vs_packer_offsets.restype = vp; L.vs_packer_offsets.argtypes = [vp]
-    L.vs_pack_text.argtypes = [vp, u64, vp, u32, vp]
-    L.vs_text_save.argtypes = [C.c_char_p, vp, u64, vp, u32]
-    L.vs_text_load.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u32)]
+    L.vs_packer_finish.argtypes = [vp, C.POINTER(TextView)]
+    L.vs_pack_text.argtypes = [vp, u64, vp, u32, vp, vp]
+    L.vs_masks_from_planes.argtypes = [vp, vp, u64, vp]
+    L.vs_masks_sparse.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.vs_text_save.argtypes = [C.c_char_p, C.POINTER(TextView)]
+    L.vs_text_load.argtypes = [C.c_char_p, C.POINTER(TextView), C.POINTER(vp)]
     L.vs_free.argtypes = [vp]
     L.vs_device_count.restype = i32
     L.vs_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.vs_ctx_destroy.argtypes = [vp]
     L.vs_last_error.restype = C.c_char_p; L.vs_last_error.argtypes = [vp]
-    L.vs_text_upload.argtypes = [vp, vp, u64, u64]
+    L.vs_ctx_set_chunk_words.argtypes = [vp, u64]
+    L.vs_text_upload.argtypes = [vp, C.POINTER(TextView), u64, u64]
     L.vs_host_alloc.restype = vp; L.vs_host_alloc.argtypes = [C.c_size_t]
     L.vs_host_free.argtypes = [vp]
     L.vs_scan.argtypes = [vp, vp, u32, i32, i32, vp, u64, C.POINTER(u64), C.POINTER(ScanStats)]
+    L.vs_scan_text.argtypes = [vp, C.POINTER(TextView), u64, u64, vp, u32, i32, i32, vp, u64, C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_scan_fetch.argtypes = [vp, vp, u64, C.POINTER(u64)]
-    L.vs_map_packed.argtypes = [vp, u64, vp, u32, i32, i32, vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(ScanStats)]
+    L.vs_map_packed.argtypes = [C.POINTER(TextView), vp, u32, i32, i32, vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_shard_bounds.argtypes = [u64, i32, vp]
     L.vs_resolve_hits.argtypes = [vp, u64, vp, u32, vp, C.POINTER(u64)]
     L.vs_md_string.argtypes = [vp, u64, vp, i32, i32, C.c_char_p]

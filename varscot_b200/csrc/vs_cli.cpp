@@ -74,14 +74,10 @@ bool read_fasta(const std::string &path, const FastaSink &sink, std::string &err
 
 struct PackedText {
     vs_packer *packer = nullptr;
-    vs_word *loaded_words = nullptr;
-    uint64_t *loaded_off = nullptr;
-    const vs_word *words = nullptr;
-    const uint64_t *off = nullptr;
-    uint64_t n_bases = 0;
-    uint32_t n_contigs = 0;
+    void *owner = nullptr;             // buffer of a loaded .vsidx
+    vs_text_view v{};
     std::vector<std::string> names;
-    ~PackedText() { vs_packer_free(packer); vs_free(loaded_words); vs_free(loaded_off); }
+    ~PackedText() { vs_packer_free(packer); vs_free(owner); }
 };
 
 bool pack_fasta(const std::string &path, PackedText &t, bool want_names, std::string &err)
@@ -94,11 +90,8 @@ bool pack_fasta(const std::string &path, PackedText &t, bool want_names, std::st
     sink.seq = [&](const char *s, size_t n) { if (rc == VS_OK) rc = vs_packer_append(t.packer, s, n); };
     sink.end_record = [&]() { if (rc == VS_OK) rc = vs_packer_end_contig(t.packer); };
     if (!read_fasta(path, sink, err)) return false;
+    if (rc == VS_OK) rc = vs_packer_finish(t.packer, &t.v);
     if (rc != VS_OK) { err = "packing failed (out of memory?)"; return false; }
-    t.words = vs_packer_words(t.packer);
-    t.off = vs_packer_offsets(t.packer);
-    t.n_bases = vs_packer_num_bases(t.packer);
-    t.n_contigs = vs_packer_num_contigs(t.packer);
     return true;
 }
 
@@ -213,10 +206,10 @@ extern "C" int vs_bidir_index_main(int argc, char **argv)
     PackedText t;
     std::string err;
     if (!pack_fasta(genome, t, false, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
-    if (t.n_bases > (1ull << 32)) { fprintf(stderr, "%s: the FASTA file may not contain more than 4 giga bases in total\n", prog); return 1; }
-    printf("Number of sequences: %u\n", t.n_contigs);
+    if (t.v.n_bases > (1ull << 32)) { fprintf(stderr, "%s: the FASTA file may not contain more than 4 giga bases in total\n", prog); return 1; }
+    printf("Number of sequences: %u\n", t.v.n_contigs);
     fflush(stdout);
-    if (vs_text_save(index.c_str(), t.words, t.n_bases, t.off, t.n_contigs) != VS_OK) {
+    if (vs_text_save(index.c_str(), &t.v) != VS_OK) {
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr));
         return 1;
     }
@@ -285,20 +278,19 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     // "index": the packed text cached by bidir_index at the -I prefix; if it is absent or unreadable, pack -G now
     PackedText t;
     std::string err;
-    bool from_cache = vs_text_load(index.c_str(), &t.loaded_words, &t.n_bases, &t.loaded_off, &t.n_contigs) == VS_OK;
+    bool from_cache = vs_text_load(index.c_str(), &t.v, &t.owner) == VS_OK;
     if (from_cache) {
-        t.words = t.loaded_words; t.off = t.loaded_off;
         // contig ids from the genome FASTA, sequences discarded (bidir_mapping.cpp:272-280)
         if (!read_names(genome, t.names, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
-        if (t.names.size() != t.n_contigs) {
-            fprintf(stderr, "%s: index %s.vsidx has %u sequences but %s has %zu; re-run bidir_index\n", prog, index.c_str(), t.n_contigs, genome.c_str(), t.names.size());
+        if (t.names.size() != t.v.n_contigs) {
+            fprintf(stderr, "%s: index %s.vsidx has %u sequences but %s has %zu; re-run bidir_index\n", prog, index.c_str(), t.v.n_contigs, genome.c_str(), t.names.size());
             return 1;
         }
     } else {
         fprintf(stderr, "%s: note: no packed text at %s.vsidx (%s); packing %s now\n", prog, index.c_str(), vs_last_error(nullptr), genome.c_str());
         if (!pack_fasta(genome, t, true, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
     }
-    if (t.n_bases > (1ull << 32)) { fprintf(stderr, "%s: text exceeds 4 giga bases\n", prog); return 1; }
+    if (t.v.n_bases > (1ull << 32)) { fprintf(stderr, "%s: text exceeds 4 giga bases\n", prog); return 1; }
     printf("Index loaded.\n");
     fflush(stdout);
 
@@ -308,20 +300,20 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
 
     std::vector<vs_hit> hits;
     const uint32_t n_guides = (uint32_t)ids.size();
-    if (n_guides && t.n_bases) {
-        std::vector<int> devices = choose_devices(t.n_bases);
+    if (n_guides && t.v.n_bases) {
+        std::vector<int> devices = choose_devices(t.v.n_bases);
         if (devices.empty()) { fprintf(stderr, "%s: no usable CUDA device: %s (this build has no CPU path)\n", prog, vs_last_error(nullptr)); fclose(out); return 1; }
         vs_scan_stats st;
-        int rc = vs::scan_text_sharded(t.words, (t.n_bases + 31) >> 5, devices, guides.data(), n_guides, (int)mism, extra_pam, hits, &st, err);
+        int rc = vs::scan_text_sharded(t.v, devices, guides.data(), n_guides, (int)mism, extra_pam, hits, &st, err);
         if (rc != VS_OK) { fprintf(stderr, "%s: scan failed: %s\n", prog, err.c_str()); fclose(out); return 1; }
         if (getenv("VARSCOT_VERBOSE"))
-            fprintf(stderr, "%s: %zu device(s), %.3f ms scan (count %.3f, extract %.3f, score %.3f), %llu candidates, %llu hits\n", prog,
-                    devices.size(), st.total_ms, st.count_ms, st.extract_ms, st.score_ms,
+            fprintf(stderr, "%s: %zu device(s), %.3f ms upload+scan (extract %.3f, score %.3f; %.1f MB H2D), %llu candidates, %llu hits\n", prog,
+                    devices.size(), st.total_ms, st.extract_ms, st.score_ms, st.h2d_bytes / 1e6,
                     (unsigned long long)(st.n_cand_fwd + st.n_cand_rev), (unsigned long long)st.n_hits);
     }
     std::vector<vs_record> rec(hits.size());
     uint64_t coll = 0;
-    if (!hits.empty() && vs_resolve_hits(hits.data(), hits.size(), t.off, t.n_contigs, rec.data(), &coll) != VS_OK) {
+    if (!hits.empty() && vs_resolve_hits(hits.data(), hits.size(), t.v.contig_off, t.v.n_contigs, rec.data(), &coll) != VS_OK) {
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr)); fclose(out); return 1;
     }
     if (coll) fprintf(stderr, "%s: note: %llu records share a (contig id mod 65536, position) key; the reference's uint16 map key would have kept one of each\n", prog, (unsigned long long)coll);
@@ -330,7 +322,7 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     for (const vs_record &r : rec) {
         char md[64];
         const uint8_t *g = guides.data() + (size_t)r.guide * VS_GLEN;
-        vs_md_string(t.words, t.off[r.contig] + r.pos, g, (r.flag >> 4) & 1, md_style, md);
+        vs_md_string(t.v.bases, t.v.contig_off[r.contig] + r.pos, g, (r.flag >> 4) & 1, md_style, md);
         const std::string &qn = ids[r.guide], &rn = t.names[r.contig];
         if (buf.size() < qn.size() + rn.size() + 256) buf.resize(qn.size() + rn.size() + 256);
         int n = vs_format_sam(&r, qn.c_str(), rn.c_str(), g, md, buf.data(), buf.size());

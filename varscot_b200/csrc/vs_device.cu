@@ -5,6 +5,7 @@
 // sm_100 device is usable.
 #include "vs_kernels.cuh"
 #include "vs_internal.h"
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -14,18 +15,30 @@ using namespace vs;
 
 static thread_local std::string g_last_error;
 
+constexpr uint64_t DEFAULT_CHUNK_WORDS = 4ull << 20;      // 128 Mi bases per pipeline chunk
+
 struct vs_ctx {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy = nullptr;         // H2D of the next chunk
     cudaEvent_t ev[6] = {};
-    // text
-    vs_word *d_words = nullptr;
-    uint64_t words_cap = 0, n_words = 0, global_base = 0;
-    // counters: [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev, [4] hits
+    std::vector<cudaEvent_t> ev_pool;    // per-chunk: copied, extracted, scored
+    uint64_t chunk_words = DEFAULT_CHUNK_WORDS;
+    // resident text shard: device word 0 = global word first_word
+    vs_bases *d_bases = nullptr;
+    vs_masks *d_masks = nullptr;
+    uint64_t words_cap = 0, n_words = 0, first_word = 0;
+    vs_mask_entry *d_sparse = nullptr;
+    uint64_t sparse_cap = 0;
+    // counters: per chunk [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev; then one hit counter
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
-    // candidate stores
+    uint64_t cnt_chunks = 0;
+    // candidate stores (one chunk at a time)
     uint32_t *d_planes[2] = {nullptr, nullptr}, *d_pos[2] = {nullptr, nullptr};
-    uint64_t blocks_cap[2] = {0, 0};
+    uint64_t blocks_cap = 0;
+    // pattern tables
+    uint32_t *d_pat = nullptr, *h_pat = nullptr;
+    uint64_t pat_cap = 0;
     // hits
     vs_hit *d_hits = nullptr;
     uint64_t hits_cap = 0, last_n_hits = 0;
@@ -89,9 +102,8 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
     ctx = new vs_ctx();
     ctx->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cnt, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_cnt, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = set_score_attr<0>();
     if (e == cudaSuccess) e = set_score_attr<1>();
     if (e == cudaSuccess) e = set_score_attr<2>();
@@ -115,14 +127,26 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (!ctx) return;
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_words);
+    if (ctx->copy) cudaStreamSynchronize(ctx->copy);
+    cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]); }
+    cudaFree(ctx->d_pat);
+    if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
     cudaFree(ctx->d_hits);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
     delete ctx;
+}
+
+extern "C" int vs_ctx_set_chunk_words(vs_ctx *ctx, uint64_t chunk_words)
+{
+    if (!ctx || chunk_words == 0) return fail(ctx, VS_ERR_ARG, "vs_ctx_set_chunk_words: bad arguments");
+    ctx->chunk_words = chunk_words;
+    return VS_OK;
 }
 
 extern "C" void *vs_host_alloc(size_t bytes)
@@ -132,26 +156,6 @@ extern "C" void *vs_host_alloc(size_t bytes)
     return p;
 }
 extern "C" void vs_host_free(void *p) { if (p) cudaFreeHost(p); }
-
-extern "C" int vs_text_upload(vs_ctx *ctx, const vs_word *words, uint64_t n_words, uint64_t global_base)
-{
-    if (!ctx || (!words && n_words)) return fail(ctx, VS_ERR_ARG, "vs_text_upload: bad arguments");
-    if (n_words * 32 + global_base > (1ull << 32))
-        return fail(ctx, VS_ERR_ARG, "vs_text_upload: text exceeds 4 Gbases (32-bit positions, as common.h:9-19)");
-    CK(cudaSetDevice(ctx->device));
-    if (n_words + 1 > ctx->words_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_words); ctx->d_words = nullptr; ctx->words_cap = 0;
-        CK(cudaMalloc(&ctx->d_words, (n_words + 1) * sizeof(vs_word)));
-        ctx->words_cap = n_words + 1;
-    }
-    if (n_words) CK(cudaMemcpyAsync(ctx->d_words, words, (n_words + 1) * sizeof(vs_word), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->n_words = n_words;
-    ctx->global_base = global_base;
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->err.clear();
-    return VS_OK;
-}
 
 static void make_pam(int extra_pam, PamParams &pp)
 {
@@ -164,31 +168,132 @@ static void make_pam(int extra_pam, PamParams &pp)
 }
 
 template <int K>
-static void launch_score(const ScoreArgs &a, cudaStream_t st)
+static void launch_score(const ScoreArgs &a, uint64_t cap, cudaStream_t st)
 {
-    unsigned grid = (unsigned)((a.n_blocks + SCORE_THREADS - 1) / SCORE_THREADS);
+    unsigned grid = (unsigned)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
     k_score<K><<<grid, SCORE_THREADS, NPLANES * SCORE_THREADS * 4, st>>>(a);
 }
 
-static void dispatch_score(int k, const ScoreArgs &a, cudaStream_t st)
+static void dispatch_score(int k, const ScoreArgs &a, uint64_t cap, cudaStream_t st)
 {
     switch (k) {
-    case 0: launch_score<0>(a, st); break;
-    case 1: launch_score<1>(a, st); break;
-    case 2: launch_score<2>(a, st); break;
-    case 3: launch_score<3>(a, st); break;
-    case 4: launch_score<4>(a, st); break;
-    case 5: launch_score<5>(a, st); break;
-    case 6: launch_score<6>(a, st); break;
-    case 7: launch_score<7>(a, st); break;
-    default: launch_score<8>(a, st); break;
+    case 0: launch_score<0>(a, cap, st); break;
+    case 1: launch_score<1>(a, cap, st); break;
+    case 2: launch_score<2>(a, cap, st); break;
+    case 3: launch_score<3>(a, cap, st); break;
+    case 4: launch_score<4>(a, cap, st); break;
+    case 5: launch_score<5>(a, cap, st); break;
+    case 6: launch_score<6>(a, cap, st); break;
+    case 7: launch_score<7>(a, cap, st); break;
+    default: launch_score<8>(a, cap, st); break;
     }
 }
 
-extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
-                       vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
+// ---- text residency ------------------------------------------------------------------------------
+static int ensure_text_buffers(vs_ctx *ctx, uint64_t n_words)
 {
-    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan: ctx is NULL");
+    if (n_words + 1 > ctx->words_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->copy));
+        cudaFree(ctx->d_bases); cudaFree(ctx->d_masks);
+        ctx->d_bases = nullptr; ctx->d_masks = nullptr; ctx->words_cap = 0;
+        CK(cudaMalloc(&ctx->d_bases, (n_words + 1) * sizeof(vs_bases)));
+        CK(cudaMalloc(&ctx->d_masks, (n_words + 1) * sizeof(vs_masks)));
+        ctx->words_cap = n_words + 1;
+    }
+    return VS_OK;
+}
+
+// Enqueue the H2D of chunk [c0, c1) (device word indices) on the copy stream.  Masks travel dense, or — when the
+// view carries a sparse list and it is smaller — as memset + sparse entries + a scatter kernel.
+static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t c0, uint64_t c1,
+                              uint64_t &sparse_used, uint64_t &bytes, uint32_t &launches)
+{
+    cudaStream_t cs = ctx->copy;
+    const uint64_t n = c1 - c0, g0 = first_word + c0;
+    // bases [c0, c1] incl. the halo word; word c0 of a later chunk already arrived as the previous chunk's halo
+    const uint64_t skip = c0 ? 1 : 0;
+    CK(cudaMemcpyAsync(ctx->d_bases + c0 + skip, t->bases + g0 + skip, (n + 1 - skip) * sizeof(vs_bases), cudaMemcpyHostToDevice, cs));
+    bytes += (n + 1 - skip) * sizeof(vs_bases);
+    bool sparse = false;
+    uint64_t e0 = 0, e1 = 0;
+    if (t->sparse) {
+        const vs_mask_entry *sb = t->sparse, *se = t->sparse + t->n_sparse;
+        auto lb = [&](uint64_t w) { return (uint64_t)(std::lower_bound(sb, se, w, [](const vs_mask_entry &x, uint64_t v) { return x.word < v; }) - sb); };
+        e0 = lb(g0); e1 = lb(g0 + n);
+        sparse = (e1 - e0) * sizeof(vs_mask_entry) < n * sizeof(vs_masks) * 3 / 4 && sparse_used + (e1 - e0) <= ctx->sparse_cap;
+    }
+    if (sparse) {
+        CK(cudaMemsetAsync(ctx->d_masks + c0, 0, n * sizeof(vs_masks), cs));
+        if (e1 > e0) {
+            vs_mask_entry *dst = ctx->d_sparse + sparse_used;
+            CK(cudaMemcpyAsync(dst, t->sparse + e0, (e1 - e0) * sizeof(vs_mask_entry), cudaMemcpyHostToDevice, cs));
+            k_scatter_masks<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, cs>>>(dst, e1 - e0, g0, ctx->d_masks + c0);
+            launches++;
+            sparse_used += e1 - e0;
+            bytes += (e1 - e0) * sizeof(vs_mask_entry);
+        }
+    } else {
+        CK(cudaMemcpyAsync(ctx->d_masks + c0, t->masks + g0, n * sizeof(vs_masks), cudaMemcpyHostToDevice, cs));
+        bytes += n * sizeof(vs_masks);
+    }
+    return VS_OK;
+}
+
+static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
+{
+    if (!t->sparse || t->n_sparse == 0) return VS_OK;
+    const vs_mask_entry *sb = t->sparse, *se = t->sparse + t->n_sparse;
+    auto lb = [&](uint64_t w) { return (uint64_t)(std::lower_bound(sb, se, w, [](const vs_mask_entry &x, uint64_t v) { return x.word < v; }) - sb); };
+    uint64_t need = lb(first_word + n_words) - lb(first_word);
+    if (need > ctx->sparse_cap) {
+        CK(cudaStreamSynchronize(ctx->copy));
+        cudaFree(ctx->d_sparse); ctx->d_sparse = nullptr; ctx->sparse_cap = 0;
+        CK(cudaMalloc(&ctx->d_sparse, need * sizeof(vs_mask_entry)));
+        ctx->sparse_cap = need;
+    }
+    return VS_OK;
+}
+
+static int check_view(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
+{
+    if (!t || !t->bases || (!t->masks && t->n_words)) return fail(ctx, VS_ERR_ARG, "text view is incomplete");
+    if (first_word + n_words > t->n_words) return fail(ctx, VS_ERR_ARG, "shard lies outside the text");
+    if (t->n_words * 32 > (1ull << 32)) return fail(ctx, VS_ERR_ARG, "text exceeds 4 Gbases (32-bit positions, as common.h:9-19)");
+    return VS_OK;
+}
+
+extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_text_upload: ctx is NULL");
+    int r = check_view(ctx, t, first_word, n_words);
+    if (r != VS_OK) return r;
+    CK(cudaSetDevice(ctx->device));
+    if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
+    if ((r = ensure_sparse_staging(ctx, t, first_word, n_words)) != VS_OK) return r;
+    uint64_t sparse_used = 0, bytes = 0;
+    uint32_t launches = 0;
+    for (uint64_t c0 = 0; c0 < n_words; c0 += ctx->chunk_words) {
+        uint64_t c1 = std::min(n_words, c0 + ctx->chunk_words);
+        if ((r = enqueue_chunk_copy(ctx, t, first_word, c0, c1, sparse_used, bytes, launches)) != VS_OK) return r;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->copy));
+    ctx->n_words = n_words;
+    ctx->first_word = first_word;
+    ctx->err.clear();
+    return VS_OK;
+}
+
+// ---- the scan -----------------------------------------------------------------------------------
+// One pass = for every chunk of the resident shard: [H2D on the copy stream when `src` is given] -> k_extract ->
+// k_score per strand and guide chunk, all enqueued without host synchronisation; counters are read back once
+// at the end.  Chunks whose candidate store overflowed are redone afterwards; a hit-buffer overflow repeats the
+// pass (from the now resident text) with a larger buffer.
+static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, uint64_t n_words,
+                     const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                     vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
+{
     if (k < 0 || k > VS_MAX_MISMATCHES) return fail(ctx, VS_ERR_ARG, "vs_scan: mismatches must lie between 0 and 8");
     if (extra_pam < -1 || extra_pam > 15) return fail(ctx, VS_ERR_ARG, "vs_scan: extra_pam must be -1 or 4*x+y");
     if (n_guides && !guides) return fail(ctx, VS_ERR_ARG, "vs_scan: guides is NULL");
@@ -201,90 +306,168 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
     memset(&S, 0, sizeof(S));
     if (n_hits) *n_hits = 0;
     ctx->last_n_hits = 0;
-    if (ctx->n_words == 0 || n_guides == 0) { if (stats) *stats = S; return VS_OK; }
-
+    int r;
+    if (src) {
+        if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
+        if ((r = ensure_sparse_staging(ctx, src, first_word, n_words)) != VS_OK) return r;
+        ctx->n_words = n_words;
+        ctx->first_word = first_word;
+    }
+    n_words = ctx->n_words;
+    if (n_words == 0 || n_guides == 0) {
+        if (src && n_words) { r = vs_text_upload(ctx, src, first_word, n_words); if (r != VS_OK) return r; }
+        if (stats) *stats = S;
+        return VS_OK;
+    }
     PamParams pp;
     make_pam(extra_pam, pp);
-    const uint32_t n_tiles = (uint32_t)((ctx->n_words + TILE_WORDS - 1) / TILE_WORDS);
+    const uint64_t chunk_words = ctx->chunk_words;
+    const uint32_t n_chunks = (uint32_t)((n_words + chunk_words - 1) / chunk_words);
+    const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
+    // tile size: about 60 blocks (both strands) per 64-thread CTA at the expected PAM density pp.n / 16 per strand
+    uint32_t tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
+    if (tile_words > (uint32_t)EX_MAX_WORDS) tile_words = EX_MAX_WORDS;
+    if (tile_words < 8) tile_words = 8;
+    S.n_chunks = n_chunks;
 
-    // pattern tables: byte offset of the selected mismatch plane per position, per strand pass
-    const uint32_t n_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
-    std::vector<uint32_t> pat((size_t)2 * n_chunks * PAT_CHUNK * PAT_STRIDE, 0u);
+    // pattern tables (byte offset of the selected mismatch plane per position), per strand pass, staged in pinned memory
+    const uint64_t pat_words = (uint64_t)2 * g_chunks * PAT_CHUNK * PAT_STRIDE;
+    if (pat_words > ctx->pat_cap) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_pat); if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
+        ctx->d_pat = ctx->h_pat = nullptr; ctx->pat_cap = 0;
+        CK(cudaMalloc(&ctx->d_pat, pat_words * sizeof(uint32_t)));
+        CK(cudaMallocHost(&ctx->h_pat, pat_words * sizeof(uint32_t)));
+        ctx->pat_cap = pat_words;
+    }
+    memset(ctx->h_pat, 0, pat_words * sizeof(uint32_t));
     for (int s = 0; s < 2; ++s)
         for (uint32_t g = 0; g < n_guides; ++g) {
-            uint32_t *dst = pat.data() + (((size_t)s * n_chunks + g / PAT_CHUNK) * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
+            uint32_t *dst = ctx->h_pat + (((size_t)s * g_chunks + g / PAT_CHUNK) * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
             const uint8_t *gd = guides + (size_t)g * VS_GLEN;
             for (int i = 0; i < VS_GLEN; ++i) {
                 int b = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];      // reverse pass scores revcomp(guide), bidir_mapping.cpp:293
                 dst[i] = (uint32_t)(4 * i + b) * SCORE_THREADS * 4u;
             }
         }
-
-    // candidate stores: sized for the expected PAM density, regrown (and the extraction repeated) on overflow
-    auto ensure_blocks = [&](int s, uint64_t need) -> int {
-        if (need <= ctx->blocks_cap[s]) return VS_OK;
-        cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
-        ctx->d_planes[s] = ctx->d_pos[s] = nullptr; ctx->blocks_cap[s] = 0;
-        CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
-        ctx->blocks_cap[s] = need;
+    // counters
+    if (n_chunks > ctx->cnt_chunks) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_cnt); if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+        ctx->d_cnt = ctx->h_cnt = nullptr; ctx->cnt_chunks = 0;
+        uint64_t nc = n_chunks + 8;
+        CK(cudaMalloc(&ctx->d_cnt, (nc * 4 + 4) * sizeof(unsigned long long)));
+        CK(cudaMallocHost(&ctx->h_cnt, (nc * 4 + 4) * sizeof(unsigned long long)));
+        ctx->cnt_chunks = nc;
+    }
+    unsigned long long *d_hitcnt = ctx->d_cnt + ctx->cnt_chunks * 4, *h_hitcnt = ctx->h_cnt + ctx->cnt_chunks * 4;
+    // candidate stores sized for one chunk at the expected density (+15 %), regrown when a chunk overflows
+    auto ensure_blocks = [&](uint64_t need) -> int {
+        if (need <= ctx->blocks_cap) return VS_OK;
+        CK(cudaStreamSynchronize(st));
+        for (int s = 0; s < 2; ++s) {
+            cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
+            ctx->d_planes[s] = ctx->d_pos[s] = nullptr;
+        }
+        ctx->blocks_cap = 0;
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
+        }
+        ctx->blocks_cap = need;
         return VS_OK;
     };
     {
-        uint64_t est = (uint64_t)((double)ctx->n_words * pp.n / 16.0 * 1.15) + n_tiles + 1024;
-        for (int s = 0; s < 2; ++s)
-            if (ctx->blocks_cap[s] == 0) { int r = ensure_blocks(s, est); if (r != VS_OK) return r; }
+        const uint64_t cw = std::min(chunk_words, n_words);
+        const uint64_t tiles = (cw + tile_words - 1) / tile_words;
+        uint64_t est = (uint64_t)((double)cw * pp.n / 16.0 * 1.15) + tiles + 256;
+        est = (est + SCORE_THREADS - 1) / SCORE_THREADS * SCORE_THREADS;
+        if ((r = ensure_blocks(est)) != VS_OK) return r;
     }
-    CK(cudaEventRecord(ctx->ev[0], st));
-    uint64_t nb[2] = {0, 0};
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned long long), st));
-        k_extract<<<n_tiles, TILE_THREADS, 0, st>>>(ctx->d_words, ctx->n_words, ctx->global_base, pp,
-                                                    ctx->d_planes[0], ctx->d_pos[0], ctx->blocks_cap[0],
-                                                    ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap[1], ctx->d_cnt);
-        S.launches += 1;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        S.n_cand_fwd = ctx->h_cnt[0]; S.n_cand_rev = ctx->h_cnt[1];
-        nb[0] = S.n_blocks_fwd = ctx->h_cnt[2]; nb[1] = S.n_blocks_rev = ctx->h_cnt[3];
-        if (nb[0] <= ctx->blocks_cap[0] && nb[1] <= ctx->blocks_cap[1]) break;
-        if (attempt == 1) return fail(ctx, VS_ERR_CUDA, "vs_scan: candidate store overflow after regrow");
-        for (int s = 0; s < 2; ++s) { int r = ensure_blocks(s, nb[s] + nb[s] / 32 + 64); if (r != VS_OK) return r; }
-    }
-    CK(cudaEventRecord(ctx->ev[3], st));
-
     if (!ctx->d_hits) {
-        uint64_t cap = 1u << 20;
+        uint64_t cap = 4u << 20;
         CK(cudaMalloc(&ctx->d_hits, cap * sizeof(vs_hit)));
         ctx->hits_cap = cap;
     }
-    uint64_t found = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(cudaMemsetAsync(ctx->d_cnt + 4, 0, sizeof(unsigned long long), st));
-        for (int s = 0; s < 2; ++s) {
-            if (nb[s] == 0) continue;
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-                uint32_t np = n_guides - c * PAT_CHUNK;
-                if (np > (uint32_t)PAT_CHUNK) np = PAT_CHUNK;
-                const uint32_t *src = pat.data() + ((size_t)s * n_chunks + c) * PAT_CHUNK * PAT_STRIDE;
-                CK(cudaMemcpyToSymbolAsync(c_pat, src, (size_t)np * PAT_STRIDE * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
+    while (ctx->ev_pool.size() < (size_t)3 * n_chunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->ev_pool.push_back(e);
+    }
+
+    auto run_chunk = [&](uint32_t c, bool timed) -> int {
+        const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
+        unsigned long long *cnt = ctx->d_cnt + (uint64_t)c * 4;
+        const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
+        k_extract<<<tiles, EX_THREADS, 0, st>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, ctx->first_word * 32, pp,
+                                                 ctx->d_planes[0], ctx->d_pos[0], ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap, cnt);
+        S.launches++;
+        if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 1], st));
+        for (int s = 0; s < 2; ++s)
+            for (uint32_t gc = 0; gc < g_chunks; ++gc) {
+                uint32_t np = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK);
+                const uint32_t *psrc = ctx->d_pat + ((size_t)s * g_chunks + gc) * PAT_CHUNK * PAT_STRIDE;
+                CK(cudaMemcpyToSymbolAsync(c_pat, psrc, (size_t)np * PAT_STRIDE * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
                 ScoreArgs a;
-                a.planes = ctx->d_planes[s]; a.pos = ctx->d_pos[s]; a.n_blocks = nb[s];
-                a.n_pat = np; a.guide_base = c * PAT_CHUNK; a.strand = (uint32_t)s;
-                a.hits = ctx->d_hits; a.n_hits = ctx->d_cnt + 4; a.hit_cap = ctx->hits_cap;
-                dispatch_score(k, a, st);
-                if (attempt == 0) { S.launches++; S.score_launches++; }
+                a.planes = ctx->d_planes[s]; a.pos = ctx->d_pos[s]; a.n_blocks_ptr = cnt + 2 + s; a.cap = ctx->blocks_cap;
+                a.n_pat = np; a.guide_base = gc * PAT_CHUNK; a.strand = (uint32_t)s;
+                a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
+                dispatch_score(k, a, ctx->blocks_cap, st);
+                S.launches++; S.score_launches++;
             }
+        if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 2], st));
+        return VS_OK;
+    };
+
+    uint64_t found = 0;
+    const vs_text_view *source = src;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        S.launches = 0; S.score_launches = 0; S.h2d_bytes = 0; S.redo_chunks = 0;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(cudaMemcpyAsync(ctx->d_pat, ctx->h_pat, pat_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        S.h2d_bytes += pat_words * sizeof(uint32_t);
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), st));
+        if (source) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[0], 0));
+        uint64_t sparse_used = 0;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            if (source) {
+                const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
+                if ((r = enqueue_chunk_copy(ctx, source, first_word, c0, c1, sparse_used, S.h2d_bytes, S.launches)) != VS_OK) return r;
+                CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c], ctx->copy));
+                CK(cudaStreamWaitEvent(st, ctx->ev_pool[(size_t)3 * c], 0));
+            } else {
+                CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c], st));
+            }
+            if ((r = run_chunk(c, true)) != VS_OK) return r;
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[4], st));
-        CK(cudaMemcpyAsync(ctx->h_cnt + 4, ctx->d_cnt + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        found = ctx->h_cnt[4];
+        source = nullptr;                                   // the text is resident from here on
+        // chunks whose candidate store overflowed were skipped by k_score: redo them with a larger store
+        S.n_cand_fwd = S.n_cand_rev = S.n_blocks_fwd = S.n_blocks_rev = 0;
+        const uint64_t cap_in_pass = ctx->blocks_cap;        // what k_score compared against during the pass
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            unsigned long long *hc = ctx->h_cnt + (uint64_t)c * 4;
+            if (hc[2] > cap_in_pass || hc[3] > cap_in_pass) {
+                uint64_t need = std::max(hc[2], hc[3]);
+                need = (need + need / 32 + SCORE_THREADS) / SCORE_THREADS * SCORE_THREADS;
+                if ((r = ensure_blocks(need)) != VS_OK) return r;
+                CK(cudaMemsetAsync(ctx->d_cnt + (uint64_t)c * 4, 0, 4 * sizeof(unsigned long long), st));
+                if ((r = run_chunk(c, false)) != VS_OK) return r;
+                CK(cudaMemcpyAsync(hc, ctx->d_cnt + (uint64_t)c * 4, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_hitcnt, d_hitcnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (hc[2] > ctx->blocks_cap || hc[3] > ctx->blocks_cap) return fail(ctx, VS_ERR_CUDA, "vs_scan: candidate store overflow after regrow");
+                S.redo_chunks++;
+            }
+            S.n_cand_fwd += hc[0]; S.n_cand_rev += hc[1]; S.n_blocks_fwd += hc[2]; S.n_blocks_rev += hc[3];
+        }
+        found = *h_hitcnt;
         if (found <= ctx->hits_cap) break;
-        if (attempt == 1) return fail(ctx, VS_ERR_CUDA, "vs_scan: hit buffer overflow after regrow");
-        // device hit buffer too small: grow and score again (candidates are kept)
+        if (attempt == 2) return fail(ctx, VS_ERR_CUDA, "vs_scan: hit buffer overflow after regrow");
+        // device hit buffer too small: grow and repeat the pass
         cudaFree(ctx->d_hits); ctx->d_hits = nullptr; ctx->hits_cap = 0;
         uint64_t cap = found + found / 8 + 1024;
         CK(cudaMalloc(&ctx->d_hits, cap * sizeof(vs_hit)));
@@ -297,14 +480,37 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
     if (out && ncopy) CK(cudaMemcpyAsync(out, ctx->d_hits, ncopy * sizeof(vs_hit), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
-    S.count_ms = 0.f;     // the separate count pass is gone: k_extract claims block ranges with atomics
-    CK(cudaEventElapsedTime(&S.extract_ms, ctx->ev[0], ctx->ev[3]));
-    CK(cudaEventElapsedTime(&S.score_ms, ctx->ev[3], ctx->ev[4]));
+    S.d2h_bytes = ncopy * sizeof(vs_hit) + (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long);
+    // per-phase device times: sums over the chunks of the last pass (same stream, so the intervals do not overlap)
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, ctx->ev_pool[(size_t)3 * c], ctx->ev_pool[(size_t)3 * c + 1]));
+        CK(cudaEventElapsedTime(&b, ctx->ev_pool[(size_t)3 * c + 1], ctx->ev_pool[(size_t)3 * c + 2]));
+        S.extract_ms += a; S.score_ms += b;
+    }
     CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[0], ctx->ev[5]));
+    if (src) CK(cudaEventElapsedTime(&S.upload_ms, ctx->ev[0], ctx->ev_pool[(size_t)3 * (n_chunks - 1)]));
     if (stats) *stats = S;
     ctx->err.clear();
     if (found > out_cap) return fail(ctx, VS_ERR_OVERFLOW, "vs_scan: caller hit buffer too small; use vs_scan_fetch");
     return VS_OK;
+}
+
+extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                       vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan: ctx is NULL");
+    return scan_core(ctx, nullptr, ctx->first_word, ctx->n_words, guides, n_guides, k, extra_pam, out, out_cap, n_hits, stats);
+}
+
+extern "C" int vs_scan_text(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words,
+                            const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                            vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan_text: ctx is NULL");
+    int r = check_view(ctx, text, first_word, n_words);
+    if (r != VS_OK) return r;
+    return scan_core(ctx, text, first_word, n_words, guides, n_guides, k, extra_pam, out, out_cap, n_hits, stats);
 }
 
 extern "C" int vs_scan_fetch(vs_ctx *ctx, vs_hit *out, uint64_t out_cap, uint64_t *n_hits)

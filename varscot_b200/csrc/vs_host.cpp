@@ -29,8 +29,48 @@ struct Lut {
 const Lut g_lut;
 }  // namespace
 
+// Window masks of one word from the N plane and the contig-end plane (n0/e0 = this word, n1/e1 = the next):
+//   iv: any N in [p, p+23)  or  any contig end in [p, p+22)   (R1, R3)
+//   lw: the window is valid and its last base (p+22) is a contig end   (R4)
+static inline vs_masks masks_of(uint32_t n0, uint32_t n1, uint32_t e0, uint32_t e1)
+{
+    uint64_t N = ((uint64_t)n1 << 32) | n0, E = ((uint64_t)e1 << 32) | e0;
+    uint64_t t = N | (N >> 1); t |= t >> 2; t |= t >> 4; t |= t >> 8;      // OR over 16 consecutive
+    uint64_t n23 = t | (t >> 7);                                             // OR over 23
+    uint64_t e = E | (E >> 1); e |= e >> 2; e |= e >> 4; e |= e >> 8;
+    uint64_t e22 = e | (e >> 6);                                             // OR over 22
+    vs_masks m;
+    m.iv = (uint32_t)(n23 | e22);
+    m.lw = (uint32_t)(E >> 22) & ~m.iv;
+    return m;
+}
+
+extern "C" int vs_masks_from_planes(const uint32_t *nm, const uint32_t *em, uint64_t n_words, vs_masks *out)
+{
+    if ((!nm || !em || !out) && n_words) return VS_ERR_ARG;
+    for (uint64_t w = 0; w < n_words; ++w) out[w] = masks_of(nm[w], nm[w + 1], em[w], em[w + 1]);
+    return VS_OK;
+}
+
+extern "C" int vs_masks_sparse(const vs_masks *masks, uint64_t n_words, vs_mask_entry **out, uint64_t *n_out)
+{
+    if (!out || !n_out || (!masks && n_words)) return VS_ERR_ARG;
+    uint64_t n = 0;
+    for (uint64_t w = 0; w < n_words; ++w) n += (masks[w].iv | masks[w].lw) != 0;
+    vs_mask_entry *e = (vs_mask_entry *)malloc((n ? n : 1) * sizeof(vs_mask_entry));
+    if (!e) return VS_ERR_NOMEM;
+    uint64_t i = 0;
+    for (uint64_t w = 0; w < n_words; ++w)
+        if (masks[w].iv | masks[w].lw) e[i++] = vs_mask_entry{(uint32_t)w, masks[w].iv, masks[w].lw};
+    *out = e; *n_out = n;
+    return VS_OK;
+}
+
 struct vs_packer {
-    std::vector<vs_word> words;
+    std::vector<vs_bases> bases;
+    std::vector<uint32_t> nm, em;
+    std::vector<vs_masks> masks;
+    std::vector<vs_mask_entry> sparse;
     std::vector<uint64_t> off{0};
     uint64_t n = 0;
     bool finalized = false;
@@ -42,22 +82,24 @@ extern "C" void vs_packer_free(vs_packer *p) { delete p; }
 extern "C" int vs_packer_append(vs_packer *p, const char *chars, size_t len)
 {
     if (!p || (!chars && len)) return VS_ERR_ARG;
-    if (p->finalized) { vs_set_last_error("vs_packer_append: packer already finalized"); return VS_ERR_ARG; }
+    if (p->finalized) { vs_set_last_error("vs_packer_append: packer already finished"); return VS_ERR_ARG; }
     uint64_t need = ((p->n + len + 31) >> 5) + 1;
-    if (p->words.size() < need) {
-        try { p->words.resize(std::max<uint64_t>(need, p->words.size() * 2), vs_word{0, 0, 0, 0}); }
-        catch (...) { return VS_ERR_NOMEM; }
+    if (p->bases.size() < need) {
+        try {
+            uint64_t cap = std::max<uint64_t>(need, p->bases.size() * 2);
+            p->bases.resize(cap, vs_bases{0, 0}); p->nm.resize(cap, 0u); p->em.resize(cap, 0u);
+        } catch (...) { return VS_ERR_NOMEM; }
     }
-    vs_word *W = p->words.data();
+    vs_bases *B = p->bases.data();
+    uint32_t *NM = p->nm.data();
     uint64_t n = p->n;
     for (size_t i = 0; i < len; ++i) {
         uint8_t c = g_lut.t[(uint8_t)chars[i]];
         if (c == 255) continue;
-        vs_word &w = W[n >> 5];
         uint32_t bit = 1u << (n & 31);
-        if (c & 2) w.hi |= bit;
-        if (c & 1) w.lo |= bit;
-        if (c & 4) w.nm |= bit;
+        if (c & 2) B[n >> 5].hi |= bit;
+        if (c & 1) B[n >> 5].lo |= bit;
+        if (c & 4) NM[n >> 5] |= bit;
         ++n;
     }
     p->n = n;
@@ -69,108 +111,140 @@ extern "C" int vs_packer_end_contig(vs_packer *p)
     if (!p || p->finalized) return VS_ERR_ARG;
     if (p->n > p->off.back()) {
         uint64_t last = p->n - 1;
-        p->words[last >> 5].em |= 1u << (last & 31);
+        p->em[last >> 5] |= 1u << (last & 31);
     }
     p->off.push_back(p->n);
     return VS_OK;
 }
 
-extern "C" uint64_t vs_packer_num_bases(const vs_packer *p) { return p ? p->n : 0; }
-extern "C" uint32_t vs_packer_num_contigs(const vs_packer *p) { return p ? (uint32_t)(p->off.size() - 1) : 0; }
-extern "C" uint64_t vs_packer_num_words(const vs_packer *p) { return p ? (p->n + 31) >> 5 : 0; }
-
-extern "C" const vs_word *vs_packer_words(vs_packer *p)
+extern "C" int vs_packer_finish(vs_packer *p, vs_text_view *out)
 {
-    if (!p) return nullptr;
-    uint64_t nw = (p->n + 31) >> 5;
-    p->words.resize(nw + 1, vs_word{0, 0, 0, 0});
-    if (p->n & 31) p->words[nw - 1].nm |= ~0u << (p->n & 31);   // padding past the end is N
-    p->words[nw] = vs_word{0u, 0u, ~0u, 0u};
-    p->finalized = true;
-    return p->words.data();
+    if (!p || !out) return VS_ERR_ARG;
+    const uint64_t nw = (p->n + 31) >> 5;
+    if (!p->finalized) {
+        try {
+            p->bases.resize(nw + 1, vs_bases{0, 0}); p->nm.resize(nw + 1, 0u); p->em.resize(nw + 1, 0u);
+            p->bases[nw] = vs_bases{0, 0};
+            if (p->n & 31) p->nm[nw - 1] |= ~0u << (p->n & 31);     // padding past the end reads as N
+            p->nm[nw] = ~0u; p->em[nw] = 0;
+            p->masks.resize(nw);
+            vs_masks_from_planes(p->nm.data(), p->em.data(), nw, p->masks.data());
+            for (uint64_t w = 0; w < nw; ++w)
+                if (p->masks[w].iv | p->masks[w].lw) p->sparse.push_back(vs_mask_entry{(uint32_t)w, p->masks[w].iv, p->masks[w].lw});
+            std::vector<uint32_t>().swap(p->nm);
+            std::vector<uint32_t>().swap(p->em);
+        } catch (...) { return VS_ERR_NOMEM; }
+        p->finalized = true;
+    }
+    out->n_bases = p->n; out->n_words = nw; out->n_contigs = (uint32_t)(p->off.size() - 1); out->reserved = 0;
+    out->contig_off = p->off.data(); out->bases = p->bases.data(); out->masks = p->masks.data();
+    out->sparse = p->sparse.data(); out->n_sparse = p->sparse.size();
+    return VS_OK;
 }
-extern "C" const uint64_t *vs_packer_offsets(vs_packer *p) { return p ? p->off.data() : nullptr; }
 
-extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs, vs_word *out)
+extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
+                            vs_bases *out_bases, vs_masks *out_masks)
 {
-    if (!out || (!ascii && n_bases) || (!contig_off && n_contigs)) return VS_ERR_ARG;
+    if (!out_bases || (!out_masks && n_bases) || (!ascii && n_bases) || (!contig_off && n_contigs)) return VS_ERR_ARG;
     if (n_contigs && (contig_off[0] != 0 || contig_off[n_contigs] != n_bases)) {
         vs_set_last_error("vs_pack_text: offsets must start at 0 and end at n_bases");
         return VS_ERR_ARG;
     }
-    uint64_t nw = (n_bases + 31) >> 5;
-    memset(out, 0, (nw + 1) * sizeof(vs_word));
+    const uint64_t nw = (n_bases + 31) >> 5;
+    std::vector<uint32_t> nm, em;
+    try { nm.assign(nw + 1, 0u); em.assign(nw + 1, 0u); } catch (...) { return VS_ERR_NOMEM; }
+    memset(out_bases, 0, (nw + 1) * sizeof(vs_bases));
     for (uint64_t i = 0; i < n_bases; ++i) {
         uint8_t c = g_lut.t[(uint8_t)ascii[i]];
         if (c == 255) c = 4;              // whitespace inside a pre-split text is just a non-base
-        vs_word &w = out[i >> 5];
         uint32_t bit = 1u << (i & 31);
-        if (c & 2) w.hi |= bit;
-        if (c & 1) w.lo |= bit;
-        if (c & 4) w.nm |= bit;
+        if (c & 2) out_bases[i >> 5].hi |= bit;
+        if (c & 1) out_bases[i >> 5].lo |= bit;
+        if (c & 4) nm[i >> 5] |= bit;
     }
     for (uint32_t c = 0; c < n_contigs; ++c) {
         if (contig_off[c + 1] < contig_off[c]) { vs_set_last_error("vs_pack_text: offsets must be non-decreasing"); return VS_ERR_ARG; }
         if (contig_off[c + 1] > contig_off[c]) {
             uint64_t last = contig_off[c + 1] - 1;
-            out[last >> 5].em |= 1u << (last & 31);
+            em[last >> 5] |= 1u << (last & 31);
         }
     }
-    if (n_bases & 31) out[nw - 1].nm |= ~0u << (n_bases & 31);
-    out[nw] = vs_word{0u, 0u, ~0u, 0u};
-    return VS_OK;
+    if (n_bases & 31) nm[nw - 1] |= ~0u << (n_bases & 31);
+    nm[nw] = ~0u;
+    return vs_masks_from_planes(nm.data(), em.data(), nw, out_masks);
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed-text cache: <prefix>.vsidx
+// packed-text cache: <prefix>.vsidx = header, offsets, bases, masks, sparse masks (all 16-byte aligned sections)
 namespace {
 struct IdxHeader {
     char magic[8];
     uint64_t n_bases;
+    uint64_t n_sparse;
     uint32_t n_contigs;
     uint32_t reserved;
 };
-const char IDX_MAGIC[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '1'};
+const char IDX_MAGIC[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
+inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
 }  // namespace
 
-extern "C" int vs_text_save(const char *prefix, const vs_word *words, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs)
+extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
 {
-    if (!prefix || !words || !contig_off) return VS_ERR_ARG;
+    if (!prefix || !t || !t->contig_off || (!t->bases) || (!t->masks && t->n_words)) return VS_ERR_ARG;
     std::string path = std::string(prefix) + ".vsidx";
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) { vs_set_last_error(("cannot open " + path + " for writing").c_str()); return VS_ERR_IO; }
+    vs_mask_entry *tmp = nullptr;
+    const vs_mask_entry *sp = t->sparse;
+    uint64_t nsp = t->n_sparse;
+    if (!sp && t->n_words) { if (vs_masks_sparse(t->masks, t->n_words, &tmp, &nsp) != VS_OK) { fclose(f); return VS_ERR_NOMEM; } sp = tmp; }
     IdxHeader h;
     memcpy(h.magic, IDX_MAGIC, 8);
-    h.n_bases = n_bases; h.n_contigs = n_contigs; h.reserved = 0;
-    uint64_t nw = ((n_bases + 31) >> 5) + 1;
-    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 &&
-              fwrite(contig_off, sizeof(uint64_t), (size_t)n_contigs + 1, f) == (size_t)n_contigs + 1 &&
-              fwrite(words, sizeof(vs_word), nw, f) == nw;
+    h.n_bases = t->n_bases; h.n_sparse = nsp; h.n_contigs = t->n_contigs; h.reserved = 0;
+    static const char zeros[16] = {0};
+    auto put = [&](const void *p, uint64_t bytes) {
+        bool ok = bytes == 0 || fwrite(p, 1, bytes, f) == bytes;
+        uint64_t pad = pad16(bytes) - bytes;
+        return ok && (pad == 0 || fwrite(zeros, 1, pad, f) == pad);
+    };
+    bool ok = put(&h, sizeof(h)) && put(t->contig_off, ((uint64_t)t->n_contigs + 1) * 8) && put(t->bases, (t->n_words + 1) * sizeof(vs_bases)) &&
+              put(t->masks, t->n_words * sizeof(vs_masks)) && put(sp, nsp * sizeof(vs_mask_entry));
     ok = (fclose(f) == 0) && ok;
+    free(tmp);
     if (!ok) { vs_set_last_error(("short write to " + path).c_str()); return VS_ERR_IO; }
     return VS_OK;
 }
 
-extern "C" int vs_text_load(const char *prefix, vs_word **words, uint64_t *n_bases, uint64_t **contig_off, uint32_t *n_contigs)
+extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
 {
-    if (!prefix || !words || !n_bases || !contig_off || !n_contigs) return VS_ERR_ARG;
-    *words = nullptr; *contig_off = nullptr;
+    if (!prefix || !out || !owner) return VS_ERR_ARG;
+    *owner = nullptr;
+    memset(out, 0, sizeof(*out));
     std::string path = std::string(prefix) + ".vsidx";
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) { vs_set_last_error(("cannot open " + path).c_str()); return VS_ERR_IO; }
     IdxHeader h;
     if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, IDX_MAGIC, 8) != 0) {
-        fclose(f); vs_set_last_error((path + " is not a VSIDX001 packed text").c_str()); return VS_ERR_IO;
+        fclose(f); vs_set_last_error((path + " is not a VSIDX002 packed text").c_str()); return VS_ERR_IO;
     }
-    uint64_t nw = ((h.n_bases + 31) >> 5) + 1;
-    uint64_t *off = (uint64_t *)malloc(((size_t)h.n_contigs + 1) * sizeof(uint64_t));
-    vs_word *w = (vs_word *)malloc(nw * sizeof(vs_word));
-    if (!off || !w) { free(off); free(w); fclose(f); return VS_ERR_NOMEM; }
-    bool ok = fread(off, sizeof(uint64_t), (size_t)h.n_contigs + 1, f) == (size_t)h.n_contigs + 1 &&
-              fread(w, sizeof(vs_word), nw, f) == nw;
+    const uint64_t nw = (h.n_bases + 31) >> 5;
+    const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)),
+                   s_m = pad16(nw * sizeof(vs_masks)), s_s = pad16(h.n_sparse * sizeof(vs_mask_entry));
+    const uint64_t total = s_off + s_b + s_m + s_s;
+    char *buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);
+    if (!buf) { fclose(f); return VS_ERR_NOMEM; }
+    // skip the header padding
+    bool ok = fseek(f, (long)pad16(sizeof(h)), SEEK_SET) == 0 && fread(buf, 1, total, f) == total;
     fclose(f);
-    if (!ok || off[h.n_contigs] != h.n_bases) { free(off); free(w); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
-    *words = w; *contig_off = off; *n_bases = h.n_bases; *n_contigs = h.n_contigs;
+    const uint64_t *off = (const uint64_t *)buf;
+    if (!ok || off[h.n_contigs] != h.n_bases) { free(buf); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
+    out->n_bases = h.n_bases; out->n_words = nw; out->n_contigs = h.n_contigs;
+    out->contig_off = off;
+    out->bases = (const vs_bases *)(buf + s_off);
+    out->masks = (const vs_masks *)(buf + s_off + s_b);
+    out->sparse = (const vs_mask_entry *)(buf + s_off + s_b + s_m);
+    out->n_sparse = h.n_sparse;
+    *owner = buf;
     return VS_OK;
 }
 
@@ -238,18 +312,17 @@ extern "C" int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *c
     return VS_OK;
 }
 
-static inline int base_at(const vs_word *words, uint64_t p)
+static inline int base_at(const vs_bases *bases, uint64_t p)
 {
-    const vs_word &w = words[p >> 5];
+    const vs_bases &w = bases[p >> 5];
     uint32_t b = (uint32_t)(p & 31);
-    if ((w.nm >> b) & 1) return 4;
-    return (int)(((w.hi >> b) & 1) << 1 | ((w.lo >> b) & 1));
+    return (int)(((w.hi >> b) & 1) << 1 | ((w.lo >> b) & 1));     // hits never contain N
 }
 
-extern "C" int vs_md_string(const vs_word *words, uint64_t gpos, const uint8_t *guide, int strand, int md_style, char *out)
+extern "C" int vs_md_string(const vs_bases *words, uint64_t gpos, const uint8_t *guide, int strand, int md_style, char *out)
 {
     if (!words || !guide || !out) return VS_ERR_ARG;
-    static const char L[5] = {'A', 'C', 'G', 'T', 'N'};
+    static const char L[4] = {'A', 'C', 'G', 'T'};
     int n = 0, run = 0;
     bool in_match = false, any = false;
     for (int i = 0; i < VS_GLEN; ++i) {
@@ -300,14 +373,14 @@ std::vector<uint64_t> shard_bounds(uint64_t n_words, int n)
     return b;
 }
 
-int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<int> &devices_in,
+int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices_in,
                       const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
                       std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err)
 {
     std::vector<int> devices = devices_in;
     if (devices.empty()) devices.push_back(0);
     const int nd = (int)devices.size();
-    std::vector<uint64_t> b = shard_bounds(n_words, nd);
+    std::vector<uint64_t> b = shard_bounds(text.n_words, nd);
     std::vector<std::vector<vs_hit>> part((size_t)nd);
     std::vector<int> rc((size_t)nd, VS_OK);
     std::vector<std::string> errs((size_t)nd);
@@ -318,12 +391,11 @@ int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<
         uint64_t w0 = b[(size_t)i], w1 = b[(size_t)i + 1];
         if (w1 <= w0) return;
         int r = vs_ctx_create(devices[(size_t)i], &ctx);
-        if (r == VS_OK) r = vs_text_upload(ctx, words + w0, w1 - w0, w0 * 32);
         if (r == VS_OK) {
             uint64_t n = 0;
             std::vector<vs_hit> &h = part[(size_t)i];
             h.resize(1u << 16);
-            r = vs_scan(ctx, guides, n_guides, k, extra_pam, h.data(), h.size(), &n, &st[(size_t)i]);
+            r = vs_scan_text(ctx, &text, w0, w1 - w0, guides, n_guides, k, extra_pam, h.data(), h.size(), &n, &st[(size_t)i]);
             if (r == VS_ERR_OVERFLOW) {
                 h.resize(n);
                 r = vs_scan_fetch(ctx, h.data(), h.size(), &n);
@@ -347,11 +419,12 @@ int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<
         hits.insert(hits.end(), part[(size_t)i].begin(), part[(size_t)i].end());
         if (agg) {
             const vs_scan_stats &s = st[(size_t)i];
-            agg->count_ms = std::max(agg->count_ms, s.count_ms); agg->extract_ms = std::max(agg->extract_ms, s.extract_ms);
+            agg->upload_ms = std::max(agg->upload_ms, s.upload_ms); agg->extract_ms = std::max(agg->extract_ms, s.extract_ms);
             agg->score_ms = std::max(agg->score_ms, s.score_ms); agg->total_ms = std::max(agg->total_ms, s.total_ms);
             agg->n_cand_fwd += s.n_cand_fwd; agg->n_cand_rev += s.n_cand_rev;
             agg->n_blocks_fwd += s.n_blocks_fwd; agg->n_blocks_rev += s.n_blocks_rev;
             agg->n_hits += s.n_hits; agg->launches += s.launches; agg->score_launches += s.score_launches;
+            agg->h2d_bytes += s.h2d_bytes; agg->d2h_bytes += s.d2h_bytes; agg->n_chunks += s.n_chunks; agg->redo_chunks += s.redo_chunks;
         }
     }
     return VS_OK;
@@ -359,17 +432,17 @@ int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<
 
 }  // namespace vs
 
-extern "C" int vs_map_packed(const vs_word *words, uint64_t n_bases, const uint8_t *guides, uint32_t n_guides,
+extern "C" int vs_map_packed(const vs_text_view *text, const uint8_t *guides, uint32_t n_guides,
                              int k, int extra_pam, const int *devices, int n_devices,
                              vs_hit **hits, uint64_t *n_hits, vs_scan_stats *stats)
 {
-    if (!hits || !n_hits || (!words && n_bases)) return VS_ERR_ARG;
+    if (!hits || !n_hits || !text) return VS_ERR_ARG;
     *hits = nullptr; *n_hits = 0;
     std::vector<int> dev;
     for (int i = 0; i < n_devices && devices; ++i) dev.push_back(devices[i]);
     std::vector<vs_hit> h;
     std::string err;
-    int rc = vs::scan_text_sharded(words, (n_bases + 31) >> 5, dev, guides, n_guides, k, extra_pam, h, stats, err);
+    int rc = vs::scan_text_sharded(*text, dev, guides, n_guides, k, extra_pam, h, stats, err);
     if (rc != VS_OK) { vs_set_last_error(err.c_str()); return rc; }
     if (!h.empty()) {
         vs_hit *o = (vs_hit *)malloc(h.size() * sizeof(vs_hit));

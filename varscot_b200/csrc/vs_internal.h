@@ -10,7 +10,7 @@ namespace vs {
 
 // Scan a packed text on one or several devices (text sharded by word ranges, one host thread and one
 // context per device, no collective) and return all hits, unordered.  devices empty -> device 0.
-int scan_text_sharded(const vs_word *words, uint64_t n_words, const std::vector<int> &devices,
+int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices,
                       const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
                       std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err);
 

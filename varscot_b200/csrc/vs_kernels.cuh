@@ -47,26 +47,16 @@ __device__ __forceinline__ uint32_t eq_plane(uint32_t h, uint32_t l, int code)
     return (h ^ mh) & (l ^ ml);
 }
 
-// Candidate masks for the 32 window starts of word a (b = next word).
-//   R1: the window must not run over a contig end (em) -> no end bit in [p, p+22)
-//   R3: no N in [p, p+23)
+// Candidate masks for the 32 window starts of one word (a = its bases, b = next word's bases, m = its masks).
+//   m.iv (precomputed by the packer): start is invalid — the window holds an N, runs over a contig end or past the
+//         text (R1, R3);  m.lw: the window ends exactly at a contig end (R4, bidir_mapping.cpp:51)
 //   R2: PAM on the genome: forward W[21..22], reverse W[0..1]   (bidir_mapping.cpp:70-76, :240-247)
-//   last = window ends exactly at a contig end (R4 needs H2 <= K there, bidir_mapping.cpp:51)
-__device__ __forceinline__ void cand_masks(const vs_word &a, const vs_word &b, const PamParams &pp,
-                                           uint32_t &fwd, uint32_t &rev, uint32_t &last)
+__device__ __forceinline__ void cand_masks(const vs_bases &a, const vs_bases &b, const vs_masks &m, const PamParams &pp,
+                                           uint32_t &fwd, uint32_t &rev)
 {
-    uint64_t N = ((uint64_t)b.nm << 32) | a.nm;
-    uint64_t E = ((uint64_t)b.em << 32) | a.em;
-    uint64_t H = ((uint64_t)b.hi << 32) | a.hi;
-    uint64_t L = ((uint64_t)b.lo << 32) | a.lo;
-    uint64_t t = N | (N >> 1); t |= t >> 2; t |= t >> 4; t |= t >> 8;   // OR over 16 consecutive
-    uint64_t n23 = t | (t >> 7);                                          // OR over 23
-    uint64_t e = E | (E >> 1); e |= e >> 2; e |= e >> 4; e |= e >> 8;
-    uint64_t e22 = e | (e >> 6);                                          // OR over 22
-    uint32_t inv = (uint32_t)(n23 | e22);
-    last = (uint32_t)(E >> 22);
-    uint32_t h21 = (uint32_t)(H >> 21), h22 = (uint32_t)(H >> 22), l21 = (uint32_t)(L >> 21), l22 = (uint32_t)(L >> 22);
-    uint32_t h0 = a.hi, l0 = a.lo, h1 = (uint32_t)(H >> 1), l1 = (uint32_t)(L >> 1);
+    const uint32_t h21 = __funnelshift_r(a.hi, b.hi, 21), h22 = __funnelshift_r(a.hi, b.hi, 22);
+    const uint32_t l21 = __funnelshift_r(a.lo, b.lo, 21), l22 = __funnelshift_r(a.lo, b.lo, 22);
+    const uint32_t h0 = a.hi, l0 = a.lo, h1 = __funnelshift_r(a.hi, b.hi, 1), l1 = __funnelshift_r(a.lo, b.lo, 1);
     uint32_t f = 0, r = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -75,160 +65,180 @@ __device__ __forceinline__ void cand_masks(const vs_word &a, const vs_word &b, c
             r |= eq_plane(h0, l0, pp.rx[j]) & eq_plane(h1, l1, pp.ry[j]);
         }
     }
-    fwd = f & ~inv;
-    rev = r & ~inv;
+    fwd = f & ~m.iv;
+    rev = r & ~m.iv;
 }
 
 // ------------------------------------------------------------------------------------------------
 // 32 x 32 bit-matrix transpose in registers (LSB-first): out[i] bit c = in[c] bit i.
-// 5 butterfly stages x 16 swaps; ptxas drops the swaps that only feed unused outputs.
-__host__ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
+// Stages 16 and 8 move whole bytes (2 PRMT per pair), stages 4, 2, 1 are masked swaps (5 ops per pair);
+// ptxas drops the swaps that only feed unused outputs.
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32])
 {
-    uint32_t m = 0x0000FFFFu;
 #pragma unroll
-    for (int j = 16; j; j >>= 1, m ^= m << j) {
+    for (int k = 0; k < 16; ++k) {                       // 16-bit halves: a[k].hi <-> a[k+16].lo
+        const uint32_t x = a[k], y = a[k + 16];
+        a[k] = __byte_perm(x, y, 0x5410);
+        a[k + 16] = __byte_perm(x, y, 0x7632);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k = ((k | 8) + 1) & ~8) {    // bytes: odd bytes of a[k] <-> even bytes of a[k+8]
+        const uint32_t x = a[k], y = a[k | 8];
+        a[k] = __byte_perm(x, y, 0x6240);
+        a[k | 8] = __byte_perm(x, y, 0x7351);
+    }
+    uint32_t m = 0x0F0F0F0Fu;
+#pragma unroll
+    for (int j = 4; j; j >>= 1, m ^= m << j) {
 #pragma unroll
         for (int k = 0; k < 32; k = ((k | j) + 1) & ~j) {
-            uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
+            const uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
             a[k | j] ^= t;
             a[k] ^= t << j;
         }
     }
 }
 
-constexpr int Q_STRIDE = 33;                                   // halfwords per queued block: odd stride -> conflict-free reads
-constexpr int Q_CAP    = (TILE_STARTS / 32) * Q_STRIDE;
+constexpr int EX_THREADS   = 64;                  // threads per extraction CTA
+constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the host picks the tile so that it holds ~60 blocks
 
-// k_extract: one CTA per tile of 8192 window starts.
-//   phase 1 (all threads, bit-parallel over 32 starts each): candidate masks, CTA-wide prefix sum, queue the
-//            candidates of each strand in shared memory as (local start | last << 15);
-//   phase 2 (one THREAD per 32-candidate block): gather the 23-base windows from the staged planes, transpose
-//            32 x 23 bits twice in registers, write 48 plane words + 32 positions.
+// k_extract: one 64-thread CTA per tile of `tile_words` words.
+//   phase 1 (bit-parallel, 32 starts per word): candidate masks per strand -> shared memory + exclusive rank prefix;
+//   phase 2 (one THREAD per 32-candidate block): walk the masks from the block's first candidate, gather the 23-base
+//            windows (funnel shifts on the staged planes), transpose 32 x 23 bits twice in registers, write
+//            48 plane words + 32 positions.
 // Block ranges are claimed with one atomicAdd per strand per tile on cnt[2], cnt[3] (layout order is not
-// deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written and the host,
-// which reads the counters back, grows the stores and launches again.
+// deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written for that tile; k_score
+// then skips the whole chunk and the host, which reads the counters back, regrows the stores and redoes the chunk.
 // Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask.
-__global__ void __launch_bounds__(TILE_THREADS)
-k_extract(const vs_word *__restrict__ W, uint64_t n_words, uint64_t global_base, PamParams pp,
-          uint32_t *__restrict__ planes_f, uint32_t *__restrict__ pos_f, uint64_t cap_f,
-          uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r, uint64_t cap_r,
+__global__ void __launch_bounds__(EX_THREADS)
+k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
+          uint64_t global_base, PamParams pp,
+          uint32_t *__restrict__ planes_f, uint32_t *__restrict__ pos_f,
+          uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r, uint64_t cap,
           unsigned long long *__restrict__ cnt)
 {
-    __shared__ uint2 s_hl[TILE_WORDS + 1];
-    __shared__ uint16_t q[2][Q_CAP];
-    __shared__ uint32_t wsum[2][TILE_THREADS / 32];
-    __shared__ uint32_t tot[2];
+    __shared__ uint2 s_hl[EX_MAX_WORDS + 2];
+    __shared__ uint32_t s_m[2][EX_MAX_WORDS + 1];      // candidate masks per strand
+    __shared__ uint32_t s_p[2][EX_MAX_WORDS + 1];      // exclusive rank prefix per word (+ total at [nw])
+    __shared__ uint32_t s_lw[EX_MAX_WORDS + 1];
+    __shared__ uint32_t wsum[2][EX_THREADS / 32];
     __shared__ unsigned long long base[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS;
-    const uint64_t w = w0 + tid;
-    uint32_t fwd = 0, rev = 0, last = 0;
-    {
-        vs_word a = {0u, 0u, ~0u, 0u}, b = {0u, 0u, ~0u, 0u};
-        if (w <= n_words) a = W[w];          // w == n_words is the halo / pad word, always readable
-        if (w < n_words) b = W[w + 1];
-        s_hl[tid] = make_uint2(a.hi, a.lo);
-        if (tid == TILE_THREADS - 1) s_hl[TILE_WORDS] = make_uint2(b.hi, b.lo);
-        if (w < n_words) cand_masks(a, b, pp, fwd, rev, last);
-    }
-    // CTA-wide exclusive scan of the per-thread candidate counts
-    const uint32_t cf = __popc(fwd), cr = __popc(rev);
-    uint32_t xf = cf, xr = cr;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t a = __shfl_up_sync(0xffffffffu, xf, o), b = __shfl_up_sync(0xffffffffu, xr, o);
-        if (lane >= o) { xf += a; xr += b; }
-    }
-    if (lane == 31) { wsum[0][wid] = xf; wsum[1][wid] = xr; }
-    __syncthreads();
-    uint32_t bf = 0, br = 0;
-#pragma unroll
-    for (int i = 0; i < TILE_THREADS / 32; ++i) {
-        uint32_t a = wsum[0][i], b = wsum[1][i];
-        if (i < wid) { bf += a; br += b; }
-    }
-    if (tid == TILE_THREADS - 1) {
-        const uint32_t nf_ = bf + xf, nr_ = br + xr;
-        tot[0] = nf_; tot[1] = nr_;
-        // claim block ranges; candidate totals are for the statistics only
-        base[0] = atomicAdd(&cnt[2], (unsigned long long)((nf_ + 31) >> 5));
-        base[1] = atomicAdd(&cnt[3], (unsigned long long)((nr_ + 31) >> 5));
-        if (nf_) atomicAdd(&cnt[0], (unsigned long long)nf_);
-        if (nr_) atomicAdd(&cnt[1], (unsigned long long)nr_);
-    }
-    {
-        uint32_t of = bf + xf - cf, orr = br + xr - cr;
-        uint32_t m = fwd;
-        while (m) {
-            int b = __ffs(m) - 1; m &= m - 1;
-            q[0][(of >> 5) * Q_STRIDE + (of & 31)] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15));
-            ++of;
+    const uint64_t w0 = w_begin + (uint64_t)blockIdx.x * tile_words;
+    const uint32_t nw = (uint32_t)min((uint64_t)tile_words, w_end - w0);      // words of this tile
+    uint32_t run_f = 0, run_r = 0;                     // candidates before the current group of 64 words
+    for (uint32_t i0 = 0; i0 < nw; i0 += EX_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint32_t fwd = 0, rev = 0;
+        if (i < nw) {
+            const vs_bases a = B[w0 + i], b = B[w0 + i + 1];    // B[w_end] is the halo / pad word, always readable
+            const vs_masks m = M[w0 + i];
+            s_hl[i] = make_uint2(a.hi, a.lo);
+            if (i == nw - 1) s_hl[i + 1] = make_uint2(b.hi, b.lo);
+            s_lw[i] = m.lw;
+            cand_masks(a, b, m, pp, fwd, rev);
+            s_m[0][i] = fwd; s_m[1][i] = rev;
         }
-        m = rev;
-        while (m) {
-            int b = __ffs(m) - 1; m &= m - 1;
-            q[1][(orr >> 5) * Q_STRIDE + (orr & 31)] = (uint16_t)((tid << 5) | b | (((last >> b) & 1u) << 15));
-            ++orr;
+        const uint32_t cf = __popc(fwd), cr = __popc(rev);
+        uint32_t xf = cf, xr = cr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t p = __shfl_up_sync(0xffffffffu, xf, o), q = __shfl_up_sync(0xffffffffu, xr, o);
+            if (lane >= o) { xf += p; xr += q; }
         }
+        if (lane == 31) { wsum[0][wid] = xf; wsum[1][wid] = xr; }
+        __syncthreads();
+        const uint32_t w0f = wsum[0][0], w0r = wsum[1][0], w1f = wsum[0][1], w1r = wsum[1][1];
+        if (i < nw) {
+            s_p[0][i] = run_f + (wid ? w0f : 0u) + xf - cf;
+            s_p[1][i] = run_r + (wid ? w0r : 0u) + xr - cr;
+        }
+        run_f += w0f + w1f; run_r += w0r + w1r;
+        __syncthreads();
     }
-    __syncthreads();
-    const uint32_t nf = tot[0], nr = tot[1];
+    const uint32_t nf = run_f, nr = run_r;
     const uint32_t nbf = (nf + 31) >> 5, nbr = (nr + 31) >> 5;
-    const uint32_t gbase = (uint32_t)(global_base + w0 * 32);
-    for (uint32_t j = tid; j < nbf + nbr; j += TILE_THREADS) {
+    if (tid == 0) {
+        s_p[0][nw] = nf; s_p[1][nw] = nr;
+        s_m[0][nw] = 0; s_m[1][nw] = 0;
+        base[0] = atomicAdd(&cnt[2], (unsigned long long)nbf);
+        base[1] = atomicAdd(&cnt[3], (unsigned long long)nbr);
+        if (nf) atomicAdd(&cnt[0], (unsigned long long)nf);
+        if (nr) atomicAdd(&cnt[1], (unsigned long long)nr);
+    }
+    __syncthreads();
+    const uint32_t gbase = (uint32_t)(global_base + w0 * 32);      // device word 0 sits at global_base
+    for (uint32_t j = tid; j < nbf + nbr; j += EX_THREADS) {
         const int s = j >= nbf;
         const uint32_t jj = s ? j - nbf : j;
         const uint32_t n = s ? nr : nf;
         const uint64_t blk = base[s] + jj;
-        if (blk >= (s ? cap_r : cap_f)) continue;          // overflow: host regrows and relaunches
+        if (blk >= cap) continue;                          // overflow: the chunk is redone by the host
         const uint32_t cntc = min(32u, n - jj * 32);
-        const uint16_t *qq = &q[s][jj * Q_STRIDE];
-        uint32_t *pl_out = (s ? planes_r : planes_f) + blk * BLK_WORDS;
-        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
-        uint32_t a[32];
+        const uint32_t *sm = s_m[s], *sp = s_p[s];
+        // word holding candidate rank r0 = 32*jj: last word with prefix <= r0
+        const uint32_t r0 = jj * 32;
+        uint32_t lo_w = 0, hi_w = nw;                      // invariant: sp[lo_w] <= r0 < sp[hi_w] (sp[nw] = n > r0)
+        while (hi_w - lo_w > 1) {
+            const uint32_t mid = (lo_w + hi_w) >> 1;
+            if (sp[mid] <= r0) lo_w = mid; else hi_w = mid;
+        }
+        uint32_t wcur = lo_w;
+        uint32_t m = sm[wcur];
+        for (uint32_t skip = r0 - sp[wcur]; skip; --skip) m &= m - 1;     // drop the candidates of earlier blocks
+        uint2 ha = s_hl[wcur], hb = s_hl[wcur + 1];
+        uint32_t lwm = s_lw[wcur];
+        uint32_t ah[32], al[32];
         uint32_t lastw = 0;
-        // hi planes (+ positions, last mask)
+        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
             uint32_t pp4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = c4 * 4 + u;
-                uint32_t hw = 0, ps = 0xFFFFFFFFu;
+                uint32_t hw = 0, lw = 0, ps = 0xFFFFFFFFu;
                 if ((uint32_t)c < cntc) {
-                    const uint32_t e = qq[c];
-                    const uint32_t lp = e & 0x1FFFu, wi = lp >> 5, o = lp & 31;
-                    hw = __funnelshift_r(s_hl[wi].x, s_hl[wi + 1].x, o) & 0x7FFFFFu;
-                    lastw |= (e >> 15) << c;
-                    ps = gbase + lp;
+                    while (m == 0) {                       // next word with candidates (the tile has >= cntc left)
+                        ++wcur;
+                        m = sm[wcur];
+                        ha = hb; hb = s_hl[wcur + 1];
+                        lwm = s_lw[wcur];
+                    }
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    hw = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
+                    lw = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
+                    lastw |= ((lwm >> b) & 1u) << c;
+                    ps = gbase + wcur * 32 + b;
                 }
-                a[c] = hw; pp4[u] = ps;
+                ah[c] = hw; al[c] = lw; pp4[u] = ps;
             }
             ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
         }
-        transpose32(a);
-        uint32_t carry = a[20], carry1 = a[21], carry2 = a[22];   // words 20..22 are stored with the first lo planes
+        uint4 *pl_out = reinterpret_cast<uint4 *>((s ? planes_r : planes_f) + blk * BLK_WORDS);
+        transpose32(ah);
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
-            reinterpret_cast<uint4 *>(pl_out)[i] = make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-        // lo planes
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            uint32_t lw = 0;
-            if ((uint32_t)c < cntc) {
-                const uint32_t lp = qq[c] & 0x1FFFu, wi = lp >> 5, o = lp & 31;
-                lw = __funnelshift_r(s_hl[wi].y, s_hl[wi + 1].y, o) & 0x7FFFFFu;
-            }
-            a[c] = lw;
-        }
-        transpose32(a);
+        for (int i = 0; i < 5; ++i) pl_out[i] = make_uint4(ah[4 * i], ah[4 * i + 1], ah[4 * i + 2], ah[4 * i + 3]);
+        transpose32(al);
         // words 20..47: hi_20, hi_21, hi_22, lo_0 .. lo_22, last, valid
-        reinterpret_cast<uint4 *>(pl_out)[5] = make_uint4(carry, carry1, carry2, a[0]);
+        pl_out[5] = make_uint4(ah[20], ah[21], ah[22], al[0]);
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
-            reinterpret_cast<uint4 *>(pl_out)[6 + i] = make_uint4(a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], a[4 * i + 4]);
+        for (int i = 0; i < 5; ++i) pl_out[6 + i] = make_uint4(al[4 * i + 1], al[4 * i + 2], al[4 * i + 3], al[4 * i + 4]);
         const uint32_t validw = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
-        reinterpret_cast<uint4 *>(pl_out)[11] = make_uint4(a[21], a[22], lastw, validw);
+        pl_out[11] = make_uint4(al[21], al[22], lastw, validw);
+    }
+}
+
+// k_scatter_masks: expand the sparse form of the window masks (only words with a non-zero mask travel over PCIe).
+__global__ void __launch_bounds__(256)
+k_scatter_masks(const vs_mask_entry *__restrict__ e, uint64_t n, uint64_t word_base, vs_masks *__restrict__ M)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        vs_mask_entry x = e[i];
+        M[x.word - word_base] = vs_masks{x.iv, x.lw};
     }
 }
 
@@ -249,7 +259,8 @@ __constant__ uint32_t c_pat[PAT_CHUNK * PAT_STRIDE];
 struct ScoreArgs {
     const uint32_t *planes;     // [n_blocks][48]
     const uint32_t *pos;        // [n_blocks][32]
-    uint64_t n_blocks;
+    const unsigned long long *n_blocks_ptr;   // blocks claimed by k_extract for this chunk and strand (device counter)
+    uint64_t cap;               // capacity of the candidate store; a chunk that overflowed it is skipped (host redoes it)
     uint32_t n_pat;             // patterns in this launch (<= PAT_CHUNK)
     uint32_t guide_base;        // index of pattern 0 of this launch in the guide list
     uint32_t strand;            // 0 forward pass, 1 reverse pass
@@ -264,10 +275,12 @@ k_score(ScoreArgs a)
 {
     extern __shared__ uint32_t sm[];     // [NPLANES][SCORE_THREADS]
     const int tid = threadIdx.x;
+    const uint64_t n_blocks = *a.n_blocks_ptr;
+    if (n_blocks > a.cap || (uint64_t)blockIdx.x * SCORE_THREADS >= n_blocks) return;     // grid is sized by capacity
     const uint64_t blk = (uint64_t)blockIdx.x * SCORE_THREADS + tid;
     uint32_t *my = sm + tid;
     uint32_t lastm = 0;
-    if (blk < a.n_blocks) {
+    if (blk < n_blocks) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.planes + blk * BLK_WORDS);
         uint32_t v[BLK_WORDS];
 #pragma unroll

@@ -9,14 +9,14 @@ library; nothing here scores windows.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
-
 import numpy as np
 
 from . import _lib
 from ._lib import GLEN, Hit, Record, ScanStats, VarscotError, check
 
-WORD_DT = np.dtype([("hi", "<u4"), ("lo", "<u4"), ("nm", "<u4"), ("em", "<u4")])
+BASES_DT = np.dtype([("hi", "<u4"), ("lo", "<u4")])
+MASKS_DT = np.dtype([("iv", "<u4"), ("lw", "<u4")])
+SPARSE_DT = np.dtype([("word", "<u4"), ("iv", "<u4"), ("lw", "<u4")])
 HIT_DT = np.dtype([("pos", "<u4"), ("info", "<u4")])
 REC_DT = np.dtype([("guide", "<u4"), ("contig", "<u4"), ("pos", "<u4"), ("flag", "<u2"), ("mm", "u1"), ("pad", "u1")])
 
@@ -49,13 +49,32 @@ def pam_code(pam) -> int:
     return 4 * lut[pam[0].upper()] + lut[pam[1].upper()]
 
 
-@dataclass
+def _copy_array(ptr, count, dt):
+    if not count:
+        return np.zeros(0, dtype=dt)
+    raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * dt.itemsize,))
+    return raw.copy().view(dt)
+
+
 class PackedText:
-    """Bit-sliced text: words[(n_words + 1)] of {hi, lo, nm, em}, contig offsets, optional names."""
-    words: np.ndarray
-    offsets: np.ndarray
-    n_bases: int
-    names: list | None = None
+    """Bit-sliced text (include/varscot_scan.h): bases[n_words + 1] of {hi, lo}, window masks[n_words] of {iv, lw},
+    the sparse form of the masks, contig offsets and optional names.  `view()` is the vs_text_view the C ABI takes."""
+
+    def __init__(self, bases, masks, offsets, n_bases, names=None, sparse=None):
+        self.bases = np.ascontiguousarray(bases, dtype=BASES_DT)
+        self.masks = np.ascontiguousarray(masks, dtype=MASKS_DT)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.n_bases = int(n_bases)
+        self.names = names
+        assert len(self.bases) == self.n_words + 1 and len(self.masks) == self.n_words
+        if sparse is None:
+            nz = np.flatnonzero((self.masks["iv"] | self.masks["lw"]) != 0)
+            sparse = np.zeros(len(nz), dtype=SPARSE_DT)
+            sparse["word"] = nz
+            sparse["iv"] = self.masks["iv"][nz]
+            sparse["lw"] = self.masks["lw"][nz]
+        self.sparse = np.ascontiguousarray(sparse, dtype=SPARSE_DT)
+        self._pinned = []
 
     @property
     def n_words(self) -> int:
@@ -65,15 +84,72 @@ class PackedText:
     def n_contigs(self) -> int:
         return len(self.offsets) - 1
 
+    def view(self, use_sparse: bool = True) -> _lib.TextView:
+        v = _lib.TextView()
+        v.n_bases, v.n_words, v.n_contigs, v.reserved = self.n_bases, self.n_words, self.n_contigs, 0
+        v.contig_off = self.offsets.ctypes.data
+        v.bases = self.bases.ctypes.data
+        v.masks = self.masks.ctypes.data
+        v.sparse = self.sparse.ctypes.data if use_sparse else None
+        v.n_sparse = len(self.sparse) if use_sparse else 0
+        return v
+
+    def pin(self):
+        """Move bases, masks and sparse masks into page-locked memory (vs_host_alloc) for full-speed H2D."""
+        L = _lib.lib()
+        for name in ("bases", "masks", "sparse"):
+            arr = getattr(self, name)
+            nbytes = max(arr.nbytes, 16)
+            p = L.vs_host_alloc(nbytes)
+            if not p:
+                raise VarscotError(_lib.VS_ERR_NOMEM, "vs_host_alloc failed")
+            buf = (C.c_uint8 * nbytes).from_address(p)
+            new = np.frombuffer(buf, dtype=arr.dtype, count=len(arr))
+            new[:] = arr
+            setattr(self, name, new)
+            self._pinned.append(p)
+        return self
+
+    def unpin(self):
+        L = _lib.lib()
+        for name in ("bases", "masks", "sparse"):
+            setattr(self, name, np.array(getattr(self, name)))
+        for p in self._pinned:
+            L.vs_host_free(p)
+        self._pinned = []
+
+    @staticmethod
+    def from_planes(hi, lo, nm, em, offsets, n_bases, names=None) -> "PackedText":
+        """From bit planes of n_words + 1 words each (nm: N / padding plane, em: contig-end plane)."""
+        L = _lib.lib()
+        nw = (int(n_bases) + 31) // 32
+        nm = np.ascontiguousarray(nm, dtype=np.uint32)
+        em = np.ascontiguousarray(em, dtype=np.uint32)
+        bases = np.zeros(nw + 1, dtype=BASES_DT)
+        bases["hi"][:nw] = np.asarray(hi[:nw], dtype=np.uint32) & ~nm[:nw]
+        bases["lo"][:nw] = np.asarray(lo[:nw], dtype=np.uint32) & ~nm[:nw]
+        masks = np.zeros(nw, dtype=MASKS_DT)
+        check(L.vs_masks_from_planes(nm.ctypes.data, em.ctypes.data, nw, masks.ctypes.data))
+        return PackedText(bases, masks, offsets, n_bases, names)
+
     @staticmethod
     def from_ascii(ascii_bytes, offsets, names=None) -> "PackedText":
         L = _lib.lib()
         a = np.frombuffer(ascii_bytes, dtype=np.uint8) if isinstance(ascii_bytes, (bytes, bytearray)) else np.ascontiguousarray(ascii_bytes, dtype=np.uint8)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = int(a.size)
-        words = np.zeros((n + 31) // 32 + 1, dtype=WORD_DT)
-        check(L.vs_pack_text(a.ctypes.data, n, off.ctypes.data, len(off) - 1, words.ctypes.data))
-        return PackedText(words, off, n, names)
+        nw = (n + 31) // 32
+        bases = np.zeros(nw + 1, dtype=BASES_DT)
+        masks = np.zeros(nw, dtype=MASKS_DT)
+        check(L.vs_pack_text(a.ctypes.data, n, off.ctypes.data, len(off) - 1, bases.ctypes.data, masks.ctypes.data))
+        return PackedText(bases, masks, off, n, names)
+
+    @staticmethod
+    def _from_view(v, names=None) -> "PackedText":
+        nw = int(v.n_words)
+        return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), _copy_array(v.masks, nw, MASKS_DT),
+                          _copy_array(v.contig_off, int(v.n_contigs) + 1, np.dtype("<u8")), int(v.n_bases), names,
+                          _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT))
 
     @staticmethod
     def from_fasta(path: str) -> "PackedText":
@@ -94,32 +170,25 @@ class PackedText:
                         check(L.vs_packer_append(p, line, len(line)))
             if have:
                 check(L.vs_packer_end_contig(p))
-            n = int(L.vs_packer_num_bases(p))
-            nc = int(L.vs_packer_num_contigs(p))
-            nw = int(L.vs_packer_num_words(p))
-            wp = L.vs_packer_words(p)
-            words = np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_uint32)), shape=((nw + 1) * 4,)).copy().view(WORD_DT)
-            off = np.ctypeslib.as_array(C.cast(L.vs_packer_offsets(p), C.POINTER(C.c_uint64)), shape=(nc + 1,)).copy()
+            v = _lib.TextView()
+            check(L.vs_packer_finish(p, C.byref(v)))
+            return PackedText._from_view(v, names)
         finally:
             L.vs_packer_free(p)
-        return PackedText(words, off, n, names)
 
     def save(self, prefix: str):
-        check(_lib.lib().vs_text_save(prefix.encode(), self.words.ctypes.data, self.n_bases, self.offsets.ctypes.data, self.n_contigs))
+        v = self.view()
+        check(_lib.lib().vs_text_save(prefix.encode(), C.byref(v)))
 
     @staticmethod
     def load(prefix: str) -> "PackedText":
         L = _lib.lib()
-        wp, op = C.c_void_p(), C.c_void_p()
-        nb, nc = C.c_uint64(), C.c_uint32()
-        check(L.vs_text_load(prefix.encode(), C.byref(wp), C.byref(nb), C.byref(op), C.byref(nc)))
+        v, owner = _lib.TextView(), C.c_void_p()
+        check(L.vs_text_load(prefix.encode(), C.byref(v), C.byref(owner)))
         try:
-            nw = (nb.value + 31) // 32
-            words = np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_uint32)), shape=((nw + 1) * 4,)).copy().view(WORD_DT)
-            off = np.ctypeslib.as_array(C.cast(op, C.POINTER(C.c_uint64)), shape=(nc.value + 1,)).copy()
+            return PackedText._from_view(v)
         finally:
-            L.vs_free(wp); L.vs_free(op)
-        return PackedText(words, off, int(nb.value))
+            L.vs_free(owner)
 
 
 class ScanContext:
@@ -149,31 +218,50 @@ class ScanContext:
         except Exception:
             pass
 
-    def upload(self, words: np.ndarray, first_word: int = 0, n_words: int | None = None, pinned_ptr: int | None = None):
-        """Upload words[first_word : first_word + n_words] (+ the following halo/pad word)."""
-        total = len(words) - 1
-        if n_words is None:
-            n_words = total - first_word
-        if first_word < 0 or first_word + n_words > total:
-            raise ValueError("shard outside the packed text")
-        ptr = pinned_ptr if pinned_ptr is not None else words.ctypes.data
-        check(self._L.vs_text_upload(self._ctx, ptr + first_word * 16, n_words, first_word * 32), self._ctx)
+    def set_chunk_words(self, n: int):
+        check(self._L.vs_ctx_set_chunk_words(self._ctx, n), self._ctx)
 
-    def scan(self, guides: np.ndarray, k: int, pam=None, cap: int = 1 << 20, out: np.ndarray | None = None):
-        """Returns (hits structured array, ScanStats). Hits are unordered."""
-        g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
-        pc = pam if isinstance(pam, int) else pam_code(pam)
-        hits = out if out is not None else np.zeros(cap, dtype=HIT_DT)
-        n = C.c_uint64()
-        st = ScanStats()
-        rc = self._L.vs_scan(self._ctx, g.ctypes.data, g.shape[0], k, pc, hits.ctypes.data, len(hits), C.byref(n), C.byref(st))
+    def upload(self, text: PackedText, first_word: int = 0, n_words: int | None = None, use_sparse: bool = True):
+        """Make words [first_word, first_word + n_words) resident (vs_text_upload)."""
+        if n_words is None:
+            n_words = text.n_words - first_word
+        v = text.view(use_sparse)
+        check(self._L.vs_text_upload(self._ctx, C.byref(v), first_word, n_words), self._ctx)
+
+    def _finish(self, rc, hits, n):
         if rc == _lib.VS_ERR_OVERFLOW:
             hits = np.zeros(n.value, dtype=HIT_DT)
             check(self._L.vs_scan_fetch(self._ctx, hits.ctypes.data, len(hits), C.byref(n)), self._ctx)
         else:
             check(rc, self._ctx)
+        return hits[: n.value]
+
+    def scan(self, guides: np.ndarray, k: int, pam=None, cap: int = 1 << 20, out: np.ndarray | None = None):
+        """Scan the resident text (vs_scan). Returns (hits structured array, ScanStats). Hits are unordered."""
+        g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
+        pc = pam if isinstance(pam, int) else pam_code(pam)
+        hits = out if out is not None else np.zeros(cap, dtype=HIT_DT)
+        n, st = C.c_uint64(), ScanStats()
+        rc = self._L.vs_scan(self._ctx, g.ctypes.data, g.shape[0], k, pc, hits.ctypes.data, len(hits), C.byref(n), C.byref(st))
+        hits = self._finish(rc, hits, n)
         self.last_stats = st
-        return hits[: n.value], st
+        return hits, st
+
+    def scan_text(self, text: PackedText, guides: np.ndarray, k: int, pam=None, first_word: int = 0, n_words: int | None = None,
+                  cap: int = 1 << 20, out: np.ndarray | None = None, use_sparse: bool = True):
+        """Upload (overlapped, chunk by chunk) and scan in one call (vs_scan_text): the end-to-end path."""
+        if n_words is None:
+            n_words = text.n_words - first_word
+        g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
+        pc = pam if isinstance(pam, int) else pam_code(pam)
+        hits = out if out is not None else np.zeros(cap, dtype=HIT_DT)
+        n, st = C.c_uint64(), ScanStats()
+        v = text.view(use_sparse)
+        rc = self._L.vs_scan_text(self._ctx, C.byref(v), first_word, n_words, g.ctypes.data, g.shape[0], k, pc,
+                                  hits.ctypes.data, len(hits), C.byref(n), C.byref(st))
+        hits = self._finish(rc, hits, n)
+        self.last_stats = st
+        return hits, st
 
     def measure_int_peaks(self):
         a, b = C.c_double(), C.c_double()
@@ -192,7 +280,8 @@ def map_packed(text: PackedText, guides: np.ndarray, k: int, pam=None, devices=N
     g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
     dev = np.asarray(devices if devices else [0], dtype=np.int32)
     hp, n, st = C.c_void_p(), C.c_uint64(), ScanStats()
-    check(L.vs_map_packed(text.words.ctypes.data, text.n_bases, g.ctypes.data, g.shape[0], k, pam_code(pam) if not isinstance(pam, int) else pam,
+    v = text.view()
+    check(L.vs_map_packed(C.byref(v), g.ctypes.data, g.shape[0], k, pam_code(pam) if not isinstance(pam, int) else pam,
                           dev.ctypes.data, len(dev), C.byref(hp), C.byref(n), C.byref(st)))
     try:
         hits = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n.value * 2,)).copy().view(HIT_DT) if n.value else np.zeros(0, HIT_DT)
@@ -222,7 +311,7 @@ def resolve_hits(hits: np.ndarray, offsets: np.ndarray):
 def md_string(text: PackedText, gpos: int, guide: np.ndarray, strand: int, md_style: int = MD_SEQAN) -> str:
     buf = C.create_string_buffer(64)
     g = np.ascontiguousarray(guide, dtype=np.uint8)
-    check(_lib.lib().vs_md_string(text.words.ctypes.data, gpos, g.ctypes.data, strand, md_style, buf))
+    check(_lib.lib().vs_md_string(text.bases.ctypes.data, gpos, g.ctypes.data, strand, md_style, buf))
     return buf.value.decode()
 
 

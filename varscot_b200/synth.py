@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .mapper import PackedText, WORD_DT
+from .mapper import PackedText
 
 # hg38 chromosome lengths in Mbp (1..22, X, Y): the "human-like length ladder" of config 2
 HUMAN_LADDER = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09, 133.28,
@@ -51,8 +51,7 @@ def synth_genome(seed: int, total_bases: int, n_contigs: int = 24, n_frac: float
     lens = contig_ladder(total_bases, n_contigs)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     nw = total_bases // 32
-    words = np.zeros(nw + 1, dtype=WORD_DT)
-    raw = rng.integers(0, 1 << 32, size=(2, nw), dtype=np.uint64).astype(np.uint32)
+    raw = rng.integers(0, 1 << 32, size=(2, nw + 1), dtype=np.uint64).astype(np.uint32)
     nm = np.zeros(nw + 1, dtype=np.uint32)
     em = np.zeros(nw + 1, dtype=np.uint32)
     for c in range(n_contigs):
@@ -69,12 +68,10 @@ def synth_genome(seed: int, total_bases: int, n_contigs: int = 24, n_frac: float
             _set_bit_range(nm, m, m + cen)
         em[(e - 1) >> 5] |= np.uint32(1) << np.uint32((e - 1) & 31)
     nm[nw] = 0xFFFFFFFF
-    words["hi"][:nw] = raw[0] & ~nm[:nw]
-    words["lo"][:nw] = raw[1] & ~nm[:nw]
-    words["nm"] = nm
-    words["em"] = em
     names = [f"chr{c + 1}" for c in range(n_contigs)]
-    return PackedText(words, off, total_bases, names)
+    t = PackedText.from_planes(raw[0], raw[1], nm, em, off, total_bases, names)
+    t._nm, t._em = nm, em          # kept for synth_variant_segments / unpack_codes
+    return t
 
 
 def _gather(plane: np.ndarray, starts: np.ndarray, length: int) -> np.ndarray:
@@ -92,13 +89,12 @@ def synth_variant_segments(genome: PackedText, seed: int, n_variants: int, snv_f
                            hom_frac: float = 0.20, max_indel: int = 10) -> PackedText:
     """The "SNP genome": per variant the REF/ALT haplotype windows cut from the packed genome."""
     rng = np.random.default_rng(seed)
-    W = genome.words
     nwg = genome.n_words
     # planes padded by two words so that _gather may read w+2
-    hi = np.concatenate([W["hi"][:nwg + 1], np.zeros(2, np.uint32)])
-    lo = np.concatenate([W["lo"][:nwg + 1], np.zeros(2, np.uint32)])
-    nm = np.concatenate([W["nm"][:nwg + 1], np.full(2, 0xFFFFFFFF, np.uint32)])
-    em = np.concatenate([W["em"][:nwg + 1], np.zeros(2, np.uint32)])
+    hi = np.concatenate([genome.bases["hi"][:nwg + 1], np.zeros(2, np.uint32)])
+    lo = np.concatenate([genome.bases["lo"][:nwg + 1], np.zeros(2, np.uint32)])
+    nm = np.concatenate([genome._nm[:nwg + 1], np.full(2, 0xFFFFFFFF, np.uint32)])
+    em = np.concatenate([genome._em[:nwg + 1], np.zeros(2, np.uint32)])
     span = 45 + max_indel
     # candidate positions: window [p-22, p-22+span) must be N-free and inside one contig
     n_try = int(n_variants * 1.25) + 1000
@@ -154,33 +150,39 @@ def synth_variant_segments(genome: PackedText, seed: int, n_variants: int, snv_f
     off = np.concatenate([[0], np.cumsum(seg_len)]).astype(np.uint64)
     n_bases = int(off[-1])
     nw = (n_bases + 31) // 32
-    words = np.zeros(nw + 1, dtype=WORD_DT)
     cols = np.arange(span, dtype=np.uint64)
     keep = cols[None, :] < seg_len[:, None].astype(np.uint64)
+    planes = {}
     for name, seg in (("hi", seg_h), ("lo", seg_l)):
         bits = ((seg[:, None] >> cols[None, :]) & one).astype(np.uint8)[keep]
         packed = np.packbits(bits, bitorder="little")
-        buf = np.zeros(nw * 4, np.uint8)
+        buf = np.zeros((nw + 1) * 4, np.uint8)
         buf[:len(packed)] = packed
-        words[name][:nw] = buf.view("<u4")
+        planes[name] = buf.view("<u4")
     emw = np.zeros(nw + 1, np.uint32)
     _set_bits(emw, off[1:].astype(np.int64) - 1)
-    words["em"] = emw
     nmw = np.zeros(nw + 1, np.uint32)
     if n_bases & 31:
         nmw[nw - 1] = np.uint32((0xFFFFFFFF << (n_bases & 31)) & 0xFFFFFFFF)
     nmw[nw] = 0xFFFFFFFF
-    words["nm"] = nmw
-    return PackedText(words, off, n_bases, None)
+    t = PackedText.from_planes(planes["hi"], planes["lo"], nmw, emw, off, n_bases, None)
+    t._nm, t._em = nmw, emw
+    return t
 
 
 def concat_texts(a: PackedText, b: PackedText) -> PackedText:
     """Concatenate two packed texts; a.n_bases must be a multiple of 32 (synth_genome guarantees it)."""
     if a.n_bases % 32:
         raise ValueError("first text must end on a word boundary")
-    words = np.concatenate([a.words[:a.n_words], b.words])
+    na = a.n_words
+    hi = np.concatenate([a.bases["hi"][:na], b.bases["hi"]])
+    lo = np.concatenate([a.bases["lo"][:na], b.bases["lo"]])
+    nm = np.concatenate([a._nm[:na], b._nm])
+    em = np.concatenate([a._em[:na], b._em])
     off = np.concatenate([a.offsets, b.offsets[1:] + np.uint64(a.n_bases)]).astype(np.uint64)
-    return PackedText(words, off, a.n_bases + b.n_bases, None)
+    t = PackedText.from_planes(hi, lo, nm, em, off, a.n_bases + b.n_bases, None)
+    t._nm, t._em = nm, em
+    return t
 
 
 def unpack_codes(text: PackedText, start: int = 0, n: int | None = None) -> np.ndarray:
@@ -190,13 +192,12 @@ def unpack_codes(text: PackedText, start: int = 0, n: int | None = None) -> np.n
     if start % 32:
         raise ValueError("start must be word aligned")
     w0, w1 = start // 32, (start + n + 31) // 32
-    W = text.words[w0:w1]
 
     def bits(x):
-        return np.unpackbits(np.ascontiguousarray(x).view(np.uint8), bitorder="little")[:n]
+        return np.unpackbits(np.ascontiguousarray(x[w0:w1]).view(np.uint8), bitorder="little")[:n]
 
-    codes = (bits(W["hi"]) << 1) | bits(W["lo"])
-    codes[bits(W["nm"]) == 1] = 4
+    codes = (bits(text.bases["hi"]) << 1) | bits(text.bases["lo"])
+    codes[bits(text._nm) == 1] = 4
     return codes
 
 
