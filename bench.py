@@ -329,5 +329,18 @@ def main():
     text.unpin()
 
 
+def _shutdown():
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()
