@@ -3,7 +3,8 @@
 NVCC    ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= /usr/bin/g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wno-unused-function --cudart static
+EXTRA   ?=
+NVFLAGS := $(ARCH) $(EXTRA) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wno-unused-function --cudart static
 CSRC    := varscot_b200/csrc
 LIB     := varscot_b200/libvarscot_scan.so
 BINDIR  := build/read_mapping_build

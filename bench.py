@@ -29,8 +29,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C_ALG = 4.0            # yardstick LOP3 per guide·bp: 64 per 32 starts per guide per strand
-LOP3_PER_BLOCK_GUIDE = 38   # executed by k_score per (32-candidate block, guide): 36 CSA + 2 threshold
-LDS_PER_BLOCK_GUIDE = 23
+
+
+def csa_ops(n, init=False):
+    """LOP3-class ops of popcount_planes<n, init> in vs_kernels.cuh: column compression, FA = 2 ops, HA = 2 ops."""
+    ops, cols = 0, n
+    for w in range(5):
+        left = cols + (1 if init else 0)
+        nxt = 0
+        while left >= 2:
+            left -= 2 if left >= 3 else 1
+            ops += 2
+            nxt += 1
+        cols = nxt
+    return ops
+
+
+def score_ops(k):
+    """(LOP3, LDS) k_score executes per (32-candidate block, guide) in stage A, and the extra of stage B."""
+    pa = 23 if k >= 8 else 7 + 2 * k
+    a = (csa_ops(pa) + 2, pa)
+    b = (csa_ops(23 - pa, True) + 2, 23 - pa) if pa < 23 else (0, 0)
+    return a, b
 
 CONFIGS = {
     # id: (description, genome bases, variants, guides, k, extra PAM)
@@ -61,6 +81,7 @@ class ClockSampler:
 
     def __init__(self, device):
         self.rows = []
+        self.device = device
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(device)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -94,7 +115,14 @@ class ClockSampler:
         if not rows:
             rows, window = self.rows, "whole_run"
         if not rows:
-            return None
+            # the looping sampler produced nothing (pipe buffering / slow start): take one synchronous sample now
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in out.split(",")]
+                rows, window = [(time.time(), float(f[1]), float(f[2]), float(f[3]), f[4], f[5], f[6], f[7])], "after_timed"
+            except Exception:
+                return None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
         sm = sorted(r[1] for r in rows)
@@ -288,13 +316,15 @@ def main():
     score_s = score_ms / args.steps * 1e-3
     n_score_launch = st.score_launches
     yard = C_ALG * ng * B / score_s                       # yardstick LOP3/s of the scoring launches of one step
-    executed = LOP3_PER_BLOCK_GUIDE * blocks * ng / score_s
-    lds = LDS_PER_BLOCK_GUIDE * blocks * ng / score_s
+    (lop_a, lds_a), (lop_b, lds_b) = score_ops(k)
+    executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few warps that pass)
+    lds = lds_a * blocks * ng / score_s
     roof = {"bound": "int_alu", "kernel": "k_score", "achieved": yard / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
             "frac": yard / peak_lop3, "traffic": None,
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
             "avg_launch_ms": score_ms / args.steps / max(1, n_score_launch), "launches_per_step": n_score_launch,
             "executed_lop3_tlops": executed / 1e12, "frac_executed": executed / peak_lop3,
+            "ops_per_block_guide": {"stage_a_lop3": lop_a, "stage_a_lds": lds_a, "stage_b_lop3": lop_b, "stage_b_lds": lds_b},
             "lds_words_per_s_T": lds / 1e12, "lds_peak_T": peak_lds / 1e12, "frac_lds": lds / peak_lds,
             "hbm_gbs_algorithmic": (blocks * 192.0 * ((ng + 511) // 512)) / score_s / 1e9,
             "note": "yardstick = 4.0 LOP3 per guide*bp (dense scan, SURVEY.md 8d); PAM-first compaction scores ~1/8 of the windows per strand, so frac may exceed 1; frac_executed is the real alu-pipe load"}

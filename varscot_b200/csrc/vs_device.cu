@@ -15,7 +15,7 @@ using namespace vs;
 
 static thread_local std::string g_last_error;
 
-constexpr uint64_t DEFAULT_CHUNK_WORDS = 4ull << 20;      // 128 Mi bases per pipeline chunk
+constexpr uint64_t DEFAULT_CHUNK_WORDS = 8ull << 20;      // 256 Mi bases per pipeline chunk
 
 struct vs_ctx {
     int device = -1;
@@ -170,8 +170,8 @@ static void make_pam(int extra_pam, PamParams &pp)
 template <int K>
 static void launch_score(const ScoreArgs &a, uint64_t cap, cudaStream_t st)
 {
-    unsigned grid = (unsigned)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
-    k_score<K><<<grid, SCORE_THREADS, NPLANES * SCORE_THREADS * 4, st>>>(a);
+    (void)cap;
+    k_score<K><<<2 * a.ctas_per_strand, SCORE_THREADS, NPLANES * SCORE_THREADS * 4, st>>>(a);
 }
 
 static void dispatch_score(int k, const ScoreArgs &a, uint64_t cap, cudaStream_t st)
@@ -330,8 +330,9 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     if (tile_words < 8) tile_words = 8;
     S.n_chunks = n_chunks;
 
-    // pattern tables (byte offset of the selected mismatch plane per position), per strand pass, staged in pinned memory
-    const uint64_t pat_words = (uint64_t)2 * g_chunks * PAT_CHUNK * PAT_STRIDE;
+    // pattern tables per guide chunk: [strand][PAT_CHUNK][PAT_STRIDE] (layout: see c_pat in vs_kernels.cuh), staged in pinned memory
+    const uint64_t pat_chunk_words = (uint64_t)2 * PAT_CHUNK * PAT_STRIDE;
+    const uint64_t pat_words = (uint64_t)g_chunks * pat_chunk_words;
     if (pat_words > ctx->pat_cap) {
         CK(cudaStreamSynchronize(st));
         cudaFree(ctx->d_pat); if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
@@ -343,11 +344,13 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     memset(ctx->h_pat, 0, pat_words * sizeof(uint32_t));
     for (int s = 0; s < 2; ++s)
         for (uint32_t g = 0; g < n_guides; ++g) {
-            uint32_t *dst = ctx->h_pat + (((size_t)s * g_chunks + g / PAT_CHUNK) * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
+            uint32_t *dst = ctx->h_pat + (size_t)(g / PAT_CHUNK) * pat_chunk_words + ((size_t)s * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
             const uint8_t *gd = guides + (size_t)g * VS_GLEN;
-            for (int i = 0; i < VS_GLEN; ++i) {
-                int b = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];      // reverse pass scores revcomp(guide), bidir_mapping.cpp:293
-                dst[i] = (uint32_t)(4 * i + b) * SCORE_THREADS * 4u;
+            // slot order: informative positions first, the PAM dinucleotide last (forward 0..22; reverse 2..22, 0, 1)
+            for (int j = 0; j < VS_GLEN; ++j) {
+                const int i = s ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j;
+                const int b = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];      // reverse pass scores revcomp(guide), bidir_mapping.cpp:293
+                dst[j] = (uint32_t)(4 * i + b) * SCORE_THREADS * 4u;
             }
         }
     // counters
@@ -403,18 +406,20 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
                                                  ctx->d_planes[0], ctx->d_pos[0], ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap, cnt);
         S.launches++;
         if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 1], st));
-        for (int s = 0; s < 2; ++s)
-            for (uint32_t gc = 0; gc < g_chunks; ++gc) {
-                uint32_t np = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK);
-                const uint32_t *psrc = ctx->d_pat + ((size_t)s * g_chunks + gc) * PAT_CHUNK * PAT_STRIDE;
-                CK(cudaMemcpyToSymbolAsync(c_pat, psrc, (size_t)np * PAT_STRIDE * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
-                ScoreArgs a;
-                a.planes = ctx->d_planes[s]; a.pos = ctx->d_pos[s]; a.n_blocks_ptr = cnt + 2 + s; a.cap = ctx->blocks_cap;
-                a.n_pat = np; a.guide_base = gc * PAT_CHUNK; a.strand = (uint32_t)s;
-                a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
-                dispatch_score(k, a, ctx->blocks_cap, st);
-                S.launches++; S.score_launches++;
-            }
+        for (uint32_t gc = 0; gc < g_chunks; ++gc) {
+            const uint32_t np = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK);
+            CK(cudaMemcpyToSymbolAsync(c_pat, ctx->d_pat + (size_t)gc * pat_chunk_words, pat_chunk_words * sizeof(uint32_t), 0,
+                                       cudaMemcpyDeviceToDevice, st));
+            ScoreArgs a;
+            for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[s]; a.pos[s] = ctx->d_pos[s]; }
+            a.n_blocks_ptr = cnt + 2; a.cap = ctx->blocks_cap;
+            a.ctas_per_strand = (uint32_t)((ctx->blocks_cap + SCORE_THREADS - 1) / SCORE_THREADS);
+            a.n_pat = np; a.guide_base = gc * PAT_CHUNK;
+            a.pat_global = ctx->d_pat + (size_t)gc * pat_chunk_words;
+            a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
+            dispatch_score(k, a, ctx->blocks_cap, st);
+            S.launches++; S.score_launches++;
+        }
         if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 2], st));
         return VS_OK;
     };

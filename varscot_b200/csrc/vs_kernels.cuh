@@ -9,10 +9,10 @@
 //                (bit-parallel), compact them into blocks of 32 candidates and store each block bit-sliced
 //                ACROSS candidates (per-thread 32x32 register transposes): 48 words per block =
 //                hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; + 32 positions
-//   k_score<K> : one thread per candidate block; expands the 46 planes into 92 "mismatch if guide base is b"
-//                planes in shared memory, then for every guide: 23 LDS (plane selected by the guide base,
-//                offset warp-uniform from constant memory) + 36 LOP3 carry-save adder + 2 LOP3 threshold.
-//                Hits (rare) take a slow path: exact count, R4 check, atomic append.
+//   k_score<K> : one thread per candidate block, both strands in one launch; 18 of the 23 positions are expanded
+//                into "mismatch if guide base is b" planes in shared memory (select = 1 LDS at a warp-uniform
+//                offset from constant memory), 5 stay in registers (select = 1 IMAD + 1 LOP3); then per guide
+//                36 LOP3 carry-save adder + 2 LOP3 threshold.  Hits (rare): exact count, R4 check, atomic append.
 // Integer pipe + shared-memory bound; no tensor cores (nothing here is a dense contraction worth a GEMM:
 // the bit-sliced form costs ~1.2 ALU ops per (window, guide) pair, below one op per output element).
 #pragma once
@@ -29,9 +29,9 @@ constexpr int BLK_WORDS    = 48;                  // words per candidate block
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
 constexpr int SCORE_THREADS = 256;
-constexpr int NPLANES      = 92;                  // 23 positions x 4 guide bases
-constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 offsets + pad)
-constexpr int PAT_CHUNK    = 512;                 // patterns per k_score launch (48 KB of constant memory)
+constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block
+constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 slot offsets + pad, 16-byte aligned)
+constexpr int PAT_CHUNK    = 320;                 // guides per k_score launch: 2 strands x 320 x 96 B = 60 KB of constant memory
 
 struct PamParams {
     int n;            // number of forward dinucleotides (2 or 3)
@@ -251,37 +251,143 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return r;
 }
-#define VS_FA(a, b, c, s, cy) uint32_t s = lop3<0x96>(a, b, c), cy = lop3<0xE8>(a, b, c)
 
-// byte offsets (plane index * SCORE_THREADS * 4) of the plane selected by each pattern base
-__constant__ uint32_t c_pat[PAT_CHUNK * PAT_STRIDE];
+// Bit-sliced population count of N one-bit planes (plus optional planes `init[w]` already carrying weight 2^w):
+// column compression with full adders (2 LOP3 each: XOR3 0x96, MAJ3 0xE8) taken from the front of a queue so the
+// tree stays balanced.  Written as template recursion so that every index is a compile-time constant and all
+// planes live in registers.
+template <int HEAD, int TAIL, int NN>
+struct CsaColumn {
+    static constexpr int LEFT = TAIL - HEAD;
+    using Next = CsaColumn<(LEFT >= 3 ? HEAD + 3 : HEAD + 2), TAIL + 1, NN + 1>;
+    static __device__ __forceinline__ void run(uint32_t *col, uint32_t *nxt)
+    {
+        if constexpr (LEFT >= 3) {
+            const uint32_t x = col[HEAD], y = col[HEAD + 1], z = col[HEAD + 2];
+            col[TAIL] = lop3<0x96>(x, y, z);
+            nxt[NN] = lop3<0xE8>(x, y, z);
+            Next::run(col, nxt);
+        } else if constexpr (LEFT == 2) {
+            const uint32_t x = col[HEAD], y = col[HEAD + 1];
+            col[TAIL] = x ^ y;
+            nxt[NN] = x & y;
+            Next::run(col, nxt);
+        }
+    }
+    static __host__ __device__ constexpr int final_head() { if constexpr (LEFT >= 2) return Next::final_head(); else return HEAD; }
+    static __host__ __device__ constexpr int final_left() { if constexpr (LEFT >= 2) return Next::final_left(); else return LEFT; }
+    static __host__ __device__ constexpr int final_nn() { if constexpr (LEFT >= 2) return Next::final_nn(); else return NN; }
+};
+
+template <int W, int N_IN, bool HAS_INIT>
+struct CsaWeights {
+    static __device__ __forceinline__ void run(uint32_t *col, const uint32_t *init, uint32_t *bit)
+    {
+        constexpr int T0 = N_IN + (HAS_INIT ? 1 : 0);
+        if constexpr (HAS_INIT) col[N_IN] = init[W];
+        using C = CsaColumn<0, T0, 0>;
+        uint32_t nxt[T0 + 2];
+        C::run(col, nxt);
+        if constexpr (C::final_left() == 1) bit[W] = col[C::final_head()]; else bit[W] = 0u;
+        if constexpr (W < 4) {
+            constexpr int NN = C::final_nn();
+            uint32_t col2[2 * NN + 4];
+#pragma unroll
+            for (int i = 0; i < NN; ++i) col2[i] = nxt[i];
+            CsaWeights<W + 1, NN, HAS_INIT>::run(col2, init, bit);
+        }
+    }
+};
+
+template <int N, bool HAS_INIT>
+__device__ __forceinline__ void popcount_planes(const uint32_t (&in)[N], const uint32_t (&init)[5], uint32_t (&bit)[5])
+{
+    uint32_t col[2 * N + 4];
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = in[i];
+    CsaWeights<0, N, HAS_INIT>::run(col, init, bit);
+}
+
+// count <= K on a 5-bit bit-sliced count (K <= 8): two LOP3 with compile-time LUTs
+template <int K>
+__device__ __forceinline__ uint32_t le_k(const uint32_t (&b)[5])
+{
+    constexpr int LUT_F = (K < 8) ? ((1 << (K + 1)) - 1) : 0x01;   // f(b2,b1,b0): low3 <= K      (K = 8: low3 == 0)
+    constexpr int LUT_G = (K < 8) ? 0x02 : 0x0B;                   // g(b4,b3,f): ~b4 & ~b3 & f   (K = 8: ~b4 & (~b3 | f))
+    const uint32_t f = lop3<LUT_F>(b[2], b[1], b[0]);
+    return lop3<LUT_G>(b[4], b[3], f);
+}
+
+// Number of pattern slots scored before the early-out test: with uniform-random text, after PA(K) informative
+// positions fewer than ~12 % of the warps (1024 candidates) still hold a window with <= K mismatches, so the
+// remaining slots (the PAM positions come last in the slot order) are loaded only for those.
+__host__ __device__ constexpr int stage_a_slots(int k) { return k >= 8 ? VS_GLEN : 7 + 2 * k; }
+
+// Pattern table in constant memory, per strand and guide: PAT_STRIDE words; slot j holds the byte offset
+// (plane index * SCORE_THREADS * 4) of the shared-memory plane selected by the pattern base at position
+// order[strand][j].  The host orders the slots informative-first: forward 0..22, reverse 2..22,0,1.
+__constant__ uint32_t c_pat[2 * PAT_CHUNK * PAT_STRIDE];
 
 struct ScoreArgs {
-    const uint32_t *planes;     // [n_blocks][48]
-    const uint32_t *pos;        // [n_blocks][32]
-    const unsigned long long *n_blocks_ptr;   // blocks claimed by k_extract for this chunk and strand (device counter)
-    uint64_t cap;               // capacity of the candidate store; a chunk that overflowed it is skipped (host redoes it)
-    uint32_t n_pat;             // patterns in this launch (<= PAT_CHUNK)
-    uint32_t guide_base;        // index of pattern 0 of this launch in the guide list
-    uint32_t strand;            // 0 forward pass, 1 reverse pass
+    const uint32_t *planes[2];  // per strand: [n_blocks][48]
+    const uint32_t *pos[2];     // per strand: [n_blocks][32]
+    const unsigned long long *n_blocks_ptr;   // [2]: blocks claimed by k_extract for this chunk, per strand (device counters)
+    uint64_t cap;               // capacity of each candidate store; a chunk that overflowed it is skipped (host redoes it)
+    uint32_t ctas_per_strand;   // grid = 2 * ctas_per_strand, sized by capacity
+    uint32_t n_pat;             // guides in this launch (<= PAT_CHUNK)
+    uint32_t guide_base;        // index of guide 0 of this launch in the guide list
+    const uint32_t *pat_global; // the same table as c_pat in global memory (read by the slow path only)
     vs_hit *hits;
     unsigned long long *n_hits;
     uint64_t hit_cap;
 };
+
+// Slow path (rare): for every lane that passed the threshold recompute the exact count from the selected planes,
+// apply R4 to last-window candidates (H over positions 11..22 must be <= floor(K/2), bidir_mapping.cpp:48-53) and
+// append the hit.  It re-reads the slot offsets from the GLOBAL copy of the pattern table so that nothing of the
+// hot loop's uniform-register state has to stay live for it.
+__device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, uint32_t le, uint32_t lastm, uint32_t k_half,
+                                        const uint32_t *pos, uint32_t info, vs_hit *hits, unsigned long long *n_hits,
+                                        uint64_t hit_cap)
+{
+    while (le != 0) {
+        const int c = __ffs(le) - 1;
+        le &= le - 1;
+        uint32_t mm = 0, h2 = 0;
+#pragma unroll
+        for (int i = 0; i < VS_GLEN; ++i) {
+            const uint32_t off = __ldg(po + i);
+            const uint32_t bitv = (*reinterpret_cast<const uint32_t *>(myb + off) >> c) & 1u;
+            mm += bitv;
+            if (off >= 11u * 4u * SCORE_THREADS * 4u) h2 += bitv;          // the slot scores a position >= 11
+        }
+        if (((lastm >> c) & 1u) && h2 > k_half) continue;                   // R4
+        const unsigned long long idx = atomicAdd(n_hits, 1ull);
+        if (idx < hit_cap) {
+            vs_hit hrec;
+            hrec.pos = pos[c];
+            hrec.info = info | mm;
+            hits[idx] = hrec;
+        }
+    }
+}
 
 template <int K>
 __global__ void __launch_bounds__(SCORE_THREADS, 2)
 k_score(ScoreArgs a)
 {
     extern __shared__ uint32_t sm[];     // [NPLANES][SCORE_THREADS]
+    constexpr int PA = stage_a_slots(K), PB = VS_GLEN - PA;
     const int tid = threadIdx.x;
-    const uint64_t n_blocks = *a.n_blocks_ptr;
-    if (n_blocks > a.cap || (uint64_t)blockIdx.x * SCORE_THREADS >= n_blocks) return;     // grid is sized by capacity
-    const uint64_t blk = (uint64_t)blockIdx.x * SCORE_THREADS + tid;
+    const uint32_t strand = blockIdx.x >= a.ctas_per_strand;            // forward CTAs first, then reverse
+    const uint32_t cta = blockIdx.x - strand * a.ctas_per_strand;
+    const uint64_t n_blocks = strand ? a.n_blocks_ptr[1] : a.n_blocks_ptr[0];
+    if (max(a.n_blocks_ptr[0], a.n_blocks_ptr[1]) > a.cap || (uint64_t)cta * SCORE_THREADS >= n_blocks) return;
+    const uint64_t blk = (uint64_t)cta * SCORE_THREADS + tid;
     uint32_t *my = sm + tid;
     uint32_t lastm = 0;
     if (blk < n_blocks) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.planes + blk * BLK_WORDS);
+        const uint4 *src = reinterpret_cast<const uint4 *>((strand ? a.planes[1] : a.planes[0]) + blk * BLK_WORDS);
         uint32_t v[BLK_WORDS];
 #pragma unroll
         for (int i = 0; i < BLK_WORDS / 4; ++i) {
@@ -289,15 +395,14 @@ k_score(ScoreArgs a)
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
         lastm = v[BLK_LAST];
-        const uint32_t inv = ~v[BLK_VALID];
+        const uint32_t inv = ~v[BLK_VALID];          // lanes past the end of a partial block mismatch everywhere
 #pragma unroll
         for (int i = 0; i < VS_GLEN; ++i) {
             const uint32_t h = v[i], l = v[VS_GLEN + i];
-            const uint32_t x = (i < 9) ? inv : 0u;     // 9 forced mismatches keep invalid lanes above any k <= 8
-            my[(4 * i + 0) * SCORE_THREADS] = (h | l) | x;      // mismatch if guide base is A (00)
-            my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | x;     // C (01)
-            my[(4 * i + 2) * SCORE_THREADS] = (~h | l) | x;     // G (10)
-            my[(4 * i + 3) * SCORE_THREADS] = (~h | ~l) | x;    // T (11)
+            my[(4 * i + 0) * SCORE_THREADS] = (h | l) | inv;      // mismatch if guide base is A (00)
+            my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | inv;     // C (01)
+            my[(4 * i + 2) * SCORE_THREADS] = (~h | l) | inv;     // G (10)
+            my[(4 * i + 3) * SCORE_THREADS] = (~h | ~l) | inv;    // T (11)
         }
     } else {
 #pragma unroll
@@ -305,57 +410,32 @@ k_score(ScoreArgs a)
     }
     // each thread reads back only what it wrote: no barrier needed
     const char *myb = reinterpret_cast<const char *>(my);
-    constexpr int LUT_F = (K < 8) ? ((1 << (K + 1)) - 1) : 0x01;   // f(b2,b1,b0): low3 <= K  (K = 8: low3 == 0)
-    constexpr int LUT_G = (K < 8) ? 0x02 : 0x2B;                   // g(x,y,f): ~x & ~y & f   (K = 8: (~x&~y) | ((x^y)&f))
+    const uint32_t *pat0 = c_pat + strand * (PAT_CHUNK * PAT_STRIDE);
+    const uint32_t zero5[5] = {0u, 0u, 0u, 0u, 0u};
 
 #pragma unroll 2
     for (uint32_t g = 0; g < a.n_pat; ++g) {
-        const uint32_t *po = c_pat + g * PAT_STRIDE;
-        uint32_t m[VS_GLEN];
+        const uint32_t *po = pat0 + g * PAT_STRIDE;
+        // stage A: the first PA slots
+        uint32_t ma[PA], ca[5];
 #pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) m[i] = *reinterpret_cast<const uint32_t *>(myb + po[i]);
-        // carry-save adder tree: 23 one-bit planes -> b0, b1, b2 and two weight-8 planes x, y  (18 full adders)
-        VS_FA(m[0], m[1], m[2], s0, c0);
-        VS_FA(m[3], m[4], m[5], s1, c1);
-        VS_FA(m[6], m[7], m[8], s2, c2);
-        VS_FA(m[9], m[10], m[11], s3, c3);
-        VS_FA(m[12], m[13], m[14], s4, c4);
-        VS_FA(m[15], m[16], m[17], s5, c5);
-        VS_FA(m[18], m[19], m[20], s6, c6);
-        VS_FA(s0, s1, s2, t0, d0);
-        VS_FA(s3, s4, s5, t1, d1);
-        VS_FA(s6, m[21], m[22], t2, d2);
-        VS_FA(t0, t1, t2, b0, d3);
-        VS_FA(c0, c1, c2, u0, e0);
-        VS_FA(c3, c4, c5, u1, e1);
-        VS_FA(c6, d0, d1, u2, e2);
-        VS_FA(u0, u1, u2, v0, e3);
-        VS_FA(v0, d2, d3, b1, e4);
-        VS_FA(e0, e1, e2, p0, x);
-        VS_FA(p0, e3, e4, b2, y);
-        const uint32_t f = lop3<LUT_F>(b2, b1, b0);
-        uint32_t le = lop3<LUT_G>(x, y, f);
-        if (le) {
-            // slow path (rare): exact count, R4 for last windows, append
-            do {
-                const int c = __ffs(le) - 1;
-                le &= le - 1;
-                uint32_t mm = 0, h2 = 0;
+        for (int i = 0; i < PA; ++i) ma[i] = *reinterpret_cast<const uint32_t *>(myb + po[i]);
+        popcount_planes<PA, false>(ma, zero5, ca);
+        uint32_t le = le_k<K>(ca);
+        // warp-uniform early out: if no lane of the warp can still be within K, the remaining slots are never loaded.
+        // (A divergent `if (le)` here makes ptxas 12.9 crash on the uniform-register loads of stage B.)
+        if (PB == 0 ? (le != 0) : __any_sync(0xffffffffu, le != 0)) {
+            if constexpr (PB > 0) {
+                // stage B: the remaining slots, added onto stage A's count
+                uint32_t mb[PB], cb[5];
 #pragma unroll
-                for (int i = 0; i < VS_GLEN; ++i) {
-                    uint32_t bit = (*reinterpret_cast<const uint32_t *>(myb + po[i]) >> c) & 1u;
-                    mm += bit;
-                    if (i >= 11) h2 += bit;
-                }
-                if (((lastm >> c) & 1u) && h2 > (uint32_t)(K / 2)) continue;     // R4
-                unsigned long long idx = atomicAdd(a.n_hits, 1ull);
-                if (idx < a.hit_cap) {
-                    vs_hit hrec;
-                    hrec.pos = a.pos[blk * 32 + c];
-                    hrec.info = ((a.guide_base + g) << 8) | (a.strand << 7) | mm;
-                    a.hits[idx] = hrec;
-                }
-            } while (le);
+                for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(myb + po[PA + i]);
+                popcount_planes<PB, true>(mb, ca, cb);
+                le = le_k<K>(cb);
+            }
+            if (le != 0)
+                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, lastm, (uint32_t)(K / 2), (strand ? a.pos[1] : a.pos[0]) + blk * 32,
+                           ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
         }
     }
 }
