@@ -7,6 +7,7 @@
 #include "vs_internal.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -326,6 +327,7 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
     // tile size: about 60 blocks (both strands) per 64-thread CTA at the expected PAM density pp.n / 16 per strand
     uint32_t tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
+    if (const char *e = getenv("VARSCOT_TILE_WORDS")) tile_words = (uint32_t)atoi(e);      // tuning knob
     if (tile_words > (uint32_t)EX_MAX_WORDS) tile_words = EX_MAX_WORDS;
     if (tile_words < 8) tile_words = 8;
     S.n_chunks = n_chunks;

@@ -111,7 +111,10 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 // deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written for that tile; k_score
 // then skips the whole chunk and the host, which reads the counters back, regrows the stores and redoes the chunk.
 // Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask.
-__global__ void __launch_bounds__(EX_THREADS)
+#ifndef VS_EX_MINBLOCKS
+#define VS_EX_MINBLOCKS 10
+#endif
+__global__ void __launch_bounds__(EX_THREADS, VS_EX_MINBLOCKS)
 k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
           uint64_t global_base, PamParams pp,
           uint32_t *__restrict__ planes_f, uint32_t *__restrict__ pos_f,
