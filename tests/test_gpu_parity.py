@@ -299,3 +299,18 @@ def test_candidate_store_regrow_and_dense_hits():
     assert len(hits) == n - 22
     assert np.array_equal(np.sort(hits["pos"]), np.arange(n - 22, dtype=np.uint32))
     assert (hits["info"] == 0).all()
+
+
+def test_map_packed_multi_device_equals_single():
+    """vs_map_packed shards the text over every visible GPU (one host thread + context each) — same records."""
+    import varscot_b200 as V
+    nd = V.device_count()
+    case = make_case(seed=71, contig_lens=[300000, 45, 45, 200000], n_guides=12, k=6)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    a, _ = V.map_packed(text, case.guides, 6, devices=[0])
+    b, st = V.map_packed(text, case.guides, 6, devices=list(range(nd)) if nd > 1 else [0, 0, 0])
+    ra, _ = V.resolve_hits(a, case.offsets)
+    rb, _ = V.resolve_hits(b, case.offsets)
+    assert ra.tolist() == rb.tolist() and len(ra) > 0
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 6)
+    assert [(x[0], x[3], x[1], x[2], x[4]) for x in ra.tolist()] == [e[:5] for e in exp]

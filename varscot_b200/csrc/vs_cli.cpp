@@ -10,6 +10,7 @@
 #include "vs_internal.h"
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,12 +39,13 @@ bool read_fasta(const std::string &path, const FastaSink &sink, std::string &err
     bool in_header = false, at_line_start = true, have_record = false;
     size_t got;
     while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        const char *b = buf.data();
         size_t i = 0;
         while (i < got) {
             if (in_header) {
-                const char *nl = (const char *)memchr(buf.data() + i, '\n', got - i);
-                size_t e = nl ? (size_t)(nl - buf.data()) : got;
-                hdr.append(buf.data() + i, e - i);
+                const char *nl = (const char *)memchr(b + i, '\n', got - i);
+                size_t e = nl ? (size_t)(nl - b) : got;
+                hdr.append(b + i, e - i);
                 i = e;
                 if (nl) {
                     while (!hdr.empty() && (hdr.back() == '\r' || hdr.back() == '\n')) hdr.pop_back();
@@ -54,16 +56,27 @@ bool read_fasta(const std::string &path, const FastaSink &sink, std::string &err
                 }
                 continue;
             }
-            if (at_line_start && buf[i] == '>') {
-                if (have_record) sink.end_record();
-                in_header = true; ++i;
-                continue;
+            // sequence data runs to the next '>' that opens a line; whole spans (newlines included) go to the sink
+            size_t j = i;
+            bool header_found = false;
+            while (j < got) {
+                const char *gt = (const char *)memchr(b + j, '>', got - j);
+                if (!gt) { j = got; break; }
+                size_t g = (size_t)(gt - b);
+                bool line_start = g == 0 ? at_line_start : (g == i ? at_line_start : b[g - 1] == '\n');
+                if (line_start) { j = g; header_found = true; break; }
+                j = g + 1;                                   // a '>' inside a line is just a (non-ACGT) character
             }
-            const char *nl = (const char *)memchr(buf.data() + i, '\n', got - i);
-            size_t e = nl ? (size_t)(nl - buf.data()) : got;
-            if (have_record && e > i) sink.seq(buf.data() + i, e - i);
-            at_line_start = nl != nullptr;
-            i = nl ? e + 1 : e;
+            if (j > i) {
+                if (have_record) sink.seq(b + i, j - i);
+                at_line_start = b[j - 1] == '\n';
+            }
+            i = j;
+            if (header_found) {
+                if (have_record) sink.end_record();
+                in_header = true;
+                ++i;
+            }
         }
     }
     fclose(f);
@@ -205,7 +218,9 @@ extern "C" int vs_bidir_index_main(int argc, char **argv)
     if (has_ext(genome, {"fastq"})) { fprintf(stderr, "%s: FASTQ input is not supported by this build; convert to FASTA\n", prog); return 1; }
     PackedText t;
     std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
     if (!pack_fasta(genome, t, false, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+    const auto t1 = std::chrono::steady_clock::now();
     if (t.v.n_bases > (1ull << 32)) { fprintf(stderr, "%s: the FASTA file may not contain more than 4 giga bases in total\n", prog); return 1; }
     printf("Number of sequences: %u\n", t.v.n_contigs);
     fflush(stdout);
@@ -213,6 +228,9 @@ extern "C" int vs_bidir_index_main(int argc, char **argv)
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr));
         return 1;
     }
+    if (getenv("VARSCOT_VERBOSE"))
+        fprintf(stderr, "%s: packed %llu bases in %.2f s, wrote the index in %.2f s\n", prog, (unsigned long long)t.v.n_bases,
+                std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     printf("Index created successfully\n");
     return 0;
 }

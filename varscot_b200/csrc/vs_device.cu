@@ -20,10 +20,11 @@ constexpr uint64_t DEFAULT_CHUNK_WORDS = 8ull << 20;      // 256 Mi bases per pi
 
 struct vs_ctx {
     int device = -1;
-    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t stream = nullptr;       // scoring + everything ordered with it
+    cudaStream_t exs = nullptr;          // extraction of the next chunk (overlaps the scoring of the current one)
     cudaStream_t copy = nullptr;         // H2D of the next chunk
     cudaEvent_t ev[6] = {};
-    std::vector<cudaEvent_t> ev_pool;    // per-chunk: copied, extracted, scored
+    std::vector<cudaEvent_t> ev_pool;    // per chunk: copied, extract start, extract done, score start, score done
     uint64_t chunk_words = DEFAULT_CHUNK_WORDS;
     // resident text shard: device word 0 = global word first_word
     vs_bases *d_bases = nullptr;
@@ -34,8 +35,8 @@ struct vs_ctx {
     // counters: per chunk [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev; then one hit counter
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
     uint64_t cnt_chunks = 0;
-    // candidate stores (one chunk at a time)
-    uint32_t *d_planes[2] = {nullptr, nullptr}, *d_pos[2] = {nullptr, nullptr};
+    // candidate stores: two buffers (chunk parity) x two strands
+    uint32_t *d_planes[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *d_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint64_t blocks_cap = 0;
     // pattern tables
     uint32_t *d_pat = nullptr, *h_pat = nullptr;
@@ -104,6 +105,7 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
     ctx->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->exs, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = set_score_attr<0>();
     if (e == cudaSuccess) e = set_score_attr<1>();
@@ -129,10 +131,11 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy) cudaStreamSynchronize(ctx->copy);
+    if (ctx->exs) cudaStreamSynchronize(ctx->exs);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
-    for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]); }
+    for (int b = 0; b < 2; ++b) for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]); }
     cudaFree(ctx->d_pat);
     if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
     cudaFree(ctx->d_hits);
@@ -140,6 +143,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    if (ctx->exs) cudaStreamDestroy(ctx->exs);
     delete ctx;
 }
 
@@ -370,15 +374,18 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     auto ensure_blocks = [&](uint64_t need) -> int {
         if (need <= ctx->blocks_cap) return VS_OK;
         CK(cudaStreamSynchronize(st));
-        for (int s = 0; s < 2; ++s) {
-            cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
-            ctx->d_planes[s] = ctx->d_pos[s] = nullptr;
-        }
+        CK(cudaStreamSynchronize(ctx->exs));
+        for (int b = 0; b < 2; ++b)
+            for (int s = 0; s < 2; ++s) {
+                cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]);
+                ctx->d_planes[b][s] = ctx->d_pos[b][s] = nullptr;
+            }
         ctx->blocks_cap = 0;
-        for (int s = 0; s < 2; ++s) {
-            CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
-            CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
-        }
+        for (int b = 0; b < 2; ++b)
+            for (int s = 0; s < 2; ++s) {
+                CK(cudaMalloc(&ctx->d_planes[b][s], need * BLK_WORDS * sizeof(uint32_t)));
+                CK(cudaMalloc(&ctx->d_pos[b][s], need * 32 * sizeof(uint32_t)));
+            }
         ctx->blocks_cap = need;
         return VS_OK;
     };
@@ -394,26 +401,31 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
         CK(cudaMalloc(&ctx->d_hits, cap * sizeof(vs_hit)));
         ctx->hits_cap = cap;
     }
-    while (ctx->ev_pool.size() < (size_t)3 * n_chunks) {
+    constexpr int EVC = 5;      // events per chunk
+    while (ctx->ev_pool.size() < (size_t)EVC * n_chunks) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->ev_pool.push_back(e);
     }
 
-    auto run_chunk = [&](uint32_t c, bool timed) -> int {
+    // extraction of chunk c into candidate buffer `buf` on stream `es`, scoring on the main stream
+    auto launch_extract = [&](uint32_t c, int buf, cudaStream_t es) -> int {
         const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
-        unsigned long long *cnt = ctx->d_cnt + (uint64_t)c * 4;
         const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
-        k_extract<<<tiles, EX_THREADS, 0, st>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, ctx->first_word * 32, pp,
-                                                 ctx->d_planes[0], ctx->d_pos[0], ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap, cnt);
+        k_extract<<<tiles, EX_THREADS, 0, es>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, ctx->first_word * 32, pp,
+                                                 ctx->d_planes[buf][0], ctx->d_pos[buf][0], ctx->d_planes[buf][1], ctx->d_pos[buf][1],
+                                                 ctx->blocks_cap, ctx->d_cnt + (uint64_t)c * 4);
         S.launches++;
-        if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 1], st));
+        return VS_OK;
+    };
+    auto launch_score = [&](uint32_t c, int buf) -> int {
+        unsigned long long *cnt = ctx->d_cnt + (uint64_t)c * 4;
         for (uint32_t gc = 0; gc < g_chunks; ++gc) {
             const uint32_t np = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK);
             CK(cudaMemcpyToSymbolAsync(c_pat, ctx->d_pat + (size_t)gc * pat_chunk_words, pat_chunk_words * sizeof(uint32_t), 0,
                                        cudaMemcpyDeviceToDevice, st));
             ScoreArgs a;
-            for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[s]; a.pos[s] = ctx->d_pos[s]; }
+            for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[buf][s]; a.pos[s] = ctx->d_pos[buf][s]; }
             a.n_blocks_ptr = cnt + 2; a.cap = ctx->blocks_cap;
             a.ctas_per_strand = (uint32_t)((ctx->blocks_cap + SCORE_THREADS - 1) / SCORE_THREADS);
             a.n_pat = np; a.guide_base = gc * PAT_CHUNK;
@@ -422,10 +434,14 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
             dispatch_score(k, a, ctx->blocks_cap, st);
             S.launches++; S.score_launches++;
         }
-        if (timed) CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c + 2], st));
         return VS_OK;
     };
 
+    // Optional: run the extraction of chunk c+1 on its own stream, concurrently with the scoring of chunk c.  Measured on
+    // B200 (config 3): no gain (13.7 vs 13.8 ms/step) — both kernels fight for the same issue slots — so it is off by
+    // default, which also keeps the per-phase event times additive.
+    const bool overlap_extract = getenv("VARSCOT_OVERLAP_EXTRACT") && atoi(getenv("VARSCOT_OVERLAP_EXTRACT")) != 0;
+    cudaStream_t es = overlap_extract ? ctx->exs : st;
     uint64_t found = 0;
     const vs_text_view *source = src;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -434,18 +450,29 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
         CK(cudaMemcpyAsync(ctx->d_pat, ctx->h_pat, pat_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         S.h2d_bytes += pat_words * sizeof(uint32_t);
         CK(cudaMemsetAsync(ctx->d_cnt, 0, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        CK(cudaStreamWaitEvent(es, ctx->ev[2], 0));                  // counters are zeroed before any extraction
         if (source) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[0], 0));
         uint64_t sparse_used = 0;
         for (uint32_t c = 0; c < n_chunks; ++c) {
+            cudaEvent_t *E = &ctx->ev_pool[(size_t)EVC * c];
+            const int buf = (int)(c & 1);
             if (source) {
                 const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
                 if ((r = enqueue_chunk_copy(ctx, source, first_word, c0, c1, sparse_used, S.h2d_bytes, S.launches)) != VS_OK) return r;
-                CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c], ctx->copy));
-                CK(cudaStreamWaitEvent(st, ctx->ev_pool[(size_t)3 * c], 0));
+                CK(cudaEventRecord(E[0], ctx->copy));
+                CK(cudaStreamWaitEvent(es, E[0], 0));
             } else {
-                CK(cudaEventRecord(ctx->ev_pool[(size_t)3 * c], st));
+                CK(cudaEventRecord(E[0], es));
             }
-            if ((r = run_chunk(c, true)) != VS_OK) return r;
+            if (c >= 2) CK(cudaStreamWaitEvent(es, ctx->ev_pool[(size_t)EVC * (c - 2) + 4], 0));   // its buffer was scored
+            CK(cudaEventRecord(E[1], es));
+            if ((r = launch_extract(c, buf, es)) != VS_OK) return r;
+            CK(cudaEventRecord(E[2], es));
+            CK(cudaStreamWaitEvent(st, E[2], 0));
+            CK(cudaEventRecord(E[3], st));
+            if ((r = launch_score(c, buf)) != VS_OK) return r;
+            CK(cudaEventRecord(E[4], st));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], st));
@@ -462,7 +489,8 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
                 need = (need + need / 32 + SCORE_THREADS) / SCORE_THREADS * SCORE_THREADS;
                 if ((r = ensure_blocks(need)) != VS_OK) return r;
                 CK(cudaMemsetAsync(ctx->d_cnt + (uint64_t)c * 4, 0, 4 * sizeof(unsigned long long), st));
-                if ((r = run_chunk(c, false)) != VS_OK) return r;
+                if ((r = launch_extract(c, 0, st)) != VS_OK) return r;
+                if ((r = launch_score(c, 0)) != VS_OK) return r;
                 CK(cudaMemcpyAsync(hc, ctx->d_cnt + (uint64_t)c * 4, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(h_hitcnt, d_hitcnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -489,14 +517,15 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     CK(cudaStreamSynchronize(st));
     S.d2h_bytes = ncopy * sizeof(vs_hit) + (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long);
     // per-phase device times: sums over the chunks of the last pass (same stream, so the intervals do not overlap)
+    // (extraction of chunk c+1 runs concurrently with the scoring of chunk c, so the two sums overlap in time)
     for (uint32_t c = 0; c < n_chunks; ++c) {
         float a = 0.f, b = 0.f;
-        CK(cudaEventElapsedTime(&a, ctx->ev_pool[(size_t)3 * c], ctx->ev_pool[(size_t)3 * c + 1]));
-        CK(cudaEventElapsedTime(&b, ctx->ev_pool[(size_t)3 * c + 1], ctx->ev_pool[(size_t)3 * c + 2]));
+        CK(cudaEventElapsedTime(&a, ctx->ev_pool[(size_t)EVC * c + 1], ctx->ev_pool[(size_t)EVC * c + 2]));
+        CK(cudaEventElapsedTime(&b, ctx->ev_pool[(size_t)EVC * c + 3], ctx->ev_pool[(size_t)EVC * c + 4]));
         S.extract_ms += a; S.score_ms += b;
     }
     CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[0], ctx->ev[5]));
-    if (src) CK(cudaEventElapsedTime(&S.upload_ms, ctx->ev[0], ctx->ev_pool[(size_t)3 * (n_chunks - 1)]));
+    if (src) CK(cudaEventElapsedTime(&S.upload_ms, ctx->ev[0], ctx->ev_pool[(size_t)EVC * (n_chunks - 1)]));
     if (stats) *stats = S;
     ctx->err.clear();
     if (found > out_cap) return fail(ctx, VS_ERR_OVERFLOW, "vs_scan: caller hit buffer too small; use vs_scan_fetch");
