@@ -8,10 +8,11 @@ NVFLAGS := $(ARCH) $(EXTRA) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompile
 CSRC    := varscot_b200/csrc
 LIB     := varscot_b200/libvarscot_scan.so
 BINDIR  := build/read_mapping_build
-SRCS    := $(CSRC)/vs_device.cu $(CSRC)/vs_host.cpp $(CSRC)/vs_cli.cpp
+SRCS    := $(CSRC)/vs_device.cu $(CSRC)/vs_host.cpp $(CSRC)/vs_cli.cpp $(CSRC)/vs_vcf.cpp
+VPDIR   := build/variant_processing_build
 HDRS    := $(CSRC)/vs_kernels.cuh $(CSRC)/vs_internal.h include/varscot_scan.h
 
-all: $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index
+all: $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader
 
 $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) -lpthread
@@ -24,11 +25,15 @@ $(BINDIR)/bidir_index: $(CSRC)/bidir_index_main.cpp $(LIB)
 	@mkdir -p $(BINDIR)
 	$(HOSTCXX) -O2 -o $@ $< -Lvarscot_b200 -lvarscot_scan -Wl,-rpath,'$$ORIGIN/../../varscot_b200' -lpthread -ldl -lrt
 
+$(VPDIR)/vcf_loader: $(CSRC)/vcf_loader_main.cpp $(LIB)
+	@mkdir -p $(VPDIR)
+	$(HOSTCXX) -O2 -o $@ $< -Lvarscot_b200 -lvarscot_scan -Wl,-rpath,'$$ORIGIN/../../varscot_b200' -lpthread -ldl -lrt
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index
+	rm -f $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -20,6 +20,7 @@
  * vs_md_string / vs_format_sam     bidir_mapping.cpp:111-123 getMDString + tags; :177-187 write(.., Sam())
  * vs_bidir_index_main              bidir_index.cpp:10-52   main (argv contract)
  * vs_bidir_mapping_main            bidir_mapping.cpp:190-312 main (argv contract, stdout lines, exit codes)
+ * vs_vcf_loader_main               variant_processing/vcf_loader.cpp:11-77 (+ process_vcf.h, overlap_sequences.h, write_fasta.h)
  */
 #ifndef VARSCOT_SCAN_H
 #define VARSCOT_SCAN_H
@@ -182,6 +183,9 @@ int vs_format_sam(const vs_record *r, const char *qname, const char *rname, cons
 /* ---- the two executables as library calls ---------------------------------------------------- */
 int vs_bidir_index_main(int argc, char **argv);
 int vs_bidir_mapping_main(int argc, char **argv);
+/* row f1 (producer of the variant segments): `vcf_loader FILE.vcf SNPGENOME.fa GENOME.fa SAMPLE SEQLENGTH THREADS`,
+ * VARSCOT_pipeline/variant_processing/vcf_loader.cpp:11-77 (host only, no GPU involved) */
+int vs_vcf_loader_main(int argc, char **argv);
 
 /* ---- microbenchmarks used by bench.py for the roofline denominators ---------------------------- */
 /* thread-level LOP3 instructions per second of the device (alu pipe), and LDS 32-bit lane-words per second */

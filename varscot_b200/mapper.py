@@ -350,3 +350,8 @@ def bidir_mapping(genome: str, index: str, reads: str, mismatches: int, output: 
     if md_style:
         args += ["--md-style", md_style]
     return _main(_lib.lib().vs_bidir_mapping_main, "bidir_mapping", args)
+
+
+def vcf_loader(vcf: str, snp_fasta: str, genome: str, sample: int = 0, seq_length: int = 23, threads: int = 1) -> int:
+    """`vcf_loader FILE.vcf SNPGENOME.fa GENOME.fa SAMPLE SEQLENGTH THREADS` (vcf_loader.cpp:13-17). Returns the exit code."""
+    return _main(_lib.lib().vs_vcf_loader_main, "vcf_loader", [vcf, snp_fasta, genome, sample, seq_length, threads])
