@@ -12,7 +12,7 @@ SRCS    := $(CSRC)/vs_device.cu $(CSRC)/vs_host.cpp $(CSRC)/vs_cli.cpp $(CSRC)/v
 VPDIR   := build/variant_processing_build
 HDRS    := $(CSRC)/vs_kernels.cuh $(CSRC)/vs_internal.h include/varscot_scan.h
 
-all: $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader
+all: $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader $(VPDIR)/fasta_writer
 
 $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) -lpthread
@@ -29,11 +29,15 @@ $(VPDIR)/vcf_loader: $(CSRC)/vcf_loader_main.cpp $(LIB)
 	@mkdir -p $(VPDIR)
 	$(HOSTCXX) -O2 -o $@ $< -Lvarscot_b200 -lvarscot_scan -Wl,-rpath,'$$ORIGIN/../../varscot_b200' -lpthread -ldl -lrt
 
+$(VPDIR)/fasta_writer: $(CSRC)/fasta_writer_main.cpp $(LIB)
+	@mkdir -p $(VPDIR)
+	$(HOSTCXX) -O2 -o $@ $< -Lvarscot_b200 -lvarscot_scan -Wl,-rpath,'$$ORIGIN/../../varscot_b200' -lpthread -ldl -lrt
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader
+	rm -f $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader $(VPDIR)/fasta_writer
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -21,6 +21,7 @@
  * vs_bidir_index_main              bidir_index.cpp:10-52   main (argv contract)
  * vs_bidir_mapping_main            bidir_mapping.cpp:190-312 main (argv contract, stdout lines, exit codes)
  * vs_vcf_loader_main               variant_processing/vcf_loader.cpp:11-77 (+ process_vcf.h, overlap_sequences.h, write_fasta.h)
+ * vs_fasta_writer_main             variant_processing/fasta_writer.cpp:8-41 (+ extract_fasta_ontargets.h)
  */
 #ifndef VARSCOT_SCAN_H
 #define VARSCOT_SCAN_H
@@ -186,6 +187,9 @@ int vs_bidir_mapping_main(int argc, char **argv);
 /* row f1 (producer of the variant segments): `vcf_loader FILE.vcf SNPGENOME.fa GENOME.fa SAMPLE SEQLENGTH THREADS`,
  * VARSCOT_pipeline/variant_processing/vcf_loader.cpp:11-77 (host only, no GPU involved) */
 int vs_vcf_loader_main(int argc, char **argv);
+/* row f4 (producer of the guide FASTA): `fasta_writer OUTPUT1.fa OUTPUT2.fa ONTARGETS.bed GENOME.fa`,
+ * VARSCOT_pipeline/variant_processing/fasta_writer.cpp:8-41 (host only) */
+int vs_fasta_writer_main(int argc, char **argv);
 
 /* ---- microbenchmarks used by bench.py for the roofline denominators ---------------------------- */
 /* thread-level LOP3 instructions per second of the device (alu pipe), and LDS 32-bit lane-words per second */

@@ -356,3 +356,34 @@ def write_fasta(path: str, records, width: int = 70):
                 f.write(seq[i:i + width] + "\n")
             if not seq:
                 f.write("\n")
+
+
+def fasta_writer(bed_path: str, genome_path: str, flanking: bool):
+    """writeFastaOntargets, extract_fasta_ontargets.h:86-138 (+ extractSequenceFromIndex :30-70): [(name, sequence)]."""
+    genome = read_genome(genome_path)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    out = []
+    with open(bed_path) as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if not line or line.startswith(("#", "track", "browser")):
+                continue
+            fld = line.split("\t")
+            if len(fld) < 6:
+                continue
+            if fld[0] not in genome:
+                raise IndexError("ERROR: Index out of range.")
+            seq = genome[fld[0]]
+            b, e, strand = int(fld[1]), int(fld[2]), fld[5][:1]
+            if flanking and strand == "+":
+                b, e = b - 4, e + 3
+            elif flanking and strand == "-":
+                b, e = b - 3, e + 4
+            b, e = min(max(b, 0), len(seq)), min(max(e, 0), len(seq))
+            if b > e:
+                e = b
+            s_ = dna5(seq[b:e])
+            if strand == "-":
+                s_ = "".join(comp[c] for c in reversed(s_))
+            out.append((fld[3], s_))
+    return out

@@ -314,3 +314,60 @@ def test_map_packed_multi_device_equals_single():
     assert ra.tolist() == rb.tolist() and len(ra) > 0
     exp = oracle_rows(case.ascii, case.offsets, case.guides, 6)
     assert [(x[0], x[3], x[1], x[2], x[4]) for x in ra.tolist()] == [e[:5] for e in exp]
+
+
+def test_pipeline_chain_bed_vcf_to_sam(tmp_path):
+    """The front of the VARSCOT pipeline with our drop-ins only (VARSCOT:260,274,296-314): fasta_writer -> guides,
+    vcf_loader -> SNP genome, bidir_index + bidir_mapping on the reference and on the SNP genome; every file is compared
+    with the oracle chain (oracle/vcf_oracle.py + oracle_bidir_mapping)."""
+    from oracle import vcf_oracle as VO
+    rng = np.random.default_rng(123)
+    lut = "ACGT"
+    seq = list("".join(rng.choice(list(lut), 60000)))
+    guides_pos = [1000, 9000, 20000, 41000]
+    bed_rows, vcf_rows = [], []
+    for gi, p in enumerate(guides_pos):
+        seq[p + 21:p + 23] = "GG"                                     # the on-target carries an NGG PAM
+        strand = "+" if gi % 2 == 0 else "-"
+        bed_rows.append(("chr1", p, p + 23, f"guide{gi}", 0, "+"))
+        # an off-target copy elsewhere with 2 reference mismatches, one of which a variant repairs
+        q = p + 3000
+        w = seq[p:p + 23]
+        for off in (3, 12):
+            w[off] = lut[(lut.index(w[off]) + 1) % 4]
+        seq[q:q + 23] = w
+        vcf_rows.append((q + 12, seq[q + 12], seq[p + 12], "0|1" if gi % 2 else "1|1"))
+    # unrelated variants, some close together
+    for p in (500, 510, 530, 15000, 15040, 33333):
+        vcf_rows.append((p, seq[p], lut[(lut.index(seq[p]) + 2) % 4], "0|1"))
+    vcf_rows.sort()
+    g, bed, vcf = str(tmp_path / "genome.fa"), str(tmp_path / "t.bed"), str(tmp_path / "v.vcf")
+    s = "".join(seq)
+    with open(g, "w") as f:
+        f.write(">chr1\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+    open(bed, "w").write("".join("\t".join(map(str, r)) + "\n" for r in bed_rows))
+    open(vcf, "w").write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n" +
+                         "".join(f"chr1\t{p + 1}\t.\t{r}\t{a}\t.\t.\t.\tGT\t{gt}\n" for p, r, a, gt in vcf_rows))
+    vp = os.path.join(ROOT, "build", "variant_processing_build")
+    guides_fa, flank_fa, snp_fa = str(tmp_path / "guides.fa"), str(tmp_path / "flank.fa"), str(tmp_path / "snp.fa")
+    assert subprocess.run([os.path.join(vp, "fasta_writer"), guides_fa, flank_fa, bed, g]).returncode == 0
+    assert subprocess.run([os.path.join(vp, "vcf_loader"), vcf, snp_fa, g, "0", "23", "1"], capture_output=True).returncode == 0
+    exp_snp = str(tmp_path / "exp_snp.fa")
+    VO.write_fasta(exp_snp, VO.vcf_loader(vcf, g))
+    assert open(snp_fa).read() == open(exp_snp).read()
+    total = 0
+    for label, fa in (("ref", g), ("snp", snp_fa)):
+        idx = str(tmp_path / f"{label}_idx")
+        assert subprocess.run([os.path.join(BIN, "bidir_index"), "-G", fa, "-I", idx], capture_output=True).returncode == 0
+        out, ref = str(tmp_path / f"{label}.sam"), str(tmp_path / f"{label}_oracle.sam")
+        r = subprocess.run([os.path.join(BIN, "bidir_mapping"), "-G", fa, "-I", idx, "-R", guides_fa, "-M", "3", "-T", "1", "-O", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        o = subprocess.run([os.path.join(ROOT, "oracle", "oracle_bidir_mapping"), "-G", fa, "-R", guides_fa, "-M", "3", "-O", ref], capture_output=True, text=True)
+        assert o.returncode == 0, o.stderr
+        a = open(out, "rb").read()
+        assert a == open(ref, "rb").read()
+        total += a.count(b"\n")
+        if label == "snp":
+            # the repaired off-targets are found in ALT segments with one mismatch fewer than on the reference
+            assert any(b"_ALT_" in l and b"NM:i:1" in l for l in a.splitlines())
+    assert total >= 8

@@ -169,3 +169,30 @@ def test_segments_feed_the_packer(tmp_path):
     t = V.PackedText.from_fasta(str(tmp_path / "snp.fa"))
     assert t.names == [r[0] for r in recs] and t.n_bases == sum(len(r[1]) for r in recs)
     assert all("_" not in n.split("_", 1)[0] for n in t.names)
+
+
+FW = os.path.join(ROOT, "build", "variant_processing_build", "fasta_writer")
+
+
+def test_fasta_writer_guides_and_flanks(tmp_path):
+    """Row f4: BED6 on-targets -> 23-nt guide FASTA + 30-nt flanking FASTA (extract_fasta_ontargets.h:44-53,65-69)."""
+    rng = np.random.default_rng(5)
+    contigs = [("chr1", rand_seq(rng, 500)), ("chr11", rand_seq(rng, 400).lower())]
+    g, bed = str(tmp_path / "g.fa"), str(tmp_path / "t.bed")
+    write_genome(g, contigs)
+    rows = [("chr1", 100, 123, "EMX1", 7, "+"), ("chr11", 50, 73, "CD151", 7, "-"), ("chr1", 2, 25, "edge", 0, "+"), ("chr1", 480, 503, "end", 0, "-")]
+    open(bed, "w").write("# comment\n" + "".join("\t".join(map(str, r)) + "\n" for r in rows))
+    o1, o2 = str(tmp_path / "guides.fa"), str(tmp_path / "flank.fa")
+    r = subprocess.run([FW, o1, o2, bed, g], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rc = lambda s: "".join({"A": "T", "C": "G", "G": "C", "T": "A"}[c] for c in reversed(s))
+    s1, s2 = contigs[0][1], contigs[1][1].upper()
+    exp1 = [("EMX1", s1[100:123]), ("CD151", rc(s2[50:73])), ("edge", s1[2:25]), ("end", rc(s1[480:500]))]
+    exp2 = [("EMX1", s1[96:126]), ("CD151", rc(s2[47:77])), ("edge", s1[0:28]), ("end", rc(s1[477:500]))]
+    for path, exp, flank in ((o1, exp1, False), (o2, exp2, True)):
+        got = open(path).read()
+        assert got == "".join(f">{n}\n{s}\n" for n, s in exp)
+        assert VO.fasta_writer(bed, g, flank) == exp
+    assert len(exp1[0][1]) == 23 and len(exp2[0][1]) == 30
+    assert subprocess.run([FW, o1], capture_output=True).returncode == 1
+    assert os.path.exists(g + ".fai")

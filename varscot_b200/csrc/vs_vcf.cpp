@@ -1,4 +1,5 @@
-// varscot_b200/csrc/vs_vcf.cpp — row f1 of SURVEY.md section 8f: drop-in for the reference's `vcf_loader`
+// varscot_b200/csrc/vs_vcf.cpp — rows f1 and f4 of SURVEY.md section 8f.
+// f1: drop-in for the reference's `vcf_loader`
 // (VARSCOT_pipeline/variant_processing/vcf_loader.cpp:11-77), the producer of the hot path's second input:
 // VCF (one sample) + genome FASTA -> "SNP genome" multi-FASTA of variant haplotype segments.
 // Host-only C++ (no SeqAn, no CUDA).  Same argv: vcf_loader FILE.vcf SNPGENOME.fa GENOME.fa SAMPLE SEQLENGTH THREADS
@@ -421,5 +422,60 @@ extern "C" int vs_vcf_loader_main(int argc, char **argv)
     }
     fclose(out);
     (void)threads;
+    return 0;
+}
+
+// ---- row f4: fasta_writer (VARSCOT_pipeline/variant_processing/fasta_writer.cpp:8-41, extract_fasta_ontargets.h) -------
+// `fasta_writer OUTPUT1.fa OUTPUT2.fa ONTARGETS.bed GENOME.fa`: BED6 on-targets -> 23-nt guide FASTA (OUTPUT1, what
+// bidir_mapping -R reads) and the 30-nt flanking FASTA for TUSCAN (OUTPUT2).  Half-open 0-based BED coordinates,
+// reverse complement on '-', flanks +4/+3 on '+', +3/+4 on '-' (extract_fasta_ontargets.h:44-53).  A flank that would
+// start before the contig (unsigned wrap in the reference) is clamped at 0.
+namespace {
+
+bool write_ontargets(const char *out_path, const char *bed_path, const Genome &g, bool flanking, std::string &err)
+{
+    FILE *out = fopen(out_path, "wb");
+    if (!out) { err = "ERROR: Could not open output file."; return false; }
+    FILE *bed = fopen(bed_path, "rb");
+    if (!bed) { fclose(out); err = "ERROR: Could not open BED file."; return false; }
+    char *line = nullptr; size_t cap = 0; ssize_t len;
+    bool ok = true;
+    while ((len = getline(&line, &cap, bed)) >= 0) {
+        while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = 0;
+        if (len == 0 || line[0] == '#' || !strncmp(line, "track", 5) || !strncmp(line, "browser", 7)) continue;
+        std::vector<std::string> f = split(std::string(line, (size_t)len), '\t');
+        if (f.size() < 6) continue;
+        auto it = g.by_name.find(f[0]);
+        if (it == g.by_name.end()) { err = "ERROR: Index out of range."; ok = false; break; }     // extract_fasta_ontargets.h:37-40
+        long b = strtol(f[1].c_str(), nullptr, 10), e = strtol(f[2].c_str(), nullptr, 10);
+        const char strand = f[5].empty() ? '.' : f[5][0];
+        if (flanking && strand == '+') { b -= 4; e += 3; }
+        else if (flanking && strand == '-') { b -= 3; e += 4; }
+        std::string seq = extract(g, it->second, b, e);
+        if (strand == '-') {
+            std::reverse(seq.begin(), seq.end());
+            for (char &c : seq) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+        }
+        std::string buf = ">" + f[3] + "\n";
+        for (size_t p = 0; p < seq.size(); p += 70) { buf.append(seq, p, 70); buf += "\n"; }
+        if (seq.empty()) buf += "\n";
+        fwrite(buf.data(), 1, buf.size(), out);
+    }
+    free(line);
+    fclose(bed);
+    fclose(out);
+    return ok;
+}
+
+}  // namespace
+
+extern "C" int vs_fasta_writer_main(int argc, char **argv)
+{
+    if (argc != 5) { fprintf(stderr, "USAGE: extract_fasta_ontargets OUTPUT1.fa OUTPUT2.fa ONTARGETS.bed GENOME.fa\n"); return 1; }
+    Genome g;
+    std::string err;
+    if (!open_genome(argv[4], g, err)) { printf("%s\n", err.c_str()); return 1; }
+    if (!write_ontargets(argv[1], argv[3], g, false, err)) { printf("%s\n", err.c_str()); return 1; }
+    if (!write_ontargets(argv[2], argv[3], g, true, err)) { printf("%s\n", err.c_str()); return 1; }
     return 0;
 }

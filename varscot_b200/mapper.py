@@ -355,3 +355,8 @@ def bidir_mapping(genome: str, index: str, reads: str, mismatches: int, output: 
 def vcf_loader(vcf: str, snp_fasta: str, genome: str, sample: int = 0, seq_length: int = 23, threads: int = 1) -> int:
     """`vcf_loader FILE.vcf SNPGENOME.fa GENOME.fa SAMPLE SEQLENGTH THREADS` (vcf_loader.cpp:13-17). Returns the exit code."""
     return _main(_lib.lib().vs_vcf_loader_main, "vcf_loader", [vcf, snp_fasta, genome, sample, seq_length, threads])
+
+
+def fasta_writer(guides_fasta: str, flanking_fasta: str, bed: str, genome: str) -> int:
+    """`fasta_writer OUTPUT1.fa OUTPUT2.fa ONTARGETS.bed GENOME.fa` (fasta_writer.cpp:11-15). Returns the exit code."""
+    return _main(_lib.lib().vs_fasta_writer_main, "fasta_writer", [guides_fasta, flanking_fasta, bed, genome])
