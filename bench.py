@@ -130,6 +130,25 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows), "window": window}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs next to its GPU (NVML affinity) BEFORE allocating page-locked buffers, so that the
+    H2D source memory is first-touched on the GPU's NUMA node; matters when 8 ranks upload at once."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,6 +264,8 @@ def main():
         cfg[3] = args.guides
     cfg = tuple(cfg)
     world, rank, local = dist_setup(args.gpus)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa(local) if args.impl == "ours" else 0
     if args.impl == "reference":
         run_reference(args, cfg, world, rank)
         return
@@ -335,13 +356,14 @@ def main():
         "config": {"workload": desc + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "guides": ng, "k": k, "extra_pam": pam,
                    "text_bases_per_gpu": B, "contigs_per_gpu": text.n_contigs, "chunks": int(st.n_chunks),
                    "l2": "inputs larger than L2 (packed text %.2f GB resident, candidate planes %.2f GB written+read per step)" % ((nw * 16) / 1e9, blocks * 192 / 1e9),
-                   "sharding": "one text shard per rank, no collective; hits merged on the host"},
+                   "sharding": "one text shard per rank, no collective; hits merged on the host", "cpus_bound_per_rank": numa_cpus},
         "wall_ms_per_step": wall_step, "phase_ms": {"extract": extract_ms / args.steps, "score": score_ms / args.steps},
         "hits_per_step": n_hits, "candidates": int(st.n_cand_fwd + st.n_cand_rev), "gpu_launches": launches,
         "roofline": roof, "e2e": e2e, "clocks": clocks, "gen_s": t_gen,
     }
     # ---- CPU baseline + hit-set diff on a bounded sample ------------------------------------------------
     if not args.no_cpu and world == 1:
+        os.sched_setaffinity(0, all_cpus)             # the CPU baseline gets every host core back
         n, dt, rec, off, cores = cpu_sample(text, guides, k, pam)
         out["cpu_baseline"] = {"value": ng * n / dt / 1e9, "unit": "guide*Gbp/s", "cores": cores, "kind": "port",
                                "sample": f"first {n} bases of the same text, all {ng} guides, one pass ({dt:.1f} s); linear-scan oracle, not SeqAn"}

@@ -28,7 +28,13 @@ constexpr int TILE_STARTS  = TILE_WORDS * 32;     // 8192
 constexpr int BLK_WORDS    = 48;                  // words per candidate block
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
-constexpr int SCORE_THREADS = 256;
+#ifndef VS_SCORE_THREADS
+#define VS_SCORE_THREADS 96           // measured on B200: 96 x 6 CTAs/SM (18 warps) 2.11 ms, 256 x 2 (16 warps) 2.20 ms, 512 x 1 2.33 ms (cfg3 x 0.25)
+#endif
+#ifndef VS_SCORE_MINBLOCKS
+#define VS_SCORE_MINBLOCKS 6
+#endif
+constexpr int SCORE_THREADS = VS_SCORE_THREADS;
 constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block
 constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 slot offsets + pad, 16-byte aligned)
 constexpr int PAT_CHUNK    = 320;                 // guides per k_score launch: 2 strands x 320 x 96 B = 60 KB of constant memory
@@ -376,7 +382,7 @@ __device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, 
 }
 
 template <int K>
-__global__ void __launch_bounds__(SCORE_THREADS, 2)
+__global__ void __launch_bounds__(SCORE_THREADS, VS_SCORE_MINBLOCKS)
 k_score(ScoreArgs a)
 {
     extern __shared__ uint32_t sm[];     // [NPLANES][SCORE_THREADS]
@@ -416,13 +422,16 @@ k_score(ScoreArgs a)
     const uint32_t *pat0 = c_pat + strand * (PAT_CHUNK * PAT_STRIDE);
     const uint32_t zero5[5] = {0u, 0u, 0u, 0u, 0u};
 
-#pragma unroll 2
-    for (uint32_t g = 0; g < a.n_pat; ++g) {
+    // Software pipeline over the guides: the stage-A planes of guide g+1 are loaded (LDS) before guide g is counted,
+    // so the shared-memory latency and the adder tree of consecutive guides overlap inside one warp.
+    auto load_a = [&](uint32_t g, uint32_t (&m)[PA]) {
         const uint32_t *po = pat0 + g * PAT_STRIDE;
-        // stage A: the first PA slots
-        uint32_t ma[PA], ca[5];
 #pragma unroll
-        for (int i = 0; i < PA; ++i) ma[i] = *reinterpret_cast<const uint32_t *>(myb + po[i]);
+        for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(myb + po[i]);
+    };
+    auto finish = [&](uint32_t g, const uint32_t (&ma)[PA]) {
+        const uint32_t *po = pat0 + g * PAT_STRIDE;
+        uint32_t ca[5];
         popcount_planes<PA, false>(ma, zero5, ca);
         uint32_t le = le_k<K>(ca);
         // warp-uniform early out: if no lane of the warp can still be within K, the remaining slots are never loaded.
@@ -437,10 +446,23 @@ k_score(ScoreArgs a)
                 le = le_k<K>(cb);
             }
             if (le != 0)
-                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, lastm, (uint32_t)(K / 2), (strand ? a.pos[1] : a.pos[0]) + blk * 32,
-                           ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
+                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, lastm, (uint32_t)(K / 2),
+                           (strand ? a.pos[1] : a.pos[0]) + blk * 32, ((a.guide_base + g) << 8) | (strand << 7),
+                           a.hits, a.n_hits, a.hit_cap);
         }
+    };
+    uint32_t m0[PA], m1[PA];
+    const uint32_t n_pat = a.n_pat;
+    if (n_pat == 0) return;
+    load_a(0, m0);
+    uint32_t g = 0;
+    for (; g + 1 < n_pat; g += 2) {
+        load_a(g + 1, m1);
+        finish(g, m0);
+        if (g + 2 < n_pat) load_a(g + 2, m0);
+        finish(g + 1, m1);
     }
+    if (g < n_pat) finish(g, m0);
 }
 
 // ------------------------------------------------------------------------------------------------
