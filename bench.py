@@ -287,12 +287,23 @@ def main():
 
     # ---- resident-text scan ----------------------------------------------------------------------
     ctx.upload(text)
+    import ctypes as C
+    from varscot_b200 import _lib
+    pinned = []
+
+    def pinned_hits(n):                          # page-locked result buffer, as a caller expecting many hits would use
+        p = _lib.lib().vs_host_alloc(n * 8)
+        if not p:
+            raise RuntimeError("vs_host_alloc failed")
+        pinned.append(p)
+        return np.frombuffer((C.c_uint8 * (n * 8)).from_address(p), dtype=V.HIT_DT, count=n)
+
     cap = 1 << 22
-    hits_buf = np.zeros(cap, dtype=V.HIT_DT)
+    hits_buf = pinned_hits(cap)
     for _ in range(args.warmup):
         hits, st = ctx.scan(guides, k, pam=pam, out=hits_buf)
         if len(hits) > cap:
-            cap = int(len(hits) * 1.2); hits_buf = np.zeros(cap, dtype=V.HIT_DT)
+            cap = int(len(hits) * 1.2); hits_buf = pinned_hits(cap)
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.15)
     barrier(world, local)
@@ -379,6 +390,9 @@ def main():
     print(json.dumps(out))
     ctx.close()
     text.unpin()
+    del hits, hits_buf
+    for p in pinned:
+        _lib.lib().vs_host_free(p)
 
 
 def _shutdown():

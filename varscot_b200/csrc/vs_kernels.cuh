@@ -351,26 +351,29 @@ struct ScoreArgs {
     uint64_t hit_cap;
 };
 
-// Slow path (rare): for every lane that passed the threshold recompute the exact count from the selected planes,
+// Slow path (rare): for every lane that passed the threshold read its exact count out of the bit-sliced counter,
 // apply R4 to last-window candidates (H over positions 11..22 must be <= floor(K/2), bidir_mapping.cpp:48-53) and
-// append the hit.  It re-reads the slot offsets from the GLOBAL copy of the pattern table so that nothing of the
-// hot loop's uniform-register state has to stay live for it.
-__device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, uint32_t le, uint32_t lastm, uint32_t k_half,
-                                        const uint32_t *pos, uint32_t info, vs_hit *hits, unsigned long long *n_hits,
-                                        uint64_t hit_cap)
+// append the hit.  Only last-window lanes re-read planes (they need the second-half count); the slot offsets for that
+// come from the GLOBAL copy of the pattern table so that nothing of the hot loop's uniform-register state stays live.
+__device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, uint32_t le, const uint32_t (&cnt)[5], uint32_t lastm,
+                                           uint32_t k_half, const uint32_t *pos, uint32_t info, vs_hit *hits,
+                                           unsigned long long *n_hits, uint64_t hit_cap)
 {
     while (le != 0) {
         const int c = __ffs(le) - 1;
         le &= le - 1;
-        uint32_t mm = 0, h2 = 0;
-#pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) {
-            const uint32_t off = __ldg(po + i);
-            const uint32_t bitv = (*reinterpret_cast<const uint32_t *>(myb + off) >> c) & 1u;
-            mm += bitv;
-            if (off >= 11u * 4u * SCORE_THREADS * 4u) h2 += bitv;          // the slot scores a position >= 11
+        const uint32_t mm = ((cnt[0] >> c) & 1u) | (((cnt[1] >> c) & 1u) << 1) | (((cnt[2] >> c) & 1u) << 2) |
+                            (((cnt[3] >> c) & 1u) << 3) | (((cnt[4] >> c) & 1u) << 4);
+        if ((lastm >> c) & 1u) {                                             // R4: last window of its contig
+            uint32_t h2 = 0;
+#pragma unroll 1
+            for (int i = 0; i < VS_GLEN; ++i) {
+                const uint32_t off = __ldg(po + i);
+                if (off >= 11u * 4u * SCORE_THREADS * 4u)                    // the slot scores a position >= 11
+                    h2 += (*reinterpret_cast<const uint32_t *>(myb + off) >> c) & 1u;
+            }
+            if (h2 > k_half) continue;
         }
-        if (((lastm >> c) & 1u) && h2 > k_half) continue;                   // R4
         const unsigned long long idx = atomicAdd(n_hits, 1ull);
         if (idx < hit_cap) {
             vs_hit hrec;
@@ -444,9 +447,11 @@ k_score(ScoreArgs a)
                 for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(myb + po[PA + i]);
                 popcount_planes<PB, true>(mb, ca, cb);
                 le = le_k<K>(cb);
+#pragma unroll
+                for (int w = 0; w < 5; ++w) ca[w] = cb[w];
             }
             if (le != 0)
-                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, lastm, (uint32_t)(K / 2),
+                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, ca, lastm, (uint32_t)(K / 2),
                            (strand ? a.pos[1] : a.pos[0]) + blk * 32, ((a.guide_base + g) << 8) | (strand << 7),
                            a.hits, a.n_hits, a.hit_cap);
         }
