@@ -219,7 +219,7 @@ extern "C" int vs_bidir_index_main(int argc, char **argv)
     PackedText t;
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
-    if (!pack_fasta(genome, t, false, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+    if (!pack_fasta(genome, t, true, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
     const auto t1 = std::chrono::steady_clock::now();
     if (t.v.n_bases > (1ull << 32)) { fprintf(stderr, "%s: the FASTA file may not contain more than 4 giga bases in total\n", prog); return 1; }
     printf("Number of sequences: %u\n", t.v.n_contigs);
@@ -227,6 +227,12 @@ extern "C" int vs_bidir_index_main(int argc, char **argv)
     if (vs_text_save(index.c_str(), &t.v) != VS_OK) {
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr));
         return 1;
+    }
+    // contig ids next to the packed text (<prefix>.vsnames, one header line per contig): bidir_mapping then does not have
+    // to re-read a multi-gigabyte FASTA just for its ids (the reference does, bidir_mapping.cpp:272-280)
+    if (FILE *nf = fopen((index + ".vsnames").c_str(), "wb")) {
+        for (const std::string &n : t.names) { fwrite(n.data(), 1, n.size(), nf); fputc('\n', nf); }
+        fclose(nf);
     }
     if (getenv("VARSCOT_VERBOSE"))
         fprintf(stderr, "%s: packed %llu bases in %.2f s, wrote the index in %.2f s\n", prog, (unsigned long long)t.v.n_bases,
@@ -298,8 +304,19 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     std::string err;
     bool from_cache = vs_text_load(index.c_str(), &t.v, &t.owner) == VS_OK;
     if (from_cache) {
-        // contig ids from the genome FASTA, sequences discarded (bidir_mapping.cpp:272-280)
-        if (!read_names(genome, t.names, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
+        // contig ids: from <index>.vsnames when bidir_index left one that matches, else from the genome FASTA with the
+        // sequences discarded (bidir_mapping.cpp:272-280)
+        if (FILE *nf = fopen((index + ".vsnames").c_str(), "rb")) {
+            char *line = nullptr; size_t cap = 0; ssize_t len;
+            while ((len = getline(&line, &cap, nf)) >= 0) {
+                while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) --len;
+                t.names.emplace_back(line, (size_t)len);
+            }
+            free(line);
+            fclose(nf);
+            if (t.names.size() != t.v.n_contigs) t.names.clear();
+        }
+        if (t.names.empty() && !read_names(genome, t.names, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
         if (t.names.size() != t.v.n_contigs) {
             fprintf(stderr, "%s: index %s.vsidx has %u sequences but %s has %zu; re-run bidir_index\n", prog, index.c_str(), t.v.n_contigs, genome.c_str(), t.names.size());
             return 1;

@@ -29,15 +29,18 @@ constexpr int BLK_WORDS    = 48;                  // words per candidate block
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
 #ifndef VS_SCORE_THREADS
-#define VS_SCORE_THREADS 96           // measured on B200: 96 x 6 CTAs/SM (18 warps) 2.11 ms, 256 x 2 (16 warps) 2.20 ms, 512 x 1 2.33 ms (cfg3 x 0.25)
+#define VS_SCORE_THREADS 128          // measured on B200 (score ms, cfg3 x 0.25 / cfg4 x 0.1): 96 thr 2.11 / 12.7, 128 thr 2.15 / 11.0, 256 thr 2.20 / 11.2
 #endif
 #ifndef VS_SCORE_MINBLOCKS
-#define VS_SCORE_MINBLOCKS 6
+#define VS_SCORE_MINBLOCKS 4
 #endif
 constexpr int SCORE_THREADS = VS_SCORE_THREADS;
 constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block
 constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 slot offsets + pad, 16-byte aligned)
-constexpr int PAT_CHUNK    = 320;                 // guides per k_score launch: 2 strands x 320 x 96 B = 60 KB of constant memory
+#ifndef VS_PAT_CHUNK
+#define VS_PAT_CHUNK 256
+#endif
+constexpr int PAT_CHUNK    = VS_PAT_CHUNK;        // guides per k_score launch: 2 strands x 256 x 96 B = 48 KB of constant memory
 
 struct PamParams {
     int n;            // number of forward dinucleotides (2 or 3)
