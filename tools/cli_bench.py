@@ -62,7 +62,7 @@ def main():
             r = subprocess.run([os.path.join(BIN, "bidir_mapping"), "-G", fa, "-I", os.path.join(d, label), "-R", rf, "-M", str(k), "-T", "8", "-O", sam],
                                capture_output=True, text=True, env=env)
             out[f"{label}_mapping_{ngpu}gpu_s"] = round(time.time() - t, 2); assert r.returncode == 0, r.stderr
-            out[f"{label}_mapping_{ngpu}gpu_note"] = r.stderr.strip().splitlines()[-1] if r.stderr.strip() else ""
+            out[f"{label}_mapping_{ngpu}gpu_note"] = " | ".join(r.stderr.strip().splitlines()[-2:]) if r.stderr.strip() else ""
             out[f"{label}_sam_lines_{ngpu}gpu"] = sum(1 for _ in open(sam))
         sams = [open(os.path.join(d, f"{label}_{n}.sam"), "rb").read() for n in sorted({1, V.device_count()})]
         out[label + "_multi_gpu_sam_identical"] = all(x == sams[0] for x in sams)

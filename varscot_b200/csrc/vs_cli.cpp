@@ -296,6 +296,7 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
         if (!read_fasta(reads, sink, err)) { fprintf(stderr, "%s: %s\n", prog, err.c_str()); return 1; }
         if (bad) { fprintf(stderr, "%s: all reads must be %d nt long (guide + PAM)\n", prog, VS_GLEN); return 1; }
     }
+    const auto tm0 = std::chrono::steady_clock::now();
     printf("Reads loaded (total: %zu).\n", ids.size());
     fflush(stdout);
 
@@ -328,6 +329,7 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     if (t.v.n_bases > (1ull << 32)) { fprintf(stderr, "%s: text exceeds 4 giga bases\n", prog); return 1; }
     printf("Index loaded.\n");
     fflush(stdout);
+    const auto tm1 = std::chrono::steady_clock::now();
 
     // output is opened only after all work in the reference (bidir_mapping.cpp:298-305); failing early is equivalent for the caller
     FILE *out = fopen(output.c_str(), "wb");
@@ -346,6 +348,7 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
                     devices.size(), st.total_ms, st.extract_ms, st.score_ms, st.h2d_bytes / 1e6,
                     (unsigned long long)(st.n_cand_fwd + st.n_cand_rev), (unsigned long long)st.n_hits);
     }
+    const auto tm2 = std::chrono::steady_clock::now();
     std::vector<vs_record> rec(hits.size());
     uint64_t coll = 0;
     if (!hits.empty() && vs_resolve_hits(hits.data(), hits.size(), t.v.contig_off, t.v.n_contigs, rec.data(), &coll) != VS_OK) {
@@ -364,5 +367,10 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
         if (n < 0 || fwrite(buf.data(), 1, (size_t)n, out) != (size_t)n) { fprintf(stderr, "%s: write error\n", prog); fclose(out); return 1; }
     }
     if (fclose(out) != 0) { fprintf(stderr, "%s: write error\n", prog); return 1; }
+    if (getenv("VARSCOT_VERBOSE")) {
+        auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "%s: wall: load %.3f s, device (context + upload + scan) %.3f s, resolve + SAM %.3f s\n", prog, sec(tm0, tm1), sec(tm1, tm2),
+                sec(tm2, std::chrono::steady_clock::now()));
+    }
     return 0;
 }

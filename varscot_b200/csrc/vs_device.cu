@@ -81,11 +81,9 @@ extern "C" int vs_device_count(void)
     return n;
 }
 
-template <int K>
-static cudaError_t set_score_attr()
-{
-    return cudaFuncSetAttribute(k_score<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, NPLANES * SCORE_THREADS * 4);
-}
+// k_score's dynamic shared memory (92 planes x 128 threads x 4 B = 46 KB) fits the default 48 KB limit, so no
+// cudaFuncSetAttribute is needed — and none of the nine k_score<K> variants is loaded before it is used.
+static_assert(NPLANES * SCORE_THREADS * 4 <= 48 * 1024, "k_score needs cudaFuncAttributeMaxDynamicSharedMemorySize above 48 KB");
 
 extern "C" int vs_ctx_create(int device, vs_ctx **out)
 {
@@ -107,15 +105,6 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->exs, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = set_score_attr<0>();
-    if (e == cudaSuccess) e = set_score_attr<1>();
-    if (e == cudaSuccess) e = set_score_attr<2>();
-    if (e == cudaSuccess) e = set_score_attr<3>();
-    if (e == cudaSuccess) e = set_score_attr<4>();
-    if (e == cudaSuccess) e = set_score_attr<5>();
-    if (e == cudaSuccess) e = set_score_attr<6>();
-    if (e == cudaSuccess) e = set_score_attr<7>();
-    if (e == cudaSuccess) e = set_score_attr<8>();
     if (e != cudaSuccess) {
         std::string m = std::string("vs_ctx_create: ") + cudaGetErrorString(e);
         vs_ctx_destroy(ctx);
