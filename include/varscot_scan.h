@@ -22,6 +22,8 @@
  * vs_bidir_mapping_main            bidir_mapping.cpp:190-312 main (argv contract, stdout lines, exit codes)
  * vs_vcf_loader_main               variant_processing/vcf_loader.cpp:11-77 (+ process_vcf.h, overlap_sequences.h, write_fasta.h)
  * vs_fasta_writer_main             variant_processing/fasta_writer.cpp:8-41 (+ extract_fasta_ontargets.h)
+ * vs_bam_merger_main,              variant_processing/bam_merger.cpp:8-62, bam_merger_ref_only.cpp:8-55 (+ merge_output_bam.h,
+ * vs_bam_merger_ref_only_main      filter_output_bam.h, feature_matrix.h, mit_score.h)
  */
 #ifndef VARSCOT_SCAN_H
 #define VARSCOT_SCAN_H
@@ -190,6 +192,11 @@ int vs_vcf_loader_main(int argc, char **argv);
 /* row f4 (producer of the guide FASTA): `fasta_writer OUTPUT1.fa OUTPUT2.fa ONTARGETS.bed GENOME.fa`,
  * VARSCOT_pipeline/variant_processing/fasta_writer.cpp:8-41 (host only) */
 int vs_fasta_writer_main(int argc, char **argv);
+/* row f3 (consumers of the mapper's SAM): `bam_merger RESULT.txt FEATURES.txt REF.sam SNP.sam TARGETS.bed GENOME.fa SNP.fa
+ * TUSCAN.txt K SEQLENGTH THREADS MIT` and `bam_merger_ref_only RESULT.txt FEATURES.txt REF.sam TARGETS.bed GENOME.fa TUSCAN.txt
+ * K SEQLENGTH MIT`, VARSCOT_pipeline/variant_processing/bam_merger.cpp:8-62, bam_merger_ref_only.cpp:8-55 (host only) */
+int vs_bam_merger_main(int argc, char **argv);
+int vs_bam_merger_ref_only_main(int argc, char **argv);
 
 /* ---- microbenchmarks used by bench.py for the roofline denominators ---------------------------- */
 /* thread-level LOP3 instructions per second of the device (alu pipe), and LDS 32-bit lane-words per second */

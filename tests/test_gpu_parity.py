@@ -371,3 +371,16 @@ def test_pipeline_chain_bed_vcf_to_sam(tmp_path):
             # the repaired off-targets are found in ALT segments with one mismatch fewer than on the reference
             assert any(b"_ALT_" in l and b"NM:i:1" in l for l in a.splitlines())
     assert total >= 8
+    # ... and the back of the pipeline (VARSCOT:332-337): bam_merger over the CUDA mapper's SAM files vs the oracle merger
+    from oracle import merge_oracle as MO
+    tus = str(tmp_path / "activity.txt")
+    open(tus, "w").write("ID Sequence Score Dir\n" + "".join(f"guide{i} {'A' * 30} {1.5 + i} +\n" for i in range(4)))
+    for mit in (0, 1):
+        out_txt, fm_txt = str(tmp_path / f"result{mit}.txt"), str(tmp_path / f"fm{mit}.txt")
+        r = subprocess.run([os.path.join(vp, "bam_merger"), out_txt, fm_txt, str(tmp_path / "ref.sam"), str(tmp_path / "snp.sam"), bed, g, snp_fa, tus,
+                            "3", "23", "1", str(mit)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        exp_text, exp_fm = MO.bam_merger(str(tmp_path / "ref_oracle.sam"), str(tmp_path / "snp_oracle.sam"), bed, g, snp_fa, tus, 23, mit)
+        assert open(out_txt).read() == exp_text and exp_text.count("\n") > 4
+        if mit:
+            assert open(fm_txt).read() == exp_fm

@@ -53,7 +53,7 @@ EXPORTS = [
     "vs_masks_from_planes", "vs_masks_sparse", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
     "vs_ctx_create", "vs_ctx_destroy", "vs_last_error", "vs_ctx_set_chunk_words", "vs_text_upload", "vs_host_alloc",
     "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits",
-    "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_vcf_loader_main", "vs_fasta_writer_main", "vs_measure_int_peaks",
+    "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_vcf_loader_main", "vs_fasta_writer_main", "vs_bam_merger_main", "vs_bam_merger_ref_only_main", "vs_measure_int_peaks",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def lib():
     L.vs_bidir_mapping_main.argtypes = [i32, C.POINTER(C.c_char_p)]
     L.vs_vcf_loader_main.argtypes = [i32, C.POINTER(C.c_char_p)]
     L.vs_fasta_writer_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    L.vs_bam_merger_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    L.vs_bam_merger_ref_only_main.argtypes = [i32, C.POINTER(C.c_char_p)]
     L.vs_measure_int_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
