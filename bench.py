@@ -351,14 +351,37 @@ def main():
     (lop_a, lds_a), (lop_b, lds_b) = score_ops(k)
     executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few warps that pass)
     lds = lds_a * blocks * ng / score_s
+    # DRAM traffic of one full-chunk k_score launch from the committed ncu capture (dram__bytes_read + dram__bytes_write)
+    traffic = None
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", "r1_score_final_summary.txt")):
+            f = line.split()
+            if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
+                rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if len(f) >= 3 and f[0] == "dram__bytes_write.sum":
+                wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        if rd is not None and wr is not None:
+            traffic = rd + wr
+    except Exception:
+        pass
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
     roof = {"bound": "int_alu", "kernel": "k_score", "achieved": yard / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
-            "frac": yard / peak_lop3, "traffic": None,
+            "frac": yard / peak_lop3, "traffic": traffic,
+            "traffic_note": "bytes per full-chunk launch (8 Mi words), ncu capture in profiles/r1_score_final_summary.txt; algorithmic = 192 B x blocks of the chunk",
+            "hbm": {"achieved_gbs": (blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9, "peak_gbs": hbm_peak,
+                    "frac": ((blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9 / hbm_peak) if hbm_peak else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "MEASURED_PEAKS.json absent"},
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
             "avg_launch_ms": score_ms / args.steps / max(1, n_score_launch), "launches_per_step": n_score_launch,
             "executed_lop3_tlops": executed / 1e12, "frac_executed": executed / peak_lop3,
             "ops_per_block_guide": {"stage_a_lop3": lop_a, "stage_a_lds": lds_a, "stage_b_lop3": lop_b, "stage_b_lds": lds_b},
             "lds_words_per_s_T": lds / 1e12, "lds_peak_T": peak_lds / 1e12, "frac_lds": lds / peak_lds,
-            "hbm_gbs_algorithmic": (blocks * 192.0 * ((ng + 511) // 512)) / score_s / 1e9,
+            "hbm_gbs_algorithmic": (blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9,
             "note": "yardstick = 4.0 LOP3 per guide*bp (dense scan, SURVEY.md 8d); PAM-first compaction scores ~1/8 of the windows per strand, so frac may exceed 1; frac_executed is the real alu-pipe load"}
     out = {
         "metric": "guide_Gbp_per_s", "value": value, "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -384,3 +384,108 @@ def test_pipeline_chain_bed_vcf_to_sam(tmp_path):
         assert open(out_txt).read() == exp_text and exp_text.count("\n") > 4
         if mit:
             assert open(fm_txt).read() == exp_fm
+
+
+def test_empty_inputs():
+    """Empty text, zero guides, text shorter than a window: no hits, no errors."""
+    import varscot_b200 as V
+    g = np.full((2, GLEN), 2, dtype=np.uint8)
+    with V.ScanContext(0) as ctx:
+        for asc, off in ((b"", [0]), (b"", [0, 0, 0]), (b"ACGTACGTAC", [0, 10]), (b"G" * 22, [0, 22])):
+            text = V.PackedText.from_ascii(asc, np.array(off, dtype=np.uint64))
+            hits, st = ctx.scan_text(text, g, 4)
+            assert len(hits) == 0 and st.n_hits == 0
+        text = V.PackedText.from_ascii(b"G" * 100, np.array([0, 100], dtype=np.uint64))
+        hits, _ = ctx.scan_text(text, np.zeros((0, GLEN), dtype=np.uint8), 4)
+        assert len(hits) == 0
+        hits, _ = ctx.scan_text(text, g[:1], 0)
+        assert len(hits) == 78
+        with pytest.raises(V.VarscotError):
+            ctx.scan(g, 9)
+        with pytest.raises(V.VarscotError):
+            ctx.scan(np.full((1, GLEN), 7, dtype=np.uint8), 4)
+
+
+def _plant(text, p, codes):
+    """Write 23 Dna codes at global position p of a PackedText (bases only; masks are untouched)."""
+    for i, c in enumerate(codes):
+        w, b = (p + i) >> 5, np.uint32(1) << np.uint32((p + i) & 31)
+        for name, bit in (("hi", (c >> 1) & 1), ("lo", c & 1)):
+            if bit:
+                text.bases[name][w] |= b
+            else:
+                text.bases[name][w] &= ~b
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 at FULL size (3.1 Gbp genome + 5 M variants, 100 guides, k <= 6), checked through
+    size-independent properties: every reported hit is re-verified from the packed planes (PAM on the genome, exact
+    mismatch count, no N, inside one contig, R4 on last windows), no hit is reported twice, every planted site is
+    found with its exact mismatch count, and the forward / reverse hit totals sit where uniform-random text puts them."""
+    import varscot_b200 as V
+    from varscot_b200 import synth
+    rng = np.random.default_rng(2024)
+    g = synth.synth_genome(11, 3_100_000_000, 24, 0.05)
+    s = synth.synth_variant_segments(g, 12, 5_000_000)
+    text = synth.concat_texts(g, s)
+    del g, s
+    guides = synth.synth_guides(13, 100)
+    k = 6
+    # plant sites at scannable positions: guide copies with j mismatches outside the PAM, both strands
+    valid_words = np.flatnonzero(text.masks["iv"] == 0)
+    planted = {}
+    for j in range(240):
+        gi, mm, strand = j % 100, j % 7, (j // 7) % 2
+        w = int(valid_words[rng.integers(0, len(valid_words))])
+        if w + 2 >= text.n_words or text.masks["iv"][w + 1] != 0:
+            continue
+        p = w * 32 + int(rng.integers(0, 32))
+        codes = guides[gi].copy()
+        idx = rng.choice(20, mm, replace=False)
+        codes[idx] = (codes[idx] + rng.integers(1, 4, mm)) % 4
+        if strand:
+            codes = revcomp_codes(codes)
+        if any(abs(p - q) < 46 for q, _ in planted):
+            continue
+        _plant(text, p, codes)
+        planted[(p, (gi << 8) | (strand << 7))] = mm
+    text.pin()
+    with V.ScanContext(0) as ctx:
+        hits, st = ctx.scan_text(text, guides, k, cap=1 << 20)
+    text.unpin()
+    assert 300_000 < len(hits) < 700_000                     # ~4.5e5 expected for uniform-random text
+    pos = hits["pos"].astype(np.int64)
+    info = hits["info"]
+    gi, strand, mm = (info >> 8).astype(np.int64), ((info >> 7) & 1).astype(np.int64), (info & 0xF).astype(np.int64)
+    # no duplicates
+    key = (pos << 16) | (gi << 1) | strand
+    assert len(np.unique(key)) == len(key)
+    # window masks: every hit starts at a scannable position
+    assert ((text.masks["iv"][pos >> 5] >> (pos & 31).astype(np.uint32)) & 1).sum() == 0
+    # re-verify every hit from the planes
+    hi = np.concatenate([text.bases["hi"], np.zeros(2, np.uint32)])
+    lo = np.concatenate([text.bases["lo"], np.zeros(2, np.uint32)])
+    wh, wl = synth._gather(hi, pos, 23), synth._gather(lo, pos, 23)
+    pat = np.where(strand[:, None] == 1, 3 - guides[gi][:, ::-1], guides[gi]).astype(np.uint64)
+    ph = ((pat >> np.uint64(1)) & np.uint64(1)) << np.arange(23, dtype=np.uint64)[None, :]
+    pl = (pat & np.uint64(1)) << np.arange(23, dtype=np.uint64)[None, :]
+    ph, pl = ph.sum(axis=1).astype(np.uint64), pl.sum(axis=1).astype(np.uint64)
+    diff = (wh ^ ph) | (wl ^ pl)
+    popc = np.array([bin(int(x)).count("1") for x in diff], dtype=np.int64)
+    assert (popc == mm).all() and (mm <= k).all()
+    code = lambda i: (((wh >> np.uint64(i)) & np.uint64(1)) << np.uint64(1)) | ((wl >> np.uint64(i)) & np.uint64(1))
+    fwd_ok = (code(21) == 2) & ((code(22) == 2) | (code(22) == 0))               # GG, GA
+    rev_ok = (code(1) == 1) & ((code(0) == 1) | (code(0) == 3))                  # CC, TC
+    assert np.where(strand == 1, rev_ok, fwd_ok).all()
+    # R4: hits on last windows have <= K = 3 mismatches in positions 11..22
+    lastw = ((text.masks["lw"][pos >> 5] >> (pos & 31).astype(np.uint32)) & 1) == 1
+    h2 = np.array([bin(int(x) >> 11).count("1") for x in diff[lastw]], dtype=np.int64)
+    assert lastw.sum() > 100 and (h2 <= k // 2).all()
+    # recall: every planted site with <= k mismatches is reported with its exact count
+    found = {(int(p), int(i) & ~0x7F): int(m) for p, i, m in zip(pos, info, mm)}
+    assert len(planted) > 150
+    for (p, gk), m in planted.items():
+        assert found.get((p, gk)) == m, (p, gk, m)
+    # strands are balanced on random text
+    nf, nr = int((strand == 0).sum()), int((strand == 1).sum())
+    assert abs(nf - nr) < 0.05 * len(hits)
