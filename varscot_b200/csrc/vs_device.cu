@@ -161,25 +161,26 @@ static void make_pam(int extra_pam, PamParams &pp)
     for (int j = 0; j < 3; ++j) { pp.rx[j] = 3 - pp.fy[j]; pp.ry[j] = 3 - pp.fx[j]; }
 }
 
+// grid = forward CTAs then reverse CTAs, sized by the capacity of the candidate stores (CTAs past the claimed block
+// count of their strand exit at once)
 template <int K>
-static void launch_score(const ScoreArgs &a, uint64_t cap, cudaStream_t st)
+static void launch_score(const ScoreArgs &a, cudaStream_t st)
 {
-    (void)cap;
     k_score<K><<<2 * a.ctas_per_strand, SCORE_THREADS, NPLANES * SCORE_THREADS * 4, st>>>(a);
 }
 
-static void dispatch_score(int k, const ScoreArgs &a, uint64_t cap, cudaStream_t st)
+static void dispatch_score(int k, const ScoreArgs &a, cudaStream_t st)
 {
     switch (k) {
-    case 0: launch_score<0>(a, cap, st); break;
-    case 1: launch_score<1>(a, cap, st); break;
-    case 2: launch_score<2>(a, cap, st); break;
-    case 3: launch_score<3>(a, cap, st); break;
-    case 4: launch_score<4>(a, cap, st); break;
-    case 5: launch_score<5>(a, cap, st); break;
-    case 6: launch_score<6>(a, cap, st); break;
-    case 7: launch_score<7>(a, cap, st); break;
-    default: launch_score<8>(a, cap, st); break;
+    case 0: launch_score<0>(a, st); break;
+    case 1: launch_score<1>(a, st); break;
+    case 2: launch_score<2>(a, st); break;
+    case 3: launch_score<3>(a, st); break;
+    case 4: launch_score<4>(a, st); break;
+    case 5: launch_score<5>(a, st); break;
+    case 6: launch_score<6>(a, st); break;
+    case 7: launch_score<7>(a, st); break;
+    default: launch_score<8>(a, st); break;
     }
 }
 
@@ -420,7 +421,7 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
             a.n_pat = np; a.guide_base = gc * PAT_CHUNK;
             a.pat_global = ctx->d_pat + (size_t)gc * pat_chunk_words;
             a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
-            dispatch_score(k, a, ctx->blocks_cap, st);
+            dispatch_score(k, a, st);
             S.launches++; S.score_launches++;
         }
         return VS_OK;

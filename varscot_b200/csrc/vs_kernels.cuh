@@ -4,17 +4,18 @@
 // SeqAn's find<0,K>(delegate, index, half, HammingDistance()) (:129-146) plus the verify
 // delegate (:34-127) — restated as a dense, PAM-first Hamming scan (rules R1-R4 of SURVEY.md 8a).
 //
-// Pipeline per scan (all on one stream):
-//   k_extract  : per tile of 8192 window starts, find the PAM-valid / N-free / in-contig windows of each strand
-//                (bit-parallel), compact them into blocks of 32 candidates and store each block bit-sliced
-//                ACROSS candidates (per-thread 32x32 register transposes): 48 words per block =
-//                hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; + 32 positions
-//   k_score<K> : one thread per candidate block, both strands in one launch; 18 of the 23 positions are expanded
-//                into "mismatch if guide base is b" planes in shared memory (select = 1 LDS at a warp-uniform
-//                offset from constant memory), 5 stay in registers (select = 1 IMAD + 1 LOP3); then per guide
-//                36 LOP3 carry-save adder + 2 LOP3 threshold.  Hits (rare): exact count, R4 check, atomic append.
+// Pipeline per scan, per pipeline chunk of the text (8 Mi words), all on one stream:
+//   k_extract  : per tile of ~240 words (7680 window starts), find the PAM-valid / scannable windows of each strand
+//                (bit-parallel on the packed planes and the precomputed window masks), compact them into blocks of 32
+//                candidates and store each block bit-sliced ACROSS candidates (per-thread 32x32 register
+//                transposes): 48 words per block = hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; + 32 positions
+//   k_score<K> : one thread per candidate block, both strands in one launch; the 46 planes are expanded into 92
+//                "mismatch if the guide base at position i is b" planes in shared memory; per guide the select is one
+//                LDS per position at a warp-uniform offset from constant memory, the count a bit-sliced carry-save
+//                adder tree (2 LOP3 per full adder), the threshold 2 LOP3; two stages with a warp-uniform early out.
+//                Hits (rare): count read from the bit-sliced counter, R4 check on last windows, atomic append.
 // Integer pipe + shared-memory bound; no tensor cores (nothing here is a dense contraction worth a GEMM:
-// the bit-sliced form costs ~1.2 ALU ops per (window, guide) pair, below one op per output element).
+// the bit-sliced form costs ~1.1 ALU ops per (window, guide) pair, below one op per output element).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,9 +23,6 @@
 
 namespace vs {
 
-constexpr int TILE_WORDS   = 256;                 // words (of 32 window starts) per tile
-constexpr int TILE_THREADS = 256;
-constexpr int TILE_STARTS  = TILE_WORDS * 32;     // 8192
 constexpr int BLK_WORDS    = 48;                  // words per candidate block
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
@@ -134,40 +132,61 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     __shared__ uint32_t s_m[2][EX_MAX_WORDS + 1];      // candidate masks per strand
     __shared__ uint32_t s_p[2][EX_MAX_WORDS + 1];      // exclusive rank prefix per word (+ total at [nw])
     __shared__ uint32_t s_lw[EX_MAX_WORDS + 1];
-    __shared__ uint32_t wsum[2][EX_THREADS / 32];
+    __shared__ uint32_t wsum[2][EX_MAX_WORDS / EX_THREADS][EX_THREADS / 32];
     __shared__ unsigned long long base[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t w0 = w_begin + (uint64_t)blockIdx.x * tile_words;
     const uint32_t nw = (uint32_t)min((uint64_t)tile_words, w_end - w0);      // words of this tile
-    uint32_t run_f = 0, run_r = 0;                     // candidates before the current group of 64 words
-    for (uint32_t i0 = 0; i0 < nw; i0 += EX_THREADS) {
-        const uint32_t i = i0 + tid;
+    // phase 1a: all global loads of the tile are issued up front (up to 4 words of bases + masks per thread, 64-bit
+    // loads), staged in shared memory, and only then consumed — the first use no longer waits on a single load
+    constexpr int EX_ITERS = EX_MAX_WORDS / EX_THREADS;
+    uint2 ab[EX_ITERS], mk[EX_ITERS];
+    const uint2 *B2 = reinterpret_cast<const uint2 *>(B), *M2 = reinterpret_cast<const uint2 *>(M);
+#pragma unroll
+    for (int it = 0; it < EX_ITERS; ++it) {
+        const uint32_t i = it * EX_THREADS + tid;
+        ab[it] = make_uint2(0u, 0u); mk[it] = make_uint2(~0u, 0u);
+        if (i < nw) { ab[it] = __ldg(B2 + w0 + i); mk[it] = __ldg(M2 + w0 + i); }
+    }
+    if (tid == 0) s_hl[nw] = __ldg(B2 + w0 + nw);                       // B[w_end] is the halo / pad word, always readable
+#pragma unroll
+    for (int it = 0; it < EX_ITERS; ++it) {
+        const uint32_t i = it * EX_THREADS + tid;
+        if (i < nw) { s_hl[i] = ab[it]; s_lw[i] = mk[it].y; }
+    }
+    __syncthreads();
+    // phase 1b: candidate masks and their rank prefix (word order: thread t owns words t, t+64, t+128, t+192)
+    uint32_t cf[EX_ITERS], cr[EX_ITERS], xf[EX_ITERS], xr[EX_ITERS];
+#pragma unroll
+    for (int it = 0; it < EX_ITERS; ++it) {
+        const uint32_t i = it * EX_THREADS + tid;
         uint32_t fwd = 0, rev = 0;
         if (i < nw) {
-            const vs_bases a = B[w0 + i], b = B[w0 + i + 1];    // B[w_end] is the halo / pad word, always readable
-            const vs_masks m = M[w0 + i];
-            s_hl[i] = make_uint2(a.hi, a.lo);
-            if (i == nw - 1) s_hl[i + 1] = make_uint2(b.hi, b.lo);
-            s_lw[i] = m.lw;
-            cand_masks(a, b, m, pp, fwd, rev);
+            const uint2 nx = s_hl[i + 1];
+            cand_masks(vs_bases{ab[it].x, ab[it].y}, vs_bases{nx.x, nx.y}, vs_masks{mk[it].x, mk[it].y}, pp, fwd, rev);
             s_m[0][i] = fwd; s_m[1][i] = rev;
         }
-        const uint32_t cf = __popc(fwd), cr = __popc(rev);
-        uint32_t xf = cf, xr = cr;
+        cf[it] = __popc(fwd); cr[it] = __popc(rev);
+        uint32_t a = cf[it], b = cr[it];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t p = __shfl_up_sync(0xffffffffu, xf, o), q = __shfl_up_sync(0xffffffffu, xr, o);
-            if (lane >= o) { xf += p; xr += q; }
+            uint32_t p = __shfl_up_sync(0xffffffffu, a, o), q = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += p; b += q; }
         }
-        if (lane == 31) { wsum[0][wid] = xf; wsum[1][wid] = xr; }
-        __syncthreads();
-        const uint32_t w0f = wsum[0][0], w0r = wsum[1][0], w1f = wsum[0][1], w1r = wsum[1][1];
+        xf[it] = a; xr[it] = b;
+        if (lane == 31) { wsum[0][it][wid] = a; wsum[1][it][wid] = b; }
+    }
+    __syncthreads();
+    uint32_t run_f = 0, run_r = 0;                     // candidates before the current group of 64 words
+#pragma unroll
+    for (int it = 0; it < EX_ITERS; ++it) {
+        const uint32_t i = it * EX_THREADS + tid;
+        const uint32_t w0f = wsum[0][it][0], w0r = wsum[1][it][0], w1f = wsum[0][it][1], w1r = wsum[1][it][1];
         if (i < nw) {
-            s_p[0][i] = run_f + (wid ? w0f : 0u) + xf - cf;
-            s_p[1][i] = run_r + (wid ? w0r : 0u) + xr - cr;
+            s_p[0][i] = run_f + (wid ? w0f : 0u) + xf[it] - cf[it];
+            s_p[1][i] = run_r + (wid ? w0r : 0u) + xr[it] - cr[it];
         }
         run_f += w0f + w1f; run_r += w0r + w1r;
-        __syncthreads();
     }
     const uint32_t nf = run_f, nr = run_r;
     const uint32_t nbf = (nf + 31) >> 5, nbr = (nr + 31) >> 5;
