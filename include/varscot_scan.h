@@ -174,6 +174,9 @@ typedef struct {
  * out must hold n records.  *key16_collisions counts records the reference's uint16 key would have merged. */
 int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
                     vs_record *out, uint64_t *key16_collisions);
+/* the same with n_threads host threads (the executables pass -T): the contig lookup and the per-pass sorts run in parallel */
+int vs_resolve_hits_mt(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
+                       vs_record *out, uint64_t *key16_collisions, int n_threads);
 
 #define VS_MD_SEQAN 0
 #define VS_MD_SAMTOOLS 1

@@ -241,3 +241,20 @@ def test_cli_contract_exit_codes(tmp_path):
     if V.device_count() == 0:
         x = run_cli("bidir_mapping", *base, "-M", 4)
         assert x.returncode == 1 and "no usable CUDA device" in x.stderr and "Reads loaded (total: 2)." in x.stdout
+
+
+def test_resolve_hits_threads_agree():
+    """vs_resolve_hits_mt with 1, 3 and 8 threads produces the same records (and the same collision count)."""
+    rng = np.random.default_rng(12)
+    nct = 70000
+    off = (np.arange(nct + 1) * 45).astype(np.uint64)
+    n = 60000
+    hits = np.zeros(n, dtype=V.HIT_DT)
+    hits["pos"] = rng.integers(0, nct, n) * 45 + rng.integers(0, 23, n)
+    hits["info"] = (rng.integers(0, 37, n).astype(np.uint32) << 8) | (rng.integers(0, 2, n).astype(np.uint32) << 7) | rng.integers(0, 7, n).astype(np.uint32)
+    hits = np.unique(hits)                      # a scan never reports the same (pos, guide, strand) twice
+    ref, c1 = V.resolve_hits(hits, off, threads=1)
+    for t in (3, 8):
+        got, c = V.resolve_hits(hits[rng.permutation(len(hits))], off, threads=t)
+        assert got.tobytes() == ref.tobytes() and c == c1
+    assert c1 > 0 and len(ref) == len(hits)

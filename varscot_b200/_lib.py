@@ -52,7 +52,7 @@ EXPORTS = [
     "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_finish", "vs_pack_text",
     "vs_masks_from_planes", "vs_masks_sparse", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
     "vs_ctx_create", "vs_ctx_destroy", "vs_last_error", "vs_ctx_set_chunk_words", "vs_text_upload", "vs_host_alloc",
-    "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits",
+    "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_resolve_hits_mt",
     "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_vcf_loader_main", "vs_fasta_writer_main", "vs_bam_merger_main", "vs_bam_merger_ref_only_main", "vs_measure_int_peaks",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.vs_map_packed.argtypes = [C.POINTER(TextView), vp, u32, i32, i32, vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_shard_bounds.argtypes = [u64, i32, vp]
     L.vs_resolve_hits.argtypes = [vp, u64, vp, u32, vp, C.POINTER(u64)]
+    L.vs_resolve_hits_mt.argtypes = [vp, u64, vp, u32, vp, C.POINTER(u64), i32]
     L.vs_md_string.argtypes = [vp, u64, vp, i32, i32, C.c_char_p]
     L.vs_format_sam.argtypes = [C.POINTER(Record), C.c_char_p, C.c_char_p, vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.vs_bidir_index_main.argtypes = [i32, C.POINTER(C.c_char_p)]

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -276,6 +277,17 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
         else fprintf(stderr, "%s: warning: additional PAM '%s' can never match a 2-base window without N; ignored\n", prog, pam.c_str());
     }
 
+    // CUDA context creation takes 0.3-4 s: start it now, in the background, on the device a small text will use, and
+    // read the inputs meanwhile (choose_devices() picks pid % n_gpus first)
+    std::thread warm([] {
+        int n = vs_device_count();
+        if (n <= 0) return;
+        int dev = (int)((unsigned)getpid() % (unsigned)n);
+        if (const char *e = getenv("VARSCOT_DEVICE")) { int i = atoi(e); if (i >= 0 && i < n) dev = i; }
+        vs_warmup_device(dev);
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
+
     // reads: StringSet<DnaString> (bidir_mapping.cpp:256,263-264): non-ACGT -> A
     std::vector<std::string> ids;
     std::vector<uint8_t> guides;
@@ -351,20 +363,41 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     const auto tm2 = std::chrono::steady_clock::now();
     std::vector<vs_record> rec(hits.size());
     uint64_t coll = 0;
-    if (!hits.empty() && vs_resolve_hits(hits.data(), hits.size(), t.v.contig_off, t.v.n_contigs, rec.data(), &coll) != VS_OK) {
+    // -T drives the host side here: hit resolution and SAM formatting (the scan itself runs on the GPUs)
+    const int host_threads = (int)std::min<long>(64, std::max<long>(1, threads));
+    if (!hits.empty() && vs_resolve_hits_mt(hits.data(), hits.size(), t.v.contig_off, t.v.n_contigs, rec.data(), &coll, host_threads) != VS_OK) {
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr)); fclose(out); return 1;
     }
     if (coll) fprintf(stderr, "%s: note: %llu records share a (contig id mod 65536, position) key; the reference's uint16 map key would have kept one of each\n", prog, (unsigned long long)coll);
-    std::string line;
-    std::vector<char> buf(1 << 16);
-    for (const vs_record &r : rec) {
-        char md[64];
-        const uint8_t *g = guides.data() + (size_t)r.guide * VS_GLEN;
-        vs_md_string(t.v.bases, t.v.contig_off[r.contig] + r.pos, g, (r.flag >> 4) & 1, md_style, md);
-        const std::string &qn = ids[r.guide], &rn = t.names[r.contig];
-        if (buf.size() < qn.size() + rn.size() + 256) buf.resize(qn.size() + rn.size() + 256);
-        int n = vs_format_sam(&r, qn.c_str(), rn.c_str(), g, md, buf.data(), buf.size());
-        if (n < 0 || fwrite(buf.data(), 1, (size_t)n, out) != (size_t)n) { fprintf(stderr, "%s: write error\n", prog); fclose(out); return 1; }
+    // SAM text: batches of records are formatted by the host threads into per-thread buffers and written in order
+    const size_t batch = (size_t)host_threads * 65536;
+    std::vector<std::string> parts((size_t)host_threads);
+    for (size_t b0 = 0; b0 < rec.size(); b0 += batch) {
+        const size_t b1 = std::min(rec.size(), b0 + batch);
+        auto format = [&](int ti) {
+            std::string &o = parts[(size_t)ti];
+            o.clear();
+            const size_t r0 = b0 + (b1 - b0) * (size_t)ti / (size_t)host_threads, r1 = b0 + (b1 - b0) * (size_t)(ti + 1) / (size_t)host_threads;
+            std::vector<char> buf(1 << 12);
+            for (size_t i = r0; i < r1; ++i) {
+                const vs_record &r = rec[i];
+                char md[64];
+                const uint8_t *g = guides.data() + (size_t)r.guide * VS_GLEN;
+                vs_md_string(t.v.bases, t.v.contig_off[r.contig] + r.pos, g, (r.flag >> 4) & 1, md_style, md);
+                const std::string &qn = ids[r.guide], &rn = t.names[r.contig];
+                if (buf.size() < qn.size() + rn.size() + 256) buf.resize(qn.size() + rn.size() + 256);
+                int n = vs_format_sam(&r, qn.c_str(), rn.c_str(), g, md, buf.data(), buf.size());
+                if (n > 0) o.append(buf.data(), (size_t)n);
+            }
+        };
+        if (host_threads == 1) format(0);
+        else {
+            std::vector<std::thread> th;
+            for (int ti = 0; ti < host_threads; ++ti) th.emplace_back(format, ti);
+            for (auto &x : th) x.join();
+        }
+        for (const std::string &o : parts)
+            if (!o.empty() && fwrite(o.data(), 1, o.size(), out) != o.size()) { fprintf(stderr, "%s: write error\n", prog); fclose(out); return 1; }
     }
     if (fclose(out) != 0) { fprintf(stderr, "%s: write error\n", prog); return 1; }
     if (getenv("VARSCOT_VERBOSE")) {

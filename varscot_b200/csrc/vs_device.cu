@@ -69,6 +69,12 @@ extern "C" const char *vs_last_error(const vs_ctx *ctx)
 
 void vs_set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
 
+void vs_warmup_device(int device)
+{
+    if (cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr);
+    (void)cudaGetLastError();
+}
+
 extern "C" int vs_device_count(void)
 {
     int n = 0;

@@ -5,6 +5,7 @@
 // come only from the CUDA kernels (vs_device.cu); nothing in this file can substitute for them.
 #include "vs_internal.h"
 #include <algorithm>
+#include <atomic>
 #include <emmintrin.h>
 #include <cstdio>
 #include <cstdlib>
@@ -290,55 +291,99 @@ struct SortRec {
 inline bool operator<(const SortRec &a, const SortRec &b) { return a.k1 != b.k1 ? a.k1 < b.k1 : a.k2 < b.k2; }
 }  // namespace
 
-extern "C" int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
-                               vs_record *out, uint64_t *key16_collisions)
+// Hits -> records in the reference's emission order.  Three steps, the first and last parallel over `n_threads`:
+//   1. global position -> (contig, pos) by binary search, sort key (guide, strand, id & 0xFFFF, pos, id >> 16);
+//   2. counting sort by pass = (guide, strand) (single pass over the keys);
+//   3. per pass: sort by the std::map key and walk it with the running-best rule of bidir_mapping.cpp:164-187.  A pass
+//      occupies the same index range before and after step 3, so passes are independent.
+extern "C" int vs_resolve_hits_mt(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
+                                  vs_record *out, uint64_t *key16_collisions, int n_threads)
 {
     if ((n && (!hits || !out)) || !contig_off || n_contigs == 0) return n ? VS_ERR_ARG : VS_OK;
     if (key16_collisions) *key16_collisions = 0;
-    std::vector<SortRec> v;
-    try { v.resize(n); } catch (...) { return VS_ERR_NOMEM; }
+    if (n == 0) return VS_OK;
+    if (n_threads < 1) n_threads = 1;
+    if ((uint64_t)n_threads > n / 4096 + 1) n_threads = (int)(n / 4096 + 1);
+    std::vector<SortRec> v, v2;
+    try { v.resize(n); v2.resize(n); } catch (...) { return VS_ERR_NOMEM; }
     const uint64_t *ob = contig_off, *oe = contig_off + n_contigs + 1;
-    for (uint64_t i = 0; i < n; ++i) {
-        uint64_t gp = hits[i].pos;
-        // last contig c with off[c] <= gp (empty contigs share an offset; the non-empty one is the last)
-        const uint64_t *it = std::upper_bound(ob, oe, gp);
-        if (it == ob || it == oe) { vs_set_last_error("vs_resolve_hits: hit position outside the text"); return VS_ERR_ARG; }
-        uint32_t c = (uint32_t)(it - ob - 1);
-        uint32_t pos = (uint32_t)(gp - contig_off[c]);
-        uint32_t info = hits[i].info;
-        uint64_t guide = info >> 8, strand = (info >> 7) & 1, mm = info & 0xF;
-        v[i].k1 = (guide << 17) | (strand << 16) | (c & 0xFFFFu);
-        v[i].k2 = ((uint64_t)pos << 32) | ((uint64_t)(c >> 16) << 8) | mm;
-        v[i].contig = c;
-    }
-    std::sort(v.begin(), v.end());
-    // running-best emission per (guide, strand) pass, bidir_mapping.cpp:164-187
-    uint64_t w = 0, coll = 0;
-    uint64_t i = 0;
-    auto emit = [&](const SortRec &r, uint16_t secondary) {
-        vs_record &o = out[w++];
-        o.guide = (uint32_t)(r.k1 >> 17);
-        o.contig = r.contig;
-        o.pos = (uint32_t)(r.k2 >> 32);
-        o.mm = (uint8_t)(r.k2 & 0xF);
-        o.flag = (uint16_t)(secondary | (((r.k1 >> 16) & 1) ? 16 : 0));
-        o.pad = 0;
+    std::vector<int> bad((size_t)n_threads, 0);
+    std::vector<uint64_t> max_pass((size_t)n_threads, 0);
+    auto run = [&](auto fn) {
+        if (n_threads == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
     };
-    while (i < n) {
-        uint64_t j = i + 1;
-        const uint64_t pass = v[i].k1 >> 16;
-        while (j < n && (v[j].k1 >> 16) == pass) ++j;
-        uint64_t best = i;
-        for (uint64_t t = i + 1; t < j; ++t) {
-            if (v[t].k1 == v[t - 1].k1 && (v[t].k2 >> 32) == (v[t - 1].k2 >> 32)) ++coll;   // same (id16, pos): uint16 key collision
-            if ((v[t].k2 & 0xF) >= (v[best].k2 & 0xF)) emit(v[t], 256);
-            else { emit(v[best], 256); best = t; }
+    run([&](int t) {
+        const uint64_t b0 = n * (uint64_t)t / (uint64_t)n_threads, b1 = n * (uint64_t)(t + 1) / (uint64_t)n_threads;
+        uint64_t mp = 0;
+        for (uint64_t i = b0; i < b1; ++i) {
+            const uint64_t gp = hits[i].pos;
+            // last contig c with off[c] <= gp (empty contigs share an offset; the non-empty one is the last)
+            const uint64_t *it = std::upper_bound(ob, oe, gp);
+            if (it == ob || it == oe) { bad[(size_t)t] = 1; return; }
+            const uint32_t c = (uint32_t)(it - ob - 1);
+            const uint32_t pos = (uint32_t)(gp - contig_off[c]);
+            const uint32_t info = hits[i].info;
+            const uint64_t guide = info >> 8, strand = (info >> 7) & 1, mm = info & 0xF;
+            v[i].k1 = (guide << 17) | (strand << 16) | (c & 0xFFFFu);
+            v[i].k2 = ((uint64_t)pos << 32) | ((uint64_t)(c >> 16) << 8) | mm;
+            v[i].contig = c;
+            mp = std::max(mp, (guide << 1) | strand);
         }
-        emit(v[best], 0);
-        i = j;
+        max_pass[(size_t)t] = mp;
+    });
+    for (int t = 0; t < n_threads; ++t) if (bad[(size_t)t]) { vs_set_last_error("vs_resolve_hits: hit position outside the text"); return VS_ERR_ARG; }
+    const uint64_t n_pass = *std::max_element(max_pass.begin(), max_pass.end()) + 1;
+    std::vector<uint64_t> start;
+    try { start.assign(n_pass + 1, 0); } catch (...) { return VS_ERR_NOMEM; }
+    for (uint64_t i = 0; i < n; ++i) start[(v[i].k1 >> 16) + 1]++;
+    for (uint64_t p = 0; p < n_pass; ++p) start[p + 1] += start[p];
+    {
+        std::vector<uint64_t> cur(start.begin(), start.end() - 1);
+        for (uint64_t i = 0; i < n; ++i) v2[cur[v[i].k1 >> 16]++] = v[i];
     }
-    if (key16_collisions) *key16_collisions = coll;
+    std::vector<SortRec>().swap(v);
+    std::vector<uint64_t> coll((size_t)n_threads, 0);
+    std::atomic<uint64_t> next{0};
+    run([&](int t) {
+        uint64_t c = 0;
+        for (;;) {
+            const uint64_t p0 = next.fetch_add(64);
+            if (p0 >= n_pass) break;
+            for (uint64_t p = p0; p < std::min(n_pass, p0 + 64); ++p) {
+                const uint64_t i = start[p], j = start[p + 1];
+                if (i == j) continue;
+                std::sort(v2.begin() + (long)i, v2.begin() + (long)j);
+                uint64_t w = i, best = i;
+                auto emit = [&](const SortRec &r, uint16_t secondary) {
+                    vs_record &o = out[w++];
+                    o.guide = (uint32_t)(r.k1 >> 17);
+                    o.contig = r.contig;
+                    o.pos = (uint32_t)(r.k2 >> 32);
+                    o.mm = (uint8_t)(r.k2 & 0xF);
+                    o.flag = (uint16_t)(secondary | (((r.k1 >> 16) & 1) ? 16 : 0));
+                    o.pad = 0;
+                };
+                for (uint64_t x = i + 1; x < j; ++x) {
+                    if (v2[x].k1 == v2[x - 1].k1 && (v2[x].k2 >> 32) == (v2[x - 1].k2 >> 32)) ++c;   // same (id16, pos): uint16 key collision
+                    if ((v2[x].k2 & 0xF) >= (v2[best].k2 & 0xF)) emit(v2[x], 256);
+                    else { emit(v2[best], 256); best = x; }
+                }
+                emit(v2[best], 0);
+            }
+        }
+        coll[(size_t)t] = c;
+    });
+    if (key16_collisions) for (uint64_t c : coll) *key16_collisions += c;
     return VS_OK;
+}
+
+extern "C" int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
+                               vs_record *out, uint64_t *key16_collisions)
+{
+    return vs_resolve_hits_mt(hits, n, contig_off, n_contigs, out, key16_collisions, 1);
 }
 
 static inline int base_at(const vs_bases *bases, uint64_t p)

@@ -6,6 +6,10 @@
 
 void vs_set_last_error(const char *msg);
 
+// Start creating the CUDA primary context of `device` (driver + module initialisation, 0.3-4 s on a cold box); the
+// executables call it from a helper thread while they read their input files.
+void vs_warmup_device(int device);
+
 namespace vs {
 
 // Scan a packed text on one or several devices (text sharded by word ranges, one host thread and one

@@ -297,14 +297,14 @@ def shard_bounds(n_words: int, n_shards: int) -> np.ndarray:
     return out
 
 
-def resolve_hits(hits: np.ndarray, offsets: np.ndarray):
-    """vs_resolve_hits: reference emission order + flags. Returns (records, key16_collisions)."""
+def resolve_hits(hits: np.ndarray, offsets: np.ndarray, threads: int = 1):
+    """vs_resolve_hits(_mt): reference emission order + flags. Returns (records, key16_collisions)."""
     L = _lib.lib()
     h = np.ascontiguousarray(hits, dtype=HIT_DT)
     off = np.ascontiguousarray(offsets, dtype=np.uint64)
     rec = np.zeros(len(h), dtype=REC_DT)
     coll = C.c_uint64()
-    check(L.vs_resolve_hits(h.ctypes.data, len(h), off.ctypes.data, len(off) - 1, rec.ctypes.data, C.byref(coll)))
+    check(L.vs_resolve_hits_mt(h.ctypes.data, len(h), off.ctypes.data, len(off) - 1, rec.ctypes.data, C.byref(coll), threads))
     return rec, int(coll.value)
 
 
