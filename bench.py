@@ -217,7 +217,7 @@ def run_reference(args, cfg, world, rank):
     desc, gbases, nvar, ng, k, pam = cfg
     guides = synth.synth_guides(13, ng)
     # bounded sample with the composition of the full workload; sized so that the whole run takes a few minutes
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    budget_s = float(os.environ.get("VARSCOT_BENCH_BUDGET_S", "150")) / max(1, args.steps + args.warmup)
     scale = min(1.0, (512 << 20) / gbases)
     text = build_text(cfg, 0, scale)
     n = text.n_bases // 32 * 32
@@ -254,6 +254,8 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the text (quick runs only; invalid as a bench number)")
     ap.add_argument("--guides", type=int, default=0, help="override the number of guides")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the contract): one text of the configured size per rank; strong: ONE text sharded over the ranks by vs_shard_bounds")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -274,11 +276,17 @@ def main():
     from varscot_b200 import synth
     desc, gbases, nvar, ng, k, pam = cfg
     guides = synth.synth_guides(13, ng)
+    strong = args.scaling == "strong" and world > 1
     t_gen = time.perf_counter()
-    text = build_text(cfg, rank, args.scale)
+    text = build_text(cfg, 0 if strong else rank, args.scale)
     t_gen = time.perf_counter() - t_gen
     B = text.n_bases
     nw = text.n_words
+    # strong scaling: every rank holds the same text and owns one shard of its window starts (no collective anywhere)
+    shard_first, shard_words = 0, nw
+    if strong:
+        sb = V.shard_bounds(nw, world)
+        shard_first, shard_words = int(sb[rank]), int(sb[rank + 1] - sb[rank])
     text.pin()                                  # page-locked host buffers: what a caller of the C ABI would hand in
     ctx = V.ScanContext(local)
     peak_lop3 = peak_lds = None
@@ -286,7 +294,7 @@ def main():
         peak_lop3, peak_lds = ctx.measure_int_peaks()
 
     # ---- resident-text scan ----------------------------------------------------------------------
-    ctx.upload(text)
+    ctx.upload(text, shard_first, shard_words)
     import ctypes as C
     from varscot_b200 import _lib
     pinned = []
@@ -320,19 +328,20 @@ def main():
     n_hits = len(hits)
     ms_step = all_max(dev_ms / args.steps, world, local)
     wall_step = all_max(wall_ms / args.steps, world, local)
-    units = all_sum(float(ng) * B, world, local)          # guide·bp per step over all ranks
+    # guide·bp per step over all ranks: the shards of one text (strong) or one whole text per rank (weak)
+    units = float(ng) * B if strong else all_sum(float(ng) * B, world, local)
     value = units / (ms_step * 1e-3) / 1e9
 
     # ---- end to end: host buffers in, hits out, every step ------------------------------------------
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
-            ctx.scan_text(text, guides, k, pam=pam, out=hits_buf)
+            ctx.scan_text(text, guides, k, pam=pam, out=hits_buf, first_word=shard_first, n_words=shard_words)
         barrier(world, local)
         t0 = time.perf_counter()
         e_dev = 0.0
         for _ in range(args.steps):
-            h2, st2 = ctx.scan_text(text, guides, k, pam=pam, out=hits_buf)
+            h2, st2 = ctx.scan_text(text, guides, k, pam=pam, out=hits_buf, first_word=shard_first, n_words=shard_words)
             e_dev += st2.total_ms
         barrier(world, local)
         e_ms = all_max((time.perf_counter() - t0) * 1e3 / args.steps, world, local)
@@ -347,7 +356,8 @@ def main():
     blocks = st.n_blocks_fwd + st.n_blocks_rev
     score_s = score_ms / args.steps * 1e-3
     n_score_launch = st.score_launches
-    yard = C_ALG * ng * B / score_s                       # yardstick LOP3/s of the scoring launches of one step
+    B_local = min(B - shard_first * 32, shard_words * 32)     # bases whose window starts this rank owns
+    yard = C_ALG * ng * B_local / score_s                 # yardstick LOP3/s of the scoring launches of one step
     (lop_a, lds_a), (lop_b, lds_b) = score_ops(k)
     executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few warps that pass)
     lds = lds_a * blocks * ng / score_s
@@ -385,12 +395,13 @@ def main():
             "note": "yardstick = 4.0 LOP3 per guide*bp (dense scan, SURVEY.md 8d); PAM-first compaction scores ~1/8 of the windows per strand, so frac may exceed 1; frac_executed is the real alu-pipe load"}
     out = {
         "metric": "guide_Gbp_per_s", "value": value, "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
         "data": "synthetic",
         "config": {"workload": desc + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "guides": ng, "k": k, "extra_pam": pam,
                    "text_bases_per_gpu": B, "contigs_per_gpu": text.n_contigs, "chunks": int(st.n_chunks),
                    "l2": "inputs larger than L2 (packed text %.2f GB resident, candidate planes %.2f GB written+read per step)" % ((nw * 16) / 1e9, blocks * 192 / 1e9),
-                   "sharding": "one text shard per rank, no collective; hits merged on the host", "cpus_bound_per_rank": numa_cpus},
+                   "sharding": ("ONE text cut into %d word ranges by vs_shard_bounds, one per rank" % world) if strong else
+                               "one text shard per rank, no collective; hits merged on the host", "cpus_bound_per_rank": numa_cpus},
         "wall_ms_per_step": wall_step, "phase_ms": {"extract": extract_ms / args.steps, "score": score_ms / args.steps},
         "hits_per_step": n_hits, "candidates": int(st.n_cand_fwd + st.n_cand_rev), "gpu_launches": launches,
         "roofline": roof, "e2e": e2e, "clocks": clocks, "gen_s": t_gen,

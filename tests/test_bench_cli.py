@@ -1,0 +1,37 @@
+"""bench.py keeps its contract: one JSON line with the required keys, for both arms.  The GPU arm runs a tiny copy of the
+workload; the reference arm (CPU oracle) runs with a one-second budget."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def test_reference_arm_line():
+    env = dict(os.environ, VARSCOT_BENCH_BUDGET_S="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "1", "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "parity"} <= set(d)
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["scaling"] == "weak" and d["n_gpus"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert d["parity"]["diff"] == 0 and d["cpu_baseline"]["value"] > 0
