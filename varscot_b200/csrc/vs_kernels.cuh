@@ -128,33 +128,40 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
           uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r, uint64_t cap,
           unsigned long long *__restrict__ cnt)
 {
-    __shared__ uint2 s_hl[EX_MAX_WORDS + 2];
+    __shared__ __align__(16) uint2 s_hl[EX_MAX_WORDS + 2];   // bases {hi, lo} per word (+ halo)
     __shared__ uint32_t s_m[2][EX_MAX_WORDS + 1];      // candidate masks per strand
     __shared__ uint32_t s_p[2][EX_MAX_WORDS + 1];      // exclusive rank prefix per word (+ total at [nw])
-    __shared__ uint32_t s_lw[EX_MAX_WORDS + 1];
+    __shared__ __align__(16) uint2 s_mk[EX_MAX_WORDS + 2];   // window masks {iv, lw} per word
     __shared__ uint32_t wsum[2][EX_MAX_WORDS / EX_THREADS][EX_THREADS / 32];
     __shared__ unsigned long long base[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t w0 = w_begin + (uint64_t)blockIdx.x * tile_words;
     const uint32_t nw = (uint32_t)min((uint64_t)tile_words, w_end - w0);      // words of this tile
-    // phase 1a: all global loads of the tile are issued up front (up to 4 words of bases + masks per thread, 64-bit
-    // loads), staged in shared memory, and only then consumed — the first use no longer waits on a single load
-    constexpr int EX_ITERS = EX_MAX_WORDS / EX_THREADS;
-    uint2 ab[EX_ITERS], mk[EX_ITERS];
-    const uint2 *B2 = reinterpret_cast<const uint2 *>(B), *M2 = reinterpret_cast<const uint2 *>(M);
-#pragma unroll
-    for (int it = 0; it < EX_ITERS; ++it) {
-        const uint32_t i = it * EX_THREADS + tid;
-        ab[it] = make_uint2(0u, 0u); mk[it] = make_uint2(~0u, 0u);
-        if (i < nw) { ab[it] = __ldg(B2 + w0 + i); mk[it] = __ldg(M2 + w0 + i); }
-    }
-    if (tid == 0) s_hl[nw] = __ldg(B2 + w0 + nw);                       // B[w_end] is the halo / pad word, always readable
-#pragma unroll
-    for (int it = 0; it < EX_ITERS; ++it) {
-        const uint32_t i = it * EX_THREADS + tid;
-        if (i < nw) { s_hl[i] = ab[it]; s_lw[i] = mk[it].y; }
+    // phase 1a: the tile's bases (+ halo word) and window masks are staged into shared memory with cp.async (LDGSTS):
+    // coalesced 128-bit copies when the tile starts on a 16-byte boundary (always, except for odd test chunk sizes),
+    // 64-bit copies otherwise; nothing passes through registers and every copy of the tile is in flight at once.
+    {
+        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_hl), smk = (uint32_t)__cvta_generic_to_shared(s_mk);
+        const char *gb = reinterpret_cast<const char *>(B + w0), *gm = reinterpret_cast<const char *>(M + w0);
+        const uint32_t nb_bytes = (nw + 1) * 8u, nm_bytes = nw * 8u;        // B[w_end] is the halo / pad word, always readable
+        if (((w0 & 1) == 0)) {
+            for (uint32_t o = tid * 16u; o + 16u <= nb_bytes; o += EX_THREADS * 16u)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + o), "l"(gb + o));
+            for (uint32_t o = tid * 16u; o + 16u <= nm_bytes; o += EX_THREADS * 16u)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smk + o), "l"(gm + o));
+            if (tid == 0 && (nb_bytes & 8u)) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb + nb_bytes - 8u), "l"(gb + nb_bytes - 8u));
+            if (tid == 1 && (nm_bytes & 8u)) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smk + nm_bytes - 8u), "l"(gm + nm_bytes - 8u));
+        } else {
+            for (uint32_t o = tid * 8u; o < nb_bytes; o += EX_THREADS * 8u)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb + o), "l"(gb + o));
+            for (uint32_t o = tid * 8u; o < nm_bytes; o += EX_THREADS * 8u)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smk + o), "l"(gm + o));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    constexpr int EX_ITERS = EX_MAX_WORDS / EX_THREADS;
     // phase 1b: candidate masks and their rank prefix (word order: thread t owns words t, t+64, t+128, t+192)
     uint32_t cf[EX_ITERS], cr[EX_ITERS], xf[EX_ITERS], xr[EX_ITERS];
 #pragma unroll
@@ -162,8 +169,8 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
         const uint32_t i = it * EX_THREADS + tid;
         uint32_t fwd = 0, rev = 0;
         if (i < nw) {
-            const uint2 nx = s_hl[i + 1];
-            cand_masks(vs_bases{ab[it].x, ab[it].y}, vs_bases{nx.x, nx.y}, vs_masks{mk[it].x, mk[it].y}, pp, fwd, rev);
+            const uint2 cur = s_hl[i], nx = s_hl[i + 1], mk = s_mk[i];
+            cand_masks(vs_bases{cur.x, cur.y}, vs_bases{nx.x, nx.y}, vs_masks{mk.x, mk.y}, pp, fwd, rev);
             s_m[0][i] = fwd; s_m[1][i] = rev;
         }
         cf[it] = __popc(fwd); cr[it] = __popc(rev);
@@ -219,7 +226,7 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
         uint32_t m = sm[wcur];
         for (uint32_t skip = r0 - sp[wcur]; skip; --skip) m &= m - 1;     // drop the candidates of earlier blocks
         uint2 ha = s_hl[wcur], hb = s_hl[wcur + 1];
-        uint32_t lwm = s_lw[wcur];
+        uint32_t lwm = s_mk[wcur].y;
         uint32_t ah[32], al[32];
         uint32_t lastw = 0;
         uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
@@ -235,7 +242,7 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
                         ++wcur;
                         m = sm[wcur];
                         ha = hb; hb = s_hl[wcur + 1];
-                        lwm = s_lw[wcur];
+                        lwm = s_mk[wcur].y;
                     }
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
