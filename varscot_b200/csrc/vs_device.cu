@@ -87,8 +87,8 @@ extern "C" int vs_device_count(void)
     return n;
 }
 
-// k_score's dynamic shared memory (92 planes x 128 threads x 4 B = 46 KB) fits the default 48 KB limit, so no
-// cudaFuncSetAttribute is needed — and none of the nine k_score<K> variants is loaded before it is used.
+// k_score's dynamic shared memory (at most 92 planes x 128 threads x 4 B = 46 KB, for k = 8) fits the default 48 KB
+// limit, so no cudaFuncSetAttribute is needed — and none of the nine k_score<K> variants is loaded before it is used.
 static_assert(NPLANES * SCORE_THREADS * 4 <= 48 * 1024, "k_score needs cudaFuncAttributeMaxDynamicSharedMemorySize above 48 KB");
 
 extern "C" int vs_ctx_create(int device, vs_ctx **out)
@@ -107,9 +107,13 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
                                                   ", this build contains sm_100a code only");
     ctx = new vs_ctx();
     ctx->device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    // the scoring stream gets the highest priority, the (optional) concurrent-extraction stream the lowest: when both
+    // kernels are runnable the scoring CTAs are placed first and extraction fills the resources they leave free
+    int prio_lo = 0, prio_hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->exs, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->exs, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
         std::string m = std::string("vs_ctx_create: ") + cudaGetErrorString(e);
@@ -172,7 +176,7 @@ static void make_pam(int extra_pam, PamParams &pp)
 template <int K>
 static void launch_score(const ScoreArgs &a, cudaStream_t st)
 {
-    k_score<K><<<2 * a.ctas_per_strand, SCORE_THREADS, NPLANES * SCORE_THREADS * 4, st>>>(a);
+    k_score<K><<<2 * a.ctas_per_strand, SCORE_THREADS, score_smem_planes(K) * SCORE_THREADS * 4, st>>>(a);
 }
 
 static void dispatch_score(int k, const ScoreArgs &a, cudaStream_t st)
@@ -333,7 +337,7 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     S.n_chunks = n_chunks;
 
     // pattern tables per guide chunk: [strand][PAT_CHUNK][PAT_STRIDE] (layout: see c_pat in vs_kernels.cuh), staged in pinned memory
-    const uint64_t pat_chunk_words = (uint64_t)2 * PAT_CHUNK * PAT_STRIDE;
+    const uint64_t pat_chunk_words = (uint64_t)PAT_TABLE_WORDS;
     const uint64_t pat_words = (uint64_t)g_chunks * pat_chunk_words;
     if (pat_words > ctx->pat_cap) {
         CK(cudaStreamSynchronize(st));
@@ -350,9 +354,9 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
             const uint8_t *gd = guides + (size_t)g * VS_GLEN;
             // slot order: informative positions first, the PAM dinucleotide last (forward 0..22; reverse 2..22, 0, 1)
             for (int j = 0; j < VS_GLEN; ++j) {
-                const int i = s ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j;
+                const int i = slot_position(s, j);
                 const int b = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];      // reverse pass scores revcomp(guide), bidir_mapping.cpp:293
-                dst[j] = (uint32_t)(4 * i + b) * SCORE_THREADS * 4u;
+                dst[j] = pat_slot(k, s, j, b);
             }
         }
     // counters
@@ -433,9 +437,10 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
         return VS_OK;
     };
 
-    // Optional: run the extraction of chunk c+1 on its own stream, concurrently with the scoring of chunk c.  Measured on
-    // B200 (config 3): no gain (13.7 vs 13.8 ms/step) — both kernels fight for the same issue slots — so it is off by
-    // default, which also keeps the per-phase event times additive.
+    // Optional: run the extraction of chunk c+1 on its own (low-priority) stream, concurrently with the scoring of chunk c.
+    // Measured on B200 (config 3) with 3, 4 and 5 resident k_score CTAs per SM and room left for k_extract CTAs: no gain
+    // (the step takes the sum of the two kernels either way), so it is off by default, which also keeps the per-phase
+    // event times additive.
     const bool overlap_extract = getenv("VARSCOT_OVERLAP_EXTRACT") && atoi(getenv("VARSCOT_OVERLAP_EXTRACT")) != 0;
     cudaStream_t es = overlap_extract ? ctx->exs : st;
     uint64_t found = 0;

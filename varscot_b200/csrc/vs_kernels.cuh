@@ -18,27 +18,33 @@
 // the bit-sliced form costs ~1.1 ALU ops per (window, guide) pair, below one op per output element).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "../../include/varscot_scan.h"
 
 namespace vs {
 
 constexpr int BLK_WORDS    = 48;                  // words per candidate block
+constexpr int BLK_GROUP    = 32;                  // blocks per layout group: word w of block b sits at plane_index(b, w), so that
+                                                  // the 32 lanes of a warp (32 consecutive blocks) touch 128 contiguous bytes per word
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
 #ifndef VS_SCORE_THREADS
 #define VS_SCORE_THREADS 128          // measured on B200 (score ms, cfg3 x 0.25 / cfg4 x 0.1): 96 thr 2.11 / 12.7, 128 thr 2.15 / 11.0, 256 thr 2.20 / 11.2
 #endif
-#ifndef VS_SCORE_MINBLOCKS
-#define VS_SCORE_MINBLOCKS 4
-#endif
 constexpr int SCORE_THREADS = VS_SCORE_THREADS;
-constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block
+constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block (k = 8: all in shared memory)
 constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 slot offsets + pad, 16-byte aligned)
 #ifndef VS_PAT_CHUNK
 #define VS_PAT_CHUNK 256
 #endif
 constexpr int PAT_CHUNK    = VS_PAT_CHUNK;        // guides per k_score launch: 2 strands x 256 x 96 B = 48 KB of constant memory
+constexpr int PAT_TABLE_WORDS = 2 * PAT_CHUNK * PAT_STRIDE;             // words of c_pat = words per guide chunk
+
+__host__ __device__ __forceinline__ uint64_t plane_index(uint64_t blk, int w)
+{
+    return (blk / BLK_GROUP) * (uint64_t)(BLK_WORDS * BLK_GROUP) + (uint64_t)w * BLK_GROUP + (blk % BLK_GROUP);
+}
 
 struct PamParams {
     int n;            // number of forward dinucleotides (2 or 3)
@@ -117,7 +123,7 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 // Block ranges are claimed with one atomicAdd per strand per tile on cnt[2], cnt[3] (layout order is not
 // deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written for that tile; k_score
 // then skips the whole chunk and the host, which reads the counters back, regrows the stores and redoes the chunk.
-// Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask.
+// Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; word w of block b at plane_index(b, w).
 #ifndef VS_EX_MINBLOCKS
 #define VS_EX_MINBLOCKS 10
 #endif
@@ -255,17 +261,17 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
             }
             ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
         }
-        uint4 *pl_out = reinterpret_cast<uint4 *>((s ? planes_r : planes_f) + blk * BLK_WORDS);
+        // word w of the block goes to plane_index(blk, w): consecutive lanes hold consecutive blocks, so every store
+        // instruction of the warp writes 128 contiguous bytes
+        uint32_t *pl_out = (s ? planes_r : planes_f) + plane_index(blk, 0);
         transpose32(ah);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) pl_out[i] = make_uint4(ah[4 * i], ah[4 * i + 1], ah[4 * i + 2], ah[4 * i + 3]);
+        for (int i = 0; i < VS_GLEN; ++i) pl_out[i * BLK_GROUP] = ah[i];
         transpose32(al);
-        // words 20..47: hi_20, hi_21, hi_22, lo_0 .. lo_22, last, valid
-        pl_out[5] = make_uint4(ah[20], ah[21], ah[22], al[0]);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) pl_out[6 + i] = make_uint4(al[4 * i + 1], al[4 * i + 2], al[4 * i + 3], al[4 * i + 4]);
-        const uint32_t validw = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
-        pl_out[11] = make_uint4(al[21], al[22], lastw, validw);
+        for (int i = 0; i < VS_GLEN; ++i) pl_out[(VS_GLEN + i) * BLK_GROUP] = al[i];
+        pl_out[BLK_LAST * BLK_GROUP] = lastw;
+        pl_out[BLK_VALID * BLK_GROUP] = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
     }
 }
 
@@ -360,11 +366,52 @@ __device__ __forceinline__ uint32_t le_k(const uint32_t (&b)[5])
 // positions fewer than ~12 % of the warps (1024 candidates) still hold a window with <= K mismatches, so the
 // remaining slots (the PAM positions come last in the slot order) are loaded only for those.
 __host__ __device__ constexpr int stage_a_slots(int k) { return k >= 8 ? VS_GLEN : 7 + 2 * k; }
+// Shared-memory planes per block: the 4 expanded "mismatch if the pattern base is b" planes of every stage-A position
+// ([base, base + PA) with base = 0 forward, 2 reverse, whose slot order is 2..22, 0, 1), then the two RAW planes {hi, lo}
+// of every stage-B slot — the few warps that reach stage B pay 2 LDS + 2 LOP3 per slot instead of 1 LDS, and the block
+// needs 4 PA + 2 PB planes instead of 92 (k = 6: 84), which lets one more CTA reside per SM.  k = 8 is single-stage.
+__host__ __device__ constexpr int score_smem_planes(int k) { return 4 * stage_a_slots(k) + 2 * (VS_GLEN - stage_a_slots(k)); }
+__host__ __device__ constexpr int score_pos_base(int k, int strand) { return (k < 8 && strand) ? 2 : 0; }
+__host__ __device__ constexpr int score_min_blocks(int k)
+{
+    // resident CTAs per SM that fit 227 KB of shared memory (1 KB reserved per CTA) and 64 K registers at <= 72 per thread
+    const int by_smem = (227 * 1024) / (score_smem_planes(k) * SCORE_THREADS * 4 + 1024);
+    const int by_regs = 65536 / (72 * SCORE_THREADS);
+#ifdef VS_SCORE_MINBLOCKS
+    return VS_SCORE_MINBLOCKS;          // tuning override: only steers the register allocation
+#endif
+    const int m = by_smem < by_regs ? by_smem : by_regs;
+    return m < 1 ? 1 : (m > 8 ? 8 : m);
+}
 
-// Pattern table in constant memory, per strand and guide: PAT_STRIDE words; slot j holds the byte offset
-// (plane index * SCORE_THREADS * 4) of the shared-memory plane selected by the pattern base at position
-// order[strand][j].  The host orders the slots informative-first: forward 0..22, reverse 2..22,0,1.
-__constant__ uint32_t c_pat[2 * PAT_CHUNK * PAT_STRIDE];
+// Pattern table in constant memory, per strand and guide: PAT_STRIDE words.  The host orders the slots
+// informative-first: forward positions 0..22, reverse 2..22,0,1.  A stage-A slot j < PA(k) holds the byte offset
+// (plane index * SCORE_THREADS * 4, plane index = 4 * (position - base) + pattern base) of the shared-memory plane it
+// selects; a stage-B slot holds the byte offset of its raw hi plane (lo follows at + SCORE_THREADS * 4) | pattern base << 16
+// (see pat_slot()).
+__constant__ uint32_t c_pat[PAT_TABLE_WORDS];
+
+// position scored by slot j of a strand's slot order
+__host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
+// table entry of slot j for pattern base b (0..3)
+__host__ __device__ constexpr uint32_t pat_slot(int k, int strand, int j, int b)
+{
+    const int i = slot_position(strand, j);
+    const int pa = stage_a_slots(k);
+    return j < pa ? (uint32_t)(4 * (i - score_pos_base(k, strand)) + b) * SCORE_THREADS * 4u
+                  : ((uint32_t)(4 * pa + 2 * (j - pa)) * SCORE_THREADS * 4u) | ((uint32_t)b << 16);
+}
+// inverse of pat_slot: position and pattern base of slot j
+__device__ __forceinline__ void pat_decode(int k, int strand, int j, uint32_t e, int &i, int &b)
+{
+    i = slot_position(strand, j);
+    b = j < stage_a_slots(k) ? (int)((e / (SCORE_THREADS * 4u)) & 3u) : (int)(e >> 16);
+}
+// "mismatch against pattern base b" plane from the two planes of a position (b warp-uniform)
+__device__ __forceinline__ uint32_t mismatch_plane(uint32_t h, uint32_t l, uint32_t b)
+{
+    return (h ^ ((b & 2u) ? ~0u : 0u)) | (l ^ ((b & 1u) ? ~0u : 0u));
+}
 
 struct ScoreArgs {
     const uint32_t *planes[2];  // per strand: [n_blocks][48]
@@ -382,10 +429,12 @@ struct ScoreArgs {
 
 // Slow path (rare): for every lane that passed the threshold read its exact count out of the bit-sliced counter,
 // apply R4 to last-window candidates (H over positions 11..22 must be <= floor(K/2), bidir_mapping.cpp:48-53) and
-// append the hit.  Only last-window lanes re-read planes (they need the second-half count); the slot offsets for that
-// come from the GLOBAL copy of the pattern table so that nothing of the hot loop's uniform-register state stays live.
-__device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, uint32_t le, const uint32_t (&cnt)[5], uint32_t lastm,
-                                           uint32_t k_half, const uint32_t *pos, uint32_t info, vs_hit *hits,
+// append the hit.  Only last-window lanes re-read planes (they need the second-half count) — from the block's global
+// copy, with the pattern decoded from the GLOBAL copy of the table so that nothing of the hot loop's uniform-register
+// state stays live.
+template <int K>
+__device__ __forceinline__ void score_hits(const uint32_t *gsrc, const uint32_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5],
+                                           uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
                                            unsigned long long *n_hits, uint64_t hit_cap)
 {
     while (le != 0) {
@@ -396,12 +445,15 @@ __device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, 
         if ((lastm >> c) & 1u) {                                             // R4: last window of its contig
             uint32_t h2 = 0;
 #pragma unroll 1
-            for (int i = 0; i < VS_GLEN; ++i) {
-                const uint32_t off = __ldg(po + i);
-                if (off >= 11u * 4u * SCORE_THREADS * 4u)                    // the slot scores a position >= 11
-                    h2 += (*reinterpret_cast<const uint32_t *>(myb + off) >> c) & 1u;
+            for (int j = 0; j < VS_GLEN; ++j) {
+                int i, b;
+                pat_decode(K, strand, j, __ldg(po + j), i, b);
+                if (i >= 11) {
+                    const uint32_t code = (((__ldg(gsrc + i * BLK_GROUP) >> c) & 1u) << 1) | ((__ldg(gsrc + (VS_GLEN + i) * BLK_GROUP) >> c) & 1u);
+                    h2 += code != (uint32_t)b;
+                }
             }
-            if (h2 > k_half) continue;
+            if (h2 > (uint32_t)(K / 2)) continue;
         }
         const unsigned long long idx = atomicAdd(n_hits, 1ull);
         if (idx < hit_cap) {
@@ -414,10 +466,10 @@ __device__ __forceinline__ void score_hits(const char *myb, const uint32_t *po, 
 }
 
 template <int K>
-__global__ void __launch_bounds__(SCORE_THREADS, VS_SCORE_MINBLOCKS)
+__global__ void __launch_bounds__(SCORE_THREADS, score_min_blocks(K))
 k_score(ScoreArgs a)
 {
-    extern __shared__ uint32_t sm[];     // [NPLANES][SCORE_THREADS]
+    extern __shared__ uint32_t sm[];     // [score_smem_planes(K)][SCORE_THREADS]
     constexpr int PA = stage_a_slots(K), PB = VS_GLEN - PA;
     const int tid = threadIdx.x;
     const uint32_t strand = blockIdx.x >= a.ctas_per_strand;            // forward CTAs first, then reverse
@@ -425,29 +477,42 @@ k_score(ScoreArgs a)
     const uint64_t n_blocks = strand ? a.n_blocks_ptr[1] : a.n_blocks_ptr[0];
     if (max(a.n_blocks_ptr[0], a.n_blocks_ptr[1]) > a.cap || (uint64_t)cta * SCORE_THREADS >= n_blocks) return;
     const uint64_t blk = (uint64_t)cta * SCORE_THREADS + tid;
+    const bool live = blk < n_blocks;
+    // threads past the last block score block 0 with every lane invalid
+    const uint32_t *gsrc = (strand ? a.planes[1] : a.planes[0]) + plane_index(live ? blk : 0, 0);      // word w at gsrc[w * BLK_GROUP]
     uint32_t *my = sm + tid;
     uint32_t lastm = 0;
-    if (blk < n_blocks) {
-        const uint4 *src = reinterpret_cast<const uint4 *>((strand ? a.planes[1] : a.planes[0]) + blk * BLK_WORDS);
+    {
         uint32_t v[BLK_WORDS];
 #pragma unroll
-        for (int i = 0; i < BLK_WORDS / 4; ++i) {
-            uint4 t = __ldg(src + i);
-            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-        }
-        lastm = v[BLK_LAST];
-        const uint32_t inv = ~v[BLK_VALID];          // lanes past the end of a partial block mismatch everywhere
+        for (int i = 0; i < BLK_WORDS; ++i) v[i] = __ldg(gsrc + i * BLK_GROUP);       // coalesced: 128 B per warp and word
+        lastm = live ? v[BLK_LAST] : 0u;
+        const uint32_t inv = live ? ~v[BLK_VALID] : ~0u;       // lanes past the end of a partial block mismatch everywhere
+        auto expand = [&](auto base_c) {
+            constexpr int BASE = decltype(base_c)::value;
 #pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) {
-            const uint32_t h = v[i], l = v[VS_GLEN + i];
-            my[(4 * i + 0) * SCORE_THREADS] = (h | l) | inv;      // mismatch if guide base is A (00)
-            my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | inv;     // C (01)
-            my[(4 * i + 2) * SCORE_THREADS] = (~h | l) | inv;     // G (10)
-            my[(4 * i + 3) * SCORE_THREADS] = (~h | ~l) | inv;    // T (11)
-        }
-    } else {
+            for (int i = 0; i < PA; ++i) {
+                const uint32_t h = v[BASE + i], l = v[VS_GLEN + BASE + i];
+                my[(4 * i + 0) * SCORE_THREADS] = (h | l) | inv;      // mismatch if the pattern base is A (00)
+                my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | inv;     // C (01)
+                my[(4 * i + 2) * SCORE_THREADS] = (~h | l) | inv;     // G (10)
+                my[(4 * i + 3) * SCORE_THREADS] = (~h | ~l) | inv;    // T (11)
+            }
+            // raw planes of the stage-B slots (an invalid lane already mismatches in all PA > K stage-A slots)
 #pragma unroll
-        for (int i = 0; i < NPLANES; ++i) my[i * SCORE_THREADS] = ~0u;
+            for (int i = 0; i < PB; ++i) {
+                constexpr int S = BASE ? 1 : 0;
+                const int p = slot_position(S, PA + i);
+                my[(4 * PA + 2 * i) * SCORE_THREADS] = v[p];
+                my[(4 * PA + 2 * i + 1) * SCORE_THREADS] = v[VS_GLEN + p];
+            }
+        };
+        if constexpr (score_pos_base(K, 1) != 0) {
+            if (strand) expand(std::integral_constant<int, score_pos_base(K, 1)>{});
+            else expand(std::integral_constant<int, 0>{});
+        } else {
+            expand(std::integral_constant<int, 0>{});
+        }
     }
     // each thread reads back only what it wrote: no barrier needed
     const char *myb = reinterpret_cast<const char *>(my);
@@ -456,6 +521,9 @@ k_score(ScoreArgs a)
 
     // Software pipeline over the guides: the stage-A planes of guide g+1 are loaded (LDS) before guide g is counted,
     // so the shared-memory latency and the adder tree of consecutive guides overlap inside one warp.
+    // (Tried and measured slower on B200: sorting the guides by their bases at slots 0/1 and keeping those two planes in
+    // registers per group — as a nested loop ptxas 12.9 drops the uniform-register slot offsets, as a flagged reload the
+    // extra uniform instructions cost more than the two shared-memory wavefronts they save.)
     auto load_a = [&](uint32_t g, uint32_t (&m)[PA]) {
         const uint32_t *po = pat0 + g * PAT_STRIDE;
 #pragma unroll
@@ -466,23 +534,27 @@ k_score(ScoreArgs a)
         uint32_t ca[5];
         popcount_planes<PA, false>(ma, zero5, ca);
         uint32_t le = le_k<K>(ca);
-        // warp-uniform early out: if no lane of the warp can still be within K, the remaining slots are never loaded.
+        // warp-uniform early out: if no lane of the warp can still be within K, the remaining slots are never scored.
         // (A divergent `if (le)` here makes ptxas 12.9 crash on the uniform-register loads of stage B.)
         if (PB == 0 ? (le != 0) : __any_sync(0xffffffffu, le != 0)) {
             if constexpr (PB > 0) {
-                // stage B: the remaining slots, added onto stage A's count
+                // stage B: the remaining slots, from their raw planes, added onto stage A's count
                 uint32_t mb[PB], cb[5];
 #pragma unroll
-                for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(myb + po[PA + i]);
+                for (int i = 0; i < PB; ++i) {
+                    const uint32_t e = po[PA + i];
+                    const char *q = myb + (e & 0xFFFFu);
+                    mb[i] = mismatch_plane(*reinterpret_cast<const uint32_t *>(q), *reinterpret_cast<const uint32_t *>(q + SCORE_THREADS * 4), e >> 16);
+                }
                 popcount_planes<PB, true>(mb, ca, cb);
                 le = le_k<K>(cb);
 #pragma unroll
                 for (int w = 0; w < 5; ++w) ca[w] = cb[w];
             }
             if (le != 0)
-                score_hits(myb, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, le, ca, lastm, (uint32_t)(K / 2),
-                           (strand ? a.pos[1] : a.pos[0]) + blk * 32, ((a.guide_base + g) << 8) | (strand << 7),
-                           a.hits, a.n_hits, a.hit_cap);
+                score_hits<K>(gsrc, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, (int)strand, le, ca, lastm,
+                              (strand ? a.pos[1] : a.pos[0]) + blk * 32, ((a.guide_base + g) << 8) | (strand << 7),
+                              a.hits, a.n_hits, a.hit_cap);
         }
     };
     uint32_t m0[PA], m1[PA];
