@@ -134,10 +134,10 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
           uint32_t *__restrict__ planes_r, uint32_t *__restrict__ pos_r, uint64_t cap,
           unsigned long long *__restrict__ cnt)
 {
-    __shared__ __align__(16) uint2 s_hl[EX_MAX_WORDS + 2];   // bases {hi, lo} per word (+ halo)
+    __shared__ __align__(16) uint2 s_hl[EX_MAX_WORDS + 2];   // bases {hi, lo} per word (+ halo, + one word read under the sentinel)
     __shared__ uint32_t s_m[2][EX_MAX_WORDS + 1];      // candidate masks per strand
     __shared__ uint32_t s_p[2][EX_MAX_WORDS + 1];      // exclusive rank prefix per word (+ total at [nw])
-    __shared__ __align__(16) uint2 s_mk[EX_MAX_WORDS + 2];   // window masks {iv, lw} per word
+    __shared__ __align__(16) uint2 s_mk[EX_MAX_WORDS + 2];   // window masks {iv, lw} per word (+ one word read under the sentinel)
     __shared__ uint32_t wsum[2][EX_MAX_WORDS / EX_THREADS][EX_THREADS / 32];
     __shared__ unsigned long long base[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -205,7 +205,7 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     const uint32_t nbf = (nf + 31) >> 5, nbr = (nr + 31) >> 5;
     if (tid == 0) {
         s_p[0][nw] = nf; s_p[1][nw] = nr;
-        s_m[0][nw] = 0; s_m[1][nw] = 0;
+        s_m[0][nw] = ~0u; s_m[1][nw] = ~0u;              // sentinel: ends the mask walk of a partial block (see phase 2)
         base[0] = atomicAdd(&cnt[2], (unsigned long long)nbf);
         base[1] = atomicAdd(&cnt[3], (unsigned long long)nbr);
         if (nf) atomicAdd(&cnt[0], (unsigned long long)nf);
@@ -236,28 +236,27 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
         uint32_t ah[32], al[32];
         uint32_t lastw = 0;
         uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
+        // The walk never tests "is this candidate past the end of a partial block": the mask array ends in an all-ones
+        // sentinel word (s_m[.][nw], set above), so the lanes past cntc gather 32 - cntc <= 31 meaningless windows from
+        // the halo / padding words and stop there; k_score ORs the complement of the valid mask into every plane.
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
             uint32_t pp4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = c4 * 4 + u;
-                uint32_t hw = 0, lw = 0, ps = 0xFFFFFFFFu;
-                if ((uint32_t)c < cntc) {
-                    while (m == 0) {                       // next word with candidates (the tile has >= cntc left)
-                        ++wcur;
-                        m = sm[wcur];
-                        ha = hb; hb = s_hl[wcur + 1];
-                        lwm = s_mk[wcur].y;
-                    }
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    hw = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
-                    lw = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
-                    lastw |= ((lwm >> b) & 1u) << c;
-                    ps = gbase + wcur * 32 + b;
+                while (m == 0) {                           // next word with candidates
+                    ++wcur;
+                    m = sm[wcur];
+                    ha = hb; hb = s_hl[wcur + 1];
+                    lwm = s_mk[wcur].y;
                 }
-                ah[c] = hw; al[c] = lw; pp4[u] = ps;
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                ah[c] = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
+                al[c] = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
+                lastw |= ((lwm >> b) & 1u) << c;
+                pp4[u] = gbase + wcur * 32 + b;
             }
             ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
         }
@@ -523,7 +522,8 @@ k_score(ScoreArgs a)
     // so the shared-memory latency and the adder tree of consecutive guides overlap inside one warp.
     // (Tried and measured slower on B200: sorting the guides by their bases at slots 0/1 and keeping those two planes in
     // registers per group — as a nested loop ptxas 12.9 drops the uniform-register slot offsets, as a flagged reload the
-    // extra uniform instructions cost more than the two shared-memory wavefronts they save.)
+    // extra uniform instructions cost more than the two shared-memory wavefronts they save; three guides in flight
+    // instead of two: +1 %.)
     auto load_a = [&](uint32_t g, uint32_t (&m)[PA]) {
         const uint32_t *po = pat0 + g * PAT_STRIDE;
 #pragma unroll
@@ -557,9 +557,9 @@ k_score(ScoreArgs a)
                               a.hits, a.n_hits, a.hit_cap);
         }
     };
-    uint32_t m0[PA], m1[PA];
     const uint32_t n_pat = a.n_pat;
     if (n_pat == 0) return;
+    uint32_t m0[PA], m1[PA];
     load_a(0, m0);
     uint32_t g = 0;
     for (; g + 1 < n_pat; g += 2) {
