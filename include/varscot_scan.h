@@ -10,7 +10,8 @@
  * Entry point                      replaces (reference file:line)
  * -------------------------------  -----------------------------------------------------------------
  * vs_packer_* / vs_pack_text /     bidir_index.cpp:36-47  readRecords -> Dna5 StringSet -> indexCreate
- * vs_masks_from_planes / _sparse
+ * vs_masks_from_planes / _sparse /
+ * vs_mask_source_build
  * vs_text_save / vs_text_load      bidir_index.cpp:47 save(index, path); bidir_mapping.cpp:268 open(index, path)
  * vs_ctx_create / vs_text_upload   bidir_mapping.cpp:268  index resident in RAM -> packed text resident in HBM
  * vs_scan / vs_scan_text           bidir_mapping.cpp:285-295 omp-parallel loop over guides calling
@@ -64,6 +65,22 @@ typedef struct { uint32_t hi, lo; } vs_bases;
 typedef struct { uint32_t iv, lw; } vs_masks;
 typedef struct { uint32_t word, iv, lw; } vs_mask_entry;
 
+/* ---- compact mask source (optional) ---------------------------------------------------------
+ * The window masks are a function of two bit planes (one bit per base, n_words + 1 words each): the N plane `nm`
+ * (base is not A/C/G/T; the padding after the last base reads as N) and the contig-end plane `em` (base is the last
+ * of its contig) — see vs_masks_from_planes().  A view that carries them in the compact form below lets the device
+ * compute the masks itself, so an upload moves only the planes: N runs of a genome collapse to a few runs, and a
+ * swarm of short contigs (variant segments) costs 4 B per word (`em`) instead of 8 B (masks).
+ *   run   {word, count, value}: words [word, word + count) of the plane all equal `value` (non-zero)
+ *   nm_runs : every non-zero word of nm, in ascending order
+ *   em      : the dense plane; read only for the blocks flagged in em_dense
+ *   em_dense: one byte per block of VS_EM_BLOCK words; 1 = the block's em words travel dense, 0 = they are listed in em_runs
+ *   em_runs : every non-zero word of em that lies in a block with em_dense == 0, ascending
+ * A view carries the source iff em and em_dense are set (nm_runs / em_runs may be NULL when their counts are 0);
+ * otherwise uploads use masks / sparse. */
+#define VS_EM_BLOCK 4096
+typedef struct { uint32_t word, count, value; } vs_plane_run;
+
 typedef struct {
     uint64_t n_bases;
     uint64_t n_words;
@@ -74,7 +91,25 @@ typedef struct {
     const vs_masks      *masks;        /* n_words */
     const vs_mask_entry *sparse;       /* n_sparse entries, or NULL */
     uint64_t n_sparse;
+    /* compact mask source, or all NULL / 0 */
+    const uint32_t      *em;           /* n_words + 1 */
+    const uint8_t       *em_dense;     /* ceil((n_words + 1) / VS_EM_BLOCK) */
+    const vs_plane_run  *nm_runs;
+    const vs_plane_run  *em_runs;
+    uint64_t n_nm_runs, n_em_runs;
 } vs_text_view;
+
+/* Build the compact mask source from the two planes (n_words + 1 words each).  The members of *out are malloc'd;
+ * release them with vs_mask_source_free.  out->em is NOT copied: it aliases the caller's plane. */
+typedef struct {
+    const uint32_t *em;
+    uint8_t        *em_dense;
+    vs_plane_run   *nm_runs;
+    vs_plane_run   *em_runs;
+    uint64_t n_nm_runs, n_em_runs, n_em_blocks;
+} vs_mask_source;
+int  vs_mask_source_build(const uint32_t *nm, const uint32_t *em, uint64_t n_words, vs_mask_source *out);
+void vs_mask_source_free(vs_mask_source *s);
 
 typedef struct vs_packer vs_packer;
 vs_packer *vs_packer_new(void);
@@ -89,6 +124,9 @@ int        vs_packer_finish(vs_packer *p, vs_text_view *out);
 /* one-shot: ASCII text of all contigs concatenated + n_contigs+1 offsets -> bases[ceil(n/32)+1], masks[ceil(n/32)] */
 int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
                  vs_bases *out_bases, vs_masks *out_masks);
+/* the same, returning the N plane and the contig-end plane (n_words + 1 words each) instead of the masks */
+int vs_pack_text_planes(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
+                        vs_bases *out_bases, uint32_t *out_nm, uint32_t *out_em);
 /* window masks from an N plane and a contig-end plane (both n_words + 1 words, the extra word is read as padding) */
 int vs_masks_from_planes(const uint32_t *nm, const uint32_t *em, uint64_t n_words, vs_masks *out);
 /* sparse form of a mask array: malloc'd list of the non-zero words (release with vs_free) */

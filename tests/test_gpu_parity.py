@@ -20,7 +20,7 @@ def oracle_rows(ascii_bytes, offsets, guides, k, pam=None):
     return r.rows()
 
 
-def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True, chunk_words=None, streamed=False, use_sparse=True):
+def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True, chunk_words=None, streamed=False, use_sparse=True, use_source=True):
     import varscot_b200 as V
     text = V.PackedText.from_ascii(ascii_bytes, offsets)
     parts = []
@@ -34,9 +34,9 @@ def gpu_rows(ascii_bytes, offsets, guides, k, pam=None, shards=1, with_md=True, 
                 ctx.set_chunk_words(chunk_words)
             if streamed:
                 hits, _ = ctx.scan_text(text, guides, k, pam=pam, first_word=bounds[i], n_words=bounds[i + 1] - bounds[i], cap=1 << 12,
-                                        use_sparse=use_sparse)
+                                        use_sparse=use_sparse, use_source=use_source)
             else:
-                ctx.upload(text, bounds[i], bounds[i + 1] - bounds[i], use_sparse=use_sparse)
+                ctx.upload(text, bounds[i], bounds[i + 1] - bounds[i], use_sparse=use_sparse, use_source=use_source)
                 hits, _ = ctx.scan(guides, k, pam=pam, cap=1 << 12)
             parts.append(hits.copy())
     hits = np.concatenate(parts) if parts else np.zeros(0, V.HIT_DT)
@@ -157,13 +157,39 @@ def test_sharded_text_equals_whole(shards):
     assert_same(case, shards=shards)
 
 
+@pytest.mark.parametrize("use_source", [True, False])
 @pytest.mark.parametrize("chunk_words,streamed,use_sparse", [(64, False, True), (64, True, True), (1000, True, False), (7, True, True),
                                                              (256, False, False), (1 << 22, True, True)])
-def test_chunked_and_streamed_scan(chunk_words, streamed, use_sparse):
-    """Pipeline chunks smaller than the text: chunk borders (halo word), per-chunk counters, dense and sparse mask upload."""
+def test_chunked_and_streamed_scan(chunk_words, streamed, use_sparse, use_source):
+    """Pipeline chunks smaller than the text: chunk borders (halo word), per-chunk counters; masks uploaded dense, sparse, or
+    computed on the device from the compact mask source (N-plane runs + contig-end plane)."""
     case = make_case(seed=61, contig_lens=[70000, 45, 45, 45, 0, 23, 40000], n_guides=9, k=6, pam="AG")
-    assert_same(case, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse)
-    assert_same(case, shards=3, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse)
+    assert_same(case, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse, use_source=use_source)
+    assert_same(case, shards=3, chunk_words=chunk_words, streamed=streamed, use_sparse=use_sparse, use_source=use_source)
+
+
+def test_mask_source_dense_blocks_and_skipped_n_runs():
+    """A contig-end plane with dense blocks (a swarm of 45-base contigs), N runs long enough for their bases to be skipped by
+    the upload (>= 16384 words), and a chunk size that cuts through both: device-computed masks give the oracle's records."""
+    rng = np.random.default_rng(77)
+    lens = [600_000] + [45] * 6000 + [23, 22, 0, 46] + [30_000]
+    asc = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), sum(lens)).tobytes())
+    asc[20_000:20_000 + 540_000] = b"N" * 540_000          # 16875 words of N inside the first contig
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    # exact forward-strand sites: inside contigs, on the last window of a 45-mer (R4), and — never to be reported — across
+    # contig borders and reaching into the N run
+    sites = (100, 600_010, 601_045, 870_000, 899_000, 600_000 + 45 * 20 + 22, 600_000 + 45 * 10 - 10, 600_000 + 45 * 3000 - 22, 19_990)
+    for p in sites:
+        asc[p + 21:p + 23] = b"GG"
+    import varscot_b200 as V
+    guides = V.guide_codes([bytes(asc[p:p + 23]) for p in sites])
+    case = type("Case", (), dict(ascii=bytes(asc), offsets=off, guides=guides, k=5, pam=None))
+    text = V.PackedText.from_ascii(case.ascii, off)
+    assert text.em_dense.sum() > 0 and text.nm_runs["count"].max() >= 16384
+    n = assert_same(case, chunk_words=5000, streamed=True)
+    assert n >= 6
+    assert_same(case, chunk_words=1 << 20, streamed=False)
+    assert_same(case, shards=2, chunk_words=4096, streamed=True, use_source=False)
 
 
 def test_streamed_scan_leaves_text_resident():

@@ -109,6 +109,67 @@ def test_streaming_packer_and_fasta_quirks(tmp_path):
     assert c.bases.tobytes() == b.bases.tobytes() and c.masks.tobytes() == b.masks.tobytes() and c.sparse.tobytes() == b.sparse.tobytes()
 
 
+def _expand_runs(runs, n):
+    out = np.zeros(n, dtype=np.uint32)
+    for w, c, v in zip(runs["word"].tolist(), runs["count"].tolist(), runs["value"].tolist()):
+        assert v != 0 and c > 0 and (out[w:w + c] == 0).all()
+        out[w:w + c] = v
+    return out
+
+
+def test_mask_source_reproduces_the_planes():
+    """vs_mask_source_build: N-plane runs + contig-end plane (dense blocks / runs elsewhere) expand to the planes they came from."""
+    rng = np.random.default_rng(5)
+    nw = 3 * 4096 + 100                       # four blocks of the contig-end plane, the last one partial
+    nm = np.zeros(nw + 1, dtype=np.uint32)
+    nm[10:5000] = 0xFFFFFFFF                  # one long run across a block border
+    nm[5000] = 0x0000FFFF
+    nm[9000:9003] = [1, 1, 2]                 # equal neighbours merge, a different value starts a new run
+    nm[nw] = 0xFFFFFFFF
+    em = np.zeros(nw + 1, dtype=np.uint32)
+    em[17] = 1 << 5                           # block 0: sparse
+    em[4096:8192] = rng.integers(1, 1 << 32, 4096, dtype=np.uint64).astype(np.uint32)       # block 1: dense
+    em[8192:8192 + 1300:1] = 7                # block 2: one run of 1300 equal words stays sparse
+    em[12288 + 3] = 1 << 31                   # block 3 (partial): sparse
+    t = V.PackedText.from_planes(np.zeros(nw + 1, np.uint32), np.zeros(nw + 1, np.uint32), nm, em, np.array([0, nw * 32], np.uint64), nw * 32)
+    assert t.has_source and t.em.tolist() == em.tolist()
+    assert t.em_dense.tolist() == [0, 1, 0, 0]
+    assert _expand_runs(t.nm_runs, nw + 1).tolist() == nm.tolist()
+    assert len(t.nm_runs) == 5 and t.nm_runs["count"].tolist() == [4990, 1, 2, 1, 1]
+    sparse_part = em.copy(); sparse_part[4096:8192] = 0
+    assert _expand_runs(t.em_runs, nw + 1).tolist() == sparse_part.tolist()
+    assert len(t.em_runs) == 3
+    # the streaming packer builds the same source as the one-shot path
+    lens = [700, 0, 45, 23, 5000]
+    asc = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), sum(lens), p=[.24, .24, .24, .24, .04]))
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    a = V.PackedText.from_ascii(asc, off)
+    assert a.has_source and len(a.em) == a.n_words + 1 and len(a.em_dense) == (a.n_words + 4096) // 4096
+
+
+def test_text_cache_keeps_the_mask_source(tmp_path):
+    case = make_case(9, [3000, 45, 45, 0, 23, 800], 1, 4)
+    p = str(tmp_path / "g.fa")
+    write_fasta(p, [f"c{i}" for i in range(6)], case.ascii, case.offsets, width=60)
+    a = V.PackedText.from_fasta(p)
+    b = V.PackedText.from_ascii(case.ascii, case.offsets)
+    assert a.has_source and b.has_source
+    for name in ("em", "em_dense", "nm_runs", "em_runs"):
+        assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
+    a.save(str(tmp_path / "idx"))
+    u = V.PackedText.load(str(tmp_path / "idx"))
+    assert u.has_source and u.masks.tobytes() == a.masks.tobytes()
+    for name in ("em", "em_dense", "nm_runs", "em_runs"):
+        assert getattr(u, name).tobytes() == getattr(a, name).tobytes(), name
+    # a view without the source is saved without it, and loads without it
+    v = a.view(use_source=False)
+    import ctypes as C
+    from varscot_b200 import _lib
+    _lib.check(_lib.lib().vs_text_save(str(tmp_path / "plain").encode(), C.byref(v)))
+    w = V.PackedText.load(str(tmp_path / "plain"))
+    assert not w.has_source and w.masks.tobytes() == a.masks.tobytes() and w.bases.tobytes() == a.bases.tobytes()
+
+
 def test_text_cache_roundtrip_and_errors(tmp_path):
     case = make_case(4, [500, 45, 45], 1, 4)
     t = V.PackedText.from_ascii(case.ascii, case.offsets)

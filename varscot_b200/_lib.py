@@ -44,13 +44,20 @@ class ScanStats(C.Structure):
 class TextView(C.Structure):
     _fields_ = [("n_bases", C.c_uint64), ("n_words", C.c_uint64), ("n_contigs", C.c_uint32), ("reserved", C.c_uint32),
                 ("contig_off", C.c_void_p), ("bases", C.c_void_p), ("masks", C.c_void_p), ("sparse", C.c_void_p),
-                ("n_sparse", C.c_uint64)]
+                ("n_sparse", C.c_uint64),
+                ("em", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
+                ("n_nm_runs", C.c_uint64), ("n_em_runs", C.c_uint64)]
+
+
+class MaskSource(C.Structure):
+    _fields_ = [("em", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
+                ("n_nm_runs", C.c_uint64), ("n_em_runs", C.c_uint64), ("n_em_blocks", C.c_uint64)]
 
 
 # every symbol include/varscot_scan.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_finish", "vs_pack_text",
-    "vs_masks_from_planes", "vs_masks_sparse", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
+    "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_finish", "vs_pack_text", "vs_pack_text_planes",
+    "vs_masks_from_planes", "vs_masks_sparse", "vs_mask_source_build", "vs_mask_source_free", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
     "vs_ctx_create", "vs_ctx_destroy", "vs_last_error", "vs_ctx_set_chunk_words", "vs_text_upload", "vs_host_alloc",
     "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_resolve_hits_mt",
     "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_vcf_loader_main", "vs_fasta_writer_main", "vs_bam_merger_main", "vs_bam_merger_ref_only_main", "vs_measure_int_peaks",
@@ -75,8 +82,11 @@ def lib():
     L.vs_packer_end_contig.argtypes = [vp]
     L.vs_packer_finish.argtypes = [vp, C.POINTER(TextView)]
     L.vs_pack_text.argtypes = [vp, u64, vp, u32, vp, vp]
+    L.vs_pack_text_planes.argtypes = [vp, u64, vp, u32, vp, vp, vp]
     L.vs_masks_from_planes.argtypes = [vp, vp, u64, vp]
     L.vs_masks_sparse.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.vs_mask_source_build.argtypes = [vp, vp, u64, C.POINTER(MaskSource)]
+    L.vs_mask_source_free.argtypes = [C.POINTER(MaskSource)]
     L.vs_text_save.argtypes = [C.c_char_p, C.POINTER(TextView)]
     L.vs_text_load.argtypes = [C.c_char_p, C.POINTER(TextView), C.POINTER(vp)]
     L.vs_free.argtypes = [vp]

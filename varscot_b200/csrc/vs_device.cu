@@ -32,6 +32,11 @@ struct vs_ctx {
     uint64_t words_cap = 0, n_words = 0, first_word = 0;
     vs_mask_entry *d_sparse = nullptr;
     uint64_t sparse_cap = 0;
+    // compact mask source path: the N and contig-end planes of the shard (+ halo word) and a staging area for their runs
+    uint32_t *d_nm = nullptr, *d_em = nullptr;
+    uint64_t planes_cap = 0;
+    vs_plane_run *d_runs = nullptr;
+    uint64_t runs_cap = 0;
     // counters: per chunk [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev; then one hit counter
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
     uint64_t cnt_chunks = 0;
@@ -107,12 +112,13 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
                                                   ", this build contains sm_100a code only");
     ctx = new vs_ctx();
     ctx->device = device;
-    // the scoring stream gets the highest priority, the (optional) concurrent-extraction stream the lowest: when both
-    // kernels are runnable the scoring CTAs are placed first and extraction fills the resources they leave free
+    // The copy stream gets the highest priority: besides the H2D copies it runs the small kernels that build the window
+    // masks of the next chunk, and those must not queue behind the scoring grid of the current one (the copy engine
+    // would idle meanwhile).  The optional concurrent-extraction stream gets the lowest.
     int prio_lo = 0, prio_hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->copy, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->exs, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
@@ -132,6 +138,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->copy) cudaStreamSynchronize(ctx->copy);
     if (ctx->exs) cudaStreamSynchronize(ctx->exs);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
+    cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_runs);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (int b = 0; b < 2; ++b) for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]); }
@@ -209,15 +216,92 @@ static int ensure_text_buffers(vs_ctx *ctx, uint64_t n_words)
     return VS_OK;
 }
 
-// Enqueue the H2D of chunk [c0, c1) (device word indices) on the copy stream.  Masks travel dense, or — when the
-// view carries a sparse list and it is smaller — as memset + sparse entries + a scatter kernel.
+static inline bool has_mask_source(const vs_text_view *t) { return t->em && t->em_dense; }
+
+// runs of a sorted run list that overlap the word range [lo, hi): index range [first, last)
+static void runs_in_range(const vs_plane_run *r, uint64_t n, uint64_t lo, uint64_t hi, uint64_t &first, uint64_t &last)
+{
+    first = (uint64_t)(std::partition_point(r, r + n, [&](const vs_plane_run &x) { return (uint64_t)x.word + x.count <= lo; }) - r);
+    last = (uint64_t)(std::partition_point(r + first, r + n, [&](const vs_plane_run &x) { return (uint64_t)x.word < hi; }) - r);
+}
+
+constexpr uint64_t SKIP_MIN_WORDS = 16384;      // all-N runs at least this long are not copied: their bases are zero
+
+// Enqueue the H2D of chunk [c0, c1) (device word indices) on the copy stream.
+//  * view with a compact mask source: bases (minus long all-N runs, which are zero-filled on the device), the N plane as
+//    runs, the contig-end plane dense or as runs per block, then k_masks_from_planes computes the chunk's masks;
+//  * otherwise the masks travel dense, or — when the view carries a sparse list and it is smaller — as memset + sparse
+//    entries + a scatter kernel.
 static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t c0, uint64_t c1,
-                              uint64_t &sparse_used, uint64_t &bytes, uint32_t &launches)
+                              uint64_t &staged, uint64_t &bytes, uint32_t &launches)
 {
     cudaStream_t cs = ctx->copy;
     const uint64_t n = c1 - c0, g0 = first_word + c0;
     // bases [c0, c1] incl. the halo word; word c0 of a later chunk already arrived as the previous chunk's halo
     const uint64_t skip = c0 ? 1 : 0;
+    if (has_mask_source(t)) {
+        const uint64_t lo = g0, hi = g0 + n + 1;                 // plane words needed: the chunk and its halo word
+        uint64_t r0 = 0, r1 = 0;
+        runs_in_range(t->nm_runs, t->n_nm_runs, lo, hi, r0, r1);
+        // bases, skipping long all-N runs
+        uint64_t w = g0 + skip;
+        auto copy_bases = [&](uint64_t a, uint64_t b) -> int {   // global words [a, b)
+            if (b <= a) return VS_OK;
+            CK(cudaMemcpyAsync(ctx->d_bases + (a - first_word), t->bases + a, (b - a) * sizeof(vs_bases), cudaMemcpyHostToDevice, cs));
+            bytes += (b - a) * sizeof(vs_bases);
+            return VS_OK;
+        };
+        int r;
+        for (uint64_t i = r0; i < r1; ++i) {
+            const vs_plane_run &x = t->nm_runs[i];
+            if (x.value != ~0u || x.count < SKIP_MIN_WORDS) continue;
+            const uint64_t a = std::max<uint64_t>(x.word, w), b = std::min<uint64_t>((uint64_t)x.word + x.count, hi);
+            if (b <= a) continue;
+            if ((r = copy_bases(w, a)) != VS_OK) return r;
+            CK(cudaMemsetAsync(ctx->d_bases + (a - first_word), 0, (b - a) * sizeof(vs_bases), cs));
+            w = b;
+        }
+        if ((r = copy_bases(w, hi)) != VS_OK) return r;
+        // N plane: zero + runs
+        CK(cudaMemsetAsync(ctx->d_nm + c0, 0, (n + 1) * sizeof(uint32_t), cs));
+        CK(cudaMemsetAsync(ctx->d_em + c0, 0, (n + 1) * sizeof(uint32_t), cs));
+        auto fill = [&](const vs_plane_run *runs, uint64_t a, uint64_t b, uint32_t *plane) -> int {
+            if (b <= a) return VS_OK;
+            if (staged + (b - a) > ctx->runs_cap) return fail(ctx, VS_ERR_CUDA, "run staging area too small");
+            vs_plane_run *dst = ctx->d_runs + staged;
+            CK(cudaMemcpyAsync(dst, runs + a, (b - a) * sizeof(vs_plane_run), cudaMemcpyHostToDevice, cs));
+            uint64_t longest = 1;                      // longest clipped run: sets the number of segments (grid.y)
+            for (uint64_t i = a; i < b; ++i)
+                longest = std::max<uint64_t>(longest, std::min<uint64_t>((uint64_t)runs[i].word + runs[i].count, hi) - std::max<uint64_t>(runs[i].word, lo));
+            k_fill_runs<<<dim3((unsigned)((b - a + 7) / 8), (unsigned)((longest + FILL_SEG - 1) / FILL_SEG)), 256, 0, cs>>>(dst, b - a, lo, hi, first_word, plane);
+            launches++;
+            staged += b - a;
+            bytes += (b - a) * sizeof(vs_plane_run);
+            return VS_OK;
+        };
+        if ((r = fill(t->nm_runs, r0, r1, ctx->d_nm)) != VS_OK) return r;
+        // contig-end plane: dense blocks as spans, the others as runs
+        uint64_t span0 = 0, span1 = 0;       // pending dense span [span0, span1) in global words
+        auto flush_span = [&]() -> int {
+            if (span1 > span0) {
+                CK(cudaMemcpyAsync(ctx->d_em + (span0 - first_word), t->em + span0, (span1 - span0) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+                bytes += (span1 - span0) * sizeof(uint32_t);
+            }
+            span0 = span1 = 0;
+            return VS_OK;
+        };
+        for (uint64_t b = lo / VS_EM_BLOCK; b * VS_EM_BLOCK < hi; ++b) {
+            if (!t->em_dense[b]) { if ((r = flush_span()) != VS_OK) return r; continue; }
+            const uint64_t a = std::max<uint64_t>(b * VS_EM_BLOCK, lo), e = std::min<uint64_t>((b + 1) * VS_EM_BLOCK, hi);
+            if (span1 == a) span1 = e; else { if ((r = flush_span()) != VS_OK) return r; span0 = a; span1 = e; }
+        }
+        if ((r = flush_span()) != VS_OK) return r;
+        runs_in_range(t->em_runs, t->n_em_runs, lo, hi, r0, r1);
+        if ((r = fill(t->em_runs, r0, r1, ctx->d_em)) != VS_OK) return r;
+        k_masks_from_planes<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(ctx->d_nm + c0, ctx->d_em + c0, n, ctx->d_masks + c0);
+        launches++;
+        return VS_OK;
+    }
     CK(cudaMemcpyAsync(ctx->d_bases + c0 + skip, t->bases + g0 + skip, (n + 1 - skip) * sizeof(vs_bases), cudaMemcpyHostToDevice, cs));
     bytes += (n + 1 - skip) * sizeof(vs_bases);
     bool sparse = false;
@@ -226,16 +310,16 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
         const vs_mask_entry *sb = t->sparse, *se = t->sparse + t->n_sparse;
         auto lb = [&](uint64_t w) { return (uint64_t)(std::lower_bound(sb, se, w, [](const vs_mask_entry &x, uint64_t v) { return x.word < v; }) - sb); };
         e0 = lb(g0); e1 = lb(g0 + n);
-        sparse = (e1 - e0) * sizeof(vs_mask_entry) < n * sizeof(vs_masks) * 3 / 4 && sparse_used + (e1 - e0) <= ctx->sparse_cap;
+        sparse = (e1 - e0) * sizeof(vs_mask_entry) < n * sizeof(vs_masks) * 3 / 4 && staged + (e1 - e0) <= ctx->sparse_cap;
     }
     if (sparse) {
         CK(cudaMemsetAsync(ctx->d_masks + c0, 0, n * sizeof(vs_masks), cs));
         if (e1 > e0) {
-            vs_mask_entry *dst = ctx->d_sparse + sparse_used;
+            vs_mask_entry *dst = ctx->d_sparse + staged;
             CK(cudaMemcpyAsync(dst, t->sparse + e0, (e1 - e0) * sizeof(vs_mask_entry), cudaMemcpyHostToDevice, cs));
             k_scatter_masks<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, cs>>>(dst, e1 - e0, g0, ctx->d_masks + c0);
             launches++;
-            sparse_used += e1 - e0;
+            staged += e1 - e0;
             bytes += (e1 - e0) * sizeof(vs_mask_entry);
         }
     } else {
@@ -245,8 +329,32 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
     return VS_OK;
 }
 
+// device staging for the sparse mask entries, or — for a view with a compact mask source — the plane buffers and the
+// staging area of their runs (a run that straddles a chunk border is staged once per chunk it touches)
 static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
 {
+    if (has_mask_source(t)) {
+        if (n_words + 1 > ctx->planes_cap) {
+            CK(cudaStreamSynchronize(ctx->copy));
+            cudaFree(ctx->d_nm); cudaFree(ctx->d_em);
+            ctx->d_nm = ctx->d_em = nullptr; ctx->planes_cap = 0;
+            CK(cudaMalloc(&ctx->d_nm, (n_words + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_em, (n_words + 1) * sizeof(uint32_t)));
+            ctx->planes_cap = n_words + 1;
+        }
+        uint64_t a0, a1, b0, b1;
+        runs_in_range(t->nm_runs, t->n_nm_runs, first_word, first_word + n_words + 1, a0, a1);
+        runs_in_range(t->em_runs, t->n_em_runs, first_word, first_word + n_words + 1, b0, b1);
+        const uint64_t n_chunks = (n_words + ctx->chunk_words - 1) / ctx->chunk_words;
+        const uint64_t need = (a1 - a0) + (b1 - b0) + 4 * n_chunks + 16;
+        if (need > ctx->runs_cap) {
+            CK(cudaStreamSynchronize(ctx->copy));
+            cudaFree(ctx->d_runs); ctx->d_runs = nullptr; ctx->runs_cap = 0;
+            CK(cudaMalloc(&ctx->d_runs, need * sizeof(vs_plane_run)));
+            ctx->runs_cap = need;
+        }
+        return VS_OK;
+    }
     if (!t->sparse || t->n_sparse == 0) return VS_OK;
     const vs_mask_entry *sb = t->sparse, *se = t->sparse + t->n_sparse;
     auto lb = [&](uint64_t w) { return (uint64_t)(std::lower_bound(sb, se, w, [](const vs_mask_entry &x, uint64_t v) { return x.word < v; }) - sb); };
@@ -265,6 +373,8 @@ static int check_view(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, u
     if (!t || !t->bases || (!t->masks && t->n_words)) return fail(ctx, VS_ERR_ARG, "text view is incomplete");
     if (first_word + n_words > t->n_words) return fail(ctx, VS_ERR_ARG, "shard lies outside the text");
     if (t->n_words * 32 > (1ull << 32)) return fail(ctx, VS_ERR_ARG, "text exceeds 4 Gbases (32-bit positions, as common.h:9-19)");
+    if ((t->em != nullptr) != (t->em_dense != nullptr) || (has_mask_source(t) && ((t->n_nm_runs && !t->nm_runs) || (t->n_em_runs && !t->em_runs))))
+        return fail(ctx, VS_ERR_ARG, "text view carries an incomplete compact mask source");
     return VS_OK;
 }
 

@@ -68,11 +68,72 @@ extern "C" int vs_masks_sparse(const vs_masks *masks, uint64_t n_words, vs_mask_
     return VS_OK;
 }
 
+// Compact mask source (include/varscot_scan.h): runs of equal non-zero words for the N plane; for the contig-end plane
+// a dense/sparse decision per block of VS_EM_BLOCK words (dense when listing the block's non-zero words as 12-byte runs
+// would cost more than its 4 bytes per word).
+static void append_run(std::vector<vs_plane_run> &runs, uint64_t w, uint32_t v)
+{
+    if (!runs.empty() && runs.back().value == v && (uint64_t)runs.back().word + runs.back().count == w) runs.back().count++;
+    else runs.push_back(vs_plane_run{(uint32_t)w, 1u, v});
+}
+
+static int build_mask_source(const uint32_t *nm, const uint32_t *em, uint64_t n_words, std::vector<vs_plane_run> &nm_runs,
+                             std::vector<vs_plane_run> &em_runs, std::vector<uint8_t> &em_dense)
+{
+    const uint64_t n = n_words + 1, n_blocks = (n + VS_EM_BLOCK - 1) / VS_EM_BLOCK;
+    try {
+        nm_runs.clear(); em_runs.clear();
+        em_dense.assign(n_blocks, 0);
+        for (uint64_t w = 0; w < n; ++w)
+            if (nm[w]) append_run(nm_runs, w, nm[w]);
+        for (uint64_t b = 0; b < n_blocks; ++b) {
+            const uint64_t w0 = b * VS_EM_BLOCK, w1 = std::min<uint64_t>(n, w0 + VS_EM_BLOCK);
+            const size_t before = em_runs.size();
+            for (uint64_t w = w0; w < w1; ++w)
+                if (em[w]) append_run(em_runs, w, em[w]);
+            if ((em_runs.size() - before) * sizeof(vs_plane_run) > (w1 - w0) * sizeof(uint32_t)) {
+                em_runs.resize(before);
+                em_dense[b] = 1;
+            }
+        }
+    } catch (...) { return VS_ERR_NOMEM; }
+    return VS_OK;
+}
+
+extern "C" int vs_mask_source_build(const uint32_t *nm, const uint32_t *em, uint64_t n_words, vs_mask_source *out)
+{
+    if (!nm || !em || !out) return VS_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    std::vector<vs_plane_run> nr, er;
+    std::vector<uint8_t> ed;
+    int r = build_mask_source(nm, em, n_words, nr, er, ed);
+    if (r != VS_OK) return r;
+    out->em = em;
+    out->em_dense = (uint8_t *)malloc(ed.size() ? ed.size() : 1);
+    out->nm_runs = (vs_plane_run *)malloc((nr.size() ? nr.size() : 1) * sizeof(vs_plane_run));
+    out->em_runs = (vs_plane_run *)malloc((er.size() ? er.size() : 1) * sizeof(vs_plane_run));
+    if (!out->em_dense || !out->nm_runs || !out->em_runs) { vs_mask_source_free(out); return VS_ERR_NOMEM; }
+    if (!ed.empty()) memcpy(out->em_dense, ed.data(), ed.size());
+    if (!nr.empty()) memcpy(out->nm_runs, nr.data(), nr.size() * sizeof(vs_plane_run));
+    if (!er.empty()) memcpy(out->em_runs, er.data(), er.size() * sizeof(vs_plane_run));
+    out->n_nm_runs = nr.size(); out->n_em_runs = er.size(); out->n_em_blocks = ed.size();
+    return VS_OK;
+}
+
+extern "C" void vs_mask_source_free(vs_mask_source *s)
+{
+    if (!s) return;
+    free(s->em_dense); free(s->nm_runs); free(s->em_runs);
+    memset(s, 0, sizeof(*s));
+}
+
 struct vs_packer {
     std::vector<vs_bases> bases;
     std::vector<uint32_t> nm, em;
     std::vector<vs_masks> masks;
     std::vector<vs_mask_entry> sparse;
+    std::vector<vs_plane_run> nm_runs, em_runs;      // compact mask source (em stays alive for it)
+    std::vector<uint8_t> em_dense;
     std::vector<uint64_t> off{0};
     uint64_t n = 0;
     bool finalized = false;
@@ -161,61 +222,82 @@ extern "C" int vs_packer_finish(vs_packer *p, vs_text_view *out)
             vs_masks_from_planes(p->nm.data(), p->em.data(), nw, p->masks.data());
             for (uint64_t w = 0; w < nw; ++w)
                 if (p->masks[w].iv | p->masks[w].lw) p->sparse.push_back(vs_mask_entry{(uint32_t)w, p->masks[w].iv, p->masks[w].lw});
+            if (build_mask_source(p->nm.data(), p->em.data(), nw, p->nm_runs, p->em_runs, p->em_dense) != VS_OK) return VS_ERR_NOMEM;
             std::vector<uint32_t>().swap(p->nm);
-            std::vector<uint32_t>().swap(p->em);
         } catch (...) { return VS_ERR_NOMEM; }
         p->finalized = true;
     }
     out->n_bases = p->n; out->n_words = nw; out->n_contigs = (uint32_t)(p->off.size() - 1); out->reserved = 0;
     out->contig_off = p->off.data(); out->bases = p->bases.data(); out->masks = p->masks.data();
     out->sparse = p->sparse.data(); out->n_sparse = p->sparse.size();
+    out->em = p->em.data(); out->em_dense = p->em_dense.data();
+    out->nm_runs = p->nm_runs.data(); out->em_runs = p->em_runs.data();
+    out->n_nm_runs = p->nm_runs.size(); out->n_em_runs = p->em_runs.size();
     return VS_OK;
 }
 
-extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
-                            vs_bases *out_bases, vs_masks *out_masks)
+extern "C" int vs_pack_text_planes(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
+                                   vs_bases *out_bases, uint32_t *out_nm, uint32_t *out_em)
 {
-    if (!out_bases || (!out_masks && n_bases) || (!ascii && n_bases) || (!contig_off && n_contigs)) return VS_ERR_ARG;
+    if (!out_bases || !out_nm || !out_em || (!ascii && n_bases) || (!contig_off && n_contigs)) return VS_ERR_ARG;
     if (n_contigs && (contig_off[0] != 0 || contig_off[n_contigs] != n_bases)) {
         vs_set_last_error("vs_pack_text: offsets must start at 0 and end at n_bases");
         return VS_ERR_ARG;
     }
     const uint64_t nw = (n_bases + 31) >> 5;
-    std::vector<uint32_t> nm, em;
-    try { nm.assign(nw + 1, 0u); em.assign(nw + 1, 0u); } catch (...) { return VS_ERR_NOMEM; }
     memset(out_bases, 0, (nw + 1) * sizeof(vs_bases));
+    memset(out_nm, 0, (nw + 1) * sizeof(uint32_t));
+    memset(out_em, 0, (nw + 1) * sizeof(uint32_t));
     for (uint64_t i = 0; i < n_bases; ++i) {
         uint8_t c = g_lut.t[(uint8_t)ascii[i]];
         if (c == 255) c = 4;              // whitespace inside a pre-split text is just a non-base
         uint32_t bit = 1u << (i & 31);
         if (c & 2) out_bases[i >> 5].hi |= bit;
         if (c & 1) out_bases[i >> 5].lo |= bit;
-        if (c & 4) nm[i >> 5] |= bit;
+        if (c & 4) out_nm[i >> 5] |= bit;
     }
     for (uint32_t c = 0; c < n_contigs; ++c) {
         if (contig_off[c + 1] < contig_off[c]) { vs_set_last_error("vs_pack_text: offsets must be non-decreasing"); return VS_ERR_ARG; }
         if (contig_off[c + 1] > contig_off[c]) {
             uint64_t last = contig_off[c + 1] - 1;
-            em[last >> 5] |= 1u << (last & 31);
+            out_em[last >> 5] |= 1u << (last & 31);
         }
     }
-    if (n_bases & 31) nm[nw - 1] |= ~0u << (n_bases & 31);
-    nm[nw] = ~0u;
+    if (n_bases & 31) out_nm[nw - 1] |= ~0u << (n_bases & 31);     // padding past the end reads as N
+    out_nm[nw] = ~0u;
+    return VS_OK;
+}
+
+extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs,
+                            vs_bases *out_bases, vs_masks *out_masks)
+{
+    if (!out_masks && n_bases) return VS_ERR_ARG;
+    const uint64_t nw = (n_bases + 31) >> 5;
+    std::vector<uint32_t> nm, em;
+    try { nm.assign(nw + 1, 0u); em.assign(nw + 1, 0u); } catch (...) { return VS_ERR_NOMEM; }
+    int r = vs_pack_text_planes(ascii, n_bases, contig_off, n_contigs, out_bases, nm.data(), em.data());
+    if (r != VS_OK) return r;
     return vs_masks_from_planes(nm.data(), em.data(), nw, out_masks);
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed-text cache: <prefix>.vsidx = header, offsets, bases, masks, sparse masks (all 16-byte aligned sections)
+// packed-text cache: <prefix>.vsidx = header, offsets, bases, masks, sparse masks, then (format 003, when the view
+// carries one) the compact mask source: em, em_dense, nm_runs, em_runs.  All sections are 16-byte aligned.
 namespace {
 struct IdxHeader {
     char magic[8];
     uint64_t n_bases;
     uint64_t n_sparse;
     uint32_t n_contigs;
-    uint32_t reserved;
+    uint32_t flags;          // 003: bit 0 = a compact mask source follows
 };
-const char IDX_MAGIC[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
+struct IdxSourceHeader {    // 003 only, directly after IdxHeader
+    uint64_t n_nm_runs, n_em_runs;
+};
+const char IDX_MAGIC2[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
+const char IDX_MAGIC3[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '3'};
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
+inline bool has_source(const vs_text_view *t) { return t->em && t->em_dense; }
 }  // namespace
 
 extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
@@ -229,16 +311,21 @@ extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
     uint64_t nsp = t->n_sparse;
     if (!sp && t->n_words) { if (vs_masks_sparse(t->masks, t->n_words, &tmp, &nsp) != VS_OK) { fclose(f); return VS_ERR_NOMEM; } sp = tmp; }
     IdxHeader h;
-    memcpy(h.magic, IDX_MAGIC, 8);
-    h.n_bases = t->n_bases; h.n_sparse = nsp; h.n_contigs = t->n_contigs; h.reserved = 0;
+    memcpy(h.magic, IDX_MAGIC3, 8);
+    h.n_bases = t->n_bases; h.n_sparse = nsp; h.n_contigs = t->n_contigs; h.flags = has_source(t) ? 1u : 0u;
+    IdxSourceHeader sh{has_source(t) ? t->n_nm_runs : 0, has_source(t) ? t->n_em_runs : 0};
     static const char zeros[16] = {0};
     auto put = [&](const void *p, uint64_t bytes) {
         bool ok = bytes == 0 || fwrite(p, 1, bytes, f) == bytes;
         uint64_t pad = pad16(bytes) - bytes;
         return ok && (pad == 0 || fwrite(zeros, 1, pad, f) == pad);
     };
-    bool ok = put(&h, sizeof(h)) && put(t->contig_off, ((uint64_t)t->n_contigs + 1) * 8) && put(t->bases, (t->n_words + 1) * sizeof(vs_bases)) &&
-              put(t->masks, t->n_words * sizeof(vs_masks)) && put(sp, nsp * sizeof(vs_mask_entry));
+    bool ok = put(&h, sizeof(h)) && put(&sh, sizeof(sh)) && put(t->contig_off, ((uint64_t)t->n_contigs + 1) * 8) &&
+              put(t->bases, (t->n_words + 1) * sizeof(vs_bases)) && put(t->masks, t->n_words * sizeof(vs_masks)) &&
+              put(sp, nsp * sizeof(vs_mask_entry));
+    if (ok && has_source(t))
+        ok = put(t->em, (t->n_words + 1) * sizeof(uint32_t)) && put(t->em_dense, (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK) &&
+             put(t->nm_runs, sh.n_nm_runs * sizeof(vs_plane_run)) && put(t->em_runs, sh.n_em_runs * sizeof(vs_plane_run));
     ok = (fclose(f) == 0) && ok;
     free(tmp);
     if (!ok) { vs_set_last_error(("short write to " + path).c_str()); return VS_ERR_IO; }
@@ -254,17 +341,27 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) { vs_set_last_error(("cannot open " + path).c_str()); return VS_ERR_IO; }
     IdxHeader h;
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, IDX_MAGIC, 8) != 0) {
-        fclose(f); vs_set_last_error((path + " is not a VSIDX002 packed text").c_str()); return VS_ERR_IO;
+    IdxSourceHeader sh{0, 0};
+    bool v3 = false;
+    if (fread(&h, sizeof(h), 1, f) != 1 || (memcmp(h.magic, IDX_MAGIC2, 8) != 0 && memcmp(h.magic, IDX_MAGIC3, 8) != 0)) {
+        fclose(f); vs_set_last_error((path + " is not a VSIDX002/003 packed text").c_str()); return VS_ERR_IO;
     }
+    v3 = memcmp(h.magic, IDX_MAGIC3, 8) == 0;
+    uint64_t data_at = pad16(sizeof(h));
+    if (v3) {
+        if (fseek(f, (long)data_at, SEEK_SET) != 0 || fread(&sh, sizeof(sh), 1, f) != 1) { fclose(f); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
+        data_at += pad16(sizeof(sh));
+    }
+    const bool src = v3 && (h.flags & 1u);
     const uint64_t nw = (h.n_bases + 31) >> 5;
     const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)),
                    s_m = pad16(nw * sizeof(vs_masks)), s_s = pad16(h.n_sparse * sizeof(vs_mask_entry));
-    const uint64_t total = s_off + s_b + s_m + s_s;
+    const uint64_t s_em = src ? pad16((nw + 1) * sizeof(uint32_t)) : 0, s_ed = src ? pad16((nw + VS_EM_BLOCK) / VS_EM_BLOCK) : 0,
+                   s_nr = src ? pad16(sh.n_nm_runs * sizeof(vs_plane_run)) : 0, s_er = src ? pad16(sh.n_em_runs * sizeof(vs_plane_run)) : 0;
+    const uint64_t total = s_off + s_b + s_m + s_s + s_em + s_ed + s_nr + s_er;
     char *buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);
     if (!buf) { fclose(f); return VS_ERR_NOMEM; }
-    // skip the header padding
-    bool ok = fseek(f, (long)pad16(sizeof(h)), SEEK_SET) == 0 && fread(buf, 1, total, f) == total;
+    bool ok = fseek(f, (long)data_at, SEEK_SET) == 0 && fread(buf, 1, total, f) == total;
     fclose(f);
     const uint64_t *off = (const uint64_t *)buf;
     if (!ok || off[h.n_contigs] != h.n_bases) { free(buf); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
@@ -274,6 +371,14 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     out->masks = (const vs_masks *)(buf + s_off + s_b);
     out->sparse = (const vs_mask_entry *)(buf + s_off + s_b + s_m);
     out->n_sparse = h.n_sparse;
+    if (src) {
+        const char *q = buf + s_off + s_b + s_m + s_s;
+        out->em = (const uint32_t *)q;
+        out->em_dense = (const uint8_t *)(q + s_em);
+        out->nm_runs = (const vs_plane_run *)(q + s_em + s_ed);
+        out->em_runs = (const vs_plane_run *)(q + s_em + s_ed + s_nr);
+        out->n_nm_runs = sh.n_nm_runs; out->n_em_runs = sh.n_em_runs;
+    }
     *owner = buf;
     return VS_OK;
 }

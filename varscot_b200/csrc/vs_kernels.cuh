@@ -286,6 +286,43 @@ k_scatter_masks(const vs_mask_entry *__restrict__ e, uint64_t n, uint64_t word_b
 }
 
 // ------------------------------------------------------------------------------------------------
+// Window masks on the device, from the compact mask source of a view (include/varscot_scan.h).
+// k_fill_runs: plane[word - word_base + i] = value for the part of every run {word, count, value} that lies inside
+// [lo, hi) (global word indices).  Warp (blockIdx.x * 8 + warp) owns a run, blockIdx.y selects a segment of FILL_SEG
+// words of it, so that a long run (an N stretch of a chromosome is 10^5 words) is filled by many warps.
+constexpr uint32_t FILL_SEG = 1024;
+__global__ void __launch_bounds__(256)
+k_fill_runs(const vs_plane_run *__restrict__ runs, uint64_t n_runs, uint64_t lo, uint64_t hi, uint64_t word_base, uint32_t *__restrict__ plane)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_runs) return;
+    const vs_plane_run x = runs[r];
+    const uint64_t a = max((uint64_t)x.word, lo) + (uint64_t)blockIdx.y * FILL_SEG;
+    const uint64_t b = min(min((uint64_t)x.word + x.count, hi), a + FILL_SEG);
+    for (uint64_t w = a + (threadIdx.x & 31); w < b; w += 32) plane[w - word_base] = x.value;
+}
+
+// k_masks_from_planes: the device twin of masks_of() in vs_host.cpp.  nm / em point at the first word of the range and
+// hold n + 1 words (the last one is the halo);
+//   iv: any N in [p, p+23)  or  any contig end in [p, p+22)   (R1, R3)
+//   lw: the window is valid and its last base (p+22) is a contig end   (R4)
+__global__ void __launch_bounds__(256)
+k_masks_from_planes(const uint32_t *__restrict__ nm, const uint32_t *__restrict__ em, uint64_t n, vs_masks *__restrict__ out)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const uint64_t N = ((uint64_t)nm[w + 1] << 32) | nm[w], E = ((uint64_t)em[w + 1] << 32) | em[w];
+    uint64_t t = N | (N >> 1); t |= t >> 2; t |= t >> 4; t |= t >> 8;      // OR over 16 consecutive
+    const uint64_t n23 = t | (t >> 7);                                       // OR over 23
+    uint64_t e = E | (E >> 1); e |= e >> 2; e |= e >> 4; e |= e >> 8;
+    const uint64_t e22 = e | (e >> 6);                                       // OR over 22
+    vs_masks m;
+    m.iv = (uint32_t)(n23 | e22);
+    m.lw = (uint32_t)(E >> 22) & ~m.iv;
+    out[w] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Scoring.
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)

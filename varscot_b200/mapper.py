@@ -17,6 +17,7 @@ from ._lib import GLEN, Hit, Record, ScanStats, VarscotError, check
 BASES_DT = np.dtype([("hi", "<u4"), ("lo", "<u4")])
 MASKS_DT = np.dtype([("iv", "<u4"), ("lw", "<u4")])
 SPARSE_DT = np.dtype([("word", "<u4"), ("iv", "<u4"), ("lw", "<u4")])
+RUN_DT = np.dtype([("word", "<u4"), ("count", "<u4"), ("value", "<u4")])
 HIT_DT = np.dtype([("pos", "<u4"), ("info", "<u4")])
 REC_DT = np.dtype([("guide", "<u4"), ("contig", "<u4"), ("pos", "<u4"), ("flag", "<u2"), ("mm", "u1"), ("pad", "u1")])
 
@@ -60,7 +61,7 @@ class PackedText:
     """Bit-sliced text (include/varscot_scan.h): bases[n_words + 1] of {hi, lo}, window masks[n_words] of {iv, lw},
     the sparse form of the masks, contig offsets and optional names.  `view()` is the vs_text_view the C ABI takes."""
 
-    def __init__(self, bases, masks, offsets, n_bases, names=None, sparse=None):
+    def __init__(self, bases, masks, offsets, n_bases, names=None, sparse=None, source=None):
         self.bases = np.ascontiguousarray(bases, dtype=BASES_DT)
         self.masks = np.ascontiguousarray(masks, dtype=MASKS_DT)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -74,6 +75,15 @@ class PackedText:
             sparse["iv"] = self.masks["iv"][nz]
             sparse["lw"] = self.masks["lw"][nz]
         self.sparse = np.ascontiguousarray(sparse, dtype=SPARSE_DT)
+        # compact mask source (include/varscot_scan.h): contig-end plane, its dense-block flags, N-plane runs, end-plane runs
+        self.em = self.em_dense = self.nm_runs = self.em_runs = None
+        if source is not None:
+            em, em_dense, nm_runs, em_runs = source
+            self.em = np.ascontiguousarray(em, dtype=np.uint32)
+            self.em_dense = np.ascontiguousarray(em_dense, dtype=np.uint8)
+            self.nm_runs = np.ascontiguousarray(nm_runs, dtype=RUN_DT)
+            self.em_runs = np.ascontiguousarray(em_runs, dtype=RUN_DT)
+            assert len(self.em) == self.n_words + 1 and len(self.em_dense) == (self.n_words + 4096) // 4096
         self._pinned = []
 
     @property
@@ -84,7 +94,13 @@ class PackedText:
     def n_contigs(self) -> int:
         return len(self.offsets) - 1
 
-    def view(self, use_sparse: bool = True) -> _lib.TextView:
+    @property
+    def has_source(self) -> bool:
+        return self.em is not None
+
+    def view(self, use_sparse: bool = True, use_source: bool = True) -> _lib.TextView:
+        """use_source: hand the compact mask source to the library when this text has one (uploads then move the planes and
+        the device computes the masks); use_sparse: otherwise offer the sparse mask list."""
         v = _lib.TextView()
         v.n_bases, v.n_words, v.n_contigs, v.reserved = self.n_bases, self.n_words, self.n_contigs, 0
         v.contig_off = self.offsets.ctypes.data
@@ -92,12 +108,19 @@ class PackedText:
         v.masks = self.masks.ctypes.data
         v.sparse = self.sparse.ctypes.data if use_sparse else None
         v.n_sparse = len(self.sparse) if use_sparse else 0
+        if use_source and self.has_source:
+            v.em, v.em_dense = self.em.ctypes.data, self.em_dense.ctypes.data
+            v.nm_runs, v.em_runs = self.nm_runs.ctypes.data, self.em_runs.ctypes.data
+            v.n_nm_runs, v.n_em_runs = len(self.nm_runs), len(self.em_runs)
         return v
 
+    def _arrays(self):
+        return ("bases", "masks", "sparse") + (("em", "em_dense", "nm_runs", "em_runs") if self.has_source else ())
+
     def pin(self):
-        """Move bases, masks and sparse masks into page-locked memory (vs_host_alloc) for full-speed H2D."""
+        """Move bases, masks, sparse masks and the mask source into page-locked memory (vs_host_alloc) for full-speed H2D."""
         L = _lib.lib()
-        for name in ("bases", "masks", "sparse"):
+        for name in self._arrays():
             arr = getattr(self, name)
             nbytes = max(arr.nbytes, 16)
             p = L.vs_host_alloc(nbytes)
@@ -112,25 +135,38 @@ class PackedText:
 
     def unpin(self):
         L = _lib.lib()
-        for name in ("bases", "masks", "sparse"):
+        for name in self._arrays():
             setattr(self, name, np.array(getattr(self, name)))
         for p in self._pinned:
             L.vs_host_free(p)
         self._pinned = []
 
     @staticmethod
+    def _with_source(bases, nm, em, offsets, n_bases, names) -> "PackedText":
+        """Masks and the compact mask source from the N plane and the contig-end plane (n_words + 1 words each)."""
+        L = _lib.lib()
+        nw = (int(n_bases) + 31) // 32
+        masks = np.zeros(nw, dtype=MASKS_DT)
+        check(L.vs_masks_from_planes(nm.ctypes.data, em.ctypes.data, nw, masks.ctypes.data))
+        ms = _lib.MaskSource()
+        check(L.vs_mask_source_build(nm.ctypes.data, em.ctypes.data, nw, C.byref(ms)))
+        try:
+            source = (em[:nw + 1].copy(), _copy_array(ms.em_dense, int(ms.n_em_blocks), np.dtype("u1")),
+                      _copy_array(ms.nm_runs, int(ms.n_nm_runs), RUN_DT), _copy_array(ms.em_runs, int(ms.n_em_runs), RUN_DT))
+        finally:
+            L.vs_mask_source_free(C.byref(ms))
+        return PackedText(bases, masks, offsets, n_bases, names, source=source)
+
+    @staticmethod
     def from_planes(hi, lo, nm, em, offsets, n_bases, names=None) -> "PackedText":
         """From bit planes of n_words + 1 words each (nm: N / padding plane, em: contig-end plane)."""
-        L = _lib.lib()
         nw = (int(n_bases) + 31) // 32
         nm = np.ascontiguousarray(nm, dtype=np.uint32)
         em = np.ascontiguousarray(em, dtype=np.uint32)
         bases = np.zeros(nw + 1, dtype=BASES_DT)
         bases["hi"][:nw] = np.asarray(hi[:nw], dtype=np.uint32) & ~nm[:nw]
         bases["lo"][:nw] = np.asarray(lo[:nw], dtype=np.uint32) & ~nm[:nw]
-        masks = np.zeros(nw, dtype=MASKS_DT)
-        check(L.vs_masks_from_planes(nm.ctypes.data, em.ctypes.data, nw, masks.ctypes.data))
-        return PackedText(bases, masks, offsets, n_bases, names)
+        return PackedText._with_source(bases, nm, em, offsets, n_bases, names)
 
     @staticmethod
     def from_ascii(ascii_bytes, offsets, names=None) -> "PackedText":
@@ -140,16 +176,20 @@ class PackedText:
         n = int(a.size)
         nw = (n + 31) // 32
         bases = np.zeros(nw + 1, dtype=BASES_DT)
-        masks = np.zeros(nw, dtype=MASKS_DT)
-        check(L.vs_pack_text(a.ctypes.data, n, off.ctypes.data, len(off) - 1, bases.ctypes.data, masks.ctypes.data))
-        return PackedText(bases, masks, off, n, names)
+        nm, em = np.zeros(nw + 1, dtype=np.uint32), np.zeros(nw + 1, dtype=np.uint32)
+        check(L.vs_pack_text_planes(a.ctypes.data, n, off.ctypes.data, len(off) - 1, bases.ctypes.data, nm.ctypes.data, em.ctypes.data))
+        return PackedText._with_source(bases, nm, em, off, n, names)
 
     @staticmethod
     def _from_view(v, names=None) -> "PackedText":
         nw = int(v.n_words)
+        source = None
+        if v.em and v.em_dense:
+            source = (_copy_array(v.em, nw + 1, np.dtype("<u4")), _copy_array(v.em_dense, (nw + 4096) // 4096, np.dtype("u1")),
+                      _copy_array(v.nm_runs, int(v.n_nm_runs), RUN_DT), _copy_array(v.em_runs, int(v.n_em_runs), RUN_DT))
         return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), _copy_array(v.masks, nw, MASKS_DT),
                           _copy_array(v.contig_off, int(v.n_contigs) + 1, np.dtype("<u8")), int(v.n_bases), names,
-                          _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT))
+                          _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT), source)
 
     @staticmethod
     def from_fasta(path: str) -> "PackedText":
@@ -221,11 +261,11 @@ class ScanContext:
     def set_chunk_words(self, n: int):
         check(self._L.vs_ctx_set_chunk_words(self._ctx, n), self._ctx)
 
-    def upload(self, text: PackedText, first_word: int = 0, n_words: int | None = None, use_sparse: bool = True):
+    def upload(self, text: PackedText, first_word: int = 0, n_words: int | None = None, use_sparse: bool = True, use_source: bool = True):
         """Make words [first_word, first_word + n_words) resident (vs_text_upload)."""
         if n_words is None:
             n_words = text.n_words - first_word
-        v = text.view(use_sparse)
+        v = text.view(use_sparse, use_source)
         check(self._L.vs_text_upload(self._ctx, C.byref(v), first_word, n_words), self._ctx)
 
     def _finish(self, rc, hits, n):
@@ -248,7 +288,7 @@ class ScanContext:
         return hits, st
 
     def scan_text(self, text: PackedText, guides: np.ndarray, k: int, pam=None, first_word: int = 0, n_words: int | None = None,
-                  cap: int = 1 << 20, out: np.ndarray | None = None, use_sparse: bool = True):
+                  cap: int = 1 << 20, out: np.ndarray | None = None, use_sparse: bool = True, use_source: bool = True):
         """Upload (overlapped, chunk by chunk) and scan in one call (vs_scan_text): the end-to-end path."""
         if n_words is None:
             n_words = text.n_words - first_word
@@ -256,7 +296,7 @@ class ScanContext:
         pc = pam if isinstance(pam, int) else pam_code(pam)
         hits = out if out is not None else np.zeros(cap, dtype=HIT_DT)
         n, st = C.c_uint64(), ScanStats()
-        v = text.view(use_sparse)
+        v = text.view(use_sparse, use_source)
         rc = self._L.vs_scan_text(self._ctx, C.byref(v), first_word, n_words, g.ctypes.data, g.shape[0], k, pc,
                                   hits.ctypes.data, len(hits), C.byref(n), C.byref(st))
         hits = self._finish(rc, hits, n)
