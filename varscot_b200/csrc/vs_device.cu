@@ -22,7 +22,9 @@ struct vs_ctx {
     int device = -1;
     cudaStream_t stream = nullptr;       // scoring + everything ordered with it
     cudaStream_t exs = nullptr;          // extraction of the next chunk (overlaps the scoring of the current one)
-    cudaStream_t copy = nullptr;         // H2D of the next chunk
+    cudaStream_t copy = nullptr;         // H2D of the next chunk (copies only, so that the copy engine never waits for a kernel)
+    cudaStream_t prep = nullptr;         // small kernels that turn the uploaded mask source of a chunk into its window masks
+    cudaEvent_t ev_copied = nullptr, ev_zeroed = nullptr;
     cudaEvent_t ev[6] = {};
     std::vector<cudaEvent_t> ev_pool;    // per chunk: copied, extract start, extract done, score start, score done
     uint64_t chunk_words = DEFAULT_CHUNK_WORDS;
@@ -112,13 +114,16 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
                                                   ", this build contains sm_100a code only");
     ctx = new vs_ctx();
     ctx->device = device;
-    // The copy stream gets the highest priority: besides the H2D copies it runs the small kernels that build the window
-    // masks of the next chunk, and those must not queue behind the scoring grid of the current one (the copy engine
-    // would idle meanwhile).  The optional concurrent-extraction stream gets the lowest.
+    // The copy and mask-preparation streams get the highest priority: the small kernels that build the window masks of
+    // the next chunk must not queue behind the scoring grid of the current one.  The optional concurrent-extraction
+    // stream gets the lowest.
     int prio_lo = 0, prio_hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->copy, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->prep, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_zeroed, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->exs, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
@@ -136,6 +141,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy) cudaStreamSynchronize(ctx->copy);
+    if (ctx->prep) cudaStreamSynchronize(ctx->prep);
     if (ctx->exs) cudaStreamSynchronize(ctx->exs);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
     cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_runs);
@@ -149,6 +155,9 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    if (ctx->prep) cudaStreamDestroy(ctx->prep);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+    if (ctx->ev_zeroed) cudaEventDestroy(ctx->ev_zeroed);
     if (ctx->exs) cudaStreamDestroy(ctx->exs);
     delete ctx;
 }
@@ -201,6 +210,24 @@ static void dispatch_score(int k, const ScoreArgs &a, cudaStream_t st)
     }
 }
 
+// Pipeline chunks of a shard of n_words words: bounds[0] = 0 < ... < bounds[n] = n_words, chunk_words apart.  For a
+// streamed scan the last chunk is cut into 1/2, 1/4, 1/8, 1/8: the scan of a chunk can only start when its copy has
+// arrived, so what follows the last copy — the tail of the pipeline — shrinks to the scan of an eighth of a chunk.
+static std::vector<uint64_t> chunk_plan(uint64_t n_words, uint64_t chunk_words, bool taper)
+{
+    std::vector<uint64_t> b{0};
+    for (uint64_t c0 = 0; c0 < n_words; c0 += chunk_words) b.push_back(std::min(n_words, c0 + chunk_words));
+    if (taper && b.size() >= 3) {                  // at least two chunks: split the last one
+        const uint64_t c0 = b[b.size() - 2], len = n_words - c0;
+        if (len >= 8192) {
+            b.pop_back();
+            for (uint64_t cut : {len / 2, len / 2 + len / 4, len / 2 + len / 4 + len / 8}) b.push_back(c0 + (cut & ~255ull));
+            b.push_back(n_words);
+        }
+    }
+    return b;
+}
+
 // ---- text residency ------------------------------------------------------------------------------
 static int ensure_text_buffers(vs_ctx *ctx, uint64_t n_words)
 {
@@ -232,10 +259,12 @@ constexpr uint64_t SKIP_MIN_WORDS = 16384;      // all-N runs at least this long
 //    runs, the contig-end plane dense or as runs per block, then k_masks_from_planes computes the chunk's masks;
 //  * otherwise the masks travel dense, or — when the view carries a sparse list and it is smaller — as memset + sparse
 //    entries + a scatter kernel.
+// `ready` returns the stream on which the chunk's data is complete (record the chunk's "arrived" event there).
 static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t c0, uint64_t c1,
-                              uint64_t &staged, uint64_t &bytes, uint32_t &launches)
+                              uint64_t &staged, uint64_t &bytes, uint32_t &launches, cudaStream_t &ready)
 {
     cudaStream_t cs = ctx->copy;
+    ready = cs;
     const uint64_t n = c1 - c0, g0 = first_word + c0;
     // bases [c0, c1] incl. the halo word; word c0 of a later chunk already arrived as the previous chunk's halo
     const uint64_t skip = c0 ? 1 : 0;
@@ -252,35 +281,39 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
             return VS_OK;
         };
         int r;
+        std::vector<std::pair<uint64_t, uint64_t>> skipped;
         for (uint64_t i = r0; i < r1; ++i) {
             const vs_plane_run &x = t->nm_runs[i];
             if (x.value != ~0u || x.count < SKIP_MIN_WORDS) continue;
             const uint64_t a = std::max<uint64_t>(x.word, w), b = std::min<uint64_t>((uint64_t)x.word + x.count, hi);
             if (b <= a) continue;
             if ((r = copy_bases(w, a)) != VS_OK) return r;
-            CK(cudaMemsetAsync(ctx->d_bases + (a - first_word), 0, (b - a) * sizeof(vs_bases), cs));
+            skipped.emplace_back(a, b);                      // zero-filled on the preparation stream below
             w = b;
         }
         if ((r = copy_bases(w, hi)) != VS_OK) return r;
-        // N plane: zero + runs
-        CK(cudaMemsetAsync(ctx->d_nm + c0, 0, (n + 1) * sizeof(uint32_t), cs));
-        CK(cudaMemsetAsync(ctx->d_em + c0, 0, (n + 1) * sizeof(uint32_t), cs));
-        auto fill = [&](const vs_plane_run *runs, uint64_t a, uint64_t b, uint32_t *plane) -> int {
-            if (b <= a) return VS_OK;
-            if (staged + (b - a) > ctx->runs_cap) return fail(ctx, VS_ERR_CUDA, "run staging area too small");
-            vs_plane_run *dst = ctx->d_runs + staged;
-            CK(cudaMemcpyAsync(dst, runs + a, (b - a) * sizeof(vs_plane_run), cudaMemcpyHostToDevice, cs));
-            uint64_t longest = 1;                      // longest clipped run: sets the number of segments (grid.y)
-            for (uint64_t i = a; i < b; ++i)
-                longest = std::max<uint64_t>(longest, std::min<uint64_t>((uint64_t)runs[i].word + runs[i].count, hi) - std::max<uint64_t>(runs[i].word, lo));
-            k_fill_runs<<<dim3((unsigned)((b - a + 7) / 8), (unsigned)((longest + FILL_SEG - 1) / FILL_SEG)), 256, 0, cs>>>(dst, b - a, lo, hi, first_word, plane);
-            launches++;
-            staged += b - a;
-            bytes += (b - a) * sizeof(vs_plane_run);
+        // N plane and contig-end plane (zeroed by begin_mask_source): the run lists go to the staging area, dense blocks
+        // of the contig-end plane straight into it; the fill and mask kernels run on the preparation stream
+        vs_plane_run *nm_dst = nullptr, *em_dst = nullptr;
+        uint64_t nm_n = 0, em_n = 0;
+        auto stage = [&](const vs_plane_run *runs, uint64_t a, uint64_t b, vs_plane_run *&dst, uint64_t &cnt) -> int {
+            cnt = b > a ? b - a : 0;
+            if (!cnt) return VS_OK;
+            if (staged + cnt > ctx->runs_cap) return fail(ctx, VS_ERR_CUDA, "run staging area too small");
+            dst = ctx->d_runs + staged;
+            CK(cudaMemcpyAsync(dst, runs + a, cnt * sizeof(vs_plane_run), cudaMemcpyHostToDevice, cs));
+            staged += cnt;
+            bytes += cnt * sizeof(vs_plane_run);
             return VS_OK;
         };
-        if ((r = fill(t->nm_runs, r0, r1, ctx->d_nm)) != VS_OK) return r;
-        // contig-end plane: dense blocks as spans, the others as runs
+        auto longest_run = [&](const vs_plane_run *runs, uint64_t a, uint64_t b) {     // clipped to [lo, hi): sets grid.y of the fill
+            uint64_t m = 1;
+            for (uint64_t i = a; i < b; ++i)
+                m = std::max<uint64_t>(m, std::min<uint64_t>((uint64_t)runs[i].word + runs[i].count, hi) - std::max<uint64_t>(runs[i].word, lo));
+            return m;
+        };
+        const uint64_t nm_long = longest_run(t->nm_runs, r0, r1);
+        if ((r = stage(t->nm_runs, r0, r1, nm_dst, nm_n)) != VS_OK) return r;
         uint64_t span0 = 0, span1 = 0;       // pending dense span [span0, span1) in global words
         auto flush_span = [&]() -> int {
             if (span1 > span0) {
@@ -293,13 +326,28 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
         for (uint64_t b = lo / VS_EM_BLOCK; b * VS_EM_BLOCK < hi; ++b) {
             if (!t->em_dense[b]) { if ((r = flush_span()) != VS_OK) return r; continue; }
             const uint64_t a = std::max<uint64_t>(b * VS_EM_BLOCK, lo), e = std::min<uint64_t>((b + 1) * VS_EM_BLOCK, hi);
-            if (span1 == a) span1 = e; else { if ((r = flush_span()) != VS_OK) return r; span0 = a; span1 = e; }
+            if (span1 == a && span1 > span0) span1 = e; else { if ((r = flush_span()) != VS_OK) return r; span0 = a; span1 = e; }
         }
         if ((r = flush_span()) != VS_OK) return r;
         runs_in_range(t->em_runs, t->n_em_runs, lo, hi, r0, r1);
-        if ((r = fill(t->em_runs, r0, r1, ctx->d_em)) != VS_OK) return r;
-        k_masks_from_planes<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(ctx->d_nm + c0, ctx->d_em + c0, n, ctx->d_masks + c0);
+        const uint64_t em_long = longest_run(t->em_runs, r0, r1);
+        if ((r = stage(t->em_runs, r0, r1, em_dst, em_n)) != VS_OK) return r;
+        // everything of this chunk is on its way: hand over to the preparation stream
+        cudaStream_t ps = ctx->prep;
+        CK(cudaEventRecord(ctx->ev_copied, cs));
+        CK(cudaStreamWaitEvent(ps, ctx->ev_copied, 0));
+        for (const auto &sk : skipped) CK(cudaMemsetAsync(ctx->d_bases + (sk.first - first_word), 0, (sk.second - sk.first) * sizeof(vs_bases), ps));
+        if (nm_n) {
+            k_fill_runs<<<dim3((unsigned)((nm_n + 7) / 8), (unsigned)((nm_long + FILL_SEG - 1) / FILL_SEG)), 256, 0, ps>>>(nm_dst, nm_n, lo, hi, first_word, ctx->d_nm);
+            launches++;
+        }
+        if (em_n) {
+            k_fill_runs<<<dim3((unsigned)((em_n + 7) / 8), (unsigned)((em_long + FILL_SEG - 1) / FILL_SEG)), 256, 0, ps>>>(em_dst, em_n, lo, hi, first_word, ctx->d_em);
+            launches++;
+        }
+        k_masks_from_planes<<<(unsigned)((n + 255) / 256), 256, 0, ps>>>(ctx->d_nm + c0, ctx->d_em + c0, n, ctx->d_masks + c0);
         launches++;
+        ready = ps;
         return VS_OK;
     }
     CK(cudaMemcpyAsync(ctx->d_bases + c0 + skip, t->bases + g0 + skip, (n + 1 - skip) * sizeof(vs_bases), cudaMemcpyHostToDevice, cs));
@@ -345,7 +393,7 @@ static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t fi
         uint64_t a0, a1, b0, b1;
         runs_in_range(t->nm_runs, t->n_nm_runs, first_word, first_word + n_words + 1, a0, a1);
         runs_in_range(t->em_runs, t->n_em_runs, first_word, first_word + n_words + 1, b0, b1);
-        const uint64_t n_chunks = (n_words + ctx->chunk_words - 1) / ctx->chunk_words;
+        const uint64_t n_chunks = (n_words + ctx->chunk_words - 1) / ctx->chunk_words + 3;     // + the tapered tail of chunk_plan()
         const uint64_t need = (a1 - a0) + (b1 - b0) + 4 * n_chunks + 16;
         if (need > ctx->runs_cap) {
             CK(cudaStreamSynchronize(ctx->copy));
@@ -365,6 +413,20 @@ static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t fi
         CK(cudaMalloc(&ctx->d_sparse, need * sizeof(vs_mask_entry)));
         ctx->sparse_cap = need;
     }
+    return VS_OK;
+}
+
+// Start of an upload of a view with a compact mask source: zero both planes of the shard on the preparation stream
+// (after `after`, an event of the caller's stream, if given) and make the copy stream wait for it — the dense blocks of
+// the contig-end plane are copied straight into the zeroed plane.
+static int begin_mask_source(vs_ctx *ctx, const vs_text_view *t, uint64_t n_words, cudaEvent_t after)
+{
+    if (!has_mask_source(t)) return VS_OK;
+    if (after) CK(cudaStreamWaitEvent(ctx->prep, after, 0));
+    CK(cudaMemsetAsync(ctx->d_nm, 0, (n_words + 1) * sizeof(uint32_t), ctx->prep));
+    CK(cudaMemsetAsync(ctx->d_em, 0, (n_words + 1) * sizeof(uint32_t), ctx->prep));
+    CK(cudaEventRecord(ctx->ev_zeroed, ctx->prep));
+    CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_zeroed, 0));
     return VS_OK;
 }
 
@@ -388,12 +450,15 @@ extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first
     if ((r = ensure_sparse_staging(ctx, t, first_word, n_words)) != VS_OK) return r;
     uint64_t sparse_used = 0, bytes = 0;
     uint32_t launches = 0;
+    cudaStream_t ready;
+    if ((r = begin_mask_source(ctx, t, n_words, nullptr)) != VS_OK) return r;
     for (uint64_t c0 = 0; c0 < n_words; c0 += ctx->chunk_words) {
         uint64_t c1 = std::min(n_words, c0 + ctx->chunk_words);
-        if ((r = enqueue_chunk_copy(ctx, t, first_word, c0, c1, sparse_used, bytes, launches)) != VS_OK) return r;
+        if ((r = enqueue_chunk_copy(ctx, t, first_word, c0, c1, sparse_used, bytes, launches, ready)) != VS_OK) return r;
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->copy));
+    CK(cudaStreamSynchronize(ctx->prep));
     ctx->n_words = n_words;
     ctx->first_word = first_word;
     ctx->err.clear();
@@ -437,7 +502,8 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     PamParams pp;
     make_pam(extra_pam, pp);
     const uint64_t chunk_words = ctx->chunk_words;
-    const uint32_t n_chunks = (uint32_t)((n_words + chunk_words - 1) / chunk_words);
+    const std::vector<uint64_t> plan = chunk_plan(n_words, chunk_words, src != nullptr);
+    const uint32_t n_chunks = (uint32_t)(plan.size() - 1);
     const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
     // tile size: about 60 blocks (both strands) per 64-thread CTA at the expected PAM density pp.n / 16 per strand
     uint32_t tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
@@ -520,7 +586,7 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
 
     // extraction of chunk c into candidate buffer `buf` on stream `es`, scoring on the main stream
     auto launch_extract = [&](uint32_t c, int buf, cudaStream_t es) -> int {
-        const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
+        const uint64_t c0 = plan[c], c1 = plan[c + 1];
         const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
         k_extract<<<tiles, EX_THREADS, 0, es>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, ctx->first_word * 32, pp,
                                                  ctx->d_planes[buf][0], ctx->d_pos[buf][0], ctx->d_planes[buf][1], ctx->d_pos[buf][1],
@@ -563,15 +629,19 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
         CK(cudaMemsetAsync(ctx->d_cnt, 0, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), st));
         CK(cudaEventRecord(ctx->ev[2], st));
         CK(cudaStreamWaitEvent(es, ctx->ev[2], 0));                  // counters are zeroed before any extraction
-        if (source) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[0], 0));
+        if (source) {
+            CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[0], 0));
+            if ((r = begin_mask_source(ctx, source, n_words, ctx->ev[0])) != VS_OK) return r;
+        }
         uint64_t sparse_used = 0;
         for (uint32_t c = 0; c < n_chunks; ++c) {
             cudaEvent_t *E = &ctx->ev_pool[(size_t)EVC * c];
             const int buf = (int)(c & 1);
             if (source) {
-                const uint64_t c0 = (uint64_t)c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
-                if ((r = enqueue_chunk_copy(ctx, source, first_word, c0, c1, sparse_used, S.h2d_bytes, S.launches)) != VS_OK) return r;
-                CK(cudaEventRecord(E[0], ctx->copy));
+                const uint64_t c0 = plan[c], c1 = plan[c + 1];
+                cudaStream_t ready;
+                if ((r = enqueue_chunk_copy(ctx, source, first_word, c0, c1, sparse_used, S.h2d_bytes, S.launches, ready)) != VS_OK) return r;
+                CK(cudaEventRecord(E[0], ready));
                 CK(cudaStreamWaitEvent(es, E[0], 0));
             } else {
                 CK(cudaEventRecord(E[0], es));
