@@ -73,12 +73,15 @@ typedef struct { uint32_t word, iv, lw; } vs_mask_entry;
  * swarm of short contigs (variant segments) costs 4 B per word (`em`) instead of 8 B (masks).
  *   run   {word, count, value}: words [word, word + count) of the plane all equal `value` (non-zero)
  *   nm_runs : every non-zero word of nm, in ascending order
- *   em      : the dense plane; read only for the blocks flagged in em_dense
- *   em_dense: one byte per block of VS_EM_BLOCK words; 1 = the block's em words travel dense, 0 = they are listed in em_runs
- *   em_runs : every non-zero word of em that lies in a block with em_dense == 0, ascending
- * A view carries the source iff em and em_dense are set (nm_runs / em_runs may be NULL when their counts are 0);
+ *   em_code : one byte per word of em: the index of the word's only set bit, or VS_EM_NONE when the word is zero or has
+ *             several bits set; read only for the blocks flagged in em_dense (a contig of >= 32 bases puts at most one end
+ *             into a word, so a swarm of 45-base contigs costs one byte per 32 bases)
+ *   em_dense: one byte per block of VS_EM_BLOCK words; 1 = the block travels as em_code, 0 = its non-zero words are in em_runs
+ *   em_runs : ascending; every non-zero word of a block with em_dense == 0, and the words with several bits of the others
+ * A view carries the source iff em_code and em_dense are set (nm_runs / em_runs may be NULL when their counts are 0);
  * otherwise uploads use masks / sparse. */
 #define VS_EM_BLOCK 4096
+#define VS_EM_NONE 32
 typedef struct { uint32_t word, count, value; } vs_plane_run;
 
 typedef struct {
@@ -92,7 +95,7 @@ typedef struct {
     const vs_mask_entry *sparse;       /* n_sparse entries, or NULL */
     uint64_t n_sparse;
     /* compact mask source, or all NULL / 0 */
-    const uint32_t      *em;           /* n_words + 1 */
+    const uint8_t       *em_code;      /* n_words + 1 */
     const uint8_t       *em_dense;     /* ceil((n_words + 1) / VS_EM_BLOCK) */
     const vs_plane_run  *nm_runs;
     const vs_plane_run  *em_runs;
@@ -100,9 +103,9 @@ typedef struct {
 } vs_text_view;
 
 /* Build the compact mask source from the two planes (n_words + 1 words each).  The members of *out are malloc'd;
- * release them with vs_mask_source_free.  out->em is NOT copied: it aliases the caller's plane. */
+ * release them with vs_mask_source_free. */
 typedef struct {
-    const uint32_t *em;
+    uint8_t        *em_code;
     uint8_t        *em_dense;
     vs_plane_run   *nm_runs;
     vs_plane_run   *em_runs;

@@ -118,7 +118,7 @@ def _expand_runs(runs, n):
 
 
 def test_mask_source_reproduces_the_planes():
-    """vs_mask_source_build: N-plane runs + contig-end plane (dense blocks / runs elsewhere) expand to the planes they came from."""
+    """vs_mask_source_build: N-plane runs + contig-end plane (code bytes in coded blocks / runs elsewhere) expand to the planes they came from."""
     rng = np.random.default_rng(5)
     nw = 3 * 4096 + 100                       # four blocks of the contig-end plane, the last one partial
     nm = np.zeros(nw + 1, dtype=np.uint32)
@@ -128,23 +128,27 @@ def test_mask_source_reproduces_the_planes():
     nm[nw] = 0xFFFFFFFF
     em = np.zeros(nw + 1, dtype=np.uint32)
     em[17] = 1 << 5                           # block 0: sparse
-    em[4096:8192] = rng.integers(1, 1 << 32, 4096, dtype=np.uint64).astype(np.uint32)       # block 1: dense
+    em[4096:8192] = np.uint32(1) << rng.integers(0, 32, 4096).astype(np.uint32)               # block 1: one end per word -> coded
+    em[5000] = 0x80000001; em[5001] = 0x80000001; em[6000] = 0x00010100                       # ... except three words with two ends
     em[8192:8192 + 1300:1] = 7                # block 2: one run of 1300 equal words stays sparse
     em[12288 + 3] = 1 << 31                   # block 3 (partial): sparse
     t = V.PackedText.from_planes(np.zeros(nw + 1, np.uint32), np.zeros(nw + 1, np.uint32), nm, em, np.array([0, nw * 32], np.uint64), nw * 32)
-    assert t.has_source and t.em.tolist() == em.tolist()
-    assert t.em_dense.tolist() == [0, 1, 0, 0]
+    assert t.has_source and t.em_dense.tolist() == [0, 1, 0, 0]
+    single = (em[4096:8192] & (em[4096:8192] - 1)) == 0
+    code = t.em_code[4096:8192]
+    assert (code[single] == np.log2(em[4096:8192][single]).astype(np.uint8)).all() and (code[~single] == 32).all()
+    assert (t.em_code[:4096] == 32).all() and (t.em_code[8192:] == 32).all()
     assert _expand_runs(t.nm_runs, nw + 1).tolist() == nm.tolist()
     assert len(t.nm_runs) == 5 and t.nm_runs["count"].tolist() == [4990, 1, 2, 1, 1]
-    sparse_part = em.copy(); sparse_part[4096:8192] = 0
+    sparse_part = em.copy(); sparse_part[4096:8192][single] = 0
     assert _expand_runs(t.em_runs, nw + 1).tolist() == sparse_part.tolist()
-    assert len(t.em_runs) == 3
+    assert len(t.em_runs) == 5                # word 17, run {5000, 2}, word 6000, the run of 1300, word 12291
     # the streaming packer builds the same source as the one-shot path
     lens = [700, 0, 45, 23, 5000]
     asc = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), sum(lens), p=[.24, .24, .24, .24, .04]))
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     a = V.PackedText.from_ascii(asc, off)
-    assert a.has_source and len(a.em) == a.n_words + 1 and len(a.em_dense) == (a.n_words + 4096) // 4096
+    assert a.has_source and len(a.em_code) == a.n_words + 1 and len(a.em_dense) == (a.n_words + 4096) // 4096
 
 
 def test_text_cache_keeps_the_mask_source(tmp_path):
@@ -154,12 +158,12 @@ def test_text_cache_keeps_the_mask_source(tmp_path):
     a = V.PackedText.from_fasta(p)
     b = V.PackedText.from_ascii(case.ascii, case.offsets)
     assert a.has_source and b.has_source
-    for name in ("em", "em_dense", "nm_runs", "em_runs"):
+    for name in ("em_code", "em_dense", "nm_runs", "em_runs"):
         assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
     a.save(str(tmp_path / "idx"))
     u = V.PackedText.load(str(tmp_path / "idx"))
     assert u.has_source and u.masks.tobytes() == a.masks.tobytes()
-    for name in ("em", "em_dense", "nm_runs", "em_runs"):
+    for name in ("em_code", "em_dense", "nm_runs", "em_runs"):
         assert getattr(u, name).tobytes() == getattr(a, name).tobytes(), name
     # a view without the source is saved without it, and loads without it
     v = a.view(use_source=False)

@@ -45,12 +45,12 @@ class TextView(C.Structure):
     _fields_ = [("n_bases", C.c_uint64), ("n_words", C.c_uint64), ("n_contigs", C.c_uint32), ("reserved", C.c_uint32),
                 ("contig_off", C.c_void_p), ("bases", C.c_void_p), ("masks", C.c_void_p), ("sparse", C.c_void_p),
                 ("n_sparse", C.c_uint64),
-                ("em", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
+                ("em_code", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
                 ("n_nm_runs", C.c_uint64), ("n_em_runs", C.c_uint64)]
 
 
 class MaskSource(C.Structure):
-    _fields_ = [("em", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
+    _fields_ = [("em_code", C.c_void_p), ("em_dense", C.c_void_p), ("nm_runs", C.c_void_p), ("em_runs", C.c_void_p),
                 ("n_nm_runs", C.c_uint64), ("n_em_runs", C.c_uint64), ("n_em_blocks", C.c_uint64)]
 
 

@@ -36,7 +36,8 @@ struct vs_ctx {
     uint64_t sparse_cap = 0;
     // compact mask source path: the N and contig-end planes of the shard (+ halo word) and a staging area for their runs
     uint32_t *d_nm = nullptr, *d_em = nullptr;
-    uint64_t planes_cap = 0;
+    uint8_t *d_emcode = nullptr, *d_dense = nullptr;     // code bytes of the shard's contig-end plane; coded-block flags of the whole text
+    uint64_t planes_cap = 0, dense_cap = 0;
     vs_plane_run *d_runs = nullptr;
     uint64_t runs_cap = 0;
     // counters: per chunk [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev; then one hit counter
@@ -144,7 +145,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->prep) cudaStreamSynchronize(ctx->prep);
     if (ctx->exs) cudaStreamSynchronize(ctx->exs);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
-    cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_runs);
+    cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_runs); cudaFree(ctx->d_emcode); cudaFree(ctx->d_dense);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (int b = 0; b < 2; ++b) for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]); }
@@ -243,7 +244,7 @@ static int ensure_text_buffers(vs_ctx *ctx, uint64_t n_words)
     return VS_OK;
 }
 
-static inline bool has_mask_source(const vs_text_view *t) { return t->em && t->em_dense; }
+static inline bool has_mask_source(const vs_text_view *t) { return t->em_code && t->em_dense; }
 
 // runs of a sorted run list that overlap the word range [lo, hi): index range [first, last)
 static void runs_in_range(const vs_plane_run *r, uint64_t n, uint64_t lo, uint64_t hi, uint64_t &first, uint64_t &last)
@@ -292,8 +293,8 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
             w = b;
         }
         if ((r = copy_bases(w, hi)) != VS_OK) return r;
-        // N plane and contig-end plane (zeroed by begin_mask_source): the run lists go to the staging area, dense blocks
-        // of the contig-end plane straight into it; the fill and mask kernels run on the preparation stream
+        // N plane and contig-end plane (zeroed by begin_mask_source): the run lists go to the staging area, the code bytes of
+        // coded blocks to their own buffer; the expand, fill and mask kernels run on the preparation stream
         vs_plane_run *nm_dst = nullptr, *em_dst = nullptr;
         uint64_t nm_n = 0, em_n = 0;
         auto stage = [&](const vs_plane_run *runs, uint64_t a, uint64_t b, vs_plane_run *&dst, uint64_t &cnt) -> int {
@@ -314,11 +315,13 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
         };
         const uint64_t nm_long = longest_run(t->nm_runs, r0, r1);
         if ((r = stage(t->nm_runs, r0, r1, nm_dst, nm_n)) != VS_OK) return r;
-        uint64_t span0 = 0, span1 = 0;       // pending dense span [span0, span1) in global words
+        uint64_t span0 = 0, span1 = 0;       // pending span [span0, span1) of coded blocks, in global words
+        bool any_coded = false;
         auto flush_span = [&]() -> int {
             if (span1 > span0) {
-                CK(cudaMemcpyAsync(ctx->d_em + (span0 - first_word), t->em + span0, (span1 - span0) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
-                bytes += (span1 - span0) * sizeof(uint32_t);
+                CK(cudaMemcpyAsync(ctx->d_emcode + (span0 - first_word), t->em_code + span0, span1 - span0, cudaMemcpyHostToDevice, cs));
+                bytes += span1 - span0;
+                any_coded = true;
             }
             span0 = span1 = 0;
             return VS_OK;
@@ -339,6 +342,10 @@ static int enqueue_chunk_copy(vs_ctx *ctx, const vs_text_view *t, uint64_t first
         for (const auto &sk : skipped) CK(cudaMemsetAsync(ctx->d_bases + (sk.first - first_word), 0, (sk.second - sk.first) * sizeof(vs_bases), ps));
         if (nm_n) {
             k_fill_runs<<<dim3((unsigned)((nm_n + 7) / 8), (unsigned)((nm_long + FILL_SEG - 1) / FILL_SEG)), 256, 0, ps>>>(nm_dst, nm_n, lo, hi, first_word, ctx->d_nm);
+            launches++;
+        }
+        if (any_coded) {
+            k_expand_em_code<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ps>>>(ctx->d_emcode + c0, ctx->d_dense, lo, n + 1, ctx->d_em + c0);
             launches++;
         }
         if (em_n) {
@@ -384,11 +391,20 @@ static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t fi
     if (has_mask_source(t)) {
         if (n_words + 1 > ctx->planes_cap) {
             CK(cudaStreamSynchronize(ctx->copy));
-            cudaFree(ctx->d_nm); cudaFree(ctx->d_em);
-            ctx->d_nm = ctx->d_em = nullptr; ctx->planes_cap = 0;
+            cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_emcode);
+            ctx->d_nm = ctx->d_em = nullptr; ctx->d_emcode = nullptr; ctx->planes_cap = 0;
             CK(cudaMalloc(&ctx->d_nm, (n_words + 1) * sizeof(uint32_t)));
             CK(cudaMalloc(&ctx->d_em, (n_words + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_emcode, n_words + 1));
             ctx->planes_cap = n_words + 1;
+        }
+        const uint64_t n_blocks = (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK;
+        if (n_blocks > ctx->dense_cap) {
+            CK(cudaStreamSynchronize(ctx->copy));
+            CK(cudaStreamSynchronize(ctx->prep));
+            cudaFree(ctx->d_dense); ctx->d_dense = nullptr; ctx->dense_cap = 0;
+            CK(cudaMalloc(&ctx->d_dense, n_blocks));
+            ctx->dense_cap = n_blocks;
         }
         uint64_t a0, a1, b0, b1;
         runs_in_range(t->nm_runs, t->n_nm_runs, first_word, first_word + n_words + 1, a0, a1);
@@ -418,13 +434,14 @@ static int ensure_sparse_staging(vs_ctx *ctx, const vs_text_view *t, uint64_t fi
 
 // Start of an upload of a view with a compact mask source: zero both planes of the shard on the preparation stream
 // (after `after`, an event of the caller's stream, if given) and make the copy stream wait for it — the dense blocks of
-// the contig-end plane are copied straight into the zeroed plane.
+// the coded-block flags of the contig-end plane go to the device once per upload.
 static int begin_mask_source(vs_ctx *ctx, const vs_text_view *t, uint64_t n_words, cudaEvent_t after)
 {
     if (!has_mask_source(t)) return VS_OK;
     if (after) CK(cudaStreamWaitEvent(ctx->prep, after, 0));
     CK(cudaMemsetAsync(ctx->d_nm, 0, (n_words + 1) * sizeof(uint32_t), ctx->prep));
     CK(cudaMemsetAsync(ctx->d_em, 0, (n_words + 1) * sizeof(uint32_t), ctx->prep));
+    CK(cudaMemcpyAsync(ctx->d_dense, t->em_dense, (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK, cudaMemcpyHostToDevice, ctx->prep));
     CK(cudaEventRecord(ctx->ev_zeroed, ctx->prep));
     CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_zeroed, 0));
     return VS_OK;
@@ -435,7 +452,7 @@ static int check_view(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, u
     if (!t || !t->bases || (!t->masks && t->n_words)) return fail(ctx, VS_ERR_ARG, "text view is incomplete");
     if (first_word + n_words > t->n_words) return fail(ctx, VS_ERR_ARG, "shard lies outside the text");
     if (t->n_words * 32 > (1ull << 32)) return fail(ctx, VS_ERR_ARG, "text exceeds 4 Gbases (32-bit positions, as common.h:9-19)");
-    if ((t->em != nullptr) != (t->em_dense != nullptr) || (has_mask_source(t) && ((t->n_nm_runs && !t->nm_runs) || (t->n_em_runs && !t->em_runs))))
+    if ((t->em_code != nullptr) != (t->em_dense != nullptr) || (has_mask_source(t) && ((t->n_nm_runs && !t->nm_runs) || (t->n_em_runs && !t->em_runs))))
         return fail(ctx, VS_ERR_ARG, "text view carries an incomplete compact mask source");
     return VS_OK;
 }

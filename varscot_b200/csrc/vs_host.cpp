@@ -69,8 +69,8 @@ extern "C" int vs_masks_sparse(const vs_masks *masks, uint64_t n_words, vs_mask_
 }
 
 // Compact mask source (include/varscot_scan.h): runs of equal non-zero words for the N plane; for the contig-end plane
-// a dense/sparse decision per block of VS_EM_BLOCK words (dense when listing the block's non-zero words as 12-byte runs
-// would cost more than its 4 bytes per word).
+// a decision per block of VS_EM_BLOCK words: as one code byte per word (+ runs for the words with several bits) when
+// that is smaller than listing the block's non-zero words as 12-byte runs.
 static void append_run(std::vector<vs_plane_run> &runs, uint64_t w, uint32_t v)
 {
     if (!runs.empty() && runs.back().value == v && (uint64_t)runs.back().word + runs.back().count == w) runs.back().count++;
@@ -78,23 +78,31 @@ static void append_run(std::vector<vs_plane_run> &runs, uint64_t w, uint32_t v)
 }
 
 static int build_mask_source(const uint32_t *nm, const uint32_t *em, uint64_t n_words, std::vector<vs_plane_run> &nm_runs,
-                             std::vector<vs_plane_run> &em_runs, std::vector<uint8_t> &em_dense)
+                             std::vector<vs_plane_run> &em_runs, std::vector<uint8_t> &em_dense, std::vector<uint8_t> &em_code)
 {
     const uint64_t n = n_words + 1, n_blocks = (n + VS_EM_BLOCK - 1) / VS_EM_BLOCK;
     try {
         nm_runs.clear(); em_runs.clear();
         em_dense.assign(n_blocks, 0);
+        em_code.assign(n, (uint8_t)VS_EM_NONE);
         for (uint64_t w = 0; w < n; ++w)
             if (nm[w]) append_run(nm_runs, w, nm[w]);
+        std::vector<vs_plane_run> all, multi;
         for (uint64_t b = 0; b < n_blocks; ++b) {
             const uint64_t w0 = b * VS_EM_BLOCK, w1 = std::min<uint64_t>(n, w0 + VS_EM_BLOCK);
-            const size_t before = em_runs.size();
+            all.clear(); multi.clear();
             for (uint64_t w = w0; w < w1; ++w)
-                if (em[w]) append_run(em_runs, w, em[w]);
-            if ((em_runs.size() - before) * sizeof(vs_plane_run) > (w1 - w0) * sizeof(uint32_t)) {
-                em_runs.resize(before);
-                em_dense[b] = 1;
-            }
+                if (em[w]) {
+                    append_run(all, w, em[w]);
+                    if (em[w] & (em[w] - 1)) append_run(multi, w, em[w]);
+                }
+            const bool coded = all.size() * sizeof(vs_plane_run) > (w1 - w0) + multi.size() * sizeof(vs_plane_run);
+            em_dense[b] = coded ? 1 : 0;
+            if (coded)
+                for (uint64_t w = w0; w < w1; ++w)
+                    if (em[w] && !(em[w] & (em[w] - 1))) em_code[w] = (uint8_t)__builtin_ctz(em[w]);
+            const std::vector<vs_plane_run> &keep = coded ? multi : all;
+            em_runs.insert(em_runs.end(), keep.begin(), keep.end());
         }
     } catch (...) { return VS_ERR_NOMEM; }
     return VS_OK;
@@ -105,14 +113,15 @@ extern "C" int vs_mask_source_build(const uint32_t *nm, const uint32_t *em, uint
     if (!nm || !em || !out) return VS_ERR_ARG;
     memset(out, 0, sizeof(*out));
     std::vector<vs_plane_run> nr, er;
-    std::vector<uint8_t> ed;
-    int r = build_mask_source(nm, em, n_words, nr, er, ed);
+    std::vector<uint8_t> ed, ec;
+    int r = build_mask_source(nm, em, n_words, nr, er, ed, ec);
     if (r != VS_OK) return r;
-    out->em = em;
+    out->em_code = (uint8_t *)malloc(ec.size() ? ec.size() : 1);
     out->em_dense = (uint8_t *)malloc(ed.size() ? ed.size() : 1);
     out->nm_runs = (vs_plane_run *)malloc((nr.size() ? nr.size() : 1) * sizeof(vs_plane_run));
     out->em_runs = (vs_plane_run *)malloc((er.size() ? er.size() : 1) * sizeof(vs_plane_run));
-    if (!out->em_dense || !out->nm_runs || !out->em_runs) { vs_mask_source_free(out); return VS_ERR_NOMEM; }
+    if (!out->em_code || !out->em_dense || !out->nm_runs || !out->em_runs) { vs_mask_source_free(out); return VS_ERR_NOMEM; }
+    if (!ec.empty()) memcpy(out->em_code, ec.data(), ec.size());
     if (!ed.empty()) memcpy(out->em_dense, ed.data(), ed.size());
     if (!nr.empty()) memcpy(out->nm_runs, nr.data(), nr.size() * sizeof(vs_plane_run));
     if (!er.empty()) memcpy(out->em_runs, er.data(), er.size() * sizeof(vs_plane_run));
@@ -123,7 +132,7 @@ extern "C" int vs_mask_source_build(const uint32_t *nm, const uint32_t *em, uint
 extern "C" void vs_mask_source_free(vs_mask_source *s)
 {
     if (!s) return;
-    free(s->em_dense); free(s->nm_runs); free(s->em_runs);
+    free(s->em_code); free(s->em_dense); free(s->nm_runs); free(s->em_runs);
     memset(s, 0, sizeof(*s));
 }
 
@@ -132,8 +141,8 @@ struct vs_packer {
     std::vector<uint32_t> nm, em;
     std::vector<vs_masks> masks;
     std::vector<vs_mask_entry> sparse;
-    std::vector<vs_plane_run> nm_runs, em_runs;      // compact mask source (em stays alive for it)
-    std::vector<uint8_t> em_dense;
+    std::vector<vs_plane_run> nm_runs, em_runs;      // compact mask source
+    std::vector<uint8_t> em_dense, em_code;
     std::vector<uint64_t> off{0};
     uint64_t n = 0;
     bool finalized = false;
@@ -222,15 +231,16 @@ extern "C" int vs_packer_finish(vs_packer *p, vs_text_view *out)
             vs_masks_from_planes(p->nm.data(), p->em.data(), nw, p->masks.data());
             for (uint64_t w = 0; w < nw; ++w)
                 if (p->masks[w].iv | p->masks[w].lw) p->sparse.push_back(vs_mask_entry{(uint32_t)w, p->masks[w].iv, p->masks[w].lw});
-            if (build_mask_source(p->nm.data(), p->em.data(), nw, p->nm_runs, p->em_runs, p->em_dense) != VS_OK) return VS_ERR_NOMEM;
+            if (build_mask_source(p->nm.data(), p->em.data(), nw, p->nm_runs, p->em_runs, p->em_dense, p->em_code) != VS_OK) return VS_ERR_NOMEM;
             std::vector<uint32_t>().swap(p->nm);
+            std::vector<uint32_t>().swap(p->em);
         } catch (...) { return VS_ERR_NOMEM; }
         p->finalized = true;
     }
     out->n_bases = p->n; out->n_words = nw; out->n_contigs = (uint32_t)(p->off.size() - 1); out->reserved = 0;
     out->contig_off = p->off.data(); out->bases = p->bases.data(); out->masks = p->masks.data();
     out->sparse = p->sparse.data(); out->n_sparse = p->sparse.size();
-    out->em = p->em.data(); out->em_dense = p->em_dense.data();
+    out->em_code = p->em_code.data(); out->em_dense = p->em_dense.data();
     out->nm_runs = p->nm_runs.data(); out->em_runs = p->em_runs.data();
     out->n_nm_runs = p->nm_runs.size(); out->n_em_runs = p->em_runs.size();
     return VS_OK;
@@ -282,7 +292,7 @@ extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t 
 
 // ------------------------------------------------------------------------------------------------
 // packed-text cache: <prefix>.vsidx = header, offsets, bases, masks, sparse masks, then (format 003, when the view
-// carries one) the compact mask source: em, em_dense, nm_runs, em_runs.  All sections are 16-byte aligned.
+// carries one) the compact mask source: em_code, em_dense, nm_runs, em_runs.  All sections are 16-byte aligned.
 namespace {
 struct IdxHeader {
     char magic[8];
@@ -297,7 +307,7 @@ struct IdxSourceHeader {    // 003 only, directly after IdxHeader
 const char IDX_MAGIC2[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
 const char IDX_MAGIC3[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '3'};
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
-inline bool has_source(const vs_text_view *t) { return t->em && t->em_dense; }
+inline bool has_source(const vs_text_view *t) { return t->em_code && t->em_dense; }
 }  // namespace
 
 extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
@@ -324,7 +334,7 @@ extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
               put(t->bases, (t->n_words + 1) * sizeof(vs_bases)) && put(t->masks, t->n_words * sizeof(vs_masks)) &&
               put(sp, nsp * sizeof(vs_mask_entry));
     if (ok && has_source(t))
-        ok = put(t->em, (t->n_words + 1) * sizeof(uint32_t)) && put(t->em_dense, (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK) &&
+        ok = put(t->em_code, t->n_words + 1) && put(t->em_dense, (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK) &&
              put(t->nm_runs, sh.n_nm_runs * sizeof(vs_plane_run)) && put(t->em_runs, sh.n_em_runs * sizeof(vs_plane_run));
     ok = (fclose(f) == 0) && ok;
     free(tmp);
@@ -356,7 +366,7 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     const uint64_t nw = (h.n_bases + 31) >> 5;
     const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)),
                    s_m = pad16(nw * sizeof(vs_masks)), s_s = pad16(h.n_sparse * sizeof(vs_mask_entry));
-    const uint64_t s_em = src ? pad16((nw + 1) * sizeof(uint32_t)) : 0, s_ed = src ? pad16((nw + VS_EM_BLOCK) / VS_EM_BLOCK) : 0,
+    const uint64_t s_em = src ? pad16(nw + 1) : 0, s_ed = src ? pad16((nw + VS_EM_BLOCK) / VS_EM_BLOCK) : 0,
                    s_nr = src ? pad16(sh.n_nm_runs * sizeof(vs_plane_run)) : 0, s_er = src ? pad16(sh.n_em_runs * sizeof(vs_plane_run)) : 0;
     const uint64_t total = s_off + s_b + s_m + s_s + s_em + s_ed + s_nr + s_er;
     char *buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);
@@ -373,7 +383,7 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     out->n_sparse = h.n_sparse;
     if (src) {
         const char *q = buf + s_off + s_b + s_m + s_s;
-        out->em = (const uint32_t *)q;
+        out->em_code = (const uint8_t *)q;
         out->em_dense = (const uint8_t *)(q + s_em);
         out->nm_runs = (const vs_plane_run *)(q + s_em + s_ed);
         out->em_runs = (const vs_plane_run *)(q + s_em + s_ed + s_nr);

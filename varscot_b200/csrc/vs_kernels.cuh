@@ -302,6 +302,18 @@ k_fill_runs(const vs_plane_run *__restrict__ runs, uint64_t n_runs, uint64_t lo,
     for (uint64_t w = a + (threadIdx.x & 31); w < b; w += 32) plane[w - word_base] = x.value;
 }
 
+// k_expand_em_code: contig-end plane words from their one-byte codes, for the words of blocks that travel coded
+// (code = index of the only set bit, VS_EM_NONE = no single bit; words with several bits arrive as runs afterwards).
+// code / out point at the first word of the range (global word index g0), dense at block 0 of the text.
+__global__ void __launch_bounds__(256)
+k_expand_em_code(const uint8_t *__restrict__ code, const uint8_t *__restrict__ dense, uint64_t g0, uint64_t n, uint32_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !dense[(g0 + i) / VS_EM_BLOCK]) return;
+    const uint32_t c = code[i];
+    out[i] = c < 32u ? 1u << c : 0u;
+}
+
 // k_masks_from_planes: the device twin of masks_of() in vs_host.cpp.  nm / em point at the first word of the range and
 // hold n + 1 words (the last one is the halo);
 //   iv: any N in [p, p+23)  or  any contig end in [p, p+22)   (R1, R3)

@@ -75,15 +75,16 @@ class PackedText:
             sparse["iv"] = self.masks["iv"][nz]
             sparse["lw"] = self.masks["lw"][nz]
         self.sparse = np.ascontiguousarray(sparse, dtype=SPARSE_DT)
-        # compact mask source (include/varscot_scan.h): contig-end plane, its dense-block flags, N-plane runs, end-plane runs
-        self.em = self.em_dense = self.nm_runs = self.em_runs = None
+        # compact mask source (include/varscot_scan.h): code bytes of the contig-end plane, its coded-block flags, N-plane runs,
+        # end-plane runs
+        self.em_code = self.em_dense = self.nm_runs = self.em_runs = None
         if source is not None:
-            em, em_dense, nm_runs, em_runs = source
-            self.em = np.ascontiguousarray(em, dtype=np.uint32)
+            em_code, em_dense, nm_runs, em_runs = source
+            self.em_code = np.ascontiguousarray(em_code, dtype=np.uint8)
             self.em_dense = np.ascontiguousarray(em_dense, dtype=np.uint8)
             self.nm_runs = np.ascontiguousarray(nm_runs, dtype=RUN_DT)
             self.em_runs = np.ascontiguousarray(em_runs, dtype=RUN_DT)
-            assert len(self.em) == self.n_words + 1 and len(self.em_dense) == (self.n_words + 4096) // 4096
+            assert len(self.em_code) == self.n_words + 1 and len(self.em_dense) == (self.n_words + 4096) // 4096
         self._pinned = []
 
     @property
@@ -96,7 +97,7 @@ class PackedText:
 
     @property
     def has_source(self) -> bool:
-        return self.em is not None
+        return self.em_code is not None
 
     def view(self, use_sparse: bool = True, use_source: bool = True) -> _lib.TextView:
         """use_source: hand the compact mask source to the library when this text has one (uploads then move the planes and
@@ -109,13 +110,13 @@ class PackedText:
         v.sparse = self.sparse.ctypes.data if use_sparse else None
         v.n_sparse = len(self.sparse) if use_sparse else 0
         if use_source and self.has_source:
-            v.em, v.em_dense = self.em.ctypes.data, self.em_dense.ctypes.data
+            v.em_code, v.em_dense = self.em_code.ctypes.data, self.em_dense.ctypes.data
             v.nm_runs, v.em_runs = self.nm_runs.ctypes.data, self.em_runs.ctypes.data
             v.n_nm_runs, v.n_em_runs = len(self.nm_runs), len(self.em_runs)
         return v
 
     def _arrays(self):
-        return ("bases", "masks", "sparse") + (("em", "em_dense", "nm_runs", "em_runs") if self.has_source else ())
+        return ("bases", "masks", "sparse") + (("em_code", "em_dense", "nm_runs", "em_runs") if self.has_source else ())
 
     def pin(self):
         """Move bases, masks, sparse masks and the mask source into page-locked memory (vs_host_alloc) for full-speed H2D."""
@@ -151,7 +152,7 @@ class PackedText:
         ms = _lib.MaskSource()
         check(L.vs_mask_source_build(nm.ctypes.data, em.ctypes.data, nw, C.byref(ms)))
         try:
-            source = (em[:nw + 1].copy(), _copy_array(ms.em_dense, int(ms.n_em_blocks), np.dtype("u1")),
+            source = (_copy_array(ms.em_code, nw + 1, np.dtype("u1")), _copy_array(ms.em_dense, int(ms.n_em_blocks), np.dtype("u1")),
                       _copy_array(ms.nm_runs, int(ms.n_nm_runs), RUN_DT), _copy_array(ms.em_runs, int(ms.n_em_runs), RUN_DT))
         finally:
             L.vs_mask_source_free(C.byref(ms))
@@ -184,8 +185,8 @@ class PackedText:
     def _from_view(v, names=None) -> "PackedText":
         nw = int(v.n_words)
         source = None
-        if v.em and v.em_dense:
-            source = (_copy_array(v.em, nw + 1, np.dtype("<u4")), _copy_array(v.em_dense, (nw + 4096) // 4096, np.dtype("u1")),
+        if v.em_code and v.em_dense:
+            source = (_copy_array(v.em_code, nw + 1, np.dtype("u1")), _copy_array(v.em_dense, (nw + 4096) // 4096, np.dtype("u1")),
                       _copy_array(v.nm_runs, int(v.n_nm_runs), RUN_DT), _copy_array(v.em_runs, int(v.n_em_runs), RUN_DT))
         return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), _copy_array(v.masks, nw, MASKS_DT),
                           _copy_array(v.contig_off, int(v.n_contigs) + 1, np.dtype("<u8")), int(v.n_bases), names,
