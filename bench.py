@@ -49,7 +49,8 @@ def score_ops(k):
     """(LOP3, LDS) k_score executes per (32-candidate block, guide) in stage A, and the extra of stage B."""
     pa = 23 if k >= 8 else 7 + 2 * k
     a = (csa_ops(pa) + 2, pa)
-    b = (csa_ops(23 - pa, True) + 2, 23 - pa) if pa < 23 else (0, 0)
+    # stage B scores its slots from raw planes: 2 LDS + 2 LOP3 per slot, then the adders onto stage A's count
+    b = (csa_ops(23 - pa, True) + 2 + 2 * (23 - pa), 2 * (23 - pa)) if pa < 23 else (0, 0)
     return a, b
 
 CONFIGS = {
