@@ -112,6 +112,28 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
     }
 }
 
+// 16 x 32 bit-matrix, both 16 x 16 halves transposed in place: out[r] bits 0..15 = bit r of in[0..15], bits 16..31 =
+// bit 16 + r of in[0..15] (transpose32 without its first stage, on 16 rows).
+__device__ __forceinline__ void transpose16(uint32_t (&a)[16])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {                        // bytes: odd bytes of a[k] <-> even bytes of a[k+8]
+        const uint32_t x = a[k], y = a[k | 8];
+        a[k] = __byte_perm(x, y, 0x6240);
+        a[k | 8] = __byte_perm(x, y, 0x7351);
+    }
+    uint32_t m = 0x0F0F0F0Fu;
+#pragma unroll
+    for (int j = 4; j; j >>= 1, m ^= m << j) {
+#pragma unroll
+        for (int k = 0; k < 16; k = ((k | j) + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
+            a[k | j] ^= t;
+            a[k] ^= t << j;
+        }
+    }
+}
+
 constexpr int EX_THREADS   = 64;                  // threads per extraction CTA
 constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the host picks the tile so that it holds ~60 blocks
 
@@ -124,8 +146,11 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 // deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written for that tile; k_score
 // then skips the whole chunk and the host, which reads the counters back, regrows the stores and redoes the chunk.
 // Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; word w of block b at plane_index(b, w).
+#ifndef VS_EX_HALF
+#define VS_EX_HALF 0                  // 1: EXPERIMENTAL, not yet run on a GPU — one thread per half block (see phase 2 below)
+#endif
 #ifndef VS_EX_MINBLOCKS
-#define VS_EX_MINBLOCKS 10
+#define VS_EX_MINBLOCKS (VS_EX_HALF ? 16 : 10)
 #endif
 __global__ void __launch_bounds__(EX_THREADS, VS_EX_MINBLOCKS)
 k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
@@ -213,6 +238,71 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     }
     __syncthreads();
     const uint32_t gbase = (uint32_t)(global_base + w0 * 32);      // device word 0 sits at global_base
+#if VS_EX_HALF
+    // EXPERIMENTAL (compiled only with -DVS_EX_HALF=1, never run on a GPU so far): one thread per HALF block of 16
+    // candidates.  Half the registers (two 16-row transposes instead of two 32-row ones) let twice as many warps reside,
+    // which is what this latency-bound kernel lacks; the plane words leave as 16-bit halves (lane pairs write one word).
+    for (uint32_t j2 = tid; j2 < 2 * (nbf + nbr); j2 += EX_THREADS) {
+        const uint32_t j = j2 >> 1, half = j2 & 1u;
+        const int s = j >= nbf;
+        const uint32_t jj = s ? j - nbf : j;
+        const uint32_t n = s ? nr : nf;
+        const uint64_t blk = base[s] + jj;
+        if (blk >= cap) continue;                          // overflow: the chunk is redone by the host
+        const uint32_t r0 = jj * 32 + half * 16;           // rank of this half's first candidate
+        const uint32_t cnth = r0 < n ? min(16u, n - r0) : 0u;
+        // 16-bit half `half` of word w of the block sits at pl_out[2 * w * BLK_GROUP]
+        uint16_t *pl_out = reinterpret_cast<uint16_t *>((s ? planes_r : planes_f) + plane_index(blk, 0)) + half;
+        pl_out[2 * BLK_VALID * BLK_GROUP] = (uint16_t)((1u << cnth) - 1u);
+        if (cnth == 0) continue;                           // upper half of a short last block: only its valid bits matter
+        const uint32_t *sm = s_m[s], *sp = s_p[s];
+        uint32_t lo_w = 0, hi_w = nw;                      // invariant: sp[lo_w] <= r0 < sp[hi_w] (sp[nw] = n > r0)
+        while (hi_w - lo_w > 1) {
+            const uint32_t mid = (lo_w + hi_w) >> 1;
+            if (sp[mid] <= r0) lo_w = mid; else hi_w = mid;
+        }
+        uint32_t wcur = lo_w;
+        uint32_t m = sm[wcur];
+        for (uint32_t skip = r0 - sp[wcur]; skip; --skip) m &= m - 1;     // drop the candidates of earlier halves
+        uint2 ha = s_hl[wcur], hb = s_hl[wcur + 1];
+        uint32_t lwm = s_mk[wcur].y;
+        uint32_t ah[16], al[16];
+        uint32_t lastw = 0;
+        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32 + half * 16);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t pp4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c4 * 4 + u;
+                while (m == 0) {                           // next word with candidates (ends at the all-ones sentinel)
+                    ++wcur;
+                    m = sm[wcur];
+                    ha = hb; hb = s_hl[wcur + 1];
+                    lwm = s_mk[wcur].y;
+                }
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                ah[c] = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
+                al[c] = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
+                lastw |= ((lwm >> b) & 1u) << c;
+                pp4[u] = gbase + wcur * 32 + b;
+            }
+            ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
+        }
+        transpose16(ah);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pl_out[2 * i * BLK_GROUP] = (uint16_t)ah[i];
+#pragma unroll
+        for (int i = 16; i < VS_GLEN; ++i) pl_out[2 * i * BLK_GROUP] = (uint16_t)(ah[i - 16] >> 16);
+        transpose16(al);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pl_out[2 * (VS_GLEN + i) * BLK_GROUP] = (uint16_t)al[i];
+#pragma unroll
+        for (int i = 16; i < VS_GLEN; ++i) pl_out[2 * (VS_GLEN + i) * BLK_GROUP] = (uint16_t)(al[i - 16] >> 16);
+        pl_out[2 * BLK_LAST * BLK_GROUP] = (uint16_t)lastw;
+    }
+#else
     for (uint32_t j = tid; j < nbf + nbr; j += EX_THREADS) {
         const int s = j >= nbf;
         const uint32_t jj = s ? j - nbf : j;
@@ -272,6 +362,7 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
         pl_out[BLK_LAST * BLK_GROUP] = lastw;
         pl_out[BLK_VALID * BLK_GROUP] = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
     }
+#endif
 }
 
 // k_scatter_masks: expand the sparse form of the window masks (only words with a non-zero mask travel over PCIe).
