@@ -151,6 +151,51 @@ def test_mask_source_reproduces_the_planes():
     assert a.has_source and len(a.em_code) == a.n_words + 1 and len(a.em_dense) == (a.n_words + 4096) // 4096
 
 
+def _masks_from_source(t):
+    """What the device does with a compact mask source (k_fill_runs, k_expand_em_code, k_masks_from_planes), in numpy."""
+    import ctypes as C
+    from varscot_b200 import _lib
+    n = t.n_words + 1
+    nm = _expand_runs(t.nm_runs, n)
+    em = np.zeros(n, dtype=np.uint32)
+    coded = np.repeat(t.em_dense.astype(bool), 4096)[:n]
+    single = coded & (t.em_code < 32)
+    em[single] = np.uint32(1) << t.em_code[single].astype(np.uint32)
+    runs = _expand_runs(t.em_runs, n)
+    em[runs != 0] = runs[runs != 0]
+    masks = np.zeros(t.n_words, dtype=V.MASKS_DT)
+    _lib.check(_lib.lib().vs_masks_from_planes(nm.ctypes.data, em.ctypes.data, t.n_words, masks.ctypes.data))
+    return masks
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mask_source_expands_to_the_packers_masks(seed):
+    """Random texts (long contigs with N runs, swarms of 45-mers, contigs shorter than a window, empty contigs): the masks
+    rebuilt from the compact source equal the masks the packer computed from the planes."""
+    rng = np.random.default_rng(100 + seed)
+    lens = []
+    for _ in range(int(rng.integers(2, 6))):
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            lens += [int(rng.integers(50_000, 300_000))]
+        elif kind == 1:
+            lens += [45] * int(rng.integers(500, 6000))
+        elif kind == 2:
+            lens += rng.integers(0, 40, int(rng.integers(5, 400))).tolist()
+        else:
+            lens += rng.integers(30, 3000, int(rng.integers(5, 200))).tolist()
+    total = int(sum(lens))
+    asc = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, total)].copy()
+    for _ in range(int(rng.integers(0, 4))):                       # N runs, some longer than a coded block
+        a = int(rng.integers(0, max(1, total - 1)))
+        asc[a:a + int(rng.integers(1, 200_000))] = ord("N")
+    asc[rng.integers(0, total, total // 5000)] = ord("n")
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    t = V.PackedText.from_ascii(asc.tobytes(), off)
+    got = _masks_from_source(t)
+    assert got.tobytes() == t.masks.tobytes()
+
+
 def test_text_cache_keeps_the_mask_source(tmp_path):
     case = make_case(9, [3000, 45, 45, 0, 23, 800], 1, 4)
     p = str(tmp_path / "g.fa")
