@@ -283,8 +283,8 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
                 }
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
-                ah[c] = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
-                al[c] = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
+                ah[c] = __funnelshift_r(ha.x, hb.x, b);    // bits 23..31 are never stored: only planes 0..22 leave
+                al[c] = __funnelshift_r(ha.y, hb.y, b);
                 lastw |= ((lwm >> b) & 1u) << c;
                 pp4[u] = gbase + wcur * 32 + b;
             }
