@@ -140,6 +140,52 @@ def test_bam_merger_ref_only_equals_oracle(tmp_path, mit):
         assert open(fm).read() == exp_fm
 
 
+def test_ref_hits_inside_overlapping_segments(tmp_path):
+    """filterRefAlignment (filter_output_bam.h:99-108) drops a reference hit that lies wholly inside ANY variant segment of
+    its chromosome.  The product answers that with a binary search over the segments sorted by start + a running maximum of
+    their ends; the oracle keeps the reference's scan over all segments.  Nested, overlapping and merely adjacent segments —
+    the nearest segment by start often does not cover the hit while an earlier, longer one does."""
+    g, bed, snp, guides, tus = build_case(tmp_path, seed=11)
+    ref_sam, snp_sam = str(tmp_path / "ref.sam"), str(tmp_path / "snp.sam")
+    assert subprocess.run([ORACLE_MAPPER, "-G", g, "-R", guides, "-M", "5", "-O", ref_sam, "--md-style", "samtools"], capture_output=True).returncode == 0
+    open(snp_sam, "w").close()
+    genome = "".join(l.strip() for l in open(g) if not l.startswith(">"))
+    hits = sorted({int(l.split("\t")[3]) - 1 for l in open(ref_sam)})
+    assert len(hits) > 20
+    rng = np.random.default_rng(3)
+    segs = set()
+    for i, p in enumerate(hits):
+        kind = i % 5
+        if kind == 0:
+            segs.add((p - 30, 90))                                   # covers
+        elif kind == 1:
+            segs.add((p + 1, 60)); segs.add((max(0, p - 40), 62))    # starts after the hit / ends one base short
+        elif kind == 2:
+            segs.add((max(0, p - 400), 900))                         # a long early segment covers ...
+            for d in (300, 200, 100, 10, 0):
+                segs.add((max(0, p - d), 22))                        # ... the nearer ones are too short
+        elif kind == 3:
+            segs.add((p, 23))                                        # exactly the window
+        # kind 4: no segment near this hit
+    for _ in range(300):
+        a = int(rng.integers(0, len(genome) - 200))
+        segs.add((a, int(rng.integers(1, 120))))
+    with open(snp, "w") as f:
+        for a, n in sorted(segs, key=lambda x: (rng.random(), x)):   # file order is not sorted
+            f.write(f">chr1_{a}_REF\n{genome[a:a + n]}\n")
+    if os.path.exists(snp + ".fai"):
+        os.remove(snp + ".fai")
+    out, fm = str(tmp_path / "out.txt"), str(tmp_path / "fm.txt")
+    r = subprocess.run([os.path.join(VP, "bam_merger"), out, fm, ref_sam, snp_sam, bed, g, snp, tus, "5", "23", "1", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exp_text, _ = MO.bam_merger(ref_sam, snp_sam, bed, g, snp, tus, 23, 0)
+    got = open(out).read()
+    assert got == exp_text
+    kept = {int(l.split("\t")[1]) for l in got.splitlines()[1:]}
+    dropped = set(hits) - kept
+    assert len(dropped) >= len(hits) // 2 and len(kept) >= len(hits) // 6
+
+
 def test_usage_errors():
     assert subprocess.run([os.path.join(VP, "bam_merger")], capture_output=True).returncode == 1
     assert subprocess.run([os.path.join(VP, "bam_merger_ref_only"), "a"], capture_output=True).returncode == 1
