@@ -291,15 +291,18 @@ extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed-text cache: <prefix>.vsidx = header, offsets, bases, masks, sparse masks, then (format 003, when the view
-// carries one) the compact mask source: em_code, em_dense, nm_runs, em_runs.  All sections are 16-byte aligned.
+// packed-text cache: <prefix>.vsidx.  Format 003: header, source header, offsets, bases, then
+//   * a view WITH a compact mask source (what bidir_index writes): em_code, em_dense, nm_runs, em_runs — the window masks
+//     are not stored; vs_text_load rebuilds them from the source (the file is half the size: 0.27 B per base);
+//   * a view without one: masks, sparse masks.
+// Format 002 (header, offsets, bases, masks, sparse masks) still loads.  All sections are 16-byte aligned.
 namespace {
 struct IdxHeader {
     char magic[8];
     uint64_t n_bases;
     uint64_t n_sparse;
     uint32_t n_contigs;
-    uint32_t flags;          // 003: bit 0 = a compact mask source follows
+    uint32_t flags;          // 003: bit 0 = compact mask source stored (and masks / sparse masks are not)
 };
 struct IdxSourceHeader {    // 003 only, directly after IdxHeader
     uint64_t n_nm_runs, n_em_runs;
@@ -308,6 +311,26 @@ const char IDX_MAGIC2[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
 const char IDX_MAGIC3[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '3'};
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
 inline bool has_source(const vs_text_view *t) { return t->em_code && t->em_dense; }
+
+// planes from a compact mask source (the host twin of k_fill_runs / k_expand_em_code), then the masks
+int masks_from_source(const vs_text_view *t, vs_masks *out)
+{
+    const uint64_t n = t->n_words + 1;
+    std::vector<uint32_t> nm, em;
+    try { nm.assign(n, 0u); em.assign(n, 0u); } catch (...) { return VS_ERR_NOMEM; }
+    auto fill = [&](const vs_plane_run *r, uint64_t cnt, std::vector<uint32_t> &plane) {
+        for (uint64_t i = 0; i < cnt; ++i) {
+            if ((uint64_t)r[i].word + r[i].count > n) return false;
+            std::fill(plane.begin() + r[i].word, plane.begin() + r[i].word + r[i].count, r[i].value);
+        }
+        return true;
+    };
+    if (!fill(t->nm_runs, t->n_nm_runs, nm)) return VS_ERR_IO;
+    for (uint64_t w = 0; w < n; ++w)
+        if (t->em_dense[w / VS_EM_BLOCK] && t->em_code[w] < 32) em[w] = 1u << t->em_code[w];
+    if (!fill(t->em_runs, t->n_em_runs, em)) return VS_ERR_IO;
+    return vs_masks_from_planes(nm.data(), em.data(), t->n_words, out);
+}
 }  // namespace
 
 extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
@@ -316,14 +339,16 @@ extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
     std::string path = std::string(prefix) + ".vsidx";
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) { vs_set_last_error(("cannot open " + path + " for writing").c_str()); return VS_ERR_IO; }
+    const bool src = has_source(t);
     vs_mask_entry *tmp = nullptr;
     const vs_mask_entry *sp = t->sparse;
     uint64_t nsp = t->n_sparse;
-    if (!sp && t->n_words) { if (vs_masks_sparse(t->masks, t->n_words, &tmp, &nsp) != VS_OK) { fclose(f); return VS_ERR_NOMEM; } sp = tmp; }
+    if (src) { sp = nullptr; nsp = 0; }
+    else if (!sp && t->n_words) { if (vs_masks_sparse(t->masks, t->n_words, &tmp, &nsp) != VS_OK) { fclose(f); return VS_ERR_NOMEM; } sp = tmp; }
     IdxHeader h;
     memcpy(h.magic, IDX_MAGIC3, 8);
-    h.n_bases = t->n_bases; h.n_sparse = nsp; h.n_contigs = t->n_contigs; h.flags = has_source(t) ? 1u : 0u;
-    IdxSourceHeader sh{has_source(t) ? t->n_nm_runs : 0, has_source(t) ? t->n_em_runs : 0};
+    h.n_bases = t->n_bases; h.n_sparse = nsp; h.n_contigs = t->n_contigs; h.flags = src ? 1u : 0u;
+    IdxSourceHeader sh{src ? t->n_nm_runs : 0, src ? t->n_em_runs : 0};
     static const char zeros[16] = {0};
     auto put = [&](const void *p, uint64_t bytes) {
         bool ok = bytes == 0 || fwrite(p, 1, bytes, f) == bytes;
@@ -331,11 +356,12 @@ extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
         return ok && (pad == 0 || fwrite(zeros, 1, pad, f) == pad);
     };
     bool ok = put(&h, sizeof(h)) && put(&sh, sizeof(sh)) && put(t->contig_off, ((uint64_t)t->n_contigs + 1) * 8) &&
-              put(t->bases, (t->n_words + 1) * sizeof(vs_bases)) && put(t->masks, t->n_words * sizeof(vs_masks)) &&
-              put(sp, nsp * sizeof(vs_mask_entry));
-    if (ok && has_source(t))
+              put(t->bases, (t->n_words + 1) * sizeof(vs_bases));
+    if (ok && src)
         ok = put(t->em_code, t->n_words + 1) && put(t->em_dense, (t->n_words + VS_EM_BLOCK) / VS_EM_BLOCK) &&
              put(t->nm_runs, sh.n_nm_runs * sizeof(vs_plane_run)) && put(t->em_runs, sh.n_em_runs * sizeof(vs_plane_run));
+    else if (ok)
+        ok = put(t->masks, t->n_words * sizeof(vs_masks)) && put(sp, nsp * sizeof(vs_mask_entry));
     ok = (fclose(f) == 0) && ok;
     free(tmp);
     if (!ok) { vs_set_last_error(("short write to " + path).c_str()); return VS_ERR_IO; }
@@ -352,11 +378,10 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     if (!f) { vs_set_last_error(("cannot open " + path).c_str()); return VS_ERR_IO; }
     IdxHeader h;
     IdxSourceHeader sh{0, 0};
-    bool v3 = false;
     if (fread(&h, sizeof(h), 1, f) != 1 || (memcmp(h.magic, IDX_MAGIC2, 8) != 0 && memcmp(h.magic, IDX_MAGIC3, 8) != 0)) {
         fclose(f); vs_set_last_error((path + " is not a VSIDX002/003 packed text").c_str()); return VS_ERR_IO;
     }
-    v3 = memcmp(h.magic, IDX_MAGIC3, 8) == 0;
+    const bool v3 = memcmp(h.magic, IDX_MAGIC3, 8) == 0;
     uint64_t data_at = pad16(sizeof(h));
     if (v3) {
         if (fseek(f, (long)data_at, SEEK_SET) != 0 || fread(&sh, sizeof(sh), 1, f) != 1) { fclose(f); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
@@ -364,30 +389,40 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     }
     const bool src = v3 && (h.flags & 1u);
     const uint64_t nw = (h.n_bases + 31) >> 5;
-    const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)),
-                   s_m = pad16(nw * sizeof(vs_masks)), s_s = pad16(h.n_sparse * sizeof(vs_mask_entry));
+    // in memory: offsets, bases, masks, then either the sparse masks (read) or the source (read; the masks are rebuilt)
+    const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)), s_m = pad16(nw * sizeof(vs_masks));
+    const uint64_t s_s = src ? 0 : pad16(h.n_sparse * sizeof(vs_mask_entry));
     const uint64_t s_em = src ? pad16(nw + 1) : 0, s_ed = src ? pad16((nw + VS_EM_BLOCK) / VS_EM_BLOCK) : 0,
                    s_nr = src ? pad16(sh.n_nm_runs * sizeof(vs_plane_run)) : 0, s_er = src ? pad16(sh.n_em_runs * sizeof(vs_plane_run)) : 0;
     const uint64_t total = s_off + s_b + s_m + s_s + s_em + s_ed + s_nr + s_er;
     char *buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);
     if (!buf) { fclose(f); return VS_ERR_NOMEM; }
-    bool ok = fseek(f, (long)data_at, SEEK_SET) == 0 && fread(buf, 1, total, f) == total;
+    char *p_masks = buf + s_off + s_b, *p_tail = p_masks + s_m;
+    bool ok = fseek(f, (long)data_at, SEEK_SET) == 0 && fread(buf, 1, s_off + s_b, f) == s_off + s_b;
+    if (ok && src) ok = fread(p_tail, 1, s_em + s_ed + s_nr + s_er, f) == s_em + s_ed + s_nr + s_er;
+    else if (ok) ok = fread(p_masks, 1, s_m + s_s, f) == s_m + s_s;
     fclose(f);
     const uint64_t *off = (const uint64_t *)buf;
     if (!ok || off[h.n_contigs] != h.n_bases) { free(buf); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
     out->n_bases = h.n_bases; out->n_words = nw; out->n_contigs = h.n_contigs;
     out->contig_off = off;
     out->bases = (const vs_bases *)(buf + s_off);
-    out->masks = (const vs_masks *)(buf + s_off + s_b);
-    out->sparse = (const vs_mask_entry *)(buf + s_off + s_b + s_m);
-    out->n_sparse = h.n_sparse;
+    out->masks = (const vs_masks *)p_masks;
     if (src) {
-        const char *q = buf + s_off + s_b + s_m + s_s;
-        out->em_code = (const uint8_t *)q;
-        out->em_dense = (const uint8_t *)(q + s_em);
-        out->nm_runs = (const vs_plane_run *)(q + s_em + s_ed);
-        out->em_runs = (const vs_plane_run *)(q + s_em + s_ed + s_nr);
+        out->em_code = (const uint8_t *)p_tail;
+        out->em_dense = (const uint8_t *)(p_tail + s_em);
+        out->nm_runs = (const vs_plane_run *)(p_tail + s_em + s_ed);
+        out->em_runs = (const vs_plane_run *)(p_tail + s_em + s_ed + s_nr);
         out->n_nm_runs = sh.n_nm_runs; out->n_em_runs = sh.n_em_runs;
+        int r = masks_from_source(out, (vs_masks *)p_masks);
+        if (r != VS_OK) {
+            free(buf); memset(out, 0, sizeof(*out));
+            vs_set_last_error((path + (r == VS_ERR_NOMEM ? ": out of memory" : " holds a corrupt mask source")).c_str());
+            return r;
+        }
+    } else {
+        out->sparse = (const vs_mask_entry *)p_tail;
+        out->n_sparse = h.n_sparse;
     }
     *owner = buf;
     return VS_OK;

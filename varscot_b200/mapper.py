@@ -190,7 +190,7 @@ class PackedText:
                       _copy_array(v.nm_runs, int(v.n_nm_runs), RUN_DT), _copy_array(v.em_runs, int(v.n_em_runs), RUN_DT))
         return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), _copy_array(v.masks, nw, MASKS_DT),
                           _copy_array(v.contig_off, int(v.n_contigs) + 1, np.dtype("<u8")), int(v.n_bases), names,
-                          _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT), source)
+                          _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT) if v.sparse else None, source)
 
     @staticmethod
     def from_fasta(path: str) -> "PackedText":
