@@ -43,6 +43,71 @@ def test_literal_equals_scan_random(seed):
         assert a.rows() == b.rows()
 
 
+def _spec_rows(ascii_bytes, offsets, guide_strs, k, pam):
+    """Third, independent statement of the path, written from the rules R1-R9 of SURVEY.md 8a (not from the C oracle):
+    plain Python over strings, one window at a time.  Small inputs only."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rc = lambda x: "".join(comp[c] for c in reversed(x))
+    text = "".join(c if c in "ACGT" else "N" for c in ascii_bytes.decode().upper().replace("U", "T"))        # R6
+    fwd = {"GG", "GA"} | ({pam.upper()} if pam else set())                                                    # R2
+    rev = {rc(x) for x in fwd}
+    rows = []
+    for gi, g in enumerate(guide_strs):
+        g = "".join(c if c in "ACGT" else "A" for c in g.upper().replace("U", "T"))                           # R5
+        for strand, pat in ((0, g), (1, rc(g))):
+            recs = []
+            for ci in range(len(offsets) - 1):
+                c = text[int(offsets[ci]):int(offsets[ci + 1])]
+                for p in range(len(c) - 22):                                                                  # R1
+                    w = c[p:p + 23]
+                    if "N" in w:                                                                              # R3
+                        continue
+                    if (w[21:23] not in fwd) if strand == 0 else (w[0:2] not in rev):                         # R2
+                        continue
+                    mm = sum(a != b for a, b in zip(pat, w))
+                    if mm > k:                                                                                # R3
+                        continue
+                    if p + 23 == len(c) and sum(a != b for a, b in zip(pat[11:], w[11:])) > k // 2:           # R4
+                        continue
+                    md, run = "", 0                                                                           # R9, SeqAn style
+                    for a, b in zip(pat, w):
+                        if a == b:
+                            run += 1
+                        else:
+                            md += (str(run) if run else "") + b
+                            run = 0
+                    md += str(run) if run else ""
+                    recs.append(((ci & 0xFFFF, p, ci >> 16), ci, p, mm, md))
+            recs.sort()                                                                                       # R8: std::map order
+            out, best = [], None
+            for _, ci, p, mm, md in recs:                                                                     # running best
+                if best is None:
+                    best = (ci, p, mm, md)
+                elif mm >= best[2]:
+                    out.append((gi, 16 * strand + 256, ci, p, mm, md))
+                else:
+                    out.append((gi, 16 * strand + 256, best[0], best[1], best[2], best[3]))
+                    best = (ci, p, mm, md)
+            if best is not None:
+                out.append((gi, 16 * strand, best[0], best[1], best[2], best[3]))
+            rows += out
+    return rows
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_python_spec_restatement_agrees_with_the_c_oracle(seed):
+    rng = np.random.default_rng(500 + seed)
+    lens = [int(x) for x in rng.choice([0, 5, 22, 23, 24, 45, 46, 300, 900], int(rng.integers(2, 7)))] + [700]
+    k = int(rng.integers(0, 9))
+    pam = [None, "AG", "TT", "cc"][seed % 4]
+    case = make_case(900 + seed, lens, 3, k, pam=pam, n_frac=0.01, iupac_frac=0.005)
+    exp = _spec_rows(case.ascii, case.offsets, case.guide_strs, k, pam)
+    for mode in (O.MODE_SCAN, O.MODE_LITERAL):
+        got = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, pam=pam, mode=mode).rows()
+        assert got == exp, (seed, mode)
+    assert len(exp) > 0
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "case_*.json"))))
 def test_golden_fixtures(path):
     d = json.load(open(path))
