@@ -370,3 +370,16 @@ def test_resolve_hits_threads_agree():
         got, c = V.resolve_hits(hits[rng.permutation(len(hits))], off, threads=t)
         assert got.tobytes() == ref.tobytes() and c == c1
     assert c1 > 0 and len(ref) == len(hits)
+
+
+def test_kernel_helpers_on_the_host(tmp_path):
+    """The pure helper functions of vs_kernels.cuh (candidate masks, register transposes, bit-sliced adders and thresholds for
+    every k, pattern-table encoding, plane layout) compiled for the host and checked against naive restatements
+    (tests/cpu_kernel_units.cpp).  The kernels themselves only run on a GPU (tests marked gpu)."""
+    exe = str(tmp_path / "kernel_units")
+    src = os.path.join(ROOT, "tests", "cpu_kernel_units.cpp")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "kernel helper units ok" in r.stdout, r.stdout + r.stderr
+

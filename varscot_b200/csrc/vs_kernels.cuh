@@ -19,7 +19,9 @@
 #pragma once
 #include <cstdint>
 #include <type_traits>
+#ifndef VS_HOST_UNIT_TEST          // tests/cpu_kernel_units.cpp compiles the pure helper functions of this header with g++
 #include <cuda_runtime.h>
+#endif
 #include "../../include/varscot_scan.h"
 
 namespace vs {
@@ -152,6 +154,7 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 #ifndef VS_EX_MINBLOCKS
 #define VS_EX_MINBLOCKS (VS_EX_HALF ? 16 : 10)
 #endif
+#ifndef VS_HOST_UNIT_TEST
 __global__ void __launch_bounds__(EX_THREADS, VS_EX_MINBLOCKS)
 k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
           uint64_t global_base, PamParams pp,
@@ -425,14 +428,23 @@ k_masks_from_planes(const uint32_t *__restrict__ nm, const uint32_t *__restrict_
     out[w] = m;
 }
 
+#endif  // VS_HOST_UNIT_TEST
+
 // ------------------------------------------------------------------------------------------------
 // Scoring.
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
 {
+#ifndef VS_HOST_UNIT_TEST
     uint32_t r;
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return r;
+#else       // the instruction's definition: bit (4a + 2b + c) of the table, per bit position
+    uint32_t r = 0;
+    for (int i = 0; i < 8; ++i)
+        if ((LUT >> i) & 1) r |= ((i & 4) ? a : ~a) & ((i & 2) ? b : ~b) & ((i & 1) ? c : ~c);
+    return r;
+#endif
 }
 
 // Bit-sliced population count of N one-bit planes (plus optional planes `init[w]` already carrying weight 2^w):
@@ -528,7 +540,9 @@ __host__ __device__ constexpr int score_min_blocks(int k)
 // (plane index * SCORE_THREADS * 4, plane index = 4 * (position - base) + pattern base) of the shared-memory plane it
 // selects; a stage-B slot holds the byte offset of its raw hi plane (lo follows at + SCORE_THREADS * 4) | pattern base << 16
 // (see pat_slot()).
+#ifndef VS_HOST_UNIT_TEST
 __constant__ uint32_t c_pat[PAT_TABLE_WORDS];
+#endif
 
 // position scored by slot j of a strand's slot order
 __host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
@@ -552,6 +566,7 @@ __device__ __forceinline__ uint32_t mismatch_plane(uint32_t h, uint32_t l, uint3
     return (h ^ ((b & 2u) ? ~0u : 0u)) | (l ^ ((b & 1u) ? ~0u : 0u));
 }
 
+#ifndef VS_HOST_UNIT_TEST
 struct ScoreArgs {
     const uint32_t *planes[2];  // per strand: [n_blocks][48]
     const uint32_t *pos[2];     // per strand: [n_blocks][32]
@@ -744,5 +759,7 @@ k_peak_lds(uint32_t *out, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
+
+#endif  // VS_HOST_UNIT_TEST
 
 }  // namespace vs
