@@ -1,6 +1,7 @@
 // tests/cpu_kernel_units.cpp — TEST INFRASTRUCTURE: the pure helper functions of varscot_b200/csrc/vs_kernels.cuh
-// (candidate masks, register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout)
-// compiled for the HOST with g++ and checked against naive per-bit restatements.  The kernels themselves are not
+// (candidate masks, register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout) and the
+// body of k_extract's phase 2 (vs_extract_block.inc, textually included by the kernel, and the experimental half-block
+// variant) compiled for the HOST with g++ and checked against naive per-bit restatements.  The kernels themselves are not
 // compiled here (VS_HOST_UNIT_TEST guards them out) and nothing in the product uses this file.
 // Built and run by tests/test_host.py::test_kernel_helpers_on_the_host.
 #include <cstdint>
@@ -28,6 +29,10 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel)
 }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
@@ -192,6 +197,101 @@ static void test_mismatch_plane()
     }
 }
 
+// ---- phase 2 of k_extract on the host: the very text the kernel includes (vs_extract_block.inc, and the experimental
+// vs_extract_half_block.inc) runs over a random tile and is compared with a naive gather of the tile's candidates.
+struct Tile {
+    uint32_t nw;
+    uint2 s_hl[EX_MAX_WORDS + 2], s_mk[EX_MAX_WORDS + 2];
+    uint32_t s_m[2][EX_MAX_WORDS + 1], s_p[2][EX_MAX_WORDS + 1];
+    uint32_t nf, nr, nbf, nbr;
+};
+
+static void make_tile(Tile &t, uint32_t nw, int density, const PamParams &pp)
+{
+    t.nw = nw;
+    for (uint32_t i = 0; i < EX_MAX_WORDS + 2; ++i) {
+        t.s_hl[i] = uint2{r32(), r32()};
+        // invalid starts: none / sparse / long runs; last-window bits: sparse
+        const uint32_t iv = density == 0 ? 0u : density == 1 ? (r32() & r32() & r32()) : ((i / 7) % 3 == 0 ? ~0u : 0u);
+        t.s_mk[i] = uint2{iv, r32() & r32() & r32()};
+    }
+    uint32_t pf = 0, pr = 0;
+    for (uint32_t i = 0; i < nw; ++i) {
+        uint32_t f, r;
+        cand_masks(vs_bases{t.s_hl[i].x, t.s_hl[i].y}, vs_bases{t.s_hl[i + 1].x, t.s_hl[i + 1].y}, vs_masks{t.s_mk[i].x, t.s_mk[i].y}, pp, f, r);
+        t.s_m[0][i] = f; t.s_m[1][i] = r;
+        t.s_p[0][i] = pf; t.s_p[1][i] = pr;
+        pf += __popc(f); pr += __popc(r);
+    }
+    t.s_p[0][nw] = t.nf = pf; t.s_p[1][nw] = t.nr = pr;
+    t.s_m[0][nw] = ~0u; t.s_m[1][nw] = ~0u;                 // the sentinel (k_extract, after phase 1)
+    t.nbf = (pf + 31) >> 5; t.nbr = (pr + 31) >> 5;
+}
+
+static void run_phase2(const Tile &t, bool half, const unsigned long long base[2], uint64_t cap, uint32_t gbase,
+                       uint32_t *planes_f, uint32_t *pos_f, uint32_t *planes_r, uint32_t *pos_r)
+{
+    const uint32_t nw = t.nw, nf = t.nf, nr = t.nr, nbf = t.nbf, nbr = t.nbr;
+    const uint2 *s_hl = t.s_hl, *s_mk = t.s_mk;
+    const uint32_t (*s_m)[EX_MAX_WORDS + 1] = t.s_m, (*s_p)[EX_MAX_WORDS + 1] = t.s_p;
+    if (half) {
+        for (uint32_t j2 = 0; j2 < 2 * (nbf + nbr); ++j2) {
+#include "../varscot_b200/csrc/vs_extract_half_block.inc"
+        }
+    } else {
+        for (uint32_t j = 0; j < nbf + nbr; ++j) {
+#include "../varscot_b200/csrc/vs_extract_block.inc"
+        }
+    }
+}
+
+static void test_extract_phase2()
+{
+    PamParams pp;
+    pp.n = 3;
+    pp.fx[0] = 2; pp.fy[0] = 2; pp.fx[1] = 2; pp.fy[1] = 0; pp.fx[2] = 0; pp.fy[2] = 2;
+    for (int j = 0; j < 3; ++j) { pp.rx[j] = 3 - pp.fy[j]; pp.ry[j] = 3 - pp.fx[j]; }
+    const unsigned long long base[2] = {37, 5};            // where the tile's blocks land in the two candidate stores
+    const uint64_t n_store = 37 + 5 + 200;                  // blocks per store, a multiple of BLK_GROUP after rounding
+    const uint64_t store_words = ((n_store + BLK_GROUP - 1) / BLK_GROUP) * BLK_GROUP * BLK_WORDS;
+    static Tile t;
+    for (int rep = 0; rep < 60; ++rep) {
+        const uint32_t nw = rep % 5 == 0 ? 1 + r32() % 8 : 8 + r32() % (EX_MAX_WORDS - 8);
+        make_tile(t, nw, rep % 3, pp);
+        const uint32_t gbase = r32() & 0x0FFFFFFFu;
+        for (int half = 0; half < 2; ++half) {
+            std::vector<uint32_t> pl[2], ps[2];
+            for (int s = 0; s < 2; ++s) { pl[s].assign(store_words, 0xDEADBEEFu); ps[s].assign(n_store * 32 + 32, 0xDEADBEEFu); }
+            run_phase2(t, half != 0, base, n_store, gbase, pl[0].data(), ps[0].data(), pl[1].data(), ps[1].data());
+            for (int s = 0; s < 2; ++s) {
+                // naive gather: the candidates of the strand in text order
+                uint32_t rank = 0;
+                const uint32_t n = s ? t.nr : t.nf;
+                for (uint32_t w = 0; w < nw; ++w)
+                    for (int b = 0; b < 32; ++b) {
+                        if (!((t.s_m[s][w] >> b) & 1)) continue;
+                        const uint64_t blk = base[s] + rank / 32;
+                        const int c = rank % 32;
+                        const uint64_t H = ((uint64_t)t.s_hl[w + 1].x << 32) | t.s_hl[w].x, L = ((uint64_t)t.s_hl[w + 1].y << 32) | t.s_hl[w].y;
+                        for (int i = 0; i < VS_GLEN; ++i) {
+                            CHECK(((pl[s][plane_index(blk, i)] >> c) & 1) == ((H >> (b + i)) & 1));
+                            CHECK(((pl[s][plane_index(blk, VS_GLEN + i)] >> c) & 1) == ((L >> (b + i)) & 1));
+                        }
+                        CHECK(((pl[s][plane_index(blk, BLK_LAST)] >> c) & 1) == ((t.s_mk[w].y >> b) & 1));
+                        CHECK(((pl[s][plane_index(blk, BLK_VALID)] >> c) & 1) == 1);
+                        CHECK(ps[s][blk * 32 + c] == gbase + w * 32 + (uint32_t)b);
+                        ++rank;
+                    }
+                CHECK(rank == n);
+                // the valid mask of the last block ends with the last candidate; blocks beyond stay untouched
+                const uint32_t nb = (n + 31) / 32;
+                if (n % 32) CHECK(pl[s][plane_index(base[s] + nb - 1, BLK_VALID)] == (1u << (n % 32)) - 1u);
+                CHECK(pl[s][plane_index(base[s] + nb, BLK_VALID)] == 0xDEADBEEFu);
+            }
+        }
+    }
+}
+
 int main()
 {
     test_plane_index();
@@ -201,6 +301,7 @@ int main()
     check_le_k<5>(); check_le_k<6>(); check_le_k<7>(); check_le_k<8>();
     test_pattern_table();
     test_mismatch_plane();
+    test_extract_phase2();
     if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
     printf("kernel helper units ok\n");
     return 0;

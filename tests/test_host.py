@@ -374,8 +374,9 @@ def test_resolve_hits_threads_agree():
 
 def test_kernel_helpers_on_the_host(tmp_path):
     """The pure helper functions of vs_kernels.cuh (candidate masks, register transposes, bit-sliced adders and thresholds for
-    every k, pattern-table encoding, plane layout) compiled for the host and checked against naive restatements
-    (tests/cpu_kernel_units.cpp).  The kernels themselves only run on a GPU (tests marked gpu)."""
+    every k, pattern-table encoding, plane layout) and the body of k_extract's phase 2 — the very text the kernel includes,
+    vs_extract_block.inc, plus the experimental half-block variant — compiled for the host and checked against naive
+    restatements (tests/cpu_kernel_units.cpp).  The kernels themselves only run on a GPU (tests marked gpu)."""
     exe = str(tmp_path / "kernel_units")
     src = os.path.join(ROOT, "tests", "cpu_kernel_units.cpp")
     r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)

@@ -246,124 +246,11 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     // candidates.  Half the registers (two 16-row transposes instead of two 32-row ones) let twice as many warps reside,
     // which is what this latency-bound kernel lacks; the plane words leave as 16-bit halves (lane pairs write one word).
     for (uint32_t j2 = tid; j2 < 2 * (nbf + nbr); j2 += EX_THREADS) {
-        const uint32_t j = j2 >> 1, half = j2 & 1u;
-        const int s = j >= nbf;
-        const uint32_t jj = s ? j - nbf : j;
-        const uint32_t n = s ? nr : nf;
-        const uint64_t blk = base[s] + jj;
-        if (blk >= cap) continue;                          // overflow: the chunk is redone by the host
-        const uint32_t r0 = jj * 32 + half * 16;           // rank of this half's first candidate
-        const uint32_t cnth = r0 < n ? min(16u, n - r0) : 0u;
-        // 16-bit half `half` of word w of the block sits at pl_out[2 * w * BLK_GROUP]
-        uint16_t *pl_out = reinterpret_cast<uint16_t *>((s ? planes_r : planes_f) + plane_index(blk, 0)) + half;
-        pl_out[2 * BLK_VALID * BLK_GROUP] = (uint16_t)((1u << cnth) - 1u);
-        if (cnth == 0) continue;                           // upper half of a short last block: only its valid bits matter
-        const uint32_t *sm = s_m[s], *sp = s_p[s];
-        uint32_t lo_w = 0, hi_w = nw;                      // invariant: sp[lo_w] <= r0 < sp[hi_w] (sp[nw] = n > r0)
-        while (hi_w - lo_w > 1) {
-            const uint32_t mid = (lo_w + hi_w) >> 1;
-            if (sp[mid] <= r0) lo_w = mid; else hi_w = mid;
-        }
-        uint32_t wcur = lo_w;
-        uint32_t m = sm[wcur];
-        for (uint32_t skip = r0 - sp[wcur]; skip; --skip) m &= m - 1;     // drop the candidates of earlier halves
-        uint2 ha = s_hl[wcur], hb = s_hl[wcur + 1];
-        uint32_t lwm = s_mk[wcur].y;
-        uint32_t ah[16], al[16];
-        uint32_t lastw = 0;
-        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32 + half * 16);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t pp4[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c4 * 4 + u;
-                while (m == 0) {                           // next word with candidates (ends at the all-ones sentinel)
-                    ++wcur;
-                    m = sm[wcur];
-                    ha = hb; hb = s_hl[wcur + 1];
-                    lwm = s_mk[wcur].y;
-                }
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                ah[c] = __funnelshift_r(ha.x, hb.x, b);    // bits 23..31 are never stored: only planes 0..22 leave
-                al[c] = __funnelshift_r(ha.y, hb.y, b);
-                lastw |= ((lwm >> b) & 1u) << c;
-                pp4[u] = gbase + wcur * 32 + b;
-            }
-            ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
-        }
-        transpose16(ah);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pl_out[2 * i * BLK_GROUP] = (uint16_t)ah[i];
-#pragma unroll
-        for (int i = 16; i < VS_GLEN; ++i) pl_out[2 * i * BLK_GROUP] = (uint16_t)(ah[i - 16] >> 16);
-        transpose16(al);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pl_out[2 * (VS_GLEN + i) * BLK_GROUP] = (uint16_t)al[i];
-#pragma unroll
-        for (int i = 16; i < VS_GLEN; ++i) pl_out[2 * (VS_GLEN + i) * BLK_GROUP] = (uint16_t)(al[i - 16] >> 16);
-        pl_out[2 * BLK_LAST * BLK_GROUP] = (uint16_t)lastw;
+#include "vs_extract_half_block.inc"
     }
 #else
     for (uint32_t j = tid; j < nbf + nbr; j += EX_THREADS) {
-        const int s = j >= nbf;
-        const uint32_t jj = s ? j - nbf : j;
-        const uint32_t n = s ? nr : nf;
-        const uint64_t blk = base[s] + jj;
-        if (blk >= cap) continue;                          // overflow: the chunk is redone by the host
-        const uint32_t cntc = min(32u, n - jj * 32);
-        const uint32_t *sm = s_m[s], *sp = s_p[s];
-        // word holding candidate rank r0 = 32*jj: last word with prefix <= r0
-        const uint32_t r0 = jj * 32;
-        uint32_t lo_w = 0, hi_w = nw;                      // invariant: sp[lo_w] <= r0 < sp[hi_w] (sp[nw] = n > r0)
-        while (hi_w - lo_w > 1) {
-            const uint32_t mid = (lo_w + hi_w) >> 1;
-            if (sp[mid] <= r0) lo_w = mid; else hi_w = mid;
-        }
-        uint32_t wcur = lo_w;
-        uint32_t m = sm[wcur];
-        for (uint32_t skip = r0 - sp[wcur]; skip; --skip) m &= m - 1;     // drop the candidates of earlier blocks
-        uint2 ha = s_hl[wcur], hb = s_hl[wcur + 1];
-        uint32_t lwm = s_mk[wcur].y;
-        uint32_t ah[32], al[32];
-        uint32_t lastw = 0;
-        uint4 *ps_out = reinterpret_cast<uint4 *>((s ? pos_r : pos_f) + blk * 32);
-        // The walk never tests "is this candidate past the end of a partial block": the mask array ends in an all-ones
-        // sentinel word (s_m[.][nw], set above), so the lanes past cntc gather 32 - cntc <= 31 meaningless windows from
-        // the halo / padding words and stop there; k_score ORs the complement of the valid mask into every plane.
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            uint32_t pp4[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c4 * 4 + u;
-                while (m == 0) {                           // next word with candidates
-                    ++wcur;
-                    m = sm[wcur];
-                    ha = hb; hb = s_hl[wcur + 1];
-                    lwm = s_mk[wcur].y;
-                }
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                ah[c] = __funnelshift_r(ha.x, hb.x, b) & 0x7FFFFFu;
-                al[c] = __funnelshift_r(ha.y, hb.y, b) & 0x7FFFFFu;
-                lastw |= ((lwm >> b) & 1u) << c;
-                pp4[u] = gbase + wcur * 32 + b;
-            }
-            ps_out[c4] = make_uint4(pp4[0], pp4[1], pp4[2], pp4[3]);
-        }
-        // word w of the block goes to plane_index(blk, w): consecutive lanes hold consecutive blocks, so every store
-        // instruction of the warp writes 128 contiguous bytes
-        uint32_t *pl_out = (s ? planes_r : planes_f) + plane_index(blk, 0);
-        transpose32(ah);
-#pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) pl_out[i * BLK_GROUP] = ah[i];
-        transpose32(al);
-#pragma unroll
-        for (int i = 0; i < VS_GLEN; ++i) pl_out[(VS_GLEN + i) * BLK_GROUP] = al[i];
-        pl_out[BLK_LAST * BLK_GROUP] = lastw;
-        pl_out[BLK_VALID * BLK_GROUP] = cntc >= 32 ? ~0u : ((1u << cntc) - 1u);
+#include "vs_extract_block.inc"
     }
 #endif
 }
