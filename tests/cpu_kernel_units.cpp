@@ -1,9 +1,11 @@
-// tests/cpu_kernel_units.cpp — TEST INFRASTRUCTURE: the pure helper functions of varscot_b200/csrc/vs_kernels.cuh
-// (candidate masks, register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout) and the
-// body of k_extract's phase 2 (vs_extract_block.inc, textually included by the kernel, and the experimental half-block
-// variant) compiled for the HOST with g++ and checked against naive per-bit restatements.  The kernels themselves are not
-// compiled here (VS_HOST_UNIT_TEST guards them out) and nothing in the product uses this file.
-// Built and run by tests/test_host.py::test_kernel_helpers_on_the_host.
+// tests/cpu_kernel_units.cpp — TEST INFRASTRUCTURE: varscot_b200/csrc/vs_kernels.cuh compiled for the HOST with g++.
+//  * the kernels whose threads never cooperate (k_score<K>, k_fill_runs, k_expand_em_code, k_masks_from_planes,
+//    k_scatter_masks) run thread by thread from their real source, against naive restatements;
+//  * k_extract (warp shuffles, cp.async) is guarded out; its phase 2 runs through the very text the kernel includes
+//    (vs_extract_block.inc, and the experimental vs_extract_half_block.inc), its phase 1 through cand_masks;
+//  * the helpers (register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout) have
+//    their own checks.
+// Nothing in the product uses this file.  Built and run by tests/test_host.py::test_device_code_on_the_host.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -29,6 +31,21 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel)
 }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+#define __global__
+#define __constant__ static
+#define __shared__
+#define __restrict__
+#define __launch_bounds__(...)
+// A kernel whose threads never cooperate runs on the host one thread at a time: set these, call it.
+struct Idx3 { unsigned x, y, z; };
+static Idx3 threadIdx, blockIdx, blockDim, gridDim;
+static inline uint32_t __ldg(const uint32_t *p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
+// warp vote of a one-thread "warp": a lane whose own stage-A result is zero can never produce a hit, so voting alone is exact
+static inline int __any_sync(unsigned, int pred) { return pred; }
+static inline uint64_t max(uint64_t a, uint64_t b) { return a > b ? a : b; }
+static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
@@ -36,7 +53,20 @@ static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
+namespace vs { uint32_t sm[NPLANES * SCORE_THREADS]; }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
 using namespace vs;
+
+template <class F>
+static void launch(unsigned grid_x, unsigned grid_y, unsigned block, F kernel)
+{
+    gridDim = Idx3{grid_x, grid_y, 1}; blockDim = Idx3{block, 1, 1};
+    for (unsigned by = 0; by < grid_y; ++by)
+        for (unsigned bx = 0; bx < grid_x; ++bx)
+            for (unsigned t = 0; t < block; ++t) {
+                blockIdx = Idx3{bx, by, 0}; threadIdx = Idx3{t, 0, 0};
+                kernel();
+            }
+}
 
 static int failures = 0;
 #define CHECK(cond)                                                                     \
@@ -292,6 +322,147 @@ static void test_extract_phase2()
     }
 }
 
+// ---- the mask kernels (k_fill_runs, k_expand_em_code, k_masks_from_planes, k_scatter_masks) thread by thread on the host
+static void test_mask_kernels()
+{
+    for (int rep = 0; rep < 20; ++rep) {
+        const uint64_t n = 3000 + r32() % 9000;            // words of the range; planes hold n + 1 (halo)
+        const uint64_t word_base = 4096ull * (r32() % 3) + r32() % 100;        // the shard starts somewhere inside the text
+        std::vector<uint32_t> nm(n + 1, 0), em(n + 1, 0);
+        // N plane: a few runs; contig-end plane: single bits (coded blocks), multi-bit words (runs) and empty stretches
+        std::vector<vs_plane_run> nm_runs, em_runs;
+        for (uint64_t w = 0; w <= n;) {
+            if (r32() % 50 == 0) {
+                const uint32_t cnt = 1 + r32() % 700, val = r32() % 3 ? ~0u : r32() | 1u;
+                const uint64_t e = w + cnt < n + 1 ? w + cnt : n + 1;
+                nm_runs.push_back(vs_plane_run{(uint32_t)(word_base + w), (uint32_t)(e - w), val});
+                for (uint64_t i = w; i < e; ++i) nm[i] = val;
+                w = e + 1;
+            } else ++w;
+        }
+        const uint64_t blocks_at = word_base / VS_EM_BLOCK, n_blocks = (word_base + n) / VS_EM_BLOCK + 1;
+        std::vector<uint8_t> dense(n_blocks, 0), code(n + 1, (uint8_t)VS_EM_NONE);
+        for (uint64_t b = blocks_at; b < n_blocks; ++b) dense[b] = r32() % 2;
+        for (uint64_t w = 0; w <= n; ++w) {
+            const bool coded = dense[(word_base + w) / VS_EM_BLOCK];
+            const uint32_t kind = r32() % 8;
+            if (kind < 3) continue;
+            uint32_t v = 1u << (r32() % 32);
+            if (kind == 7) v |= 1u << (r32() % 32);
+            em[w] = v;
+            if (coded && !(v & (v - 1))) code[w] = (uint8_t)__builtin_ctz(v);
+            else em_runs.push_back(vs_plane_run{(uint32_t)(word_base + w), 1u, v});
+        }
+        // device buffers of a shard whose word 0 is global word `word_base`
+        std::vector<uint32_t> d_nm(n + 1, 0), d_em(n + 1, 0);
+        const uint64_t lo = word_base, hi = word_base + n + 1;
+        uint64_t longest = 1;
+        for (const auto &x : nm_runs) longest = longest > x.count ? longest : x.count;
+        launch((unsigned)((nm_runs.size() + 7) / 8), (unsigned)((longest + FILL_SEG - 1) / FILL_SEG), 256,
+               [&] { k_fill_runs(nm_runs.data(), nm_runs.size(), lo, hi, word_base, d_nm.data()); });
+        launch((unsigned)((n + 1 + 255) / 256), 1, 256, [&] { k_expand_em_code(code.data(), dense.data(), lo, n + 1, d_em.data()); });
+        launch((unsigned)((em_runs.size() + 7) / 8), 1, 256, [&] { k_fill_runs(em_runs.data(), em_runs.size(), lo, hi, word_base, d_em.data()); });
+        for (uint64_t w = 0; w <= n; ++w) { CHECK(d_nm[w] == nm[w]); CHECK(d_em[w] == em[w]); }
+        std::vector<vs_masks> got(n), sparse_got(n, vs_masks{0, 0});
+        launch((unsigned)((n + 255) / 256), 1, 256, [&] { k_masks_from_planes(d_nm.data(), d_em.data(), n, got.data()); });
+        std::vector<vs_mask_entry> entries;
+        for (uint64_t w = 0; w < n; ++w) {
+            // the definition (include/varscot_scan.h): iv = N in [p, p+23) or contig end in [p, p+22); lw = end at p+22, valid
+            const uint64_t N = ((uint64_t)nm[w + 1] << 32) | nm[w], E = ((uint64_t)em[w + 1] << 32) | em[w];
+            uint32_t iv = 0, lw = 0;
+            for (int p = 0; p < 32; ++p) {
+                const bool bad = ((N >> p) & 0x7FFFFF) != 0 || ((E >> p) & 0x3FFFFF) != 0;
+                if (bad) iv |= 1u << p;
+                else if ((E >> (p + 22)) & 1) lw |= 1u << p;
+            }
+            CHECK(got[w].iv == iv && got[w].lw == lw);
+            if (iv | lw) entries.push_back(vs_mask_entry{(uint32_t)(word_base + w), iv, lw});
+        }
+        launch((unsigned)((entries.size() + 255) / 256), 1, 256, [&] { k_scatter_masks(entries.data(), entries.size(), word_base, sparse_got.data()); });
+        for (uint64_t w = 0; w < n; ++w) CHECK(sparse_got[w].iv == got[w].iv && sparse_got[w].lw == got[w].lw);
+    }
+}
+
+// ---- k_score<K> thread by thread on the host: random candidate blocks (with planted near matches, last-window flags and
+// a partial last block) against random guides, both strands; the hits must be exactly those of a naive count.
+template <int K>
+static void check_k_score()
+{
+    const uint32_t nb[2] = {SCORE_THREADS + 37, 2 * SCORE_THREADS + 5};        // blocks per strand (not multiples of the CTA)
+    const uint32_t n_guides = 9;
+    const uint64_t cap = 3 * SCORE_THREADS;
+    std::vector<uint8_t> guides(n_guides * VS_GLEN);
+    for (auto &g : guides) g = r32() % 4;
+    // candidates: [strand][block][lane] -> 23 codes, last-window flag, position; some lanes are near copies of a pattern
+    std::vector<uint32_t> planes[2], pos[2];
+    std::vector<uint8_t> cand[2];
+    std::vector<uint32_t> valid_n[2];
+    for (int s = 0; s < 2; ++s) {
+        planes[s].assign(cap * BLK_WORDS, 0);
+        pos[s].assign(cap * 32, 0);
+        cand[s].assign((size_t)nb[s] * 32 * VS_GLEN, 0);
+        valid_n[s].assign(nb[s], 32);
+        valid_n[s][nb[s] - 1] = 1 + r32() % 31;                                // partial last block
+        for (uint32_t b = 0; b < nb[s]; ++b) {
+            uint32_t w[BLK_WORDS] = {0};
+            for (int c = 0; c < 32; ++c) {
+                uint8_t *x = &cand[s][((size_t)b * 32 + c) * VS_GLEN];
+                for (int i = 0; i < VS_GLEN; ++i) x[i] = r32() % 4;
+                if (r32() % 4 == 0) {                                          // near copy: 0..K+2 mismatches
+                    const uint8_t *g = &guides[(r32() % n_guides) * VS_GLEN];
+                    for (int i = 0; i < VS_GLEN; ++i) x[i] = s ? 3 - g[VS_GLEN - 1 - i] : g[i];
+                    for (int m = r32() % (K + 3); m > 0; --m) { const int i = r32() % VS_GLEN; x[i] = (x[i] + 1 + r32() % 3) % 4; }
+                }
+                for (int i = 0; i < VS_GLEN; ++i) {
+                    w[i] |= (uint32_t)((x[i] >> 1) & 1) << c;
+                    w[VS_GLEN + i] |= (uint32_t)(x[i] & 1) << c;
+                }
+                if (r32() % 3 == 0) w[BLK_LAST] |= 1u << c;
+                if ((uint32_t)c < valid_n[s][b]) w[BLK_VALID] |= 1u << c;
+                pos[s][(size_t)b * 32 + c] = (uint32_t)(s * 1000000 + b * 32 + c);
+            }
+            for (int i = 0; i < BLK_WORDS; ++i) planes[s][plane_index(b, i)] = w[i];
+        }
+    }
+    // pattern table as scan_core builds it
+    std::vector<uint32_t> pat(PAT_TABLE_WORDS, 0);
+    for (int s = 0; s < 2; ++s)
+        for (uint32_t g = 0; g < n_guides; ++g)
+            for (int j = 0; j < VS_GLEN; ++j) {
+                const int i = slot_position(s, j);
+                const int b = s ? 3 - guides[g * VS_GLEN + VS_GLEN - 1 - i] : guides[g * VS_GLEN + i];
+                pat[((size_t)s * PAT_CHUNK + g) * PAT_STRIDE + j] = pat_slot(K, s, j, b);
+            }
+    for (size_t i = 0; i < pat.size(); ++i) c_pat[i] = pat[i];
+    unsigned long long n_blocks[2] = {nb[0], nb[1]}, n_hits = 0;
+    std::vector<vs_hit> hits(1 << 20);
+    ScoreArgs a;
+    for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
+    a.n_blocks_ptr = n_blocks; a.cap = cap; a.ctas_per_strand = (uint32_t)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
+    a.n_pat = n_guides; a.guide_base = 256; a.pat_global = pat.data();
+    a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
+    launch(2 * a.ctas_per_strand, 1, SCORE_THREADS, [&] { k_score<K>(a); });
+    std::set<std::pair<uint32_t, uint32_t>> got, want;
+    CHECK(n_hits <= hits.size());
+    for (unsigned long long i = 0; i < n_hits; ++i) CHECK(got.insert({hits[i].pos, hits[i].info}).second);
+    for (int s = 0; s < 2; ++s)
+        for (uint32_t b = 0; b < nb[s]; ++b)
+            for (uint32_t c = 0; c < valid_n[s][b]; ++c)
+                for (uint32_t g = 0; g < n_guides; ++g) {
+                    const uint8_t *x = &cand[s][((size_t)b * 32 + c) * VS_GLEN], *gd = &guides[g * VS_GLEN];
+                    int mm = 0, h2 = 0;
+                    for (int i = 0; i < VS_GLEN; ++i) {
+                        const int p = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];
+                        mm += x[i] != p;
+                        if (i >= 11) h2 += x[i] != p;
+                    }
+                    const bool last = (planes[s][plane_index(b, BLK_LAST)] >> c) & 1;
+                    if (mm <= K && (!last || h2 <= K / 2)) want.insert({pos[s][(size_t)b * 32 + c], ((256 + g) << 8) | ((uint32_t)s << 7) | (uint32_t)mm});
+                }
+    CHECK(got == want);
+    CHECK(want.size() > 20);
+}
+
 int main()
 {
     test_plane_index();
@@ -302,6 +473,9 @@ int main()
     test_pattern_table();
     test_mismatch_plane();
     test_extract_phase2();
+    test_mask_kernels();
+    check_k_score<0>(); check_k_score<1>(); check_k_score<2>(); check_k_score<3>(); check_k_score<4>();
+    check_k_score<5>(); check_k_score<6>(); check_k_score<7>(); check_k_score<8>();
     if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
     printf("kernel helper units ok\n");
     return 0;

@@ -372,15 +372,14 @@ def test_resolve_hits_threads_agree():
     assert c1 > 0 and len(ref) == len(hits)
 
 
-def test_kernel_helpers_on_the_host(tmp_path):
-    """The pure helper functions of vs_kernels.cuh (candidate masks, register transposes, bit-sliced adders and thresholds for
-    every k, pattern-table encoding, plane layout) and the body of k_extract's phase 2 — the very text the kernel includes,
-    vs_extract_block.inc, plus the experimental half-block variant — compiled for the host and checked against naive
-    restatements (tests/cpu_kernel_units.cpp).  The kernels themselves only run on a GPU (tests marked gpu)."""
+def test_device_code_on_the_host(tmp_path):
+    """vs_kernels.cuh compiled for the host (tests/cpu_kernel_units.cpp): k_score<K> for every k and the mask kernels run thread
+    by thread from their real source against naive restatements; k_extract's phase 2 runs through the very text the kernel
+    includes (vs_extract_block.inc, plus the experimental half-block variant); transposes, candidate masks, adders, <= k tests,
+    pattern table and plane layout have their own checks.  Launch geometry, streams and ptxas are what the gpu tests add."""
     exe = str(tmp_path / "kernel_units")
     src = os.path.join(ROOT, "tests", "cpu_kernel_units.cpp")
     r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "kernel helper units ok" in r.stdout, r.stdout + r.stderr
-

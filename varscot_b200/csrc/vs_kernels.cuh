@@ -19,7 +19,8 @@
 #pragma once
 #include <cstdint>
 #include <type_traits>
-#ifndef VS_HOST_UNIT_TEST          // tests/cpu_kernel_units.cpp compiles the pure helper functions of this header with g++
+#ifndef VS_HOST_UNIT_TEST          // tests/cpu_kernel_units.cpp compiles this header with g++ and runs the kernels that need no
+                                   // cooperation between threads (k_score, the mask kernels) thread by thread on the host
 #include <cuda_runtime.h>
 #endif
 #include "../../include/varscot_scan.h"
@@ -255,6 +256,8 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
 #endif
 }
 
+#endif  // VS_HOST_UNIT_TEST (k_extract needs warp shuffles and cp.async; its phase 2 runs on the host through the .inc files)
+
 // k_scatter_masks: expand the sparse form of the window masks (only words with a non-zero mask travel over PCIe).
 __global__ void __launch_bounds__(256)
 k_scatter_masks(const vs_mask_entry *__restrict__ e, uint64_t n, uint64_t word_base, vs_masks *__restrict__ M)
@@ -314,8 +317,6 @@ k_masks_from_planes(const uint32_t *__restrict__ nm, const uint32_t *__restrict_
     m.lw = (uint32_t)(E >> 22) & ~m.iv;
     out[w] = m;
 }
-
-#endif  // VS_HOST_UNIT_TEST
 
 // ------------------------------------------------------------------------------------------------
 // Scoring.
@@ -427,9 +428,7 @@ __host__ __device__ constexpr int score_min_blocks(int k)
 // (plane index * SCORE_THREADS * 4, plane index = 4 * (position - base) + pattern base) of the shared-memory plane it
 // selects; a stage-B slot holds the byte offset of its raw hi plane (lo follows at + SCORE_THREADS * 4) | pattern base << 16
 // (see pat_slot()).
-#ifndef VS_HOST_UNIT_TEST
 __constant__ uint32_t c_pat[PAT_TABLE_WORDS];
-#endif
 
 // position scored by slot j of a strand's slot order
 __host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
@@ -453,7 +452,6 @@ __device__ __forceinline__ uint32_t mismatch_plane(uint32_t h, uint32_t l, uint3
     return (h ^ ((b & 2u) ? ~0u : 0u)) | (l ^ ((b & 1u) ? ~0u : 0u));
 }
 
-#ifndef VS_HOST_UNIT_TEST
 struct ScoreArgs {
     const uint32_t *planes[2];  // per strand: [n_blocks][48]
     const uint32_t *pos[2];     // per strand: [n_blocks][32]
@@ -618,6 +616,7 @@ k_score(ScoreArgs a)
 
 // ------------------------------------------------------------------------------------------------
 // Microbenchmarks for the roofline denominators (alu-pipe LOP3 issue rate, shared-memory LDS rate).
+#ifndef VS_HOST_UNIT_TEST
 __global__ void __launch_bounds__(256)
 k_peak_lop3(uint32_t *out, int iters)
 {
