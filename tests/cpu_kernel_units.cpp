@@ -13,60 +13,11 @@
 #include <set>
 #include <vector>
 
-#define VS_HOST_UNIT_TEST
-#define __host__
-#define __device__
-#define __forceinline__ inline
-static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s)
-{
-    s &= 31;
-    return s ? (lo >> s) | (hi << (32 - s)) : lo;
-}
-static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel)
-{
-    const uint64_t v = ((uint64_t)y << 32) | x;
-    uint32_t r = 0;
-    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
-    return r;
-}
-static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
-#define __global__
-#define __constant__ static
-#define __shared__
-#define __restrict__
-#define __launch_bounds__(...)
-// A kernel whose threads never cooperate runs on the host one thread at a time: set these, call it.
-struct Idx3 { unsigned x, y, z; };
-static Idx3 threadIdx, blockIdx, blockDim, gridDim;
-static inline uint32_t __ldg(const uint32_t *p) { return *p; }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
-// warp vote of a one-thread "warp": a lane whose own stage-A result is zero can never produce a hit, so voting alone is exact
-static inline int __any_sync(unsigned, int pred) { return pred; }
-static inline uint64_t max(uint64_t a, uint64_t b) { return a > b ? a : b; }
-static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
-static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-struct uint2 { uint32_t x, y; };
-struct uint4 { uint32_t x, y, z, w; };
-static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
-static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
-
+#include "cuda_on_host.h"
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
 namespace vs { uint32_t sm[NPLANES * SCORE_THREADS]; }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
 using namespace vs;
-
-template <class F>
-static void launch(unsigned grid_x, unsigned grid_y, unsigned block, F kernel)
-{
-    gridDim = Idx3{grid_x, grid_y, 1}; blockDim = Idx3{block, 1, 1};
-    for (unsigned by = 0; by < grid_y; ++by)
-        for (unsigned bx = 0; bx < grid_x; ++bx)
-            for (unsigned t = 0; t < block; ++t) {
-                blockIdx = Idx3{bx, by, 0}; threadIdx = Idx3{t, 0, 0};
-                kernel();
-            }
-}
 
 static int failures = 0;
 #define CHECK(cond)                                                                     \

@@ -1,0 +1,110 @@
+// tests/cpu_scan_emulator.cpp — TEST INFRASTRUCTURE: the device code of the scan (k_extract, k_score<K>, compiled from
+// varscot_b200/csrc/vs_kernels.cuh under tests/cuda_on_host.h) run on the HOST over a packed text, chunk by chunk as
+// scan_core (vs_device.cu) drives it on the GPU.  tests/test_host.py feeds it texts packed by the library and compares the
+// hits, resolved by the library's host side, with the oracle: the kernels' logic end to end, without a GPU.  What it
+// cannot show — ptxas, launch geometry, streams, the upload path — is what the tests marked gpu are for.
+// Never linked into the product; far too slow to be a fallback (one OS thread per CUDA thread).
+//
+// usage: cpu_scan_emulator IN OUT
+//   IN : u64 n_words, u32 n_guides, i32 k, i32 extra_pam, u32 tile_words (0 = scan_core's choice), u64 chunk_words,
+//        bases[(n_words + 1)], masks[n_words], guides[n_guides][23]
+//   OUT: u64 n_hits, hits[n_hits]
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "cuda_on_host.h"
+#include "../varscot_b200/csrc/vs_kernels.cuh"
+
+namespace vs { uint32_t sm[NPLANES * SCORE_THREADS]; }
+using namespace vs;
+
+template <int K>
+static void run_score(const ScoreArgs &a) { launch(2 * a.ctas_per_strand, 1, SCORE_THREADS, [&] { k_score<K>(a); }); }
+
+static void dispatch_score(int k, const ScoreArgs &a)
+{
+    switch (k) {
+    case 0: run_score<0>(a); break; case 1: run_score<1>(a); break; case 2: run_score<2>(a); break;
+    case 3: run_score<3>(a); break; case 4: run_score<4>(a); break; case 5: run_score<5>(a); break;
+    case 6: run_score<6>(a); break; case 7: run_score<7>(a); break; default: run_score<8>(a); break;
+    }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc != 3) { fprintf(stderr, "usage: cpu_scan_emulator IN OUT\n"); return 2; }
+    FILE *f = fopen(argv[1], "rb");
+    if (!f) { perror(argv[1]); return 2; }
+    uint64_t n_words = 0, chunk_words = 0;
+    uint32_t n_guides = 0, tile_words = 0;
+    int32_t k = 0, extra_pam = -1;
+    bool ok = fread(&n_words, 8, 1, f) == 1 && fread(&n_guides, 4, 1, f) == 1 && fread(&k, 4, 1, f) == 1 && fread(&extra_pam, 4, 1, f) == 1 &&
+              fread(&tile_words, 4, 1, f) == 1 && fread(&chunk_words, 8, 1, f) == 1;
+    std::vector<vs_bases> bases(n_words + 1);
+    std::vector<vs_masks> masks(n_words ? n_words : 1);
+    std::vector<uint8_t> guides((size_t)n_guides * VS_GLEN + 1);
+    ok = ok && fread(bases.data(), sizeof(vs_bases), n_words + 1, f) == n_words + 1 && fread(masks.data(), sizeof(vs_masks), n_words, f) == n_words &&
+         fread(guides.data(), 1, (size_t)n_guides * VS_GLEN, f) == (size_t)n_guides * VS_GLEN;
+    fclose(f);
+    if (!ok || k < 0 || k > VS_MAX_MISMATCHES || chunk_words == 0) { fprintf(stderr, "bad input\n"); return 2; }
+
+    // as scan_core (vs_device.cu): PAM lists, tile size, pattern tables per guide chunk, one extract + score pass per chunk
+    PamParams pp;
+    pp.n = 2;
+    pp.fx[0] = 2; pp.fy[0] = 2; pp.fx[1] = 2; pp.fy[1] = 0; pp.fx[2] = 0; pp.fy[2] = 0;
+    if (extra_pam >= 0) { pp.fx[2] = extra_pam / 4; pp.fy[2] = extra_pam % 4; pp.n = 3; }
+    for (int j = 0; j < 3; ++j) { pp.rx[j] = 3 - pp.fy[j]; pp.ry[j] = 3 - pp.fx[j]; }
+    if (tile_words == 0) tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
+    tile_words = std::min<uint32_t>(std::max<uint32_t>(tile_words, 8), EX_MAX_WORDS);
+    const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
+    std::vector<uint32_t> pat((size_t)std::max<uint32_t>(g_chunks, 1) * PAT_TABLE_WORDS, 0);
+    for (int s = 0; s < 2; ++s)
+        for (uint32_t g = 0; g < n_guides; ++g) {
+            uint32_t *dst = pat.data() + (size_t)(g / PAT_CHUNK) * PAT_TABLE_WORDS + ((size_t)s * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
+            const uint8_t *gd = guides.data() + (size_t)g * VS_GLEN;
+            for (int j = 0; j < VS_GLEN; ++j) {
+                const int i = slot_position(s, j);
+                dst[j] = pat_slot(k, s, j, s ? 3 - gd[VS_GLEN - 1 - i] : gd[i]);
+            }
+        }
+    std::vector<vs_hit> hits(1 << 16);
+    unsigned long long n_hits = 0;
+    for (uint64_t c0 = 0; c0 < n_words && n_guides; c0 += chunk_words) {
+        const uint64_t c1 = std::min(n_words, c0 + chunk_words);
+        const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
+        uint64_t cap = (c1 - c0) + tiles + 256;                    // generous: at most 32 candidates per word and strand
+        cap = (cap + SCORE_THREADS - 1) / SCORE_THREADS * SCORE_THREADS;
+        std::vector<uint32_t> planes[2], pos[2];
+        for (int s = 0; s < 2; ++s) { planes[s].assign(cap * BLK_WORDS, 0xDEADBEEFu); pos[s].assign(cap * 32, 0xDEADBEEFu); }
+        unsigned long long cnt[4] = {0, 0, 0, 0};
+        launch_cta(tiles, EX_THREADS, [&] {
+            k_extract(bases.data(), masks.data(), c0, c1, tile_words, 0, pp, planes[0].data(), pos[0].data(), planes[1].data(), pos[1].data(), cap, cnt);
+        });
+        if (cnt[2] > cap || cnt[3] > cap) { fprintf(stderr, "candidate store overflow\n"); return 3; }
+        for (uint32_t gc = 0; gc < g_chunks; ++gc) {
+            const uint32_t *table = pat.data() + (size_t)gc * PAT_TABLE_WORDS;
+            memcpy(c_pat, table, sizeof(uint32_t) * PAT_TABLE_WORDS);
+            for (;;) {
+                ScoreArgs a;
+                for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
+                a.n_blocks_ptr = cnt + 2; a.cap = cap; a.ctas_per_strand = (uint32_t)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
+                a.n_pat = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK); a.guide_base = gc * PAT_CHUNK;
+                a.pat_global = table;
+                const unsigned long long before = n_hits;
+                a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
+                dispatch_score(k, a);
+                if (n_hits <= hits.size()) break;
+                hits.resize(n_hits + n_hits / 4);                  // hit buffer overflow: grow and redo this launch
+                n_hits = before;
+            }
+        }
+    }
+    f = fopen(argv[2], "wb");
+    if (!f) { perror(argv[2]); return 2; }
+    const uint64_t n = n_hits;
+    ok = fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(hits.data(), sizeof(vs_hit), n, f) == n);
+    ok = fclose(f) == 0 && ok;
+    return ok ? 0 : 2;
+}

@@ -19,8 +19,8 @@
 #pragma once
 #include <cstdint>
 #include <type_traits>
-#ifndef VS_HOST_UNIT_TEST          // tests/cpu_kernel_units.cpp compiles this header with g++ and runs the kernels that need no
-                                   // cooperation between threads (k_score, the mask kernels) thread by thread on the host
+#ifndef VS_HOST_UNIT_TEST          // tests/cpu_kernel_units.cpp and tests/cpu_scan_emulator.cpp compile this header with g++ and run the
+                                   // kernels on the host (k_extract with one OS thread per CUDA thread, the others thread by thread)
 #include <cuda_runtime.h>
 #endif
 #include "../../include/varscot_scan.h"
@@ -155,7 +155,6 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 #ifndef VS_EX_MINBLOCKS
 #define VS_EX_MINBLOCKS (VS_EX_HALF ? 16 : 10)
 #endif
-#ifndef VS_HOST_UNIT_TEST
 __global__ void __launch_bounds__(EX_THREADS, VS_EX_MINBLOCKS)
 k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
           uint64_t global_base, PamParams pp,
@@ -175,6 +174,7 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     // phase 1a: the tile's bases (+ halo word) and window masks are staged into shared memory with cp.async (LDGSTS):
     // coalesced 128-bit copies when the tile starts on a 16-byte boundary (always, except for odd test chunk sizes),
     // 64-bit copies otherwise; nothing passes through registers and every copy of the tile is in flight at once.
+#ifndef VS_HOST_UNIT_TEST
     {
         const uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_hl), smk = (uint32_t)__cvta_generic_to_shared(s_mk);
         const char *gb = reinterpret_cast<const char *>(B + w0), *gm = reinterpret_cast<const char *>(M + w0);
@@ -195,6 +195,10 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+#else       // host emulation (tests/cpu_kernel_units.cpp): plain copies
+    for (uint32_t i = tid; i < nw + 1; i += EX_THREADS) s_hl[i] = uint2{B[w0 + i].hi, B[w0 + i].lo};
+    for (uint32_t i = tid; i < nw; i += EX_THREADS) s_mk[i] = uint2{M[w0 + i].iv, M[w0 + i].lw};
+#endif
     __syncthreads();
     constexpr int EX_ITERS = EX_MAX_WORDS / EX_THREADS;
     // phase 1b: candidate masks and their rank prefix (word order: thread t owns words t, t+64, t+128, t+192)
@@ -255,8 +259,6 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     }
 #endif
 }
-
-#endif  // VS_HOST_UNIT_TEST (k_extract needs warp shuffles and cp.async; its phase 2 runs on the host through the .inc files)
 
 // k_scatter_masks: expand the sparse form of the window masks (only words with a non-zero mask travel over PCIe).
 __global__ void __launch_bounds__(256)
@@ -511,7 +513,9 @@ template <int K>
 __global__ void __launch_bounds__(SCORE_THREADS, score_min_blocks(K))
 k_score(ScoreArgs a)
 {
+#ifndef VS_HOST_UNIT_TEST       // (the host emulation declares vs::sm itself)
     extern __shared__ uint32_t sm[];     // [score_smem_planes(K)][SCORE_THREADS]
+#endif
     constexpr int PA = stage_a_slots(K), PB = VS_GLEN - PA;
     const int tid = threadIdx.x;
     const uint32_t strand = blockIdx.x >= a.ctas_per_strand;            // forward CTAs first, then reverse
