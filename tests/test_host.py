@@ -379,7 +379,7 @@ def test_device_code_on_the_host(tmp_path):
     pattern table and plane layout have their own checks.  Launch geometry, streams and ptxas are what the gpu tests add."""
     exe = str(tmp_path / "kernel_units")
     src = os.path.join(ROOT, "tests", "cpu_kernel_units.cpp")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "kernel helper units ok" in r.stdout, r.stdout + r.stderr
