@@ -17,7 +17,8 @@
  * vs_scan / vs_scan_text           bidir_mapping.cpp:285-295 omp-parallel loop over guides calling
  *                                  searchAndVerifyEntireRead -> searchAndVerify (:31-148, :150-188):
  *                                  seed search + verify delegate, for both strands
- * vs_resolve_hits                  bidir_mapping.cpp:154,164-187  std::map order + primary/secondary flags
+ * vs_scan_resolved                 the same + the std::map<TOccType,..> order of :13,154 (contig lookup and sort on the device)
+ * vs_resolve_hits / vs_merge_resolved  bidir_mapping.cpp:154,164-187  std::map order + primary/secondary flags
  * vs_md_string / vs_format_sam     bidir_mapping.cpp:111-123 getMDString + tags; :177-187 write(.., Sam())
  * vs_bidir_index_main              bidir_index.cpp:10-52   main (argv contract)
  * vs_bidir_mapping_main            bidir_mapping.cpp:190-312 main (argv contract, stdout lines, exit codes)
@@ -137,6 +138,9 @@ int vs_masks_sparse(const vs_masks *masks, uint64_t n_words, vs_mask_entry **out
 
 /* packed-text cache at the -I prefix (file <prefix>.vsidx) */
 int vs_text_save(const char *prefix, const vs_text_view *text);
+/* window masks of a view on the host: a copy of text->masks, or — for a view that carries only the compact mask source
+ * (what vs_text_load returns for a cache written by bidir_index) — rebuilt from it.  out: n_words entries. */
+int vs_text_masks(const vs_text_view *text, vs_masks *out);
 /* loads into ONE malloc'd buffer (returned in *owner, release with vs_free) that the view points into */
 int vs_text_load(const char *prefix, vs_text_view *out, void **owner);
 void vs_free(void *p);
@@ -173,8 +177,22 @@ typedef struct {
     uint32_t launches;                                    /* kernels launched by this call */
     uint32_t score_launches;
     uint32_t n_chunks;
-    uint32_t redo_chunks;                                 /* chunks redone because a candidate store overflowed */
+    uint32_t redo_chunks;                                 /* passes repeated because a device buffer was too small (0 on uniform text) */
+    float    resolve_ms;                                  /* device-side hit resolution + sort + download (vs_scan_resolved) */
+    uint32_t index_reused;                                /* 1: the resident candidate index was scored, nothing was extracted */
+    uint32_t guide_passes;                                /* passes over the candidate index (guide super-chunks) */
+    uint32_t reserved;
 } vs_scan_stats;
+
+/* ---- resident candidate index ---------------------------------------------------------------------------------
+ * The first scan of a resident text extracts the PAM-valid windows of both strands into a candidate store (bit-sliced
+ * blocks of 32) that stays in HBM: the analogue of the reference's split between bidir_index (bidir_index.cpp:45-47,
+ * build once) and bidir_mapping (bidir_mapping.cpp:268, open and search).  Later scans with the same PAM set score the
+ * store directly.  It is dropped by a new upload, a different -P, vs_index_drop(), or kept off with VS_OPT_KEEP_INDEX 0. */
+#define VS_OPT_KEEP_INDEX   1     /* 0 / 1 (default 1) */
+#define VS_OPT_HIT_CAPACITY 2     /* entries of the device hit buffer; 0 (default) = sized from k, the PAM set and the shard */
+int vs_ctx_set_option(vs_ctx *ctx, int option, int64_t value);
+int vs_index_drop(vs_ctx *ctx);
 
 /* Scan the RESIDENT text for every window within k mismatches of each guide, both strands (rules R1-R4,
  * SURVEY.md section 8a).  guides: n_guides x 23 Dna codes (0..3).  extra_pam: -1 or 4*x+y for -P XY.
@@ -188,6 +206,26 @@ int vs_scan_text(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uin
                  const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
                  vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats);
 int vs_scan_fetch(vs_ctx *ctx, vs_hit *out, uint64_t out_cap, uint64_t *n_hits);
+
+/* ---- scans that resolve and sort their hits on the device ---------------------------------------------------
+ * The contig of every hit is looked up on the device (contig starts derived from the contig-end plane, or uploaded when
+ * the view has no mask source) and the hits are radix-sorted into the reference's emission order
+ * (guide; forward pass then reverse pass; std::map key (contig & 0xFFFF, pos), bidir_mapping.cpp:13,154,285-295), so the
+ * host only merges the lists of the shards (vs_merge_resolved).  The text view must carry contig_off.
+ *   key    = (guide - guide_lo of the delivery) << 49 | strand << 48 | (contig & 0xFFFF) << 32 | pos in contig
+ *   contig = full 32-bit id;  info = guide << 8 | strand << 7 | mm  (as vs_hit)
+ * Guides are processed in super-chunks sized to the device hit buffer (one for configs 1-4); with a `sink` every
+ * super-chunk is handed over as soon as it is sorted (host memory stays O(super-chunk), config 5), otherwise the lists
+ * are concatenated in `out` (guide-ascending, so the concatenation is sorted as a whole). */
+typedef struct { uint64_t key; uint32_t contig; uint32_t info; } vs_loc_hit;
+typedef int (*vs_hit_sink)(void *user, const vs_loc_hit *hits, uint64_t n, uint32_t guide_lo, uint32_t guide_hi);   /* non-zero aborts */
+/* text == NULL: scan the resident shard (first_word / n_words ignored); otherwise upload + scan as vs_scan_text */
+int vs_scan_resolved(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words,
+                     const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                     vs_loc_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_hit_sink sink, void *user, vs_scan_stats *stats);
+/* page-lock / unlock memory the caller owns (e.g. a shared-memory segment the hits are downloaded into) */
+int vs_host_register(void *p, size_t bytes);
+int vs_host_unregister(void *p);
 
 /* Convenience used by the executables and bindings: shard a packed text by word ranges over the given
  * devices (devices == NULL or n_devices == 0 -> device 0; one host thread + one context per device, no
@@ -218,6 +256,17 @@ int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, 
 /* the same with n_threads host threads (the executables pass -T): the contig lookup and the per-pass sorts run in parallel */
 int vs_resolve_hits_mt(const vs_hit *hits, uint64_t n, const uint64_t *contig_off, uint32_t n_contigs,
                        vs_record *out, uint64_t *key16_collisions, int n_threads);
+
+/* Merge the sorted lists of n_lists shards (vs_scan_resolved) into records in emission order and apply the running-best
+ * primary/secondary rule (bidir_mapping.cpp:164-187).  out must hold the sum of the counts. */
+int vs_merge_resolved(const vs_loc_hit *const *lists, const uint64_t *counts, int n_lists,
+                      vs_record *out, uint64_t *key16_collisions, int n_threads);
+
+/* The whole mapping step of the executables: shard, scan with device-side resolution, merge; records in emission order
+ * in a malloc'd array (release with vs_free). */
+int vs_map_records(const vs_text_view *text, const uint8_t *guides, uint32_t n_guides,
+                   int k, int extra_pam, const int *devices, int n_devices, int n_threads,
+                   vs_record **records, uint64_t *n_records, uint64_t *key16_collisions, vs_scan_stats *stats);
 
 #define VS_MD_SEQAN 0
 #define VS_MD_SAMTOOLS 1

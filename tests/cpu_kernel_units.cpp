@@ -1,6 +1,7 @@
 // tests/cpu_kernel_units.cpp — TEST INFRASTRUCTURE: varscot_b200/csrc/vs_kernels.cuh compiled for the HOST with g++.
-//  * the kernels whose threads never cooperate (k_score<K>, k_fill_runs, k_expand_em_code, k_masks_from_planes,
-//    k_scatter_masks) run thread by thread from their real source, against naive restatements;
+//  * the kernels whose threads never cooperate (k_fill_runs, k_expand_em_code, k_masks_from_planes, k_scatter_masks,
+//    k_extract_mark, k_resolve_hits, k_pack_loc_hits) run thread by thread from their real source, against naive restatements;
+//    k_score<K> and the contig-start kernels (barriers) run with one OS thread per CUDA thread;
 //  * k_extract (warp shuffles, cp.async) is guarded out; its phase 2 runs through the very text the kernel includes
 //    (vs_extract_block.inc, and the experimental vs_extract_half_block.inc), its phase 1 through cand_masks;
 //  * the helpers (register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout) have
@@ -11,12 +12,13 @@
 #include <cstdlib>
 #include <random>
 #include <set>
+#include <algorithm>
 #include <vector>
 
 #include "cuda_on_host.h"
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
-namespace vs { uint32_t sm[NPLANES * SCORE_THREADS]; }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
+namespace vs { uint32_t sm[SC_NB * SC_STRIDE + SC_NB] __attribute__((aligned(16))); }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
 using namespace vs;
 
 static int failures = 0;
@@ -133,48 +135,34 @@ static void test_pattern_table()
     for (int k = 0; k <= VS_MAX_MISMATCHES; ++k) {
         const int pa = stage_a_slots(k);
         CHECK(pa > k && pa <= VS_GLEN);                     // an invalid lane (mismatch in all stage-A planes) can never pass
-        CHECK(score_smem_planes(k) * SCORE_THREADS * 4 <= 48 * 1024);
-        CHECK((score_smem_planes(k) * SCORE_THREADS * 4 + 1024) * score_min_blocks(k) <= 227 * 1024 + 1024 * score_min_blocks(k));
-        for (int s = 0; s < 2; ++s) {
-            std::set<int> pos;
-            std::set<uint32_t> planes;
-            for (int j = 0; j < VS_GLEN; ++j) {
-                const int i = slot_position(s, j);
-                CHECK(i >= 0 && i < VS_GLEN);
-                pos.insert(i);
-                if (j < pa) CHECK(i == score_pos_base(k, s) + j || (k >= 8));      // stage A covers a contiguous position range
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t e = pat_slot(k, s, j, b);
-                    int di, db;
-                    pat_decode(k, s, j, e, di, db);
-                    CHECK(di == i && db == b);
-                    const uint32_t off = j < pa ? e : (e & 0xFFFFu);
-                    CHECK(off % (SCORE_THREADS * 4u) == 0);
-                    const uint32_t plane = off / (SCORE_THREADS * 4u);
-                    if (j < pa) {
-                        CHECK(plane < (uint32_t)(4 * pa) && planes.insert(plane).second);
-                    } else {
-                        CHECK(plane >= (uint32_t)(4 * pa) && plane + 1 < (uint32_t)score_smem_planes(k) && (plane - 4 * pa) % 2 == 0);
-                        CHECK((e >> 16) == (uint32_t)b);
-                    }
-                }
+    }
+    CHECK(SC_SMEM_BYTES <= 48 * 1024);
+    for (int s = 0; s < 2; ++s) {
+        std::set<int> pos;
+        std::set<uint32_t> planes;
+        for (int j = 0; j < VS_GLEN; ++j) {
+            const int i = slot_position(s, j);
+            CHECK(i >= 0 && i < VS_GLEN);
+            pos.insert(i);
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t e = pat_slot(s, j, b);
+                int di, db;
+                pat_decode(s, j, e, di, db);
+                CHECK(di == i && db == b);
+                CHECK(e % 4 == 0 && e / 4 == (uint32_t)(4 * i + b) && e / 4 < (uint32_t)SC_STRIDE);
+                CHECK(planes.insert(e).second);
             }
-            CHECK((int)pos.size() == VS_GLEN);             // the slot order is a permutation of the 23 positions
-            CHECK((int)planes.size() == 4 * pa);
         }
+        CHECK((int)pos.size() == VS_GLEN);                 // the slot order is a permutation of the 23 positions
+        CHECK((int)planes.size() == 4 * VS_GLEN);
     }
     // the PAM dinucleotide is scored last on both strands
     CHECK(slot_position(0, 21) == 21 && slot_position(0, 22) == 22 && slot_position(1, 21) == 0 && slot_position(1, 22) == 1);
-}
-
-static void test_mismatch_plane()
-{
-    for (int rep = 0; rep < 100; ++rep) {
-        const uint32_t h = r32(), l = r32();
-        for (uint32_t b = 0; b < 4; ++b) {
-            const uint32_t m = mismatch_plane(h, l, b);
-            for (int c = 0; c < 32; ++c) CHECK(((m >> c) & 1) == ((((h >> c) & 1) * 2 + ((l >> c) & 1)) != b));
-        }
+    // shared-memory banks: the 4-word groups of up to 8 consecutive block rows fall into distinct banks
+    for (int i = 0; i < VS_GLEN; ++i) {
+        std::set<int> banks;
+        for (int blk = 0; blk < 8; ++blk)
+            for (int b = 0; b < 4; ++b) CHECK(banks.insert((blk * SC_STRIDE + 4 * i + b) % 32).second);
     }
 }
 
@@ -334,14 +322,15 @@ static void test_mask_kernels()
     }
 }
 
-// ---- k_score<K> thread by thread on the host: random candidate blocks (with planted near matches, last-window flags and
-// a partial last block) against random guides, both strands; the hits must be exactly those of a naive count.
+// ---- k_score<K> on the host (one OS thread per CUDA thread): random candidate blocks (with planted near matches,
+// last-window flags, a partial last block and padding blocks with an empty valid mask) against random guides, both
+// strands, a guide count that exercises the 32 / 16 / 8 / 4-guide segments; the hits must be exactly those of a naive count.
 template <int K>
-static void check_k_score()
+static void check_k_score(uint32_t n_guides)
 {
-    const uint32_t nb[2] = {SCORE_THREADS + 37, 2 * SCORE_THREADS + 5};        // blocks per strand (not multiples of the CTA)
-    const uint32_t n_guides = 9;
-    const uint64_t cap = 3 * SCORE_THREADS;
+    const uint32_t nb[2] = {SC_NB + 7, 2 * SC_NB + 5};                         // blocks per strand (not multiples of the batch)
+    const uint32_t lo[2] = {SC_NB, 0};                                         // the forward range starts inside the store
+    const uint64_t cap = 4 * SC_NB;
     std::vector<uint8_t> guides(n_guides * VS_GLEN);
     for (auto &g : guides) g = r32() % 4;
     // candidates: [strand][block][lane] -> 23 codes, last-window flag, position; some lanes are near copies of a pattern
@@ -349,11 +338,12 @@ static void check_k_score()
     std::vector<uint8_t> cand[2];
     std::vector<uint32_t> valid_n[2];
     for (int s = 0; s < 2; ++s) {
-        planes[s].assign(cap * BLK_WORDS, 0);
+        planes[s].assign(cap * BLK_WORDS, 0xA5A5A5A5u);
         pos[s].assign(cap * 32, 0);
         cand[s].assign((size_t)nb[s] * 32 * VS_GLEN, 0);
         valid_n[s].assign(nb[s], 32);
         valid_n[s][nb[s] - 1] = 1 + r32() % 31;                                // partial last block
+        valid_n[s][nb[s] / 2] = 0;                                             // a padding block (k_extract_mark): garbage planes, empty valid mask
         for (uint32_t b = 0; b < nb[s]; ++b) {
             uint32_t w[BLK_WORDS] = {0};
             for (int c = 0; c < 32; ++c) {
@@ -370,29 +360,30 @@ static void check_k_score()
                 }
                 if (r32() % 3 == 0) w[BLK_LAST] |= 1u << c;
                 if ((uint32_t)c < valid_n[s][b]) w[BLK_VALID] |= 1u << c;
-                pos[s][(size_t)b * 32 + c] = (uint32_t)(s * 1000000 + b * 32 + c);
+                pos[s][(size_t)(lo[s] + b) * 32 + c] = (uint32_t)(s * 1000000 + b * 32 + c);
             }
-            for (int i = 0; i < BLK_WORDS; ++i) planes[s][plane_index(b, i)] = w[i];
+            for (int i = 0; i < BLK_WORDS; ++i) planes[s][plane_index(lo[s] + b, i)] = w[i];
         }
     }
-    // pattern table as scan_core builds it
-    std::vector<uint32_t> pat(PAT_TABLE_WORDS, 0);
+    // pattern table as scan_engine builds it; the launch scores rows [3, 3 + n_guides) of a larger table
+    const uint32_t rows = n_guides + 5, g_base = 3;
+    std::vector<uint16_t> store((size_t)2 * rows * PAT_STRIDE + 8, 0);
+    uint16_t *pat = (uint16_t *)(((uintptr_t)store.data() + 15) & ~(uintptr_t)15);
     for (int s = 0; s < 2; ++s)
         for (uint32_t g = 0; g < n_guides; ++g)
             for (int j = 0; j < VS_GLEN; ++j) {
                 const int i = slot_position(s, j);
                 const int b = s ? 3 - guides[g * VS_GLEN + VS_GLEN - 1 - i] : guides[g * VS_GLEN + i];
-                pat[((size_t)s * PAT_CHUNK + g) * PAT_STRIDE + j] = pat_slot(K, s, j, b);
+                pat[((size_t)s * rows + g_base + g) * PAT_STRIDE + j] = pat_slot(s, j, b);
             }
-    for (size_t i = 0; i < pat.size(); ++i) c_pat[i] = pat[i];
-    unsigned long long n_blocks[2] = {nb[0], nb[1]}, n_hits = 0;
+    unsigned long long rng[4] = {lo[0], lo[1], lo[0] + nb[0], lo[1] + nb[1]}, n_hits = 0;
     std::vector<vs_hit> hits(1 << 20);
     ScoreArgs a;
     for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
-    a.n_blocks_ptr = n_blocks; a.cap = cap; a.ctas_per_strand = (uint32_t)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
-    a.n_pat = n_guides; a.guide_base = 256; a.pat_global = pat.data();
+    a.rng = rng; a.cap = cap;
+    a.n_guides = n_guides; a.guide_base = g_base; a.pat_guides = rows; a.pat = pat;
     a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
-    launch(2 * a.ctas_per_strand, 1, SCORE_THREADS, [&] { k_score<K>(a); });
+    launch_cta(2, std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32), [&] { k_score<K>(a); });
     std::set<std::pair<uint32_t, uint32_t>> got, want;
     CHECK(n_hits <= hits.size());
     for (unsigned long long i = 0; i < n_hits; ++i) CHECK(got.insert({hits[i].pos, hits[i].info}).second);
@@ -407,11 +398,84 @@ static void check_k_score()
                         mm += x[i] != p;
                         if (i >= 11) h2 += x[i] != p;
                     }
-                    const bool last = (planes[s][plane_index(b, BLK_LAST)] >> c) & 1;
-                    if (mm <= K && (!last || h2 <= K / 2)) want.insert({pos[s][(size_t)b * 32 + c], ((256 + g) << 8) | ((uint32_t)s << 7) | (uint32_t)mm});
+                    const bool last = (planes[s][plane_index(lo[s] + b, BLK_LAST)] >> c) & 1;
+                    if (mm <= K && (!last || h2 <= K / 2))
+                        want.insert({pos[s][(size_t)(lo[s] + b) * 32 + c], ((g_base + g) << 8) | ((uint32_t)s << 7) | (uint32_t)mm});
                 }
     CHECK(got == want);
     CHECK(want.size() > 20);
+}
+
+// ---- k_extract_mark: closes a chunk's block range, pads the claims to a layout group, empties the padding blocks
+static void test_extract_mark()
+{
+    const uint64_t cap = 8 * BLK_GROUP;
+    std::vector<uint32_t> pl[2];
+    for (int s = 0; s < 2; ++s) pl[s].assign(cap * BLK_WORDS, 0xDEADBEEFu);
+    unsigned long long cnt[4] = {1000, 2000, 37, 64}, rng[8] = {0, 32, 0, 0, 0, 0, 0, 0}, all[4] = {9, 9, 9, 9};
+    launch(1, 1, 32, [&] { k_extract_mark(cnt, rng, all, pl[0].data(), pl[1].data(), cap); });
+    CHECK(rng[0] == 0 && rng[1] == 32 && rng[2] == 37 && rng[3] == 64);       // this chunk's range
+    CHECK(rng[4] == 64 && rng[5] == 64 && cnt[2] == 64 && cnt[3] == 64);      // the next chunk starts on a group boundary
+    CHECK(all[0] == 0 && all[1] == 0 && all[2] == 64 && all[3] == 64);
+    for (uint64_t b = 0; b < cap; ++b) {
+        const bool pad = b >= 37 && b < 64;
+        CHECK(pl[0][plane_index(b, BLK_VALID)] == (pad ? 0u : 0xDEADBEEFu));
+        CHECK(pl[1][plane_index(b, BLK_VALID)] == 0xDEADBEEFu);
+    }
+    // claims past the capacity: nothing is written out of bounds, the counters still advance
+    unsigned long long cnt2[4] = {0, 0, cap + 5, 3}, rng2[8] = {0}, all2[4] = {0};
+    launch(1, 1, 32, [&] { k_extract_mark(cnt2, rng2, all2, pl[0].data(), pl[1].data(), cap); });
+    CHECK(cnt2[2] == cap + BLK_GROUP && rng2[2] == cap + 5);
+}
+
+// ---- contig starts from the contig-end plane, and the hit resolution that uses them
+static void test_contig_starts_and_resolve()
+{
+    for (int rep = 0; rep < 6; ++rep) {
+        const uint64_t n_words = rep == 0 ? 1 : 100 + r32() % (3 * CS_TILE);
+        const uint64_t first_word = r32() % 1000;
+        std::vector<uint32_t> em(n_words + 1, 0);
+        std::vector<uint32_t> want;
+        const uint32_t first_start = (uint32_t)(first_word * 32 - (rep % 2 ? 17 : 0));
+        want.push_back(first_start);
+        for (uint64_t w = 0; w < n_words; ++w) {
+            const uint32_t kind = r32() % 6;
+            em[w] = kind == 0 ? (1u << (r32() % 32)) | (1u << (r32() % 32)) : kind == 1 ? 1u << (r32() % 32) : kind == 2 && rep == 3 ? ~0u : 0u;
+            for (int b = 0; b < 32; ++b) if ((em[w] >> b) & 1) want.push_back((uint32_t)((first_word + w) * 32 + b + 1));
+        }
+        em[n_words] = ~0u;                                   // the halo word does not count
+        const unsigned tiles = (unsigned)((n_words + CS_TILE - 1) / CS_TILE);
+        std::vector<uint32_t> tile(tiles + 1, 0xFFu), starts(want.size() + 4, 0xDEADBEEFu);
+        uint32_t total = 0;
+        launch_cta(tiles, 256, [&] { k_contig_starts_count(em.data(), n_words, tile.data()); });
+        launch_cta(1, 1024, [&] { k_contig_starts_scan(tile.data(), tiles, &total); });
+        launch_cta(tiles, 256, [&] { k_contig_starts_scatter(em.data(), n_words, tile.data(), first_word * 32, first_start, starts.data()); });
+        CHECK(total + 1 == want.size());
+        for (size_t i = 0; i < want.size(); ++i) CHECK(starts[i] == want[i]);
+        CHECK(starts[want.size()] == 0xDEADBEEFu);
+        // resolution: random hits inside the shard -> (contig, pos) by a linear search
+        const uint64_t n = 500;
+        std::vector<vs_hit> hits(n);
+        std::vector<unsigned long long> keys(n), vals(n);
+        const uint32_t first_contig = 70000 + r32() % 1000, guide_lo = 256;
+        for (auto &h : hits) {
+            h.pos = (uint32_t)(first_word * 32 + r32() % (n_words * 32));
+            h.info = ((guide_lo + r32() % 300) << 8) | ((r32() & 1) << 7) | (r32() % 9);
+        }
+        launch((unsigned)((n + 255) / 256), 1, 256, [&] {
+            k_resolve_hits(hits.data(), n, starts.data(), (uint32_t)want.size(), first_contig, guide_lo, keys.data(), vals.data());
+        });
+        std::vector<vs_loc_hit> loc(n);
+        launch((unsigned)((n + 255) / 256), 1, 256, [&] { k_pack_loc_hits(keys.data(), vals.data(), n, loc.data()); });
+        for (uint64_t i = 0; i < n; ++i) {
+            size_t c = 0;
+            while (c + 1 < want.size() && want[c + 1] <= hits[i].pos) ++c;
+            const uint32_t contig = first_contig + (uint32_t)c, pos = hits[i].pos - want[c];
+            CHECK(loc[i].contig == contig && loc[i].info == hits[i].info);
+            CHECK((uint32_t)loc[i].key == pos && ((loc[i].key >> 32) & 0xFFFF) == (contig & 0xFFFF));
+            CHECK(((loc[i].key >> 48) & 1) == ((hits[i].info >> 7) & 1) && (loc[i].key >> 49) == (hits[i].info >> 8) - guide_lo);
+        }
+    }
 }
 
 int main()
@@ -422,11 +486,12 @@ int main()
     check_le_k<0>(); check_le_k<1>(); check_le_k<2>(); check_le_k<3>(); check_le_k<4>();
     check_le_k<5>(); check_le_k<6>(); check_le_k<7>(); check_le_k<8>();
     test_pattern_table();
-    test_mismatch_plane();
     test_extract_phase2();
     test_mask_kernels();
-    check_k_score<0>(); check_k_score<1>(); check_k_score<2>(); check_k_score<3>(); check_k_score<4>();
-    check_k_score<5>(); check_k_score<6>(); check_k_score<7>(); check_k_score<8>();
+    test_extract_mark();
+    test_contig_starts_and_resolve();
+    check_k_score<0>(9); check_k_score<1>(33); check_k_score<2>(5); check_k_score<3>(60); check_k_score<4>(128 + 28);
+    check_k_score<5>(20); check_k_score<6>(100); check_k_score<7>(12); check_k_score<8>(4);
     if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
     printf("kernel helper units ok\n");
     return 0;

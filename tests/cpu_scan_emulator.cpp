@@ -13,22 +13,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "cuda_on_host.h"
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
-namespace vs { uint32_t sm[NPLANES * SCORE_THREADS]; }
+namespace vs { uint32_t sm[SC_NB * SC_STRIDE + SC_NB] __attribute__((aligned(16))); }
 using namespace vs;
 
 template <int K>
-static void run_score(const ScoreArgs &a) { launch(2 * a.ctas_per_strand, 1, SCORE_THREADS, [&] { k_score<K>(a); }); }
+static void run_score(const ScoreArgs &a, unsigned ctas, unsigned threads) { launch_cta(ctas, threads, [&] { k_score<K>(a); }); }
 
-static void dispatch_score(int k, const ScoreArgs &a)
+static void dispatch_score(int k, const ScoreArgs &a, unsigned ctas, unsigned threads)
 {
     switch (k) {
-    case 0: run_score<0>(a); break; case 1: run_score<1>(a); break; case 2: run_score<2>(a); break;
-    case 3: run_score<3>(a); break; case 4: run_score<4>(a); break; case 5: run_score<5>(a); break;
-    case 6: run_score<6>(a); break; case 7: run_score<7>(a); break; default: run_score<8>(a); break;
+    case 0: run_score<0>(a, ctas, threads); break; case 1: run_score<1>(a, ctas, threads); break; case 2: run_score<2>(a, ctas, threads); break;
+    case 3: run_score<3>(a, ctas, threads); break; case 4: run_score<4>(a, ctas, threads); break; case 5: run_score<5>(a, ctas, threads); break;
+    case 6: run_score<6>(a, ctas, threads); break; case 7: run_score<7>(a, ctas, threads); break; default: run_score<8>(a, ctas, threads); break;
     }
 }
 
@@ -50,7 +51,9 @@ int main(int argc, char **argv)
     fclose(f);
     if (!ok || k < 0 || k > VS_MAX_MISMATCHES || chunk_words == 0) { fprintf(stderr, "bad input\n"); return 2; }
 
-    // as scan_core (vs_device.cu): PAM lists, tile size, pattern tables per guide chunk, one extract + score pass per chunk
+    // as scan_engine (vs_device.cu): PAM lists, tile size, the pattern table, one whole-shard candidate store; per pipeline
+    // chunk k_extract -> k_extract_mark -> k_score of the chunk's block range; then ONE k_score over the whole store (what
+    // a scan of the resident index runs), which must find the same hits
     PamParams pp;
     pp.n = 2;
     pp.fx[0] = 2; pp.fy[0] = 2; pp.fx[1] = 2; pp.fy[1] = 0; pp.fx[2] = 0; pp.fy[2] = 0;
@@ -58,48 +61,60 @@ int main(int argc, char **argv)
     for (int j = 0; j < 3; ++j) { pp.rx[j] = 3 - pp.fy[j]; pp.ry[j] = 3 - pp.fx[j]; }
     if (tile_words == 0) tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
     tile_words = std::min<uint32_t>(std::max<uint32_t>(tile_words, 8), EX_MAX_WORDS);
-    const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
-    std::vector<uint32_t> pat((size_t)std::max<uint32_t>(g_chunks, 1) * PAT_TABLE_WORDS, 0);
+    std::vector<uint16_t> pat((size_t)2 * std::max<uint32_t>(n_guides, 1) * PAT_STRIDE + 8, 0);
+    uint16_t *pat16 = (uint16_t *)(((uintptr_t)pat.data() + 15) & ~(uintptr_t)15);         // rows are read with 16-byte loads
     for (int s = 0; s < 2; ++s)
         for (uint32_t g = 0; g < n_guides; ++g) {
-            uint32_t *dst = pat.data() + (size_t)(g / PAT_CHUNK) * PAT_TABLE_WORDS + ((size_t)s * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
+            uint16_t *dst = pat16 + ((size_t)s * n_guides + g) * PAT_STRIDE;
             const uint8_t *gd = guides.data() + (size_t)g * VS_GLEN;
             for (int j = 0; j < VS_GLEN; ++j) {
                 const int i = slot_position(s, j);
-                dst[j] = pat_slot(k, s, j, s ? 3 - gd[VS_GLEN - 1 - i] : gd[i]);
+                dst[j] = pat_slot(s, j, s ? 3 - gd[VS_GLEN - 1 - i] : gd[i]);
             }
         }
-    std::vector<vs_hit> hits(1 << 16);
+    const uint64_t n_chunks = (n_words + chunk_words - 1) / chunk_words;
+    uint64_t cap = n_words + (n_words + tile_words - 1) / tile_words + 64 * n_chunks + 256;   // generous: at most 32 candidates per word and strand
+    cap = (cap + BLK_GROUP - 1) / BLK_GROUP * BLK_GROUP;
+    std::vector<uint32_t> planes[2], pos[2];
+    for (int s = 0; s < 2; ++s) { planes[s].assign(cap * BLK_WORDS, 0xDEADBEEFu); pos[s].assign(cap * 32, 0xDEADBEEFu); }
+    std::vector<unsigned long long> cnt(4 + 4 * (n_chunks + 1) + 4, 0);
+    unsigned long long *rng = cnt.data() + 4, *all = cnt.data() + 4 + 4 * (n_chunks + 1);
+    std::vector<vs_hit> hits(1 << 16), hits2;
     unsigned long long n_hits = 0;
-    for (uint64_t c0 = 0; c0 < n_words && n_guides; c0 += chunk_words) {
-        const uint64_t c1 = std::min(n_words, c0 + chunk_words);
-        const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
-        uint64_t cap = (c1 - c0) + tiles + 256;                    // generous: at most 32 candidates per word and strand
-        cap = (cap + SCORE_THREADS - 1) / SCORE_THREADS * SCORE_THREADS;
-        std::vector<uint32_t> planes[2], pos[2];
-        for (int s = 0; s < 2; ++s) { planes[s].assign(cap * BLK_WORDS, 0xDEADBEEFu); pos[s].assign(cap * 32, 0xDEADBEEFu); }
-        unsigned long long cnt[4] = {0, 0, 0, 0};
-        launch_cta(tiles, EX_THREADS, [&] {
-            k_extract(bases.data(), masks.data(), c0, c1, tile_words, 0, pp, planes[0].data(), pos[0].data(), planes[1].data(), pos[1].data(), cap, cnt);
-        });
-        if (cnt[2] > cap || cnt[3] > cap) { fprintf(stderr, "candidate store overflow\n"); return 3; }
-        for (uint32_t gc = 0; gc < g_chunks; ++gc) {
-            const uint32_t *table = pat.data() + (size_t)gc * PAT_TABLE_WORDS;
-            memcpy(c_pat, table, sizeof(uint32_t) * PAT_TABLE_WORDS);
-            for (;;) {
-                ScoreArgs a;
-                for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
-                a.n_blocks_ptr = cnt + 2; a.cap = cap; a.ctas_per_strand = (uint32_t)((cap + SCORE_THREADS - 1) / SCORE_THREADS);
-                a.n_pat = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK); a.guide_base = gc * PAT_CHUNK;
-                a.pat_global = table;
-                const unsigned long long before = n_hits;
-                a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
-                dispatch_score(k, a);
-                if (n_hits <= hits.size()) break;
-                hits.resize(n_hits + n_hits / 4);                  // hit buffer overflow: grow and redo this launch
-                n_hits = before;
-            }
+    const unsigned threads = std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32);
+    auto score = [&](const unsigned long long *r, std::vector<vs_hit> &out, unsigned long long &n) {
+        for (;;) {
+            ScoreArgs a;
+            for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
+            a.rng = r; a.cap = cap; a.n_guides = n_guides; a.guide_base = 0; a.pat_guides = n_guides; a.pat = pat16;
+            const unsigned long long before = n;
+            a.hits = out.data(); a.n_hits = &n; a.hit_cap = out.size();
+            dispatch_score(k, a, 3, threads);                  // 3 persistent CTAs stride over the batches
+            if (n <= out.size()) break;
+            out.resize(n + n / 4);                             // hit buffer overflow: grow and redo this launch
+            n = before;
         }
+    };
+    for (uint64_t c = 0; c < n_chunks && n_guides; ++c) {
+        const uint64_t c0 = c * chunk_words, c1 = std::min(n_words, c0 + chunk_words);
+        const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
+        launch_cta(tiles, EX_THREADS, [&] {
+            k_extract(bases.data(), masks.data(), c0, c1, tile_words, 0, pp, planes[0].data(), pos[0].data(), planes[1].data(), pos[1].data(), cap, cnt.data());
+        });
+        launch(1, 1, 32, [&] { k_extract_mark(cnt.data(), rng + 4 * c, all, planes[0].data(), planes[1].data(), cap); });
+        if (cnt[2] > cap || cnt[3] > cap) { fprintf(stderr, "candidate store overflow\n"); return 3; }
+        score(rng + 4 * c, hits, n_hits);
+    }
+    if (n_guides && n_words) {
+        hits2.resize(hits.size());
+        unsigned long long n2 = 0;
+        score(all, hits2, n2);
+        auto key = [](const vs_hit &x) { return ((uint64_t)x.pos << 32) | x.info; };
+        std::vector<uint64_t> a, b;
+        for (unsigned long long i = 0; i < n_hits; ++i) a.push_back(key(hits[i]));
+        for (unsigned long long i = 0; i < n2; ++i) b.push_back(key(hits2[i]));
+        std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+        if (a != b) { fprintf(stderr, "the scan of the whole store (%llu hits) differs from the chunk-by-chunk scan (%llu hits)\n", n2, n_hits); return 4; }
     }
     f = fopen(argv[2], "wb");
     if (!f) { perror(argv[2]); return 2; }

@@ -2,10 +2,11 @@
 // the device code of the scan can be exercised in the CPU test suite (tests/cpu_kernel_units.cpp, tests/cpu_scan_emulator.cpp).
 // Two ways to run a kernel:
 //   launch(grid, block, f)      one thread after the other — for kernels whose threads never cooperate
-//                               (k_score, the mask kernels); a warp vote sees only its own lane, __syncthreads is a no-op
-//   launch_cta(grid, block, f)  one OS thread per CUDA thread of a CTA, CTAs one after the other — for k_extract
-//                               (__syncthreads is a barrier, __shfl_up_sync exchanges through a buffer, __shared__ arrays
-//                               are function-local statics)
+//                               (the mask kernels, k_resolve_hits); __syncthreads is a no-op
+//   launch_cta(grid, block, f)  one OS thread per CUDA thread of a CTA, CTAs one after the other — for k_extract, k_score
+//                               and the contig-start kernels (__syncthreads is a barrier, __shfl_up_sync exchanges through
+//                               a buffer, __shared__ arrays are function-local statics); a warp vote sees only its own
+//                               lane, which is exact for k_score: a lane whose own stage-A result is zero never hits
 // Nothing in the product includes this file; the product has no CPU path.
 #pragma once
 #include <barrier>
@@ -57,8 +58,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel)
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline uint32_t __ldg(const uint32_t *p) { return *p; }
-// only one thread of a CTA ever adds (k_extract) or the threads run one after the other (k_score)
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
+// (k_score runs under launch_cta: its threads are concurrent OS threads)
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
@@ -66,6 +67,7 @@ static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint64_t max(uint64_t a, uint64_t b) { return a > b ? a : b; }
 static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 
 namespace vs { extern uint32_t sm[]; }                   // k_score's dynamic shared memory; defined by the including test
 

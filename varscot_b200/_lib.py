@@ -35,10 +35,19 @@ class ScanStats(C.Structure):
                 ("n_cand_fwd", C.c_uint64), ("n_cand_rev", C.c_uint64),
                 ("n_blocks_fwd", C.c_uint64), ("n_blocks_rev", C.c_uint64),
                 ("n_hits", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("launches", C.c_uint32), ("score_launches", C.c_uint32), ("n_chunks", C.c_uint32), ("redo_chunks", C.c_uint32)]
+                ("launches", C.c_uint32), ("score_launches", C.c_uint32), ("n_chunks", C.c_uint32), ("redo_chunks", C.c_uint32),
+                ("resolve_ms", C.c_float), ("index_reused", C.c_uint32), ("guide_passes", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class LocHit(C.Structure):
+    _fields_ = [("key", C.c_uint64), ("contig", C.c_uint32), ("info", C.c_uint32)]
+
+
+HIT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32)
+VS_OPT_KEEP_INDEX, VS_OPT_HIT_CAPACITY = 1, 2
 
 
 class TextView(C.Structure):
@@ -57,9 +66,10 @@ class MaskSource(C.Structure):
 # every symbol include/varscot_scan.h declares (tests check the library exports all of them)
 EXPORTS = [
     "vs_packer_new", "vs_packer_free", "vs_packer_append", "vs_packer_end_contig", "vs_packer_finish", "vs_pack_text", "vs_pack_text_planes",
-    "vs_masks_from_planes", "vs_masks_sparse", "vs_mask_source_build", "vs_mask_source_free", "vs_text_save", "vs_text_load", "vs_free", "vs_device_count",
+    "vs_masks_from_planes", "vs_masks_sparse", "vs_mask_source_build", "vs_mask_source_free", "vs_text_save", "vs_text_load", "vs_text_masks", "vs_map_records", "vs_free", "vs_device_count",
     "vs_ctx_create", "vs_ctx_destroy", "vs_last_error", "vs_ctx_set_chunk_words", "vs_text_upload", "vs_host_alloc",
-    "vs_host_free", "vs_scan", "vs_scan_text", "vs_scan_fetch", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_resolve_hits_mt",
+    "vs_host_free", "vs_host_register", "vs_host_unregister", "vs_ctx_set_option", "vs_index_drop", "vs_scan", "vs_scan_text", "vs_scan_fetch",
+    "vs_scan_resolved", "vs_merge_resolved", "vs_map_packed", "vs_shard_bounds", "vs_resolve_hits", "vs_resolve_hits_mt",
     "vs_md_string", "vs_format_sam", "vs_bidir_index_main", "vs_bidir_mapping_main", "vs_vcf_loader_main", "vs_fasta_writer_main", "vs_bam_merger_main", "vs_bam_merger_ref_only_main", "vs_measure_int_peaks",
 ]
 
@@ -89,6 +99,8 @@ def lib():
     L.vs_mask_source_free.argtypes = [C.POINTER(MaskSource)]
     L.vs_text_save.argtypes = [C.c_char_p, C.POINTER(TextView)]
     L.vs_text_load.argtypes = [C.c_char_p, C.POINTER(TextView), C.POINTER(vp)]
+    L.vs_text_masks.argtypes = [C.POINTER(TextView), vp]
+    L.vs_map_records.argtypes = [C.POINTER(TextView), vp, u32, i32, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_free.argtypes = [vp]
     L.vs_device_count.restype = i32
     L.vs_ctx_create.argtypes = [i32, C.POINTER(vp)]
@@ -101,6 +113,12 @@ def lib():
     L.vs_scan.argtypes = [vp, vp, u32, i32, i32, vp, u64, C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_scan_text.argtypes = [vp, C.POINTER(TextView), u64, u64, vp, u32, i32, i32, vp, u64, C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_scan_fetch.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.vs_scan_resolved.argtypes = [vp, C.POINTER(TextView), u64, u64, vp, u32, i32, i32, vp, u64, C.POINTER(u64), HIT_SINK, vp, C.POINTER(ScanStats)]
+    L.vs_merge_resolved.argtypes = [vp, vp, i32, vp, C.POINTER(u64), i32]
+    L.vs_ctx_set_option.argtypes = [vp, i32, C.c_int64]
+    L.vs_index_drop.argtypes = [vp]
+    L.vs_host_register.argtypes = [vp, C.c_size_t]
+    L.vs_host_unregister.argtypes = [vp]
     L.vs_map_packed.argtypes = [C.POINTER(TextView), vp, u32, i32, i32, vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(ScanStats)]
     L.vs_shard_bounds.argtypes = [u64, i32, vp]
     L.vs_resolve_hits.argtypes = [vp, u64, vp, u32, vp, C.POINTER(u64)]

@@ -347,27 +347,33 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     FILE *out = fopen(output.c_str(), "wb");
     if (!out) { fprintf(stderr, "ERROR: Could not open output path.\n"); return 1; }
 
-    std::vector<vs_hit> hits;
+    // the scan: every device resolves its hits to (contig, pos) and sorts them into the reference's emission order; the host
+    // merges the shards' lists and applies the primary / secondary rule.  -T drives the host side (merge, SAM formatting).
+    const int host_threads = (int)std::min<long>(64, std::max<long>(1, threads));
+    std::vector<std::vector<vs_loc_hit>> lists;
     const uint32_t n_guides = (uint32_t)ids.size();
     if (n_guides && t.v.n_bases) {
         std::vector<int> devices = choose_devices(t.v.n_bases);
         if (devices.empty()) { fprintf(stderr, "%s: no usable CUDA device: %s (this build has no CPU path)\n", prog, vs_last_error(nullptr)); fclose(out); return 1; }
         vs_scan_stats st;
-        int rc = vs::scan_text_sharded(t.v, devices, guides.data(), n_guides, (int)mism, extra_pam, hits, &st, err);
+        int rc = vs::scan_text_sharded_resolved(t.v, devices, guides.data(), n_guides, (int)mism, extra_pam, lists, &st, err);
         if (rc != VS_OK) { fprintf(stderr, "%s: scan failed: %s\n", prog, err.c_str()); fclose(out); return 1; }
         if (getenv("VARSCOT_VERBOSE"))
-            fprintf(stderr, "%s: %zu device(s), %.3f ms upload+scan (extract %.3f, score %.3f; %.1f MB H2D), %llu candidates, %llu hits\n", prog,
-                    devices.size(), st.total_ms, st.extract_ms, st.score_ms, st.h2d_bytes / 1e6,
+            fprintf(stderr, "%s: %zu device(s), %.3f ms upload+scan (extract %.3f, score %.3f, resolve+sort %.3f; %.1f MB H2D), %llu candidates, %llu hits\n", prog,
+                    devices.size(), st.total_ms, st.extract_ms, st.score_ms, st.resolve_ms, st.h2d_bytes / 1e6,
                     (unsigned long long)(st.n_cand_fwd + st.n_cand_rev), (unsigned long long)st.n_hits);
     }
     const auto tm2 = std::chrono::steady_clock::now();
-    std::vector<vs_record> rec(hits.size());
+    std::vector<const vs_loc_hit *> lp;
+    std::vector<uint64_t> lc;
+    uint64_t n_rec = 0;
+    for (auto &l : lists) { lp.push_back(l.data()); lc.push_back(l.size()); n_rec += l.size(); }
+    std::vector<vs_record> rec(n_rec);
     uint64_t coll = 0;
-    // -T drives the host side here: hit resolution and SAM formatting (the scan itself runs on the GPUs)
-    const int host_threads = (int)std::min<long>(64, std::max<long>(1, threads));
-    if (!hits.empty() && vs_resolve_hits_mt(hits.data(), hits.size(), t.v.contig_off, t.v.n_contigs, rec.data(), &coll, host_threads) != VS_OK) {
+    if (n_rec && vs_merge_resolved(lp.data(), lc.data(), (int)lp.size(), rec.data(), &coll, host_threads) != VS_OK) {
         fprintf(stderr, "%s: %s\n", prog, vs_last_error(nullptr)); fclose(out); return 1;
     }
+    lists.clear();
     if (coll) fprintf(stderr, "%s: note: %llu records share a (contig id mod 65536, position) key; the reference's uint16 map key would have kept one of each\n", prog, (unsigned long long)coll);
     // SAM text: batches of records are formatted by the host threads into per-thread buffers and written in order
     const size_t batch = (size_t)host_threads * 65536;

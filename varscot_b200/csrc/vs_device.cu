@@ -5,7 +5,9 @@
 // sm_100 device is usable.
 #include "vs_kernels.cuh"
 #include "vs_internal.h"
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,12 +22,12 @@ constexpr uint64_t DEFAULT_CHUNK_WORDS = 8ull << 20;      // 256 Mi bases per pi
 
 struct vs_ctx {
     int device = -1;
-    cudaStream_t stream = nullptr;       // scoring + everything ordered with it
-    cudaStream_t exs = nullptr;          // extraction of the next chunk (overlaps the scoring of the current one)
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;       // extraction + scoring + hit resolution
     cudaStream_t copy = nullptr;         // H2D of the next chunk (copies only, so that the copy engine never waits for a kernel)
     cudaStream_t prep = nullptr;         // small kernels that turn the uploaded mask source of a chunk into its window masks
-    cudaEvent_t ev_copied = nullptr, ev_zeroed = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_copied = nullptr, ev_zeroed = nullptr, ev_starts = nullptr;
+    cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;    // per chunk: copied, extract start, extract done, score start, score done
     uint64_t chunk_words = DEFAULT_CHUNK_WORDS;
     // resident text shard: device word 0 = global word first_word
@@ -40,18 +42,36 @@ struct vs_ctx {
     uint64_t planes_cap = 0, dense_cap = 0;
     vs_plane_run *d_runs = nullptr;
     uint64_t runs_cap = 0;
-    // counters: per chunk [0] cand fwd, [1] cand rev, [2] blocks fwd, [3] blocks rev; then one hit counter
+    // contig starts of the shard (device-side hit resolution): derived from d_em, or uploaded
+    uint32_t *d_cstart = nullptr, *d_tilecnt = nullptr, *d_cs_total = nullptr, *h_cs_total = nullptr;
+    uint64_t cstart_cap = 0, tilecnt_cap = 0;
+    uint32_t n_cstart = 0, first_contig = 0;
+    bool cstart_valid = false;
+    // counters (u64): [0..3] running candidates fwd / rev, block claims fwd / rev; [4 + 4 c ..] block range of chunk c
+    // {lo fwd, lo rev, hi fwd, hi rev}; then the whole-store range [4]; then the hit counter
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
     uint64_t cnt_chunks = 0;
-    // candidate stores: two buffers (chunk parity) x two strands
-    uint32_t *d_planes[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *d_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    // candidate store of the whole shard, per strand (the resident index)
+    uint32_t *d_planes[2] = {nullptr, nullptr}, *d_pos[2] = {nullptr, nullptr};
     uint64_t blocks_cap = 0;
-    // pattern tables
-    uint32_t *d_pat = nullptr, *h_pat = nullptr;
+    bool idx_valid = false;
+    int idx_pam = -2;
+    uint64_t idx_blocks[2] = {0, 0}, idx_cand[2] = {0, 0};
+    uint32_t idx_chunks = 0;
+    int keep_index = 1;
+    uint64_t hit_cap_opt = 0;
+    // pattern table [2][n_guides][PAT_STRIDE] of uint16
+    uint16_t *d_pat = nullptr, *h_pat = nullptr;
     uint64_t pat_cap = 0;
     // hits
     vs_hit *d_hits = nullptr;
     uint64_t hits_cap = 0, last_n_hits = 0;
+    // resolution: sort keys / payloads (double buffers of the radix sort), packed records, sort scratch, pinned staging
+    unsigned long long *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+    vs_loc_hit *d_loc = nullptr, *h_stage = nullptr;
+    uint64_t loc_cap = 0, stage_cap = 0;
+    void *d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     std::string err;
 };
 
@@ -95,10 +115,6 @@ extern "C" int vs_device_count(void)
     return n;
 }
 
-// k_score's dynamic shared memory (at most 92 planes x 128 threads x 4 B = 46 KB, for k = 8) fits the default 48 KB
-// limit, so no cudaFuncSetAttribute is needed — and none of the nine k_score<K> variants is loaded before it is used.
-static_assert(NPLANES * SCORE_THREADS * 4 <= 48 * 1024, "k_score needs cudaFuncAttributeMaxDynamicSharedMemorySize above 48 KB");
-
 extern "C" int vs_ctx_create(int device, vs_ctx **out)
 {
     vs_ctx *ctx = nullptr;
@@ -115,9 +131,9 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
                                                   ", this build contains sm_100a code only");
     ctx = new vs_ctx();
     ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
     // The copy and mask-preparation streams get the highest priority: the small kernels that build the window masks of
-    // the next chunk must not queue behind the scoring grid of the current one.  The optional concurrent-extraction
-    // stream gets the lowest.
+    // the next chunk must not queue behind the scoring grid of the current one.
     int prio_lo = 0, prio_hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_hi);
@@ -125,8 +141,10 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->prep, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_zeroed, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->exs, cudaStreamNonBlocking, prio_lo);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_starts, cudaEventDisableTiming);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cs_total, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_cs_total, sizeof(uint32_t));
     if (e != cudaSuccess) {
         std::string m = std::string("vs_ctx_create: ") + cudaGetErrorString(e);
         vs_ctx_destroy(ctx);
@@ -143,24 +161,60 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy) cudaStreamSynchronize(ctx->copy);
     if (ctx->prep) cudaStreamSynchronize(ctx->prep);
-    if (ctx->exs) cudaStreamSynchronize(ctx->exs);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_masks); cudaFree(ctx->d_sparse);
     cudaFree(ctx->d_nm); cudaFree(ctx->d_em); cudaFree(ctx->d_runs); cudaFree(ctx->d_emcode); cudaFree(ctx->d_dense);
+    cudaFree(ctx->d_cstart); cudaFree(ctx->d_tilecnt); cudaFree(ctx->d_cs_total);
+    if (ctx->h_cs_total) cudaFreeHost(ctx->h_cs_total);
     cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
-    for (int b = 0; b < 2; ++b) for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]); }
+    for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]); cudaFree(ctx->d_keys[s]); cudaFree(ctx->d_vals[s]); }
     cudaFree(ctx->d_pat);
     if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
-    cudaFree(ctx->d_hits);
-    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaFree(ctx->d_hits); cudaFree(ctx->d_loc); cudaFree(ctx->d_sort_tmp);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->prep) cudaStreamDestroy(ctx->prep);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->ev_zeroed) cudaEventDestroy(ctx->ev_zeroed);
-    if (ctx->exs) cudaStreamDestroy(ctx->exs);
+    if (ctx->ev_starts) cudaEventDestroy(ctx->ev_starts);
     delete ctx;
+}
+
+extern "C" int vs_ctx_set_option(vs_ctx *ctx, int option, int64_t value)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_ctx_set_option: ctx is NULL");
+    switch (option) {
+    case VS_OPT_KEEP_INDEX: ctx->keep_index = value != 0; if (!ctx->keep_index) ctx->idx_valid = false; return VS_OK;
+    case VS_OPT_HIT_CAPACITY: if (value < 0) break; ctx->hit_cap_opt = (uint64_t)value; return VS_OK;
+    default: break;
+    }
+    return fail(ctx, VS_ERR_ARG, "vs_ctx_set_option: unknown option or bad value");
+}
+
+extern "C" int vs_index_drop(vs_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_index_drop: ctx is NULL");
+    ctx->idx_valid = false;
+    return VS_OK;
+}
+
+extern "C" int vs_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return VS_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        g_last_error = std::string("cudaHostRegister: ") + cudaGetErrorString(cudaGetLastError());
+        return VS_ERR_CUDA;
+    }
+    return VS_OK;
+}
+extern "C" int vs_host_unregister(void *p)
+{
+    if (!p) return VS_ERR_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return VS_ERR_CUDA; }
+    return VS_OK;
 }
 
 extern "C" int vs_ctx_set_chunk_words(vs_ctx *ctx, uint64_t chunk_words)
@@ -188,26 +242,25 @@ static void make_pam(int extra_pam, PamParams &pp)
     for (int j = 0; j < 3; ++j) { pp.rx[j] = 3 - pp.fy[j]; pp.ry[j] = 3 - pp.fx[j]; }
 }
 
-// grid = forward CTAs then reverse CTAs, sized by the capacity of the candidate stores (CTAs past the claimed block
-// count of their strand exit at once)
+// persistent grid: `ctas` CTAs of `threads` threads stride over the batches of the block range in a.rng
 template <int K>
-static void launch_score(const ScoreArgs &a, cudaStream_t st)
+static void launch_score(const ScoreArgs &a, unsigned ctas, unsigned threads, cudaStream_t st)
 {
-    k_score<K><<<2 * a.ctas_per_strand, SCORE_THREADS, score_smem_planes(K) * SCORE_THREADS * 4, st>>>(a);
+    k_score<K><<<ctas, threads, SC_SMEM_BYTES, st>>>(a);
 }
 
-static void dispatch_score(int k, const ScoreArgs &a, cudaStream_t st)
+static void dispatch_score(int k, const ScoreArgs &a, unsigned ctas, unsigned threads, cudaStream_t st)
 {
     switch (k) {
-    case 0: launch_score<0>(a, st); break;
-    case 1: launch_score<1>(a, st); break;
-    case 2: launch_score<2>(a, st); break;
-    case 3: launch_score<3>(a, st); break;
-    case 4: launch_score<4>(a, st); break;
-    case 5: launch_score<5>(a, st); break;
-    case 6: launch_score<6>(a, st); break;
-    case 7: launch_score<7>(a, st); break;
-    default: launch_score<8>(a, st); break;
+    case 0: launch_score<0>(a, ctas, threads, st); break;
+    case 1: launch_score<1>(a, ctas, threads, st); break;
+    case 2: launch_score<2>(a, ctas, threads, st); break;
+    case 3: launch_score<3>(a, ctas, threads, st); break;
+    case 4: launch_score<4>(a, ctas, threads, st); break;
+    case 5: launch_score<5>(a, ctas, threads, st); break;
+    case 6: launch_score<6>(a, ctas, threads, st); break;
+    case 7: launch_score<7>(a, ctas, threads, st); break;
+    default: launch_score<8>(a, ctas, threads, st); break;
     }
 }
 
@@ -449,12 +502,103 @@ static int begin_mask_source(vs_ctx *ctx, const vs_text_view *t, uint64_t n_word
 
 static int check_view(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
 {
-    if (!t || !t->bases || (!t->masks && t->n_words)) return fail(ctx, VS_ERR_ARG, "text view is incomplete");
+    if (!t || !t->bases) return fail(ctx, VS_ERR_ARG, "text view is incomplete");
     if (first_word + n_words > t->n_words) return fail(ctx, VS_ERR_ARG, "shard lies outside the text");
     if (t->n_words * 32 > (1ull << 32)) return fail(ctx, VS_ERR_ARG, "text exceeds 4 Gbases (32-bit positions, as common.h:9-19)");
     if ((t->em_code != nullptr) != (t->em_dense != nullptr) || (has_mask_source(t) && ((t->n_nm_runs && !t->nm_runs) || (t->n_em_runs && !t->em_runs))))
         return fail(ctx, VS_ERR_ARG, "text view carries an incomplete compact mask source");
+    // the window masks may be absent when the view carries their source: the device computes them
+    if (!has_mask_source(t) && !t->masks && t->n_words) return fail(ctx, VS_ERR_ARG, "text view has neither window masks nor a mask source");
     return VS_OK;
+}
+
+// ---- contig starts of the shard, for the device-side hit resolution --------------------------------------------------
+// Contigs c_first .. c_last overlap the shard.  With a mask source the starts come from the shard's contig-end plane on the
+// device (nothing travels); the number of end bits tells whether the range holds empty contigs (an empty contig has no
+// end bit), in which case — and for views without a source — the host's offsets are uploaded instead.
+struct StartsPlan {
+    bool usable = false;          // the view has contig offsets and the shard holds bases
+    uint32_t c_first = 0, c_last = 0;
+    uint32_t expect_bits = 0;     // end bits inside the shard's words if no contig of the range is empty
+};
+
+static StartsPlan plan_contig_starts(const vs_text_view *t, uint64_t first_word, uint64_t n_words)
+{
+    StartsPlan p;
+    if (!t->contig_off || t->n_contigs == 0 || n_words == 0) return p;
+    const uint64_t b0 = first_word * 32, b1 = std::min<uint64_t>(t->n_bases, (first_word + n_words) * 32);
+    if (b0 >= b1) return p;
+    const uint64_t *ob = t->contig_off, *oe = t->contig_off + t->n_contigs + 1;
+    p.c_first = (uint32_t)(std::upper_bound(ob, oe, b0) - ob - 1);          // last contig starting at or before the first base
+    p.c_last = (uint32_t)(std::upper_bound(ob, oe, b1 - 1) - ob - 1);
+    const uint64_t shard_end = (first_word + n_words) * 32;                  // end bits are counted over whole words
+    p.expect_bits = p.c_last - p.c_first + (ob[p.c_last + 1] - 1 < shard_end ? 1u : 0u);
+    p.usable = true;
+    return p;
+}
+
+static int ensure_starts_buffers(vs_ctx *ctx, const StartsPlan &p, uint64_t n_words)
+{
+    const uint64_t need = (uint64_t)(p.c_last - p.c_first) + 4;
+    if (need > ctx->cstart_cap) {
+        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->prep));
+        cudaFree(ctx->d_cstart); ctx->d_cstart = nullptr; ctx->cstart_cap = 0;
+        CK(cudaMalloc(&ctx->d_cstart, need * sizeof(uint32_t)));
+        ctx->cstart_cap = need;
+    }
+    const uint64_t tiles = (n_words + CS_TILE - 1) / CS_TILE + 1;
+    if (tiles > ctx->tilecnt_cap) {
+        CK(cudaStreamSynchronize(ctx->prep));
+        cudaFree(ctx->d_tilecnt); ctx->d_tilecnt = nullptr; ctx->tilecnt_cap = 0;
+        CK(cudaMalloc(&ctx->d_tilecnt, tiles * sizeof(uint32_t)));
+        ctx->tilecnt_cap = tiles;
+    }
+    return VS_OK;
+}
+
+// enqueue the derivation from the contig-end plane on `st` (after the last chunk's planes are complete on that stream)
+static int enqueue_starts_from_plane(vs_ctx *ctx, const vs_text_view *t, const StartsPlan &p, uint64_t first_word, uint64_t n_words,
+                                     cudaStream_t st, uint32_t &launches)
+{
+    const unsigned tiles = (unsigned)((n_words + CS_TILE - 1) / CS_TILE);
+    k_contig_starts_count<<<tiles, 256, 0, st>>>(ctx->d_em, n_words, ctx->d_tilecnt);
+    k_contig_starts_scan<<<1, 1024, 0, st>>>(ctx->d_tilecnt, tiles, ctx->d_cs_total);
+    k_contig_starts_scatter<<<tiles, 256, 0, st>>>(ctx->d_em, n_words, ctx->d_tilecnt, first_word * 32, (uint32_t)t->contig_off[p.c_first], ctx->d_cstart);
+    launches += 3;
+    CK(cudaMemcpyAsync(ctx->h_cs_total, ctx->d_cs_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return VS_OK;
+}
+
+// after the stream that ran enqueue_starts_from_plane has been synchronised: accept the derived starts, or upload the host's
+static int finish_contig_starts(vs_ctx *ctx, const vs_text_view *t, const StartsPlan &p, bool derived, uint64_t &h2d_bytes)
+{
+    ctx->cstart_valid = false;
+    if (!p.usable) return VS_OK;
+    ctx->first_contig = p.c_first;
+    if (derived && *ctx->h_cs_total == p.expect_bits) {
+        ctx->n_cstart = p.c_last - p.c_first + 1;
+        ctx->cstart_valid = true;
+        return VS_OK;
+    }
+    // empty contigs inside the range, or no contig-end plane on the device: the offsets themselves (32-bit positions)
+    const uint32_t n = p.c_last - p.c_first + 1;
+    std::vector<uint32_t> h(n);
+    for (uint32_t i = 0; i < n; ++i) h[i] = (uint32_t)t->contig_off[p.c_first + i];
+    CK(cudaMemcpyAsync(ctx->d_cstart, h.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    h2d_bytes += (uint64_t)n * sizeof(uint32_t);
+    ctx->n_cstart = n;
+    ctx->cstart_valid = true;
+    return VS_OK;
+}
+
+// leave no copy in flight that still reads the caller's buffers, and no half-resident text behind
+static int abandon_upload(vs_ctx *ctx, int rc)
+{
+    cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->prep); cudaStreamSynchronize(ctx->stream);
+    (void)cudaGetLastError();
+    ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;
+    return rc;
 }
 
 extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first_word, uint64_t n_words)
@@ -463,19 +607,24 @@ extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first
     int r = check_view(ctx, t, first_word, n_words);
     if (r != VS_OK) return r;
     CK(cudaSetDevice(ctx->device));
+    ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;      // nothing is resident until the upload has completed
     if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
     if ((r = ensure_sparse_staging(ctx, t, first_word, n_words)) != VS_OK) return r;
+    const StartsPlan sp = plan_contig_starts(t, first_word, n_words);
+    if (sp.usable && (r = ensure_starts_buffers(ctx, sp, n_words)) != VS_OK) return r;
     uint64_t sparse_used = 0, bytes = 0;
     uint32_t launches = 0;
-    cudaStream_t ready;
-    if ((r = begin_mask_source(ctx, t, n_words, nullptr)) != VS_OK) return r;
+    cudaStream_t ready = ctx->copy;
+    if ((r = begin_mask_source(ctx, t, n_words, nullptr)) != VS_OK) return abandon_upload(ctx, r);
     for (uint64_t c0 = 0; c0 < n_words; c0 += ctx->chunk_words) {
         uint64_t c1 = std::min(n_words, c0 + ctx->chunk_words);
-        if ((r = enqueue_chunk_copy(ctx, t, first_word, c0, c1, sparse_used, bytes, launches, ready)) != VS_OK) return r;
+        if ((r = enqueue_chunk_copy(ctx, t, first_word, c0, c1, sparse_used, bytes, launches, ready)) != VS_OK) return abandon_upload(ctx, r);
     }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->copy));
-    CK(cudaStreamSynchronize(ctx->prep));
+    const bool derive = sp.usable && has_mask_source(t);
+    if (derive && (r = enqueue_starts_from_plane(ctx, t, sp, first_word, n_words, ctx->prep, launches)) != VS_OK) return abandon_upload(ctx, r);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->copy) != cudaSuccess || cudaStreamSynchronize(ctx->prep) != cudaSuccess)
+        return abandon_upload(ctx, fail(ctx, VS_ERR_CUDA, "vs_text_upload: the upload failed on the device"));
+    if ((r = finish_contig_starts(ctx, t, sp, derive, bytes)) != VS_OK) return abandon_upload(ctx, r);
     ctx->n_words = n_words;
     ctx->first_word = first_word;
     ctx->err.clear();
@@ -483,45 +632,84 @@ extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first
 }
 
 // ---- the scan -----------------------------------------------------------------------------------
-// One pass = for every chunk of the resident shard: [H2D on the copy stream when `src` is given] -> k_extract ->
-// k_score per strand and guide chunk, all enqueued without host synchronisation; counters are read back once
-// at the end.  Chunks whose candidate store overflowed are redone afterwards; a hit-buffer overflow repeats the
-// pass (from the now resident text) with a larger buffer.
-static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, uint64_t n_words,
-                     const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
-                     vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
+// Expected hits per guide and text base on uniform-random text: both strands, sum over the PAMs of
+// (1/16) P[Bin(21, 3/4) <= k] (no credit for a guide whose own PAM differs from the site's: an upper bound).
+static double hit_density(int k, int n_pam)
 {
+    double p = 0, c = 1;                                    // c = C(21, j)
+    for (int j = 0; j <= k && j <= 21; ++j) {
+        p += c * std::pow(0.75, j) * std::pow(0.25, 21 - j);
+        c = c * (21 - j) / (j + 1);
+    }
+    return 2.0 * n_pam / 16.0 * p;
+}
+
+struct ScanReq {
+    const vs_text_view *src = nullptr;       // stream the text from the host (vs_scan_text) or scan the resident shard
+    uint64_t first_word = 0, n_words = 0;
+    const uint8_t *guides = nullptr;
+    uint32_t n_guides = 0;
+    int k = 0, extra_pam = -1;
+    bool resolved = false;                   // raw unordered vs_hit, or resolved + sorted vs_loc_hit
+    vs_hit *out_raw = nullptr;
+    vs_loc_hit *out_loc = nullptr;
+    uint64_t out_cap = 0;
+    uint64_t *n_hits = nullptr;
+    vs_hit_sink sink = nullptr;
+    void *user = nullptr;
+    vs_scan_stats *stats = nullptr;
+};
+
+// One scan = guide super-chunks (sized to the device hit buffer; a single one for all but the densest configs) x
+//   * the candidate index is not resident: for every pipeline chunk of the shard [H2D on the copy stream when the text
+//     comes from the host] -> k_extract into the whole-shard store -> k_score of that chunk's block range, all enqueued
+//     without host synchronisation; this leaves the index resident;
+//   * the index is resident (later super-chunks; later scans with the same PAM set): one k_score launch over the store.
+// After each super-chunk the counters are read back; raw hits are downloaded as they are, resolved hits go through
+// k_resolve_hits -> radix sort -> k_pack_loc_hits first.  A buffer that proves too small (candidate store or hit buffer:
+// only on text far from uniform) is regrown and the pass repeated from the resident text / index.
+static int scan_engine(vs_ctx *ctx, const ScanReq &q)
+{
+    const int k = q.k;
+    const uint32_t n_guides = q.n_guides;
     if (k < 0 || k > VS_MAX_MISMATCHES) return fail(ctx, VS_ERR_ARG, "vs_scan: mismatches must lie between 0 and 8");
-    if (extra_pam < -1 || extra_pam > 15) return fail(ctx, VS_ERR_ARG, "vs_scan: extra_pam must be -1 or 4*x+y");
-    if (n_guides && !guides) return fail(ctx, VS_ERR_ARG, "vs_scan: guides is NULL");
+    if (q.extra_pam < -1 || q.extra_pam > 15) return fail(ctx, VS_ERR_ARG, "vs_scan: extra_pam must be -1 or 4*x+y");
+    if (n_guides && !q.guides) return fail(ctx, VS_ERR_ARG, "vs_scan: guides is NULL");
     if (n_guides >= (1u << 24)) return fail(ctx, VS_ERR_ARG, "vs_scan: at most 2^24-1 guides per call");
     for (uint64_t i = 0; i < (uint64_t)n_guides * VS_GLEN; ++i)
-        if (guides[i] > 3) return fail(ctx, VS_ERR_ARG, "vs_scan: guide codes must be 0..3");
+        if (q.guides[i] > 3) return fail(ctx, VS_ERR_ARG, "vs_scan: guide codes must be 0..3");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     vs_scan_stats S;
     memset(&S, 0, sizeof(S));
-    if (n_hits) *n_hits = 0;
+    if (q.n_hits) *q.n_hits = 0;
     ctx->last_n_hits = 0;
     int r;
+    const vs_text_view *src = q.src;
+    uint64_t n_words = src ? q.n_words : ctx->n_words;
+    const uint64_t first_word = src ? q.first_word : ctx->first_word;
+    StartsPlan sp;
     if (src) {
+        ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;      // nothing is resident until the pass has completed
         if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
         if ((r = ensure_sparse_staging(ctx, src, first_word, n_words)) != VS_OK) return r;
-        ctx->n_words = n_words;
-        ctx->first_word = first_word;
+        sp = plan_contig_starts(src, first_word, n_words);
+        if (sp.usable && (r = ensure_starts_buffers(ctx, sp, n_words)) != VS_OK) return r;
     }
-    n_words = ctx->n_words;
     if (n_words == 0 || n_guides == 0) {
         if (src && n_words) { r = vs_text_upload(ctx, src, first_word, n_words); if (r != VS_OK) return r; }
-        if (stats) *stats = S;
+        if (q.stats) *q.stats = S;
+        ctx->err.clear();
         return VS_OK;
     }
+    if (q.resolved && !src && !ctx->cstart_valid)
+        return fail(ctx, VS_ERR_ARG, "vs_scan_resolved: the resident text was uploaded from a view without contig offsets");
+    if (q.resolved && src && !sp.usable) return fail(ctx, VS_ERR_ARG, "vs_scan_resolved: the text view carries no contig offsets");
     PamParams pp;
-    make_pam(extra_pam, pp);
+    make_pam(q.extra_pam, pp);
     const uint64_t chunk_words = ctx->chunk_words;
     const std::vector<uint64_t> plan = chunk_plan(n_words, chunk_words, src != nullptr);
     const uint32_t n_chunks = (uint32_t)(plan.size() - 1);
-    const uint32_t g_chunks = (n_guides + PAT_CHUNK - 1) / PAT_CHUNK;
     // tile size: about 60 blocks (both strands) per 64-thread CTA at the expected PAM density pp.n / 16 per strand
     uint32_t tile_words = (uint32_t)(60.0 * 16.0 / (2.0 * pp.n)) & ~7u;
     if (const char *e = getenv("VARSCOT_TILE_WORDS")) tile_words = (uint32_t)atoi(e);      // tuning knob
@@ -529,28 +717,26 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
     if (tile_words < 8) tile_words = 8;
     S.n_chunks = n_chunks;
 
-    // pattern tables per guide chunk: [strand][PAT_CHUNK][PAT_STRIDE] (layout: see c_pat in vs_kernels.cuh), staged in pinned memory
-    const uint64_t pat_chunk_words = (uint64_t)PAT_TABLE_WORDS;
-    const uint64_t pat_words = (uint64_t)g_chunks * pat_chunk_words;
-    if (pat_words > ctx->pat_cap) {
+    // pattern table [strand][guide][PAT_STRIDE] (uint16 plane offsets, see pat_slot), staged in pinned memory
+    const uint64_t pat_entries = 2ull * n_guides * PAT_STRIDE;
+    if (pat_entries > ctx->pat_cap) {
         CK(cudaStreamSynchronize(st));
         cudaFree(ctx->d_pat); if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
         ctx->d_pat = ctx->h_pat = nullptr; ctx->pat_cap = 0;
-        CK(cudaMalloc(&ctx->d_pat, pat_words * sizeof(uint32_t)));
-        CK(cudaMallocHost(&ctx->h_pat, pat_words * sizeof(uint32_t)));
-        ctx->pat_cap = pat_words;
+        CK(cudaMalloc(&ctx->d_pat, pat_entries * sizeof(uint16_t)));
+        CK(cudaMallocHost(&ctx->h_pat, pat_entries * sizeof(uint16_t)));
+        ctx->pat_cap = pat_entries;
     }
-    memset(ctx->h_pat, 0, pat_words * sizeof(uint32_t));
     for (int s = 0; s < 2; ++s)
         for (uint32_t g = 0; g < n_guides; ++g) {
-            uint32_t *dst = ctx->h_pat + (size_t)(g / PAT_CHUNK) * pat_chunk_words + ((size_t)s * PAT_CHUNK + g % PAT_CHUNK) * PAT_STRIDE;
-            const uint8_t *gd = guides + (size_t)g * VS_GLEN;
-            // slot order: informative positions first, the PAM dinucleotide last (forward 0..22; reverse 2..22, 0, 1)
+            uint16_t *dst = ctx->h_pat + ((size_t)s * n_guides + g) * PAT_STRIDE;
+            const uint8_t *gd = q.guides + (size_t)g * VS_GLEN;
             for (int j = 0; j < VS_GLEN; ++j) {
                 const int i = slot_position(s, j);
                 const int b = s ? 3 - gd[VS_GLEN - 1 - i] : gd[i];      // reverse pass scores revcomp(guide), bidir_mapping.cpp:293
-                dst[j] = pat_slot(k, s, j, b);
+                dst[j] = pat_slot(s, j, b);
             }
+            dst[VS_GLEN] = 0;
         }
     // counters
     if (n_chunks > ctx->cnt_chunks) {
@@ -558,175 +744,255 @@ static int scan_core(vs_ctx *ctx, const vs_text_view *src, uint64_t first_word, 
         cudaFree(ctx->d_cnt); if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
         ctx->d_cnt = ctx->h_cnt = nullptr; ctx->cnt_chunks = 0;
         uint64_t nc = n_chunks + 8;
-        CK(cudaMalloc(&ctx->d_cnt, (nc * 4 + 4) * sizeof(unsigned long long)));
-        CK(cudaMallocHost(&ctx->h_cnt, (nc * 4 + 4) * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_cnt, (4 + 4 * (nc + 1) + 4 + 4) * sizeof(unsigned long long)));
+        CK(cudaMallocHost(&ctx->h_cnt, (4 + 4 * (nc + 1) + 4 + 4) * sizeof(unsigned long long)));
         ctx->cnt_chunks = nc;
+        ctx->idx_valid = false;                              // the whole-store range lived in the old buffer
     }
-    unsigned long long *d_hitcnt = ctx->d_cnt + ctx->cnt_chunks * 4, *h_hitcnt = ctx->h_cnt + ctx->cnt_chunks * 4;
-    // candidate stores sized for one chunk at the expected density (+15 %), regrown when a chunk overflows
+    const uint64_t cnt_words = 4 + 4 * (ctx->cnt_chunks + 1) + 4 + 4;
+    unsigned long long *d_rng = ctx->d_cnt + 4, *d_all = ctx->d_cnt + 4 + 4 * (ctx->cnt_chunks + 1), *d_hitcnt = d_all + 4;
+    unsigned long long *h_rng = ctx->h_cnt + 4, *h_hitcnt = ctx->h_cnt + (d_hitcnt - ctx->d_cnt);
+    // candidate store sized for the shard at the expected density (+15 %), regrown when it overflows
     auto ensure_blocks = [&](uint64_t need) -> int {
         if (need <= ctx->blocks_cap) return VS_OK;
         CK(cudaStreamSynchronize(st));
-        CK(cudaStreamSynchronize(ctx->exs));
-        for (int b = 0; b < 2; ++b)
-            for (int s = 0; s < 2; ++s) {
-                cudaFree(ctx->d_planes[b][s]); cudaFree(ctx->d_pos[b][s]);
-                ctx->d_planes[b][s] = ctx->d_pos[b][s] = nullptr;
-            }
-        ctx->blocks_cap = 0;
-        for (int b = 0; b < 2; ++b)
-            for (int s = 0; s < 2; ++s) {
-                CK(cudaMalloc(&ctx->d_planes[b][s], need * BLK_WORDS * sizeof(uint32_t)));
-                CK(cudaMalloc(&ctx->d_pos[b][s], need * 32 * sizeof(uint32_t)));
-            }
+        for (int s = 0; s < 2; ++s) {
+            cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
+            ctx->d_planes[s] = ctx->d_pos[s] = nullptr;
+        }
+        ctx->blocks_cap = 0; ctx->idx_valid = false;
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
+        }
         ctx->blocks_cap = need;
         return VS_OK;
     };
-    {
-        const uint64_t cw = std::min(chunk_words, n_words);
-        const uint64_t tiles = (cw + tile_words - 1) / tile_words;
-        uint64_t est = (uint64_t)((double)cw * pp.n / 16.0 * 1.15) + tiles + 256;
-        est = (est + SCORE_THREADS - 1) / SCORE_THREADS * SCORE_THREADS;
+    const bool reuse = !src && ctx->idx_valid && ctx->idx_pam == q.extra_pam;
+    if (!reuse) {
+        ctx->idx_valid = false;
+        const uint64_t tiles = (n_words + tile_words - 1) / tile_words;
+        uint64_t est = (uint64_t)((double)n_words * pp.n / 16.0 * 1.15) + tiles + 64ull * n_chunks + 256;
+        est = (est + BLK_GROUP - 1) / BLK_GROUP * BLK_GROUP;
         if ((r = ensure_blocks(est)) != VS_OK) return r;
     }
-    if (!ctx->d_hits) {
-        uint64_t cap = 4u << 20;
+    // hit buffer and guide super-chunks
+    const double per_guide = (double)n_words * 32.0 * hit_density(k, pp.n);
+    uint64_t want_hits = ctx->hit_cap_opt ? ctx->hit_cap_opt
+                                          : std::min<uint64_t>(64ull << 20, std::max<uint64_t>(4ull << 20, (uint64_t)(per_guide * n_guides * 1.5) + 65536));
+    auto ensure_hits = [&](uint64_t cap) -> int {
+        if (cap <= ctx->hits_cap) return VS_OK;
+        CK(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_hits); ctx->d_hits = nullptr; ctx->hits_cap = 0;
         CK(cudaMalloc(&ctx->d_hits, cap * sizeof(vs_hit)));
         ctx->hits_cap = cap;
-    }
+        return VS_OK;
+    };
+    if ((r = ensure_hits(want_hits)) != VS_OK) return r;
+    auto guides_per_pass = [&]() -> uint32_t {
+        const double fit = per_guide > 0 ? (double)ctx->hits_cap / (per_guide * 1.5) : 1e30;
+        uint64_t g = fit >= (double)n_guides ? n_guides : (uint64_t)std::max(1.0, fit);
+        if (g > 32768) g = 32768;                            // the sort key holds 15 bits of guide index per delivery
+        if (g < n_guides && g > SC_THREADS) g = g / SC_THREADS * SC_THREADS;
+        return (uint32_t)g;
+    };
     constexpr int EVC = 5;      // events per chunk
     while (ctx->ev_pool.size() < (size_t)EVC * n_chunks) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->ev_pool.push_back(e);
     }
+    const unsigned score_threads = std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32);
+    const unsigned score_ctas = (unsigned)ctx->n_sm * 16;   // persistent: a multiple of the SM count, about two waves of resident CTAs
 
-    // extraction of chunk c into candidate buffer `buf` on stream `es`, scoring on the main stream
-    auto launch_extract = [&](uint32_t c, int buf, cudaStream_t es) -> int {
+    auto launch_extract = [&](uint32_t c) {
         const uint64_t c0 = plan[c], c1 = plan[c + 1];
         const unsigned tiles = (unsigned)((c1 - c0 + tile_words - 1) / tile_words);
-        k_extract<<<tiles, EX_THREADS, 0, es>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, ctx->first_word * 32, pp,
-                                                 ctx->d_planes[buf][0], ctx->d_pos[buf][0], ctx->d_planes[buf][1], ctx->d_pos[buf][1],
-                                                 ctx->blocks_cap, ctx->d_cnt + (uint64_t)c * 4);
-        S.launches++;
-        return VS_OK;
+        k_extract<<<tiles, EX_THREADS, 0, st>>>(ctx->d_bases, ctx->d_masks, c0, c1, tile_words, first_word * 32, pp,
+                                                 ctx->d_planes[0], ctx->d_pos[0], ctx->d_planes[1], ctx->d_pos[1], ctx->blocks_cap, ctx->d_cnt);
+        k_extract_mark<<<1, 32, 0, st>>>(ctx->d_cnt, d_rng + 4ull * c, d_all, ctx->d_planes[0], ctx->d_planes[1], ctx->blocks_cap);
+        S.launches += 2;
     };
-    auto launch_score = [&](uint32_t c, int buf) -> int {
-        unsigned long long *cnt = ctx->d_cnt + (uint64_t)c * 4;
-        for (uint32_t gc = 0; gc < g_chunks; ++gc) {
-            const uint32_t np = std::min<uint32_t>(PAT_CHUNK, n_guides - gc * PAT_CHUNK);
-            CK(cudaMemcpyToSymbolAsync(c_pat, ctx->d_pat + (size_t)gc * pat_chunk_words, pat_chunk_words * sizeof(uint32_t), 0,
-                                       cudaMemcpyDeviceToDevice, st));
-            ScoreArgs a;
-            for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[buf][s]; a.pos[s] = ctx->d_pos[buf][s]; }
-            a.n_blocks_ptr = cnt + 2; a.cap = ctx->blocks_cap;
-            a.ctas_per_strand = (uint32_t)((ctx->blocks_cap + SCORE_THREADS - 1) / SCORE_THREADS);
-            a.n_pat = np; a.guide_base = gc * PAT_CHUNK;
-            a.pat_global = ctx->d_pat + (size_t)gc * pat_chunk_words;
-            a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
-            dispatch_score(k, a, st);
-            S.launches++; S.score_launches++;
-        }
-        return VS_OK;
+    auto launch_score = [&](const unsigned long long *rng, uint32_t g0, uint32_t ng) {
+        ScoreArgs a;
+        for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[s]; a.pos[s] = ctx->d_pos[s]; }
+        a.rng = rng; a.cap = ctx->blocks_cap;
+        a.n_guides = ng; a.guide_base = g0; a.pat_guides = n_guides; a.pat = ctx->d_pat;
+        a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
+        dispatch_score(k, a, score_ctas, score_threads, st);
+        S.launches++; S.score_launches++;
     };
 
-    // Optional: run the extraction of chunk c+1 on its own (low-priority) stream, concurrently with the scoring of chunk c.
-    // Measured on B200 (config 3) with 3, 4 and 5 resident k_score CTAs per SM and room left for k_extract CTAs: no gain
-    // (the step takes the sum of the two kernels either way), so it is off by default, which also keeps the per-phase
-    // event times additive.
-    const bool overlap_extract = getenv("VARSCOT_OVERLAP_EXTRACT") && atoi(getenv("VARSCOT_OVERLAP_EXTRACT")) != 0;
-    cudaStream_t es = overlap_extract ? ctx->exs : st;
-    uint64_t found = 0;
+    uint64_t total_out = 0;              // hits delivered so far (all super-chunks)
+    bool out_overflow = false;
+    uint32_t g0 = 0;
+    bool first_pass = true;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemcpyAsync(ctx->d_pat, ctx->h_pat, pat_entries * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    S.h2d_bytes += pat_entries * sizeof(uint16_t);
     const vs_text_view *source = src;
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        S.launches = 0; S.score_launches = 0; S.h2d_bytes = 0; S.redo_chunks = 0;
-        CK(cudaEventRecord(ctx->ev[0], st));
-        CK(cudaMemcpyAsync(ctx->d_pat, ctx->h_pat, pat_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        S.h2d_bytes += pat_words * sizeof(uint32_t);
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), st));
-        CK(cudaEventRecord(ctx->ev[2], st));
-        CK(cudaStreamWaitEvent(es, ctx->ev[2], 0));                  // counters are zeroed before any extraction
-        if (source) {
-            CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[0], 0));
-            if ((r = begin_mask_source(ctx, source, n_words, ctx->ev[0])) != VS_OK) return r;
-        }
-        uint64_t sparse_used = 0;
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            cudaEvent_t *E = &ctx->ev_pool[(size_t)EVC * c];
-            const int buf = (int)(c & 1);
-            if (source) {
-                const uint64_t c0 = plan[c], c1 = plan[c + 1];
-                cudaStream_t ready;
-                if ((r = enqueue_chunk_copy(ctx, source, first_word, c0, c1, sparse_used, S.h2d_bytes, S.launches, ready)) != VS_OK) return r;
-                CK(cudaEventRecord(E[0], ready));
-                CK(cudaStreamWaitEvent(es, E[0], 0));
+    bool derive_starts = false;
+    while (g0 < n_guides) {
+        uint32_t ng = std::min<uint32_t>(guides_per_pass(), n_guides - g0);
+        uint64_t found = 0;
+        for (int attempt = 0;; ++attempt) {
+            if (attempt == 4) return fail(ctx, VS_ERR_CUDA, "vs_scan: device buffers still too small after regrowing");
+            CK(cudaMemsetAsync(d_hitcnt, 0, sizeof(unsigned long long), st));
+            if (ctx->idx_valid) {
+                // the index is resident: one launch over the whole store
+                CK(cudaEventRecord(ctx->ev[2], st));
+                launch_score(d_all, g0, ng);
+                CK(cudaEventRecord(ctx->ev[3], st));
+                S.index_reused = first_pass && reuse ? 1u : S.index_reused;
             } else {
-                CK(cudaEventRecord(E[0], es));
+                CK(cudaMemsetAsync(ctx->d_cnt, 0, (4 + 4 * (ctx->cnt_chunks + 1) + 4) * sizeof(unsigned long long), st));
+                CK(cudaEventRecord(ctx->ev[1], st));
+                if (source) {
+                    CK(cudaStreamWaitEvent(ctx->copy, ctx->ev[1], 0));
+                    if ((r = begin_mask_source(ctx, source, n_words, ctx->ev[1])) != VS_OK) return abandon_upload(ctx, r);
+                }
+                uint64_t sparse_used = 0;
+                for (uint32_t c = 0; c < n_chunks; ++c) {
+                    cudaEvent_t *E = &ctx->ev_pool[(size_t)EVC * c];
+                    if (source) {
+                        cudaStream_t ready;
+                        if ((r = enqueue_chunk_copy(ctx, source, first_word, plan[c], plan[c + 1], sparse_used, S.h2d_bytes, S.launches, ready)) != VS_OK)
+                            return abandon_upload(ctx, r);
+                        if (c + 1 == n_chunks && sp.usable && has_mask_source(source)) {
+                            if ((r = enqueue_starts_from_plane(ctx, source, sp, first_word, n_words, ctx->prep, S.launches)) != VS_OK) return abandon_upload(ctx, r);
+                            derive_starts = true;
+                            CK(cudaEventRecord(ctx->ev_starts, ctx->prep));
+                        }
+                        CK(cudaEventRecord(E[0], ready));
+                        CK(cudaStreamWaitEvent(st, E[0], 0));
+                    } else {
+                        CK(cudaEventRecord(E[0], st));
+                    }
+                    CK(cudaEventRecord(E[1], st));
+                    launch_extract(c);
+                    CK(cudaEventRecord(E[2], st));
+                    CK(cudaEventRecord(E[3], st));
+                    launch_score(d_rng + 4ull * c, g0, ng);
+                    CK(cudaEventRecord(E[4], st));
+                }
+                if (derive_starts) CK(cudaStreamWaitEvent(st, ctx->ev_starts, 0));
             }
-            if (c >= 2) CK(cudaStreamWaitEvent(es, ctx->ev_pool[(size_t)EVC * (c - 2) + 4], 0));   // its buffer was scored
-            CK(cudaEventRecord(E[1], es));
-            if ((r = launch_extract(c, buf, es)) != VS_OK) return r;
-            CK(cudaEventRecord(E[2], es));
-            CK(cudaStreamWaitEvent(st, E[2], 0));
-            CK(cudaEventRecord(E[3], st));
-            if ((r = launch_score(c, buf)) != VS_OK) return r;
-            CK(cudaEventRecord(E[4], st));
+            if (cudaGetLastError() != cudaSuccess) return abandon_upload(ctx, fail(ctx, VS_ERR_CUDA, "vs_scan: a kernel launch failed"));
+            CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, cnt_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if (cudaStreamSynchronize(st) != cudaSuccess) return abandon_upload(ctx, fail(ctx, VS_ERR_CUDA, std::string("vs_scan: ") + cudaGetErrorString(cudaGetLastError())));
+            S.d2h_bytes += cnt_words * sizeof(unsigned long long);
+            if (!ctx->idx_valid) {
+                if (source) {                                // the text is resident from here on
+                    if ((r = finish_contig_starts(ctx, source, sp, derive_starts, S.h2d_bytes)) != VS_OK) return abandon_upload(ctx, r);
+                    ctx->n_words = n_words; ctx->first_word = first_word;
+                    source = nullptr;
+                }
+                const uint64_t bf = ctx->h_cnt[2], br = ctx->h_cnt[3];
+                if (std::max(bf, br) > ctx->blocks_cap) {    // the store overflowed (k_score skipped everything): regrow, extract again
+                    uint64_t need = std::max(bf, br);
+                    need = (need + need / 32 + 64ull * n_chunks + BLK_GROUP) / BLK_GROUP * BLK_GROUP;
+                    if ((r = ensure_blocks(need)) != VS_OK) return r;
+                    S.redo_chunks += n_chunks;
+                    continue;
+                }
+                ctx->idx_valid = true; ctx->idx_pam = q.extra_pam; ctx->idx_chunks = n_chunks;
+                ctx->idx_cand[0] = ctx->h_cnt[0]; ctx->idx_cand[1] = ctx->h_cnt[1];
+                ctx->idx_blocks[0] = 0; ctx->idx_blocks[1] = 0;
+                for (uint32_t c = 0; c < n_chunks; ++c) { ctx->idx_blocks[0] += h_rng[4 * c + 2] - h_rng[4 * c]; ctx->idx_blocks[1] += h_rng[4 * c + 3] - h_rng[4 * c + 1]; }
+                for (uint32_t c = 0; c < n_chunks; ++c) {
+                    float a = 0.f, b = 0.f;
+                    CK(cudaEventElapsedTime(&a, ctx->ev_pool[(size_t)EVC * c + 1], ctx->ev_pool[(size_t)EVC * c + 2]));
+                    CK(cudaEventElapsedTime(&b, ctx->ev_pool[(size_t)EVC * c + 3], ctx->ev_pool[(size_t)EVC * c + 4]));
+                    S.extract_ms += a; S.score_ms += b;
+                }
+                if (src) CK(cudaEventElapsedTime(&S.upload_ms, ctx->ev[1], ctx->ev_pool[(size_t)EVC * (n_chunks - 1)]));
+            } else {
+                float b = 0.f;
+                CK(cudaEventElapsedTime(&b, ctx->ev[2], ctx->ev[3]));
+                S.score_ms += b;
+            }
+            found = *h_hitcnt;
+            if (found <= ctx->hits_cap) break;
+            // device hit buffer too small: grow it (or halve the super-chunk once it is large) and repeat the pass over the index
+            S.redo_chunks += n_chunks;
+            if (found > (256ull << 20) && ng > 1) { ng = (ng + 1) / 2; continue; }
+            if ((r = ensure_hits(found + found / 8 + 1024)) != VS_OK) return r;
         }
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[1], st));
-        CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        S.guide_passes++;
+        first_pass = false;
+        // ---- deliver the super-chunk ----------------------------------------------------------------------
+        CK(cudaEventRecord(ctx->ev[4], st));
+        if (!q.resolved) {
+            const uint64_t room = q.out_cap > total_out ? q.out_cap - total_out : 0, ncopy = std::min(found, room);
+            if (q.out_raw && ncopy) CK(cudaMemcpyAsync(q.out_raw + total_out, ctx->d_hits, ncopy * sizeof(vs_hit), cudaMemcpyDeviceToHost, st));
+            S.d2h_bytes += ncopy * sizeof(vs_hit);
+            if (found > room) out_overflow = true;
+        } else if (found) {
+            if (found > ctx->loc_cap) {
+                for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_keys[s]); cudaFree(ctx->d_vals[s]); ctx->d_keys[s] = ctx->d_vals[s] = nullptr; }
+                cudaFree(ctx->d_loc); ctx->d_loc = nullptr; ctx->loc_cap = 0;
+                const uint64_t cap = std::max<uint64_t>(found + found / 8, 1u << 16);
+                for (int s = 0; s < 2; ++s) { CK(cudaMalloc(&ctx->d_keys[s], cap * 8)); CK(cudaMalloc(&ctx->d_vals[s], cap * 8)); }
+                CK(cudaMalloc(&ctx->d_loc, cap * sizeof(vs_loc_hit)));
+                ctx->loc_cap = cap;
+            }
+            int guide_bits = 1;
+            while ((1u << guide_bits) < ng) ++guide_bits;
+            cub::DoubleBuffer<unsigned long long> dk(ctx->d_keys[0], ctx->d_keys[1]), dv(ctx->d_vals[0], ctx->d_vals[1]);
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (unsigned long long)found, 0, 49 + guide_bits, st));
+            if (tmp > ctx->sort_tmp_bytes) {
+                cudaFree(ctx->d_sort_tmp); ctx->d_sort_tmp = nullptr; ctx->sort_tmp_bytes = 0;
+                CK(cudaMalloc(&ctx->d_sort_tmp, tmp + tmp / 4));
+                ctx->sort_tmp_bytes = tmp + tmp / 4;
+            }
+            const unsigned gb = (unsigned)((found + 255) / 256);
+            k_resolve_hits<<<gb, 256, 0, st>>>(ctx->d_hits, found, ctx->d_cstart, ctx->n_cstart, ctx->first_contig, g0, ctx->d_keys[0], ctx->d_vals[0]);
+            tmp = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp, tmp, dk, dv, (unsigned long long)found, 0, 49 + guide_bits, st));
+            k_pack_loc_hits<<<gb, 256, 0, st>>>(dk.Current(), dv.Current(), found, ctx->d_loc);
+            S.launches += 2 + 8;                              // + the radix sort's passes (CUB: histogram + one pass per 8 key bits)
+            CK(cudaGetLastError());
+            if (q.sink) {
+                if (found > ctx->stage_cap) {
+                    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+                    ctx->h_stage = nullptr; ctx->stage_cap = 0;
+                    CK(cudaMallocHost(&ctx->h_stage, (found + found / 8) * sizeof(vs_loc_hit)));
+                    ctx->stage_cap = found + found / 8;
+                }
+                CK(cudaMemcpyAsync(ctx->h_stage, ctx->d_loc, found * sizeof(vs_loc_hit), cudaMemcpyDeviceToHost, st));
+                S.d2h_bytes += found * sizeof(vs_loc_hit);
+            } else {
+                const uint64_t room = q.out_cap > total_out ? q.out_cap - total_out : 0, ncopy = std::min(found, room);
+                if (q.out_loc && ncopy) CK(cudaMemcpyAsync(q.out_loc + total_out, ctx->d_loc, ncopy * sizeof(vs_loc_hit), cudaMemcpyDeviceToHost, st));
+                S.d2h_bytes += ncopy * sizeof(vs_loc_hit);
+                if (found > room) out_overflow = true;
+            }
+        }
+        CK(cudaEventRecord(ctx->ev[5], st));
         CK(cudaStreamSynchronize(st));
-        source = nullptr;                                   // the text is resident from here on
-        // chunks whose candidate store overflowed were skipped by k_score: redo them with a larger store
-        S.n_cand_fwd = S.n_cand_rev = S.n_blocks_fwd = S.n_blocks_rev = 0;
-        const uint64_t cap_in_pass = ctx->blocks_cap;        // what k_score compared against during the pass
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            unsigned long long *hc = ctx->h_cnt + (uint64_t)c * 4;
-            if (hc[2] > cap_in_pass || hc[3] > cap_in_pass) {
-                uint64_t need = std::max(hc[2], hc[3]);
-                need = (need + need / 32 + SCORE_THREADS) / SCORE_THREADS * SCORE_THREADS;
-                if ((r = ensure_blocks(need)) != VS_OK) return r;
-                CK(cudaMemsetAsync(ctx->d_cnt + (uint64_t)c * 4, 0, 4 * sizeof(unsigned long long), st));
-                if ((r = launch_extract(c, 0, st)) != VS_OK) return r;
-                if ((r = launch_score(c, 0)) != VS_OK) return r;
-                CK(cudaMemcpyAsync(hc, ctx->d_cnt + (uint64_t)c * 4, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h_hitcnt, d_hitcnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (hc[2] > ctx->blocks_cap || hc[3] > ctx->blocks_cap) return fail(ctx, VS_ERR_CUDA, "vs_scan: candidate store overflow after regrow");
-                S.redo_chunks++;
-            }
-            S.n_cand_fwd += hc[0]; S.n_cand_rev += hc[1]; S.n_blocks_fwd += hc[2]; S.n_blocks_rev += hc[3];
+        { float a = 0.f; CK(cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5])); S.resolve_ms += a; }
+        if (q.resolved && q.sink && found) {
+            if (q.sink(q.user, ctx->h_stage, found, g0, g0 + ng) != 0) return fail(ctx, VS_ERR_ARG, "vs_scan_resolved: the sink aborted the scan");
         }
-        found = *h_hitcnt;
-        if (found <= ctx->hits_cap) break;
-        if (attempt == 2) return fail(ctx, VS_ERR_CUDA, "vs_scan: hit buffer overflow after regrow");
-        // device hit buffer too small: grow and repeat the pass
-        cudaFree(ctx->d_hits); ctx->d_hits = nullptr; ctx->hits_cap = 0;
-        uint64_t cap = found + found / 8 + 1024;
-        CK(cudaMalloc(&ctx->d_hits, cap * sizeof(vs_hit)));
-        ctx->hits_cap = cap;
+        total_out += found;
+        ctx->last_n_hits = found;                            // vs_scan_fetch serves the last super-chunk only (single-pass scans)
+        g0 += ng;
     }
-    ctx->last_n_hits = found;
-    S.n_hits = found;
-    if (n_hits) *n_hits = found;
-    uint64_t ncopy = found < out_cap ? found : out_cap;
-    if (out && ncopy) CK(cudaMemcpyAsync(out, ctx->d_hits, ncopy * sizeof(vs_hit), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaEventRecord(ctx->ev[6], st));
     CK(cudaStreamSynchronize(st));
-    S.d2h_bytes = ncopy * sizeof(vs_hit) + (ctx->cnt_chunks * 4 + 4) * sizeof(unsigned long long);
-    // per-phase device times: sums over the chunks of the last pass (same stream, so the intervals do not overlap)
-    // (extraction of chunk c+1 runs concurrently with the scoring of chunk c, so the two sums overlap in time)
-    for (uint32_t c = 0; c < n_chunks; ++c) {
-        float a = 0.f, b = 0.f;
-        CK(cudaEventElapsedTime(&a, ctx->ev_pool[(size_t)EVC * c + 1], ctx->ev_pool[(size_t)EVC * c + 2]));
-        CK(cudaEventElapsedTime(&b, ctx->ev_pool[(size_t)EVC * c + 3], ctx->ev_pool[(size_t)EVC * c + 4]));
-        S.extract_ms += a; S.score_ms += b;
-    }
-    CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[0], ctx->ev[5]));
-    if (src) CK(cudaEventElapsedTime(&S.upload_ms, ctx->ev[0], ctx->ev_pool[(size_t)EVC * (n_chunks - 1)]));
-    if (stats) *stats = S;
+    CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[0], ctx->ev[6]));
+    S.n_cand_fwd = ctx->idx_cand[0]; S.n_cand_rev = ctx->idx_cand[1];
+    S.n_blocks_fwd = ctx->idx_blocks[0]; S.n_blocks_rev = ctx->idx_blocks[1];
+    S.n_hits = total_out;
+    if (q.n_hits) *q.n_hits = total_out;
+    if (!ctx->keep_index) ctx->idx_valid = false;
+    if (q.stats) *q.stats = S;
     ctx->err.clear();
-    if (found > out_cap) return fail(ctx, VS_ERR_OVERFLOW, "vs_scan: caller hit buffer too small; use vs_scan_fetch");
+    if (out_overflow && !q.sink) {
+        if (S.guide_passes > 1) return fail(ctx, VS_ERR_OVERFLOW, "vs_scan: caller hit buffer too small (several guide passes: enlarge it or use a sink)");
+        return fail(ctx, VS_ERR_OVERFLOW, "vs_scan: caller hit buffer too small; use vs_scan_fetch");
+    }
     return VS_OK;
 }
 
@@ -734,7 +1000,10 @@ extern "C" int vs_scan(vs_ctx *ctx, const uint8_t *guides, uint32_t n_guides, in
                        vs_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_scan_stats *stats)
 {
     if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan: ctx is NULL");
-    return scan_core(ctx, nullptr, ctx->first_word, ctx->n_words, guides, n_guides, k, extra_pam, out, out_cap, n_hits, stats);
+    ScanReq q;
+    q.guides = guides; q.n_guides = n_guides; q.k = k; q.extra_pam = extra_pam;
+    q.out_raw = out; q.out_cap = out_cap; q.n_hits = n_hits; q.stats = stats;
+    return scan_engine(ctx, q);
 }
 
 extern "C" int vs_scan_text(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words,
@@ -744,7 +1013,27 @@ extern "C" int vs_scan_text(vs_ctx *ctx, const vs_text_view *text, uint64_t firs
     if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan_text: ctx is NULL");
     int r = check_view(ctx, text, first_word, n_words);
     if (r != VS_OK) return r;
-    return scan_core(ctx, text, first_word, n_words, guides, n_guides, k, extra_pam, out, out_cap, n_hits, stats);
+    ScanReq q;
+    q.src = text; q.first_word = first_word; q.n_words = n_words;
+    q.guides = guides; q.n_guides = n_guides; q.k = k; q.extra_pam = extra_pam;
+    q.out_raw = out; q.out_cap = out_cap; q.n_hits = n_hits; q.stats = stats;
+    return scan_engine(ctx, q);
+}
+
+extern "C" int vs_scan_resolved(vs_ctx *ctx, const vs_text_view *text, uint64_t first_word, uint64_t n_words,
+                                const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                                vs_loc_hit *out, uint64_t out_cap, uint64_t *n_hits, vs_hit_sink sink, void *user, vs_scan_stats *stats)
+{
+    if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_scan_resolved: ctx is NULL");
+    if (text) {
+        int r = check_view(ctx, text, first_word, n_words);
+        if (r != VS_OK) return r;
+    }
+    ScanReq q;
+    q.src = text; q.first_word = first_word; q.n_words = n_words;
+    q.guides = guides; q.n_guides = n_guides; q.k = k; q.extra_pam = extra_pam;
+    q.resolved = true; q.out_loc = out; q.out_cap = out_cap; q.n_hits = n_hits; q.sink = sink; q.user = user; q.stats = stats;
+    return scan_engine(ctx, q);
 }
 
 extern "C" int vs_scan_fetch(vs_ctx *ctx, vs_hit *out, uint64_t out_cap, uint64_t *n_hits)

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -333,9 +335,25 @@ int masks_from_source(const vs_text_view *t, vs_masks *out)
 }
 }  // namespace
 
+// window masks of a view on the host: copied, or rebuilt from the compact mask source when the view carries no masks
+extern "C" int vs_text_masks(const vs_text_view *t, vs_masks *out)
+{
+    if (!t || (!out && t->n_words)) return VS_ERR_ARG;
+    if (t->masks) { memcpy(out, t->masks, t->n_words * sizeof(vs_masks)); return VS_OK; }
+    if (!has_source(t)) return VS_ERR_ARG;
+    return masks_from_source(t, out);
+}
+
+// buffers handed out by vs_text_load are page-locked when a CUDA device is usable (the upload then runs at PCIe speed);
+// vs_free() has to know which ones
+namespace {
+std::mutex g_pinned_mu;
+std::unordered_set<void *> g_pinned;
+}
+
 extern "C" int vs_text_save(const char *prefix, const vs_text_view *t)
 {
-    if (!prefix || !t || !t->contig_off || (!t->bases) || (!t->masks && t->n_words)) return VS_ERR_ARG;
+    if (!prefix || !t || !t->contig_off || (!t->bases) || (!t->masks && !has_source(t) && t->n_words)) return VS_ERR_ARG;
     std::string path = std::string(prefix) + ".vsidx";
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) { vs_set_last_error(("cannot open " + path + " for writing").c_str()); return VS_ERR_IO; }
@@ -389,46 +407,60 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     }
     const bool src = v3 && (h.flags & 1u);
     const uint64_t nw = (h.n_bases + 31) >> 5;
-    // in memory: offsets, bases, masks, then either the sparse masks (read) or the source (read; the masks are rebuilt)
-    const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)), s_m = pad16(nw * sizeof(vs_masks));
+    // in memory: offsets, bases, then either masks + sparse masks (read) or the source (read; a view with a source carries
+    // no masks: the device computes them during the upload, vs_text_masks() rebuilds them on the host for who needs them)
+    const uint64_t s_off = pad16(((uint64_t)h.n_contigs + 1) * 8), s_b = pad16((nw + 1) * sizeof(vs_bases)), s_m = src ? 0 : pad16(nw * sizeof(vs_masks));
     const uint64_t s_s = src ? 0 : pad16(h.n_sparse * sizeof(vs_mask_entry));
     const uint64_t s_em = src ? pad16(nw + 1) : 0, s_ed = src ? pad16((nw + VS_EM_BLOCK) / VS_EM_BLOCK) : 0,
                    s_nr = src ? pad16(sh.n_nm_runs * sizeof(vs_plane_run)) : 0, s_er = src ? pad16(sh.n_em_runs * sizeof(vs_plane_run)) : 0;
     const uint64_t total = s_off + s_b + s_m + s_s + s_em + s_ed + s_nr + s_er;
-    char *buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);
+    char *buf = (char *)vs_host_alloc((total + 63) & ~63ull);
+    const bool pinned = buf != nullptr;
+    if (!buf) buf = (char *)aligned_alloc(64, (total + 63) & ~63ull);       // no usable device: the caller will find out when it scans
     if (!buf) { fclose(f); return VS_ERR_NOMEM; }
+    auto release = [&]() { if (pinned) vs_host_free(buf); else free(buf); };
     char *p_masks = buf + s_off + s_b, *p_tail = p_masks + s_m;
     bool ok = fseek(f, (long)data_at, SEEK_SET) == 0 && fread(buf, 1, s_off + s_b, f) == s_off + s_b;
     if (ok && src) ok = fread(p_tail, 1, s_em + s_ed + s_nr + s_er, f) == s_em + s_ed + s_nr + s_er;
     else if (ok) ok = fread(p_masks, 1, s_m + s_s, f) == s_m + s_s;
     fclose(f);
     const uint64_t *off = (const uint64_t *)buf;
-    if (!ok || off[h.n_contigs] != h.n_bases) { free(buf); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
+    if (!ok || off[h.n_contigs] != h.n_bases) { release(); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }
     out->n_bases = h.n_bases; out->n_words = nw; out->n_contigs = h.n_contigs;
     out->contig_off = off;
     out->bases = (const vs_bases *)(buf + s_off);
-    out->masks = (const vs_masks *)p_masks;
+    out->masks = src ? nullptr : (const vs_masks *)p_masks;
     if (src) {
         out->em_code = (const uint8_t *)p_tail;
         out->em_dense = (const uint8_t *)(p_tail + s_em);
         out->nm_runs = (const vs_plane_run *)(p_tail + s_em + s_ed);
         out->em_runs = (const vs_plane_run *)(p_tail + s_em + s_ed + s_nr);
         out->n_nm_runs = sh.n_nm_runs; out->n_em_runs = sh.n_em_runs;
-        int r = masks_from_source(out, (vs_masks *)p_masks);
-        if (r != VS_OK) {
-            free(buf); memset(out, 0, sizeof(*out));
-            vs_set_last_error((path + (r == VS_ERR_NOMEM ? ": out of memory" : " holds a corrupt mask source")).c_str());
-            return r;
+        // the runs are trusted by the upload: check them here
+        bool good = true;
+        for (uint64_t i = 0; i < sh.n_nm_runs && good; ++i) good = (uint64_t)out->nm_runs[i].word + out->nm_runs[i].count <= nw + 1;
+        for (uint64_t i = 0; i < sh.n_em_runs && good; ++i) good = (uint64_t)out->em_runs[i].word + out->em_runs[i].count <= nw + 1;
+        if (!good) {
+            release(); memset(out, 0, sizeof(*out));
+            vs_set_last_error((path + " holds a corrupt mask source").c_str());
+            return VS_ERR_IO;
         }
     } else {
         out->sparse = (const vs_mask_entry *)p_tail;
         out->n_sparse = h.n_sparse;
     }
+    if (pinned) { std::lock_guard<std::mutex> lk(g_pinned_mu); g_pinned.insert(buf); }
     *owner = buf;
     return VS_OK;
 }
 
-extern "C" void vs_free(void *p) { free(p); }
+extern "C" void vs_free(void *p)
+{
+    if (!p) return;
+    bool pinned = false;
+    { std::lock_guard<std::mutex> lk(g_pinned_mu); pinned = g_pinned.erase(p) != 0; }
+    if (pinned) vs_host_free(p); else free(p);
+}
 
 // ------------------------------------------------------------------------------------------------
 // hit resolution
@@ -536,6 +568,93 @@ extern "C" int vs_resolve_hits(const vs_hit *hits, uint64_t n, const uint64_t *c
     return vs_resolve_hits_mt(hits, n, contig_off, n_contigs, out, key16_collisions, 1);
 }
 
+// Merge of the device-sorted lists of the shards (vs_scan_resolved).  Every list is ascending in (guide, strand, contig &
+// 0xFFFF, pos); the lists are cut at the same pass boundaries into n_threads ranges of passes, each range is gathered
+// into its final place in `out`'s index space, sorted when more than one list contributed (or when records tie on the
+// 16-bit key: the order among those is by the full contig id), and walked with the running-best rule of
+// bidir_mapping.cpp:164-187.
+extern "C" int vs_merge_resolved(const vs_loc_hit *const *lists, const uint64_t *counts, int n_lists,
+                                 vs_record *out, uint64_t *key16_collisions, int n_threads)
+{
+    if (key16_collisions) *key16_collisions = 0;
+    if (n_lists < 0 || (n_lists && (!lists || !counts))) return VS_ERR_ARG;
+    uint64_t total = 0;
+    int biggest = 0;
+    for (int l = 0; l < n_lists; ++l) {
+        if (counts[l] && !lists[l]) return VS_ERR_ARG;
+        total += counts[l];
+        if (counts[l] > counts[biggest]) biggest = l;
+    }
+    if (total == 0) return VS_OK;
+    if (!out) return VS_ERR_ARG;
+    if (n_threads < 1) n_threads = 1;
+    if ((uint64_t)n_threads > total / 2048 + 1) n_threads = (int)(total / 2048 + 1);
+    auto pass_of = [](const vs_loc_hit &h) { return (uint64_t)(h.info >> 7); };                 // guide << 1 | strand
+    // pass boundaries of the thread ranges: quantiles of the biggest list
+    std::vector<uint64_t> cut((size_t)n_threads + 1, 0);
+    cut[(size_t)n_threads] = ~0ull;
+    for (int t = 1; t < n_threads; ++t) cut[(size_t)t] = pass_of(lists[biggest][counts[biggest] * (uint64_t)t / (uint64_t)n_threads]);
+    // start of every range in every list (first record whose pass is >= the cut), and in the output
+    std::vector<uint64_t> at((size_t)(n_threads + 1) * (size_t)n_lists, 0), out_at((size_t)n_threads + 1, 0);
+    for (int t = 0; t <= n_threads; ++t)
+        for (int l = 0; l < n_lists; ++l) {
+            const vs_loc_hit *b = lists[l], *e = lists[l] + counts[l];
+            const uint64_t i = t == n_threads ? counts[l] : (uint64_t)(std::partition_point(b, e, [&](const vs_loc_hit &h) { return pass_of(h) < cut[(size_t)t]; }) - b);
+            at[(size_t)t * (size_t)n_lists + (size_t)l] = i;
+            out_at[(size_t)t] += i;
+        }
+    std::vector<uint64_t> coll((size_t)n_threads, 0);
+    std::vector<int> rc((size_t)n_threads, VS_OK);
+    constexpr uint64_t KEY48 = (1ull << 49) - 1;                                                  // strand, contig & 0xFFFF, pos
+    auto less = [&](const vs_loc_hit &a, const vs_loc_hit &b) {
+        const uint64_t pa = pass_of(a), pb = pass_of(b);
+        if (pa != pb) return pa < pb;
+        if ((a.key & KEY48) != (b.key & KEY48)) return (a.key & KEY48) < (b.key & KEY48);
+        return a.contig < b.contig;
+    };
+    auto work = [&](int t) {
+        const uint64_t o0 = out_at[(size_t)t], o1 = out_at[(size_t)t + 1];
+        if (o1 == o0) return;
+        std::vector<vs_loc_hit> v;
+        try { v.reserve(o1 - o0); } catch (...) { rc[(size_t)t] = VS_ERR_NOMEM; return; }
+        for (int l = 0; l < n_lists; ++l)
+            v.insert(v.end(), lists[l] + at[(size_t)t * (size_t)n_lists + (size_t)l], lists[l] + at[(size_t)(t + 1) * (size_t)n_lists + (size_t)l]);
+        if (!std::is_sorted(v.begin(), v.end(), less)) std::sort(v.begin(), v.end(), less);
+        uint64_t w = o0, c = 0;
+        auto emit = [&](const vs_loc_hit &h, uint16_t secondary) {
+            vs_record &o = out[w++];
+            o.guide = h.info >> 8;
+            o.contig = h.contig;
+            o.pos = (uint32_t)h.key;
+            o.mm = (uint8_t)(h.info & 0x7F);
+            o.flag = (uint16_t)(secondary | ((h.info & 0x80) ? 16 : 0));
+            o.pad = 0;
+        };
+        for (uint64_t i = 0; i < v.size();) {
+            uint64_t j = i + 1;
+            while (j < v.size() && pass_of(v[j]) == pass_of(v[i])) ++j;
+            uint64_t best = i;
+            for (uint64_t x = i + 1; x < j; ++x) {
+                if ((v[x].key & KEY48) == (v[x - 1].key & KEY48)) ++c;                        // same (id16, pos): uint16 key collision
+                if ((v[x].info & 0x7F) >= (v[best].info & 0x7F)) emit(v[x], 256);
+                else { emit(v[best], 256); best = x; }
+            }
+            emit(v[best], 0);
+            i = j;
+        }
+        coll[(size_t)t] = c;
+    };
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < n_threads; ++t) if (rc[(size_t)t] != VS_OK) return rc[(size_t)t];
+    if (key16_collisions) for (uint64_t c : coll) *key16_collisions += c;
+    return VS_OK;
+}
+
 static inline int base_at(const vs_bases *bases, uint64_t p)
 {
     const vs_bases &w = bases[p >> 5];
@@ -597,15 +716,26 @@ std::vector<uint64_t> shard_bounds(uint64_t n_words, int n)
     return b;
 }
 
-int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices_in,
-                      const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
-                      std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err)
+static void add_stats(vs_scan_stats *agg, const vs_scan_stats &s)
+{
+    agg->upload_ms = std::max(agg->upload_ms, s.upload_ms); agg->extract_ms = std::max(agg->extract_ms, s.extract_ms);
+    agg->score_ms = std::max(agg->score_ms, s.score_ms); agg->total_ms = std::max(agg->total_ms, s.total_ms);
+    agg->resolve_ms = std::max(agg->resolve_ms, s.resolve_ms);
+    agg->n_cand_fwd += s.n_cand_fwd; agg->n_cand_rev += s.n_cand_rev;
+    agg->n_blocks_fwd += s.n_blocks_fwd; agg->n_blocks_rev += s.n_blocks_rev;
+    agg->n_hits += s.n_hits; agg->launches += s.launches; agg->score_launches += s.score_launches;
+    agg->h2d_bytes += s.h2d_bytes; agg->d2h_bytes += s.d2h_bytes; agg->n_chunks += s.n_chunks; agg->redo_chunks += s.redo_chunks;
+    agg->guide_passes = std::max(agg->guide_passes, s.guide_passes);
+}
+
+// One host thread + one context per device, each scanning its word range of the text; `run(i, ctx, w0, n)` does the scan.
+template <class Run>
+static int for_each_shard(const vs_text_view &text, const std::vector<int> &devices_in, vs_scan_stats *agg, std::string &err, Run run)
 {
     std::vector<int> devices = devices_in;
     if (devices.empty()) devices.push_back(0);
     const int nd = (int)devices.size();
     std::vector<uint64_t> b = shard_bounds(text.n_words, nd);
-    std::vector<std::vector<vs_hit>> part((size_t)nd);
     std::vector<int> rc((size_t)nd, VS_OK);
     std::vector<std::string> errs((size_t)nd);
     std::vector<vs_scan_stats> st((size_t)nd);
@@ -615,17 +745,7 @@ int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices_
         uint64_t w0 = b[(size_t)i], w1 = b[(size_t)i + 1];
         if (w1 <= w0) return;
         int r = vs_ctx_create(devices[(size_t)i], &ctx);
-        if (r == VS_OK) {
-            uint64_t n = 0;
-            std::vector<vs_hit> &h = part[(size_t)i];
-            h.resize(1u << 16);
-            r = vs_scan_text(ctx, &text, w0, w1 - w0, guides, n_guides, k, extra_pam, h.data(), h.size(), &n, &st[(size_t)i]);
-            if (r == VS_ERR_OVERFLOW) {
-                h.resize(n);
-                r = vs_scan_fetch(ctx, h.data(), h.size(), &n);
-            }
-            if (r == VS_OK) h.resize(n);
-        }
+        if (r == VS_OK) r = run(i, ctx, w0, w1 - w0, &st[(size_t)i]);
         if (r != VS_OK) errs[(size_t)i] = vs_last_error(ctx);
         rc[(size_t)i] = r;
         vs_ctx_destroy(ctx);
@@ -636,22 +756,59 @@ int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices_
         for (int i = 0; i < nd; ++i) th.emplace_back(work, i);
         for (auto &t : th) t.join();
     }
-    hits.clear();
     if (agg) memset(agg, 0, sizeof(*agg));
     for (int i = 0; i < nd; ++i) {
         if (rc[(size_t)i] != VS_OK) { err = "device " + std::to_string(devices[(size_t)i]) + ": " + errs[(size_t)i]; return rc[(size_t)i]; }
-        hits.insert(hits.end(), part[(size_t)i].begin(), part[(size_t)i].end());
-        if (agg) {
-            const vs_scan_stats &s = st[(size_t)i];
-            agg->upload_ms = std::max(agg->upload_ms, s.upload_ms); agg->extract_ms = std::max(agg->extract_ms, s.extract_ms);
-            agg->score_ms = std::max(agg->score_ms, s.score_ms); agg->total_ms = std::max(agg->total_ms, s.total_ms);
-            agg->n_cand_fwd += s.n_cand_fwd; agg->n_cand_rev += s.n_cand_rev;
-            agg->n_blocks_fwd += s.n_blocks_fwd; agg->n_blocks_rev += s.n_blocks_rev;
-            agg->n_hits += s.n_hits; agg->launches += s.launches; agg->score_launches += s.score_launches;
-            agg->h2d_bytes += s.h2d_bytes; agg->d2h_bytes += s.d2h_bytes; agg->n_chunks += s.n_chunks; agg->redo_chunks += s.redo_chunks;
-        }
+        if (agg) add_stats(agg, st[(size_t)i]);
     }
     return VS_OK;
+}
+
+int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices_in,
+                      const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                      std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err)
+{
+    const size_t nd = devices_in.empty() ? 1 : devices_in.size();
+    std::vector<std::vector<vs_hit>> part(nd);
+    int rc = for_each_shard(text, devices_in, agg, err, [&](int i, vs_ctx *ctx, uint64_t w0, uint64_t n, vs_scan_stats *st) {
+        uint64_t cnt = 0;
+        std::vector<vs_hit> &h = part[(size_t)i];
+        h.resize(1u << 16);
+        vs_ctx_set_option(ctx, VS_OPT_KEEP_INDEX, 0);
+        int r = vs_scan_text(ctx, &text, w0, n, guides, n_guides, k, extra_pam, h.data(), h.size(), &cnt, st);
+        if (r == VS_ERR_OVERFLOW && st->guide_passes <= 1) {
+            h.resize(cnt);
+            r = vs_scan_fetch(ctx, h.data(), h.size(), &cnt);
+        }
+        if (r == VS_OK) h.resize(cnt);
+        return r;
+    });
+    hits.clear();
+    if (rc != VS_OK) return rc;
+    for (auto &p : part) hits.insert(hits.end(), p.begin(), p.end());
+    return VS_OK;
+}
+
+// the same with the hits resolved and sorted on every device (vs_scan_resolved): one list per shard, ready for vs_merge_resolved
+int scan_text_sharded_resolved(const vs_text_view &text, const std::vector<int> &devices_in,
+                               const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                               std::vector<std::vector<vs_loc_hit>> &lists, vs_scan_stats *agg, std::string &err)
+{
+    const size_t nd = devices_in.empty() ? 1 : devices_in.size();
+    lists.assign(nd, {});
+    struct Sink {
+        static int put(void *user, const vs_loc_hit *h, uint64_t n, uint32_t, uint32_t)
+        {
+            auto *v = static_cast<std::vector<vs_loc_hit> *>(user);
+            try { v->insert(v->end(), h, h + n); } catch (...) { return 1; }
+            return 0;
+        }
+    };
+    return for_each_shard(text, devices_in, agg, err, [&](int i, vs_ctx *ctx, uint64_t w0, uint64_t n, vs_scan_stats *st) {
+        uint64_t cnt = 0;
+        vs_ctx_set_option(ctx, VS_OPT_KEEP_INDEX, 0);
+        return vs_scan_resolved(ctx, &text, w0, n, guides, n_guides, k, extra_pam, nullptr, 0, &cnt, &Sink::put, &lists[(size_t)i], st);
+    });
 }
 
 }  // namespace vs
@@ -675,6 +832,31 @@ extern "C" int vs_map_packed(const vs_text_view *text, const uint8_t *guides, ui
         *hits = o;
     }
     *n_hits = h.size();
+    return VS_OK;
+}
+
+extern "C" int vs_map_records(const vs_text_view *text, const uint8_t *guides, uint32_t n_guides,
+                              int k, int extra_pam, const int *devices, int n_devices, int n_threads,
+                              vs_record **records, uint64_t *n_records, uint64_t *key16_collisions, vs_scan_stats *stats)
+{
+    if (!records || !n_records || !text) return VS_ERR_ARG;
+    *records = nullptr; *n_records = 0;
+    std::vector<int> dev;
+    for (int i = 0; i < n_devices && devices; ++i) dev.push_back(devices[i]);
+    std::vector<std::vector<vs_loc_hit>> lists;
+    std::string err;
+    int rc = vs::scan_text_sharded_resolved(*text, dev, guides, n_guides, k, extra_pam, lists, stats, err);
+    if (rc != VS_OK) { vs_set_last_error(err.c_str()); return rc; }
+    std::vector<const vs_loc_hit *> ptr;
+    std::vector<uint64_t> cnt;
+    uint64_t total = 0;
+    for (auto &l : lists) { ptr.push_back(l.data()); cnt.push_back(l.size()); total += l.size(); }
+    if (total == 0) return VS_OK;
+    vs_record *o = (vs_record *)malloc(total * sizeof(vs_record));
+    if (!o) return VS_ERR_NOMEM;
+    rc = vs_merge_resolved(ptr.data(), cnt.data(), (int)ptr.size(), o, key16_collisions, n_threads);
+    if (rc != VS_OK) { free(o); return rc; }
+    *records = o; *n_records = total;
     return VS_OK;
 }
 

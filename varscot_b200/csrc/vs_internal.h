@@ -18,6 +18,12 @@ int scan_text_sharded(const vs_text_view &text, const std::vector<int> &devices,
                       const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
                       std::vector<vs_hit> &hits, vs_scan_stats *agg, std::string &err);
 
+// The same with every shard's hits resolved to (contig, pos) and sorted on its device (vs_scan_resolved): one list per
+// shard, ready for vs_merge_resolved.
+int scan_text_sharded_resolved(const vs_text_view &text, const std::vector<int> &devices,
+                               const uint8_t *guides, uint32_t n_guides, int k, int extra_pam,
+                               std::vector<std::vector<vs_loc_hit>> &lists, vs_scan_stats *agg, std::string &err);
+
 // Split [0, n_words) into n contiguous shards of (almost) equal size, tile-aligned.
 std::vector<uint64_t> shard_bounds(uint64_t n_words, int n);
 

@@ -32,17 +32,6 @@ constexpr int BLK_GROUP    = 32;                  // blocks per layout group: wo
                                                   // the 32 lanes of a warp (32 consecutive blocks) touch 128 contiguous bytes per word
 constexpr int BLK_LAST     = 46;                  // word index of the last-window mask
 constexpr int BLK_VALID    = 47;                  // word index of the valid mask
-#ifndef VS_SCORE_THREADS
-#define VS_SCORE_THREADS 128          // measured on B200 (score ms, cfg3 x 0.25 / cfg4 x 0.1): 96 thr 2.11 / 12.7, 128 thr 2.15 / 11.0, 256 thr 2.20 / 11.2
-#endif
-constexpr int SCORE_THREADS = VS_SCORE_THREADS;
-constexpr int NPLANES      = 4 * VS_GLEN;         // 92 "mismatch if the guide base at position i is b" planes per block (k = 8: all in shared memory)
-constexpr int PAT_STRIDE   = 24;                  // uint32 per pattern in constant memory (23 slot offsets + pad, 16-byte aligned)
-#ifndef VS_PAT_CHUNK
-#define VS_PAT_CHUNK 256
-#endif
-constexpr int PAT_CHUNK    = VS_PAT_CHUNK;        // guides per k_score launch: 2 strands x 256 x 96 B = 48 KB of constant memory
-constexpr int PAT_TABLE_WORDS = 2 * PAT_CHUNK * PAT_STRIDE;             // words of c_pat = words per guide chunk
 
 __host__ __device__ __forceinline__ uint64_t plane_index(uint64_t blk, int w)
 {
@@ -404,80 +393,92 @@ __device__ __forceinline__ uint32_t le_k(const uint32_t (&b)[5])
 }
 
 // Number of pattern slots scored before the early-out test: with uniform-random text, after PA(K) informative
-// positions fewer than ~12 % of the warps (1024 candidates) still hold a window with <= K mismatches, so the
-// remaining slots (the PAM positions come last in the slot order) are loaded only for those.
+// positions fewer than ~12 % of the warp iterations (1024 window x guide pairs) still hold a pair with <= K mismatches, so
+// the remaining slots (the PAM positions come last in the slot order) are loaded only for those.
 __host__ __device__ constexpr int stage_a_slots(int k) { return k >= 8 ? VS_GLEN : 7 + 2 * k; }
-// Shared-memory planes per block: the 4 expanded "mismatch if the pattern base is b" planes of every stage-A position
-// ([base, base + PA) with base = 0 forward, 2 reverse, whose slot order is 2..22, 0, 1), then the two RAW planes {hi, lo}
-// of every stage-B slot — the few warps that reach stage B pay 2 LDS + 2 LOP3 per slot instead of 1 LDS, and the block
-// needs 4 PA + 2 PB planes instead of 92 (k = 6: 84), which lets one more CTA reside per SM.  k = 8 is single-stage.
-__host__ __device__ constexpr int score_smem_planes(int k) { return 4 * stage_a_slots(k) + 2 * (VS_GLEN - stage_a_slots(k)); }
-__host__ __device__ constexpr int score_pos_base(int k, int strand) { return (k < 8 && strand) ? 2 : 0; }
+
+// ---- k_score: "guide per lane" ------------------------------------------------------------------------------------
+// One CTA scores one BATCH of SC_NB consecutive candidate blocks (one layout group: 6 KB of contiguous plane words)
+// of one strand against every guide of the launch.
+//   expand : the CTA turns the 46 raw planes of each block into the 92 planes "mismatch if the pattern base at position
+//            i is b" in shared memory, block-major: word (4 i + b) of block j at s_planes[j * SC_STRIDE + 4 i + b]
+//            (one 16-byte store per position).  Invalid lanes of a partial block mismatch everywhere.
+//   score  : LANE = GUIDE.  A warp takes 32 guides (or, for the tail of the guide list, GW = 16 / 8 / 4 guides x 32 / GW
+//            blocks at a time); each lane holds the byte offsets of ITS pattern's planes in registers — loaded once per
+//            (batch, guide segment) from the pattern table in global memory — and walks the blocks of the batch:
+//            per block PA(K) x [LDS at lane offset + uniform block base], a bit-sliced carry-save adder tree over the 32
+//            candidates of the block (2 LOP3 per full adder), a 2-LOP3 threshold and a warp vote; the few iterations that
+//            pass score the remaining slots and, on a hit (rare), read the exact count out of the bit-sliced counter,
+//            apply R4 and append.
+// Compared with one-candidate-block-per-lane this needs no per-guide uniform loads in the hot loop (the offsets live
+// in registers), 12 KB of shared memory per CTA instead of 43 KB (occupancy is set by registers alone), reads every
+// block from HBM once per launch whatever the number of guides, and keeps the pattern table per context in global
+// memory (no __constant__ symbol shared by the contexts of a device).
+// Shared-memory banks: the lanes of a warp read at most 4 words per block (one per pattern base), (32 / GW) blocks at a
+// time; SC_STRIDE = 92 = 4 (mod 8) puts the 4-word groups of up to 8 consecutive blocks in distinct banks, and lanes
+// reading the same word are served by broadcast, so every LDS is a single wavefront.
+#ifndef VS_SCORE_WARPS
+#define VS_SCORE_WARPS 4
+#endif
+#ifndef VS_SCORE_UNROLL
+#define VS_SCORE_UNROLL 8              // block iterations per trip of the walk
+#endif
+constexpr int SC_UNROLL = VS_SCORE_UNROLL;
+constexpr int SC_WARPS   = VS_SCORE_WARPS;
+constexpr int SC_THREADS = 32 * SC_WARPS;         // guides per pass of a CTA over its batch
+constexpr int SC_NB      = BLK_GROUP;             // blocks per batch
+constexpr int SC_STRIDE  = 4 * VS_GLEN;           // words per block in shared memory
+static_assert(SC_STRIDE % 8 == 4, "block stride must be 4 mod 8 words: conflict-free reads of up to 8 blocks at a time");
+constexpr int SC_SMEM_BYTES = (SC_NB * SC_STRIDE + SC_NB) * 4;      // planes + last-window masks
+constexpr int PAT_STRIDE = 24;                    // uint16 per pattern (23 slot offsets + pad; 48 bytes = 3 x 16)
+
+// position scored by slot j of a strand's slot order: informative positions first, the PAM dinucleotide last
+// (forward 0..22; reverse 2..22, 0, 1)
+__host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
+// table entry of slot j for pattern base b (0..3): byte offset of plane (4 position + b) inside a block's shared-memory row
+__host__ __device__ constexpr uint16_t pat_slot(int strand, int j, int b) { return (uint16_t)((4 * slot_position(strand, j) + b) * 4); }
+// inverse of pat_slot
+__host__ __device__ __forceinline__ void pat_decode(int strand, int j, uint32_t e, int &i, int &b)
+{
+    i = slot_position(strand, j);
+    b = (int)((e >> 2) & 3u);
+}
 __host__ __device__ constexpr int score_min_blocks(int k)
 {
-    // resident CTAs per SM that fit 227 KB of shared memory (1 KB reserved per CTA) and 64 K registers at <= 72 per thread
-    const int by_smem = (227 * 1024) / (score_smem_planes(k) * SCORE_THREADS * 4 + 1024);
-    const int by_regs = 65536 / (72 * SCORE_THREADS);
 #ifdef VS_SCORE_MINBLOCKS
     return VS_SCORE_MINBLOCKS;          // tuning override: only steers the register allocation
 #endif
-    const int m = by_smem < by_regs ? by_smem : by_regs;
-    return m < 1 ? 1 : (m > 8 ? 8 : m);
-}
-
-// Pattern table in constant memory, per strand and guide: PAT_STRIDE words.  The host orders the slots
-// informative-first: forward positions 0..22, reverse 2..22,0,1.  A stage-A slot j < PA(k) holds the byte offset
-// (plane index * SCORE_THREADS * 4, plane index = 4 * (position - base) + pattern base) of the shared-memory plane it
-// selects; a stage-B slot holds the byte offset of its raw hi plane (lo follows at + SCORE_THREADS * 4) | pattern base << 16
-// (see pat_slot()).
-__constant__ uint32_t c_pat[PAT_TABLE_WORDS];
-
-// position scored by slot j of a strand's slot order
-__host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
-// table entry of slot j for pattern base b (0..3)
-__host__ __device__ constexpr uint32_t pat_slot(int k, int strand, int j, int b)
-{
-    const int i = slot_position(strand, j);
-    const int pa = stage_a_slots(k);
-    return j < pa ? (uint32_t)(4 * (i - score_pos_base(k, strand)) + b) * SCORE_THREADS * 4u
-                  : ((uint32_t)(4 * pa + 2 * (j - pa)) * SCORE_THREADS * 4u) | ((uint32_t)b << 16);
-}
-// inverse of pat_slot: position and pattern base of slot j
-__device__ __forceinline__ void pat_decode(int k, int strand, int j, uint32_t e, int &i, int &b)
-{
-    i = slot_position(strand, j);
-    b = j < stage_a_slots(k) ? (int)((e / (SCORE_THREADS * 4u)) & 3u) : (int)(e >> 16);
-}
-// "mismatch against pattern base b" plane from the two planes of a position (b warp-uniform)
-__device__ __forceinline__ uint32_t mismatch_plane(uint32_t h, uint32_t l, uint32_t b)
-{
-    return (h ^ ((b & 2u) ? ~0u : 0u)) | (l ^ ((b & 1u) ? ~0u : 0u));
+    // registers: PA offsets + PA loaded planes + adder temporaries; 64 per thread for k <= 6, 80 above
+    return (k <= 6 ? 1024 : 768) / SC_THREADS;
 }
 
 struct ScoreArgs {
-    const uint32_t *planes[2];  // per strand: [n_blocks][48]
-    const uint32_t *pos[2];     // per strand: [n_blocks][32]
-    const unsigned long long *n_blocks_ptr;   // [2]: blocks claimed by k_extract for this chunk, per strand (device counters)
-    uint64_t cap;               // capacity of each candidate store; a chunk that overflowed it is skipped (host redoes it)
-    uint32_t ctas_per_strand;   // grid = 2 * ctas_per_strand, sized by capacity
-    uint32_t n_pat;             // guides in this launch (<= PAT_CHUNK)
-    uint32_t guide_base;        // index of guide 0 of this launch in the guide list
-    const uint32_t *pat_global; // the same table as c_pat in global memory (read by the slow path only)
+    const uint32_t *planes[2];  // per strand: candidate blocks, word w of block b at plane_index(b, w)
+    const uint32_t *pos[2];     // per strand: [n_blocks][32] global positions
+    const unsigned long long *rng;  // device: {lo_fwd, lo_rev, hi_fwd, hi_rev} block range to score (written by k_extract_mark)
+    uint64_t cap;               // capacity of each candidate store; a range that ran past it is skipped (the host redoes the pass)
+    uint32_t n_guides;          // guides of this launch: rows [guide_base, guide_base + n_guides) of the table
+    uint32_t guide_base;
+    uint32_t pat_guides;        // rows per strand of the table
+    const uint16_t *pat;        // [2][pat_guides][PAT_STRIDE] slot offsets (pat_slot), 16-byte aligned rows
     vs_hit *hits;
     unsigned long long *n_hits;
     uint64_t hit_cap;
 };
 
-// (One atomicAdd per hit on purpose: a warp-aggregated append — prefix sum of the per-lane hit counts, one atomic per
-// warp — measured SLOWER on B200 in every config, including the dense one (config 5 at 0.02 scale, 34.7 M hits per
-// scan: 28.4 vs 26.6 ms), because the whole warp then walks the slow path; 1.3 G atomics/s on one counter is no limit.)
-// Slow path (rare): for every lane that passed the threshold read its exact count out of the bit-sliced counter,
-// apply R4 to last-window candidates (H over positions 11..22 must be <= floor(K/2), bidir_mapping.cpp:48-53) and
-// append the hit.  Only last-window lanes re-read planes (they need the second-half count) — from the block's global
-// copy, with the pattern decoded from the GLOBAL copy of the table so that nothing of the hot loop's uniform-register
-// state stays live.
+// (One atomicAdd per hit on purpose: a warp-aggregated append measured slower on B200 in every config, including the
+// dense one, because the whole warp then walks the slow path.)
+// Slow path (rare): for every candidate of the lane's block that passed the threshold read its exact count out of the
+// bit-sliced counter, apply R4 to last-window candidates (H over positions 11..22 must be <= floor(K/2),
+// bidir_mapping.cpp:48-53) and append the hit.  `row` = the block's expanded planes in shared memory, `po` = the lane's
+// pattern in the global table.
+#if defined(VS_SCORE_NOINLINE_HITS) && !defined(VS_HOST_UNIT_TEST)
+#define VS_NOINLINE __noinline__          // tuning variant: smaller unrolled walk, at the price of spills around the call
+#else
+#define VS_NOINLINE __forceinline__
+#endif
 template <int K>
-__device__ __forceinline__ void score_hits(const uint32_t *gsrc, const uint32_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5],
+__device__ VS_NOINLINE void score_hits(const char *row, const uint16_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5],
                                            uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
                                            unsigned long long *n_hits, uint64_t hit_cap)
 {
@@ -489,14 +490,8 @@ __device__ __forceinline__ void score_hits(const uint32_t *gsrc, const uint32_t 
         if ((lastm >> c) & 1u) {                                             // R4: last window of its contig
             uint32_t h2 = 0;
 #pragma unroll 1
-            for (int j = 0; j < VS_GLEN; ++j) {
-                int i, b;
-                pat_decode(K, strand, j, __ldg(po + j), i, b);
-                if (i >= 11) {
-                    const uint32_t code = (((__ldg(gsrc + i * BLK_GROUP) >> c) & 1u) << 1) | ((__ldg(gsrc + (VS_GLEN + i) * BLK_GROUP) >> c) & 1u);
-                    h2 += code != (uint32_t)b;
-                }
-            }
+            for (int j = 0; j < VS_GLEN; ++j)
+                if (slot_position(strand, j) >= 11) h2 += (*reinterpret_cast<const uint32_t *>(row + po[j]) >> c) & 1u;
             if (h2 > (uint32_t)(K / 2)) continue;
         }
         const unsigned long long idx = atomicAdd(n_hits, 1ull);
@@ -510,112 +505,226 @@ __device__ __forceinline__ void score_hits(const uint32_t *gsrc, const uint32_t 
 }
 
 template <int K>
-__global__ void __launch_bounds__(SCORE_THREADS, score_min_blocks(K))
+__global__ void __launch_bounds__(SC_THREADS, score_min_blocks(K))
 k_score(ScoreArgs a)
 {
 #ifndef VS_HOST_UNIT_TEST       // (the host emulation declares vs::sm itself)
-    extern __shared__ uint32_t sm[];     // [score_smem_planes(K)][SCORE_THREADS]
+    extern __shared__ __align__(16) uint32_t sm[];     // [SC_NB][SC_STRIDE] planes, then [SC_NB] last-window masks
 #endif
     constexpr int PA = stage_a_slots(K), PB = VS_GLEN - PA;
-    const int tid = threadIdx.x;
-    const uint32_t strand = blockIdx.x >= a.ctas_per_strand;            // forward CTAs first, then reverse
-    const uint32_t cta = blockIdx.x - strand * a.ctas_per_strand;
-    const uint64_t n_blocks = strand ? a.n_blocks_ptr[1] : a.n_blocks_ptr[0];
-    if (max(a.n_blocks_ptr[0], a.n_blocks_ptr[1]) > a.cap || (uint64_t)cta * SCORE_THREADS >= n_blocks) return;
-    const uint64_t blk = (uint64_t)cta * SCORE_THREADS + tid;
-    const bool live = blk < n_blocks;
-    // threads past the last block score block 0 with every lane invalid
-    const uint32_t *gsrc = (strand ? a.planes[1] : a.planes[0]) + plane_index(live ? blk : 0, 0);      // word w at gsrc[w * BLK_GROUP]
-    uint32_t *my = sm + tid;
-    uint32_t lastm = 0;
-    {
-        uint32_t v[BLK_WORDS];
-#pragma unroll
-        for (int i = 0; i < BLK_WORDS; ++i) v[i] = __ldg(gsrc + i * BLK_GROUP);       // coalesced: 128 B per warp and word
-        lastm = live ? v[BLK_LAST] : 0u;
-        const uint32_t inv = live ? ~v[BLK_VALID] : ~0u;       // lanes past the end of a partial block mismatch everywhere
-        auto expand = [&](auto base_c) {
-            constexpr int BASE = decltype(base_c)::value;
-#pragma unroll
-            for (int i = 0; i < PA; ++i) {
-                const uint32_t h = v[BASE + i], l = v[VS_GLEN + BASE + i];
-                my[(4 * i + 0) * SCORE_THREADS] = (h | l) | inv;      // mismatch if the pattern base is A (00)
-                my[(4 * i + 1) * SCORE_THREADS] = (h | ~l) | inv;     // C (01)
-                my[(4 * i + 2) * SCORE_THREADS] = (~h | l) | inv;     // G (10)
-                my[(4 * i + 3) * SCORE_THREADS] = (~h | ~l) | inv;    // T (11)
-            }
-            // raw planes of the stage-B slots (an invalid lane already mismatches in all PA > K stage-A slots)
-#pragma unroll
-            for (int i = 0; i < PB; ++i) {
-                constexpr int S = BASE ? 1 : 0;
-                const int p = slot_position(S, PA + i);
-                my[(4 * PA + 2 * i) * SCORE_THREADS] = v[p];
-                my[(4 * PA + 2 * i + 1) * SCORE_THREADS] = v[VS_GLEN + p];
-            }
-        };
-        if constexpr (score_pos_base(K, 1) != 0) {
-            if (strand) expand(std::integral_constant<int, score_pos_base(K, 1)>{});
-            else expand(std::integral_constant<int, 0>{});
-        } else {
-            expand(std::integral_constant<int, 0>{});
-        }
-    }
-    // each thread reads back only what it wrote: no barrier needed
-    const char *myb = reinterpret_cast<const char *>(my);
-    const uint32_t *pat0 = c_pat + strand * (PAT_CHUNK * PAT_STRIDE);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (max(a.rng[2], a.rng[3]) > a.cap) return;          // the candidate store overflowed: the host regrows it and redoes the pass
+    // persistent CTAs: batches of the forward range first, then of the reverse range, strided over the grid — the grid does
+    // not depend on the block counts, which only the device knows while a pass is in flight
+    const unsigned long long nbat_f = (a.rng[2] - a.rng[0] + SC_NB - 1) / SC_NB, nbat = nbat_f + (a.rng[3] - a.rng[1] + SC_NB - 1) / SC_NB;
+    uint32_t *lastm_s = sm + SC_NB * SC_STRIDE;
     const uint32_t zero5[5] = {0u, 0u, 0u, 0u, 0u};
+    for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x) {
+    const uint32_t strand = bat >= nbat_f;
+    const unsigned long long hi = a.rng[2 + strand];
+    const unsigned long long blk0 = a.rng[strand] + (bat - (strand ? nbat_f : 0ull)) * SC_NB;
+    const uint32_t nb = (uint32_t)min((unsigned long long)SC_NB, hi - blk0);
+    // expand: thread -> (block tid % 32, positions tid / 32, tid / 32 + warps, ...); rows past the range mismatch everywhere
+    {
+        const uint32_t b = (uint32_t)lane;
+        const uint32_t *gsrc = (strand ? a.planes[1] : a.planes[0]) + plane_index(blk0 + (b < nb ? b : 0), 0);   // word w at gsrc[w * BLK_GROUP]
+        const uint32_t inv = b < nb ? ~__ldg(gsrc + BLK_VALID * BLK_GROUP) : ~0u;
+        for (int p = wid; p < VS_GLEN; p += (int)(blockDim.x >> 5)) {
+            const uint32_t h = __ldg(gsrc + p * BLK_GROUP), l = __ldg(gsrc + (VS_GLEN + p) * BLK_GROUP);
+            *reinterpret_cast<uint4 *>(sm + b * SC_STRIDE + 4 * p) =
+                make_uint4((h | l) | inv, (h | ~l) | inv, (~h | l) | inv, (~h | ~l) | inv);     // pattern base A, C, G, T
+        }
+        if (wid == 0) lastm_s[b] = b < nb ? __ldg(gsrc + BLK_LAST * BLK_GROUP) : 0u;
+    }
+    __syncthreads();
+    const uint16_t *pat0 = a.pat + ((size_t)strand * a.pat_guides + a.guide_base) * PAT_STRIDE;
+    const uint32_t *posb = (strand ? a.pos[1] : a.pos[0]) + blk0 * 32;
 
-    // Software pipeline over the guides: the stage-A planes of guide g+1 are loaded (LDS) before guide g is counted,
-    // so the shared-memory latency and the adder tree of consecutive guides overlap inside one warp.
-    // (Tried and measured slower on B200: sorting the guides by their bases at slots 0/1 and keeping those two planes in
-    // registers per group — as a nested loop ptxas 12.9 drops the uniform-register slot offsets, as a flagged reload the
-    // extra uniform instructions cost more than the two shared-memory wavefronts they save; three guides in flight
-    // instead of two: +1 %.)
-    auto load_a = [&](uint32_t g, uint32_t (&m)[PA]) {
-        const uint32_t *po = pat0 + g * PAT_STRIDE;
+    // one guide segment: GW = 2^L guides [seg, seg + GW) x (32 / GW) blocks per warp iteration.  The walk always covers the
+    // SC_NB rows of the batch (rows past the range mismatch everywhere), so its trip count and the block base are
+    // compile-time / warp-uniform and every LDS is [lane register + uniform register + immediate].
+    auto segment = [&](uint32_t seg, auto gw_log2_c) {
+        constexpr uint32_t L = decltype(gw_log2_c)::value, GW = 1u << L, STEP = 32u >> L;
+        const uint32_t sub = (uint32_t)lane >> L;
+        const uint32_t g = seg + ((uint32_t)lane & (GW - 1u));
+        const bool real = g < a.n_guides;                  // padding lanes score the segment's first guide; their hits are dropped
+        const uint16_t *po = pat0 + (size_t)(real ? g : seg) * PAT_STRIDE;
+        const char *smb = reinterpret_cast<const char *>(sm) + sub * (SC_STRIDE * 4u);     // the lane's first block row
+        const char *adr[PA];                               // the lane's stage-A planes in that row
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(po);
+            uint32_t w[12];
 #pragma unroll
-        for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(myb + po[i]);
-    };
-    auto finish = [&](uint32_t g, const uint32_t (&ma)[PA]) {
-        const uint32_t *po = pat0 + g * PAT_STRIDE;
-        uint32_t ca[5];
-        popcount_planes<PA, false>(ma, zero5, ca);
-        uint32_t le = le_k<K>(ca);
-        // warp-uniform early out: if no lane of the warp can still be within K, the remaining slots are never scored.
-        // (A divergent `if (le)` here makes ptxas 12.9 crash on the uniform-register loads of stage B.)
-        if (PB == 0 ? (le != 0) : __any_sync(0xffffffffu, le != 0)) {
-            if constexpr (PB > 0) {
-                // stage B: the remaining slots, from their raw planes, added onto stage A's count
-                uint32_t mb[PB], cb[5];
+            for (int i = 0; i < 3; ++i) { const uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
 #pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    const uint32_t e = po[PA + i];
-                    const char *q = myb + (e & 0xFFFFu);
-                    mb[i] = mismatch_plane(*reinterpret_cast<const uint32_t *>(q), *reinterpret_cast<const uint32_t *>(q + SCORE_THREADS * 4), e >> 16);
+            for (int i = 0; i < PA; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        }
+        // UNR iterations per trip with compile-time offsets; the address registers advance once per trip
+        constexpr uint32_t UNR = (uint32_t)SC_UNROLL < (uint32_t)SC_NB / STEP ? (uint32_t)SC_UNROLL : (uint32_t)SC_NB / STEP;
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < (uint32_t)SC_NB; j0 += STEP * UNR) {
+#pragma unroll
+            for (uint32_t u = 0; u < UNR; ++u) {
+                constexpr uint32_t ROW = SC_STRIDE * 4u;
+                const uint32_t j = j0 + u * STEP;              // first block of the iteration
+                uint32_t m[PA], ca[5];
+#pragma unroll
+                for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(adr[i] + u * STEP * ROW);
+                popcount_planes<PA, false>(m, zero5, ca);
+                uint32_t le = le_k<K>(ca);
+                // warp-uniform early out: if no pair of the iteration can still be within K, the remaining slots are never scored
+                if (PB == 0 ? (le != 0) : __any_sync(0xffffffffu, le != 0)) {
+                    const char *row = smb + j * ROW;
+                    if constexpr (PB > 0) {
+                        uint32_t mb[PB], cb[5];
+#pragma unroll
+                        for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(row + po[PA + i]);
+                        popcount_planes<PB, true>(mb, ca, cb);
+                        le = le_k<K>(cb);
+#pragma unroll
+                        for (int w = 0; w < 5; ++w) ca[w] = cb[w];
+                    }
+                    if (le != 0 && real)
+                        score_hits<K>(row, po, (int)strand, le, ca, lastm_s[j + sub], posb + (size_t)(j + sub) * 32,
+                                      ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
                 }
-                popcount_planes<PB, true>(mb, ca, cb);
-                le = le_k<K>(cb);
-#pragma unroll
-                for (int w = 0; w < 5; ++w) ca[w] = cb[w];
             }
-            if (le != 0)
-                score_hits<K>(gsrc, a.pat_global + (strand * PAT_CHUNK + g) * PAT_STRIDE, (int)strand, le, ca, lastm,
-                              (strand ? a.pos[1] : a.pos[0]) + blk * 32, ((a.guide_base + g) << 8) | (strand << 7),
-                              a.hits, a.n_hits, a.hit_cap);
+#pragma unroll
+            for (int i = 0; i < PA; ++i) adr[i] += STEP * UNR * SC_STRIDE * 4u;
         }
     };
-    const uint32_t n_pat = a.n_pat;
-    if (n_pat == 0) return;
-    uint32_t m0[PA], m1[PA];
-    load_a(0, m0);
-    uint32_t g = 0;
-    for (; g + 1 < n_pat; g += 2) {
-        load_a(g + 1, m1);
-        finish(g, m0);
-        if (g + 2 < n_pat) load_a(g + 2, m0);
-        finish(g + 1, m1);
+    const uint32_t warps = blockDim.x >> 5;
+    for (uint32_t gc = 0; gc < a.n_guides; gc += 32u * warps) {
+        const uint32_t g_w = gc + 32u * (uint32_t)wid;
+        if (g_w >= a.n_guides) break;
+        const uint32_t n = min(32u, a.n_guides - g_w);
+        if (n == 32u) { segment(g_w, std::integral_constant<uint32_t, 5>{}); continue; }
+        // tail of the guide list: pad to a multiple of 4 and split into 16 / 8 / 4 guides x 2 / 4 / 8 blocks per iteration
+        const uint32_t np = (n + 3u) & ~3u;
+        uint32_t seg = g_w;
+        if (np & 16u) { segment(seg, std::integral_constant<uint32_t, 4>{}); seg += 16u; }
+        if (np & 8u) { segment(seg, std::integral_constant<uint32_t, 3>{}); seg += 8u; }
+        if (np & 4u) { segment(seg, std::integral_constant<uint32_t, 2>{}); }
     }
-    if (g < n_pat) finish(g, m0);
+    __syncthreads();                                       // the next batch overwrites the planes
+    }
+}
+
+// k_extract_mark: closes the block range of one pipeline chunk.  cnt[2], cnt[3] are the running block claims of the two
+// strands; the chunk's range {lo, hi} goes to rng[0..3], the claims are rounded up to a whole layout group (so that the
+// next chunk — and every batch of k_score — starts on a 4 KB boundary of the store), the padding blocks get an empty valid
+// mask, the next chunk's lo is written to rng[4..5] and the whole-store range {0, 0, end, end} to all[0..3].
+__global__ void __launch_bounds__(32)
+k_extract_mark(unsigned long long *cnt, unsigned long long *rng, unsigned long long *all, uint32_t *planes_f, uint32_t *planes_r, uint64_t cap)
+{
+    const int s = threadIdx.x;                             // one thread per strand (at most 31 padding blocks each)
+    if (s > 1) return;
+    const unsigned long long hi = cnt[2 + s], end = (hi + BLK_GROUP - 1) / BLK_GROUP * BLK_GROUP;
+    uint32_t *pl = s ? planes_r : planes_f;
+    for (unsigned long long b = hi; b < end && b < cap; ++b) { pl[plane_index(b, BLK_VALID)] = 0u; pl[plane_index(b, BLK_LAST)] = 0u; }
+    rng[2 + s] = hi;
+    rng[4 + s] = end;
+    all[s] = 0ull; all[2 + s] = end;
+    cnt[2 + s] = end;
+}
+
+// ---- hit resolution on the device ---------------------------------------------------------------------------------------
+// k_contig_starts_*: the start positions of the contigs that overlap the shard, from the shard's contig-end plane
+// (em, one bit per base, set on the last base of a contig): starts[0] = first_start (given by the host: the contig that
+// holds the shard's first base), starts[r + 1] = position after the r-th end bit.  Three steps: bits per tile of
+// CS_TILE words, exclusive scan of the tile counts (one CTA), scatter.
+constexpr int CS_TILE = 2048;              // words per CTA of 256 threads (8 per thread)
+__global__ void __launch_bounds__(256)
+k_contig_starts_count(const uint32_t *__restrict__ em, uint64_t n_words, uint32_t *__restrict__ tile_cnt)
+{
+    __shared__ uint32_t s_c[256];
+    const uint64_t w0 = (uint64_t)blockIdx.x * CS_TILE + (uint64_t)threadIdx.x * 8;
+    uint32_t c = 0;
+    for (int i = 0; i < 8; ++i) if (w0 + i < n_words) c += __popc(em[w0 + i]);
+    s_c[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {                                // the bit count of a tile is small work: 8 adds per lane, 32 by lane 0
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += s_c[threadIdx.x * 8 + i];
+        s_c[threadIdx.x * 8] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 32; ++i) t += s_c[i * 8]; tile_cnt[blockIdx.x] = t; }
+}
+// exclusive scan of n tile counts in place (single CTA of 1024 threads), total to *total
+__global__ void __launch_bounds__(1024)
+k_contig_starts_scan(uint32_t *tile_cnt, uint32_t n, uint32_t *total)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (n + 1023) / 1024, a = min(n, threadIdx.x * per), b = min(n, a + per);
+    uint32_t sum = 0;
+    for (uint32_t i = a; i < b; ++i) sum += tile_cnt[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; } *total = run; }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t i = a; i < b; ++i) { const uint32_t v = tile_cnt[i]; tile_cnt[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256)
+k_contig_starts_scatter(const uint32_t *__restrict__ em, uint64_t n_words, const uint32_t *__restrict__ tile_off, uint64_t first_base,
+                        uint32_t first_start, uint32_t *__restrict__ starts)
+{
+    __shared__ uint32_t s_c[256 + 32];
+    const uint64_t w0 = (uint64_t)blockIdx.x * CS_TILE + (uint64_t)threadIdx.x * 8;
+    uint32_t c = 0;
+    for (int i = 0; i < 8; ++i) if (w0 + i < n_words) c += __popc(em[w0 + i]);
+    s_c[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) { uint32_t t = 0; for (int i = 0; i < 8; ++i) t += s_c[threadIdx.x * 8 + i]; s_c[256 + threadIdx.x] = t; }
+    __syncthreads();
+    // end bits of the tile before this thread's words: whole groups of 8 threads, then the threads of its own group
+    uint32_t r = tile_off[blockIdx.x];
+    for (uint32_t i = 0; i < threadIdx.x / 8; ++i) r += s_c[256 + i];
+    for (uint32_t i = threadIdx.x & ~7u; i < threadIdx.x; ++i) r += s_c[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) starts[0] = first_start;
+    for (int i = 0; i < 8; ++i) {
+        if (w0 + i >= n_words) break;
+        uint32_t m = em[w0 + i];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            starts[++r] = (uint32_t)(first_base + (w0 + i) * 32 + b + 1);
+        }
+    }
+}
+
+// k_resolve_hits: hit {global position, info} -> sort key + payload.  The contig is the last one whose start is <= the
+// position (binary search over the shard's n_starts contig starts; contig id = first_contig + index);
+//   key = (guide - guide_lo) << 49 | strand << 48 | (contig & 0xFFFF) << 32 | pos in contig     (the std::map order of
+//         bidir_mapping.cpp:13,154 inside the pass order of :285-295)
+//   val = contig << 32 | info
+__global__ void __launch_bounds__(256)
+k_resolve_hits(const vs_hit *__restrict__ hits, uint64_t n, const uint32_t *__restrict__ starts, uint32_t n_starts, uint32_t first_contig,
+               uint32_t guide_lo, unsigned long long *__restrict__ keys, unsigned long long *__restrict__ vals)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vs_hit h = hits[i];
+    uint32_t lo = 0, hi = n_starts;                        // invariant: starts[lo] <= pos < starts[hi] (starts[n_starts] = +inf)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (starts[mid] <= h.pos) lo = mid; else hi = mid;
+    }
+    const uint32_t contig = first_contig + lo, pos = h.pos - starts[lo];
+    const unsigned long long guide = (h.info >> 8) - guide_lo, strand = (h.info >> 7) & 1u;
+    keys[i] = (guide << 49) | (strand << 48) | ((unsigned long long)(contig & 0xFFFFu) << 32) | pos;
+    vals[i] = ((unsigned long long)contig << 32) | h.info;
+}
+// sorted {key, val} pairs -> vs_loc_hit records
+__global__ void __launch_bounds__(256)
+k_pack_loc_hits(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vals, uint64_t n, vs_loc_hit *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vs_loc_hit r;
+    r.key = keys[i]; r.contig = (uint32_t)(vals[i] >> 32); r.info = (uint32_t)vals[i];
+    out[i] = r;
 }
 
 // ------------------------------------------------------------------------------------------------

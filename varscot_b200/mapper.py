@@ -19,6 +19,7 @@ MASKS_DT = np.dtype([("iv", "<u4"), ("lw", "<u4")])
 SPARSE_DT = np.dtype([("word", "<u4"), ("iv", "<u4"), ("lw", "<u4")])
 RUN_DT = np.dtype([("word", "<u4"), ("count", "<u4"), ("value", "<u4")])
 HIT_DT = np.dtype([("pos", "<u4"), ("info", "<u4")])
+LOC_DT = np.dtype([("key", "<u8"), ("contig", "<u4"), ("info", "<u4")])
 REC_DT = np.dtype([("guide", "<u4"), ("contig", "<u4"), ("pos", "<u4"), ("flag", "<u2"), ("mm", "u1"), ("pad", "u1")])
 
 MD_SEQAN, MD_SAMTOOLS = 0, 1
@@ -188,7 +189,12 @@ class PackedText:
         if v.em_code and v.em_dense:
             source = (_copy_array(v.em_code, nw + 1, np.dtype("u1")), _copy_array(v.em_dense, (nw + 4096) // 4096, np.dtype("u1")),
                       _copy_array(v.nm_runs, int(v.n_nm_runs), RUN_DT), _copy_array(v.em_runs, int(v.n_em_runs), RUN_DT))
-        return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), _copy_array(v.masks, nw, MASKS_DT),
+        if v.masks:
+            masks = _copy_array(v.masks, nw, MASKS_DT)
+        else:                                   # a cache written by bidir_index carries only the mask source
+            masks = np.zeros(nw, dtype=MASKS_DT)
+            check(_lib.lib().vs_text_masks(C.byref(v), masks.ctypes.data))
+        return PackedText(_copy_array(v.bases, nw + 1, BASES_DT), masks,
                           _copy_array(v.contig_off, int(v.n_contigs) + 1, np.dtype("<u8")), int(v.n_bases), names,
                           _copy_array(v.sparse, int(v.n_sparse), SPARSE_DT) if v.sparse else None, source)
 
@@ -304,6 +310,47 @@ class ScanContext:
         self.last_stats = st
         return hits, st
 
+    def set_option(self, option: int, value: int):
+        """vs_ctx_set_option: _lib.VS_OPT_KEEP_INDEX (keep the candidate index resident between scans), VS_OPT_HIT_CAPACITY."""
+        check(self._L.vs_ctx_set_option(self._ctx, option, value), self._ctx)
+
+    def drop_index(self):
+        check(self._L.vs_index_drop(self._ctx), self._ctx)
+
+    def scan_resolved(self, guides: np.ndarray, k: int, pam=None, text: PackedText | None = None, first_word: int = 0, n_words: int | None = None,
+                      cap: int = 1 << 20, out: np.ndarray | None = None, sink=None):
+        """vs_scan_resolved: hits resolved to (contig, pos) and sorted into emission order ON THE DEVICE.  text=None scans the
+        resident shard, otherwise the shard is uploaded (overlapped) first.  sink(hits, guide_lo, guide_hi), if given, receives
+        every guide super-chunk as a LOC_DT array (a view valid during the call only).  Returns (hits or None, ScanStats)."""
+        g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
+        pc = pam if isinstance(pam, int) else pam_code(pam)
+        n, st = C.c_uint64(), ScanStats()
+        v = text.view() if text is not None else None
+        if text is not None and n_words is None:
+            n_words = text.n_words - first_word
+        vref = C.byref(v) if v is not None else None
+        if sink is not None:
+            def _cb(_user, ptr, cnt, lo, hi):
+                arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cnt * LOC_DT.itemsize,)).view(LOC_DT)
+                return int(sink(arr, lo, hi) or 0)
+            cb = _lib.HIT_SINK(_cb)
+            rc = self._L.vs_scan_resolved(self._ctx, vref, first_word, n_words or 0, g.ctypes.data, g.shape[0], k, pc, None, 0, C.byref(n), cb, None, C.byref(st))
+            check(rc, self._ctx)
+            self.last_stats = st
+            return None, st
+        hits = out if out is not None else np.zeros(cap, dtype=LOC_DT)
+        null_sink = C.cast(None, _lib.HIT_SINK)
+        rc = self._L.vs_scan_resolved(self._ctx, vref, first_word, n_words or 0, g.ctypes.data, g.shape[0], k, pc, hits.ctypes.data, len(hits),
+                                      C.byref(n), null_sink, None, C.byref(st))
+        if rc == _lib.VS_ERR_OVERFLOW and out is None:
+            # the caller's buffer was a guess: scan the (now resident) index again with room for every hit
+            hits = np.zeros(n.value, dtype=LOC_DT)
+            rc = self._L.vs_scan_resolved(self._ctx, None, 0, 0, g.ctypes.data, g.shape[0], k, pc, hits.ctypes.data, len(hits),
+                                          C.byref(n), null_sink, None, C.byref(st))
+        check(rc, self._ctx)
+        self.last_stats = st
+        return hits[: n.value], st
+
     def measure_int_peaks(self):
         a, b = C.c_double(), C.c_double()
         check(self._L.vs_measure_int_peaks(self._ctx, C.byref(a), C.byref(b)), self._ctx)
@@ -331,6 +378,23 @@ def map_packed(text: PackedText, guides: np.ndarray, k: int, pam=None, devices=N
     return hits, st
 
 
+def map_records(text: PackedText, guides: np.ndarray, k: int, pam=None, devices=None, threads: int = 1):
+    """vs_map_records: what the bidir_mapping executable runs — shard over devices, scan with device-side hit resolution,
+    merge.  Returns (records in emission order, key16_collisions, stats)."""
+    L = _lib.lib()
+    g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, GLEN)
+    dev = np.asarray(devices if devices else [0], dtype=np.int32)
+    rp, n, coll, st = C.c_void_p(), C.c_uint64(), C.c_uint64(), ScanStats()
+    v = text.view()
+    check(L.vs_map_records(C.byref(v), g.ctypes.data, g.shape[0], k, pam_code(pam) if not isinstance(pam, int) else pam,
+                           dev.ctypes.data, len(dev), threads, C.byref(rp), C.byref(n), C.byref(coll), C.byref(st)))
+    try:
+        rec = _copy_array(rp, n.value, REC_DT) if n.value else np.zeros(0, REC_DT)
+    finally:
+        L.vs_free(rp)
+    return rec, int(coll.value), st
+
+
 def shard_bounds(n_words: int, n_shards: int) -> np.ndarray:
     """vs_shard_bounds: word ranges owned by each of n_shards ranks / devices."""
     out = np.zeros(n_shards + 1, dtype=np.uint64)
@@ -346,6 +410,19 @@ def resolve_hits(hits: np.ndarray, offsets: np.ndarray, threads: int = 1):
     rec = np.zeros(len(h), dtype=REC_DT)
     coll = C.c_uint64()
     check(L.vs_resolve_hits_mt(h.ctypes.data, len(h), off.ctypes.data, len(off) - 1, rec.ctypes.data, C.byref(coll), threads))
+    return rec, int(coll.value)
+
+
+def merge_resolved(lists, threads: int = 1):
+    """vs_merge_resolved: the device-sorted hit lists of the shards -> records in emission order with FLAGs.
+    Returns (records, key16_collisions)."""
+    L = _lib.lib()
+    arrs = [np.ascontiguousarray(x, dtype=LOC_DT) for x in lists]
+    ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    counts = np.array([len(a) for a in arrs] or [0], dtype=np.uint64)
+    rec = np.zeros(int(sum(len(a) for a in arrs)), dtype=REC_DT)
+    coll = C.c_uint64()
+    check(L.vs_merge_resolved(ptrs, counts.ctypes.data, len(arrs), rec.ctypes.data, C.byref(coll), threads))
     return rec, int(coll.value)
 
 
