@@ -1,21 +1,32 @@
 #!/usr/bin/env python
 """bench.py — guide·Gbp/s of the off-target scan (BASELINE.json metric) on 1..8 B200.
 
-A step = one full scan of all guides (both strands, <= k mismatches, PAM on the genome) over this
-rank's synthetic text: reference genome + variant haplotype segments ("SNP genome").
-  value : whole-job guide·Gbp/s with the packed text resident in HBM; timed with CUDA events on the
-          library's stream from the first kernel to the last hit in host memory, max over ranks
-  e2e   : same metric through the C-ABI call with HOST buffers: H2D of the packed text + guides, scan,
-          D2H of the hits, every step
-  roofline : the scoring kernel against the MEASURED alu-pipe LOP3 rate, in the yardstick of SURVEY.md 8d
-             (4.0 LOP3 per guide·bp for a dense bit-sliced scan) and in executed instructions
-  cpu_baseline : the CPU oracle (a port: linear XOR/popcount scan, not SeqAn's FM index) on a bounded sample
-`--impl reference` times that CPU oracle alone (the reference binary needs SeqAn, absent here).
+A step = one full scan of all guides (both strands, <= k mismatches, PAM on the genome) over the synthetic text of the
+config: reference genome + variant haplotype segments ("SNP genome").  With N > 1 ranks ONE text is cut into N word
+ranges by vs_shard_bounds (the partition north_star names; `--scaling weak` keeps round 1's one-text-per-rank mode); there
+is no collective on the data path, the ranks' hit lists meet in host shared memory and rank 0 merges them.
+  value      : whole-job guide·Gbp/s with the packed text AND the candidate index resident in HBM (the analogue of the
+               reference's prebuilt FM index); timed with CUDA events on the library's stream from the first kernel to the
+               last resolved + sorted hit in host memory, max over ranks
+  value_cold : the same with the index dropped before every step (extraction of the PAM-valid windows included)
+  e2e        : same metric through the C-ABI call with HOST buffers, wall clock: H2D of the rank's packed shard + guides,
+               extraction, scoring, hit resolution + sort on the device, D2H, hand-over to rank 0 and the merge into
+               records in emission order (vs_merge_resolved) — every step
+  e2e_resident_genome : the per-sample call of a batch (parallel.py:86-90): the reference genome stays resident, only the
+               variant segments and the guides travel
+  roofline   : the scoring kernel against the MEASURED alu-pipe LOP3 rate: `frac` = executed LOP3 / peak; the dense-scan
+               yardstick of SURVEY.md 8d (4.0 LOP3 per guide·bp) is reported as `frac_yardstick`
+  cpu_baseline / parity : the CPU oracle (a port: linear XOR/popcount scan, not SeqAn's FM index) on a bounded sample, and
+               the hit-set diff of the merged GPU records against it
+  target_cfg4 : config 4 (1000 guides, k <= 6, +AG) on the same text and ranks — north_star's target
+`--impl reference` times the CPU oracle alone on the same text and sample (the reference binary needs SeqAn, absent here).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import datetime
+import importlib.util
 import json
 import os
 import subprocess
@@ -49,30 +60,35 @@ def score_ops(k):
     """(LOP3, LDS) k_score executes per (32-candidate block, guide) in stage A, and the extra of stage B."""
     pa = 23 if k >= 8 else 7 + 2 * k
     a = (csa_ops(pa) + 2, pa)
-    # stage B scores its slots from raw planes: 2 LDS + 2 LOP3 per slot, then the adders onto stage A's count
-    b = (csa_ops(23 - pa, True) + 2 + 2 * (23 - pa), 2 * (23 - pa)) if pa < 23 else (0, 0)
+    b = (csa_ops(23 - pa, True) + 2, 23 - pa) if pa < 23 else (0, 0)
     return a, b
 
+
 CONFIGS = {
-    # id: (description, genome bases, variants, guides, k, extra PAM)
-    1: ("cfg1: 10 guides vs 50 Mbp + 10k SNVs, <=4 mm", 50_000_000, 10_000, 10, 4, None),
-    2: ("cfg2: 100 guides vs 3.1 Gbp, reference only, <=4 mm", 3_100_000_000, 0, 100, 4, None),
-    3: ("cfg3: 100 guides vs 3.1 Gbp + 5M variants, <=6 mm", 3_100_000_000, 5_000_000, 100, 6, None),
-    4: ("cfg4: 1000 guides vs 3.1 Gbp + 5M variants, <=6 mm, NGG+NAG", 3_100_000_000, 5_000_000, 1000, 6, "AG"),
-    5: ("cfg5: 10000 guides vs 3.1 Gbp + 5M variants, <=8 mm", 3_100_000_000, 5_000_000, 10000, 8, None),
+    # id: (description, genome bases, variants, guides, k, extra PAM, guide seed)
+    1: ("cfg1: 10 guides vs 50 Mbp + 10k SNVs, <=4 mm", 50_000_000, 10_000, 10, 4, None, 3),
+    2: ("cfg2: 100 guides vs 3.1 Gbp, reference only, <=4 mm", 3_100_000_000, 0, 100, 4, None, 13),
+    3: ("cfg3: 100 guides vs 3.1 Gbp + 5M variants, <=6 mm", 3_100_000_000, 5_000_000, 100, 6, None, 13),
+    4: ("cfg4: 1000 guides vs 3.1 Gbp + 5M variants, <=6 mm, NGG+NAG", 3_100_000_000, 5_000_000, 1000, 6, "AG", 14),
+    5: ("cfg5: 10000 guides vs 3.1 Gbp + 5M variants, <=8 mm", 3_100_000_000, 5_000_000, 10000, 8, None, 15),
 }
 
 
-def build_text(cfg, rank, scale=1.0):
-    from varscot_b200 import synth
-    _, gbases, nvar, _, _, _ = cfg
-    gbases = int(gbases * scale)
-    nvar = int(nvar * scale)
-    g = synth.synth_genome(11 + 1000 * rank, gbases, 24, 0.05)
-    if nvar > 0:
-        s = synth.synth_variant_segments(g, 12 + 1000 * rank, nvar)
-        return synth.concat_texts(g, s)
-    return g
+def load_synth_core():
+    """varscot_b200/synth_core.py by path: numpy only, does not load the CUDA library (the reference arm uses it)."""
+    spec = importlib.util.spec_from_file_location("vs_synth_core", os.path.join(ROOT, "varscot_b200", "synth_core.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["vs_synth_core"] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def config_dict(cfg, n_bases, n_contigs, scaling, scale):
+    """The `config` object: identical in both arms."""
+    desc, _, _, ng, k, pam, _ = cfg
+    return {"workload": desc + (f" (scale {scale})" if scale != 1.0 else ""), "guides": ng, "k": k, "extra_pam": pam,
+            "text_bases": int(n_bases), "contigs": int(n_contigs), "scaling": scaling,
+            "l2": "inputs larger than L2 (126 MB): 2-bit text 0.25 B/base, candidate index 10 B per PAM-valid window"}
 
 
 class ClockSampler:
@@ -116,7 +132,6 @@ class ClockSampler:
         if not rows:
             rows, window = self.rows, "whole_run"
         if not rows:
-            # the looping sampler produced nothing (pipe buffering / slow start): take one synchronous sample now
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
                                      capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
@@ -132,8 +147,7 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa(local):
-    """Pin this process to the CPUs next to its GPU (NVML affinity) BEFORE allocating page-locked buffers, so that the
-    H2D source memory is first-touched on the GPU's NUMA node; matters when 8 ranks upload at once."""
+    """Pin this process to the CPUs next to its GPU (NVML affinity) BEFORE allocating page-locked buffers."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -150,7 +164,19 @@ def bind_to_gpu_numa(local):
         return 0
 
 
-def dist_setup(n_gpus):
+def host_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu_model": model, "cpus": len(os.sched_getaffinity(0))}
+
+
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,30 +196,82 @@ def barrier(world, local):
         torch.cuda.synchronize()
 
 
-def all_max(x, world, local):
+def all_reduce(x, world, local, op):
     if world == 1:
         return x
     import torch
     import torch.distributed as dist
     t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
 
 
-def all_sum(x, world, local):
-    if world == 1:
-        return x
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+class HostExchange:
+    """Hand-over of the ranks' sorted hit lists to rank 0 through POSIX shared memory ("merged on the host", north_star):
+    every rank downloads its hits straight into its page-locked segment, publishes the count with a sequence number, rank 0
+    spins on the sequence numbers, merges, and publishes `done`."""
+
+    def __init__(self, V, world, rank, cap, pin=True, tag=None):
+        from varscot_b200 import _lib
+        self.V, self.world, self.rank, self.cap, self.pin = V, world, rank, cap, pin
+        self.L = _lib.lib()
+        tag = tag or (os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", "x"))
+        base = f"/dev/shm/varscot_bench_{tag}"
+        self.paths = [f"{base}_{r}.bin" for r in range(world)]
+        self.ctl_path = f"{base}_ctl.bin"
+        if rank == 0:
+            np.zeros(2 * world + 2, dtype=np.int64).tofile(self.ctl_path)
+        with open(self.paths[rank], "wb") as f:
+            f.truncate(cap * 16)
+        self.mine = np.memmap(self.paths[rank], dtype=V.LOC_DT, mode="r+", shape=(cap,))
+        self.mine[:] = 0                                         # touch the pages before page-locking them
+        if pin and self.L.vs_host_register(self.mine.ctypes.data, cap * 16) != 0:
+            raise RuntimeError("vs_host_register failed")
+        self.ctl = None
+        self.others = None
+
+    def attach(self):
+        """after a barrier: every segment exists"""
+        self.ctl = np.memmap(self.ctl_path, dtype=np.int64, mode="r+", shape=(2 * self.world + 2,))
+        if self.rank == 0:
+            self.others = [self.mine if r == 0 else np.memmap(self.paths[r], dtype=self.V.LOC_DT, mode="r", shape=(self.cap,)) for r in range(self.world)]
+
+    def publish(self, step, n):
+        self.ctl[2 * self.rank + 1] = n
+        self.ctl[2 * self.rank] = step                           # x86 keeps the store order; rank 0 reads the count after the sequence number
+
+    def collect(self, step):
+        """rank 0: wait for every rank's list of this step"""
+        lists = []
+        for r in range(self.world):
+            while self.ctl[2 * r] < step:
+                pass
+            lists.append(self.others[r][: int(self.ctl[2 * r + 1])])
+        return lists
+
+    def done(self, step):
+        self.ctl[2 * self.world] = step
+
+    def wait_done(self, step):
+        while self.ctl[2 * self.world] < step:
+            pass
+
+    def close(self):
+        try:
+            if self.pin:
+                self.L.vs_host_unregister(self.mine.ctypes.data)
+        except Exception:
+            pass
+        for p in ([self.paths[self.rank]] + ([self.ctl_path] if self.rank == 0 else [])):
+            try:
+                os.unlink(p)
+            except OSError:
+                pass
 
 
-def cpu_sample(text, guides, k, pam, target_s=12.0, max_bases=1 << 30):
+def cpu_sample(text, guides, k, pam, synth, target_s=12.0, max_bases=1 << 30):
     """Time the oracle (all host threads) on a bounded, word-aligned prefix of the text; return its records too."""
     from oracle import oracle as O
-    from varscot_b200 import synth
     probe = min(text.n_bases // 32 * 32, 16 << 20)
     codes = synth.unpack_codes(text, 0, probe)
     off = synth.slice_offsets(text, 0, probe)
@@ -209,24 +287,34 @@ def cpu_sample(text, guides, k, pam, target_s=12.0, max_bases=1 << 30):
     return n, dt, rec, off, O.num_procs()
 
 
+def parity_on_sample(rec_gpu, offsets, rec_cpu, off_cpu, n):
+    """Hit-set diff (guide, strand, global position, NM) on the windows starting before n - 23 (the slice end is an artificial contig end)."""
+    gpos = offsets[rec_gpu["contig"]].astype(np.int64) + rec_gpu["pos"].astype(np.int64)
+    sel = gpos < n - 23
+    gk = set(zip(rec_gpu["guide"][sel].tolist(), ((rec_gpu["flag"][sel] & 16) >> 4).tolist(), gpos[sel].tolist(), rec_gpu["mm"][sel].tolist()))
+    opos = off_cpu[rec_cpu.contig].astype(np.int64) + rec_cpu.pos.astype(np.int64)
+    osel = opos < n - 23
+    ok = set(zip(rec_cpu.guide[osel].tolist(), ((rec_cpu.flag[osel] & 16) >> 4).tolist(), opos[osel].tolist(), rec_cpu.mm[osel].tolist()))
+    return {"sample_bases": int(n), "hits_cpu": len(ok), "hits_gpu": len(gk), "diff": len(ok ^ gk)}
+
+
 def run_reference(args, cfg, world, rank):
-    """--impl reference: the CPU oracle port on the host cores (SeqAn's bidir_mapping cannot be built here)."""
+    """--impl reference: the CPU oracle port on the host cores (SeqAn's bidir_mapping cannot be built here).  Same text
+    (seeds, scale) and the same kind of sample as the GPU arm's cpu_baseline; the product library is never loaded."""
     if rank != 0:
         return
     from oracle import oracle as O
-    from varscot_b200 import synth
-    desc, gbases, nvar, ng, k, pam = cfg
-    guides = synth.synth_guides(13, ng)
-    # bounded sample with the composition of the full workload; sized so that the whole run takes a few minutes
+    core = load_synth_core()
+    desc, gbases, nvar, ng, k, pam, gseed = cfg
+    guides = core.synth_guides(gseed, ng)
+    text = core.build_workload(gbases, nvar, args.scale)
     budget_s = float(os.environ.get("VARSCOT_BENCH_BUDGET_S", "150")) / max(1, args.steps + args.warmup)
-    scale = min(1.0, (512 << 20) / gbases)
-    text = build_text(cfg, 0, scale)
-    n = text.n_bases // 32 * 32
-    codes = synth.unpack_codes(text, 0, n)
-    off = synth.slice_offsets(text, 0, n)
-    t = time.perf_counter(); O.scan_count(codes[: 8 << 20], synth.slice_offsets(text, 0, 8 << 20), guides, k, pam); dt = max(time.perf_counter() - t, 1e-4)
-    want = int(min(n, max(8 << 20, (8 << 20) * budget_s / dt))) // 32 * 32
-    codes, off = codes[:want], synth.slice_offsets(text, 0, want)
+    probe = min(text.n_bases // 32 * 32, 8 << 20)
+    t = time.perf_counter()
+    O.scan_count(core.unpack_codes(text, 0, probe), core.slice_offsets(text, 0, probe), guides, k, pam)
+    dt = max(time.perf_counter() - t, 1e-4)
+    want = int(min(text.n_bases, 1 << 30, max(probe, probe * budget_s / dt))) // 32 * 32
+    codes, off = core.unpack_codes(text, 0, want), core.slice_offsets(text, 0, want)
     for _ in range(args.warmup):
         O.scan_count(codes, off, guides, k, pam)
     t0 = time.perf_counter()
@@ -235,15 +323,109 @@ def run_reference(args, cfg, world, rank):
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     val = ng * want / dt / 1e9
     cores = O.num_procs()
-    sample = f"first {want} bases of a {scale:.4f}-scale copy of the workload, all {ng} guides, per step"
+    sample = f"first {want} bases of the same text (seeds 11/12, scale {args.scale}), all {ng} guides, per step"
+    scaling = "strong" if (world > 1 and args.scaling != "weak") else ("weak" if world > 1 else "single")
     print(json.dumps({
         "impl": "reference", "metric": "guide_Gbp_per_s", "value": val, "unit": "guide*Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64 xor+popcount", "data": "synthetic", "config": {"workload": desc, "k": k, "guides": ng, "extra_pam": pam},
-        "cpu_baseline": {"value": val, "unit": "guide*Gbp/s", "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if scaling != "weak" else "weak", "vs_baseline": None,
+        "dtype": "u64 xor+popcount", "data": "synthetic", "config": config_dict(cfg, text.n_bases, len(text.offsets) - 1, scaling, args.scale),
+        "cpu_baseline": {"value": val, "unit": "guide*Gbp/s", "cores": cores, "kind": "port", "sample": sample, **host_info()},
         "e2e": {"value": val, "unit": "guide*Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle port (linear 2-bit XOR/popcount scan, OpenMP); the reference's SeqAn FM-index binary cannot be built: SeqAn 2.4.0rc2 is not vendored",
+        "note": "CPU oracle port (linear 2-bit XOR/popcount scan, OpenMP, %d threads); the reference's SeqAn FM-index binary cannot be built: "
+                "SeqAn 2.4.0rc2 is not vendored" % cores,
     }))
+
+
+class Workload:
+    """One config on this rank: pinned text, shard, context(s), hit buffers."""
+
+    def __init__(self, V, text, shard_first, shard_words, local):
+        self.V, self.text, self.first, self.words, self.local = V, text, shard_first, shard_words, local
+        self.ctx = V.ScanContext(local)
+
+    def close(self):
+        self.ctx.close()
+
+
+def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, local, hits_buf, exchange, n_total_bases, ng, host_threads,
+            do_e2e=True, genome_words=None):
+    """value / value_cold / e2e (/ e2e_resident_genome) of one config on the given shard.  Returns a dict (rank 0: complete)."""
+    from varscot_b200 import _lib
+    res = {}
+    units = float(ng) * n_total_bases                     # guide·bp per step over all ranks (strong: ONE text)
+    ctx.upload(text, first, words)
+    ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
+    # ---- index resident -------------------------------------------------------------------------
+    for _ in range(max(1, warmup)):
+        hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+    barrier(world, local)
+    dev = score = resolve = 0.0
+    launches = 0
+    for _ in range(steps):
+        hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+        assert st.index_reused == 1
+        dev += st.total_ms; score += st.score_ms; resolve += st.resolve_ms; launches += st.launches
+    barrier(world, local)
+    ms = all_reduce(dev / steps, world, local, "MAX")
+    res["warm"] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "resolve_ms": resolve / steps, "launches": launches,
+                   "score_launches": int(st.score_launches), "blocks": int(st.n_blocks_fwd + st.n_blocks_rev),
+                   "cands": int(st.n_cand_fwd + st.n_cand_rev), "hits": int(all_reduce(float(len(hits)), world, local, "SUM"))}
+    # ---- cold: the index is extracted again every step ------------------------------------------------
+    ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 0)
+    for _ in range(2):
+        ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+    barrier(world, local)
+    dev = score = extract = 0.0
+    for _ in range(steps):
+        hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+        dev += st.total_ms; score += st.score_ms; extract += st.extract_ms; launches += st.launches
+    barrier(world, local)
+    ms = all_reduce(dev / steps, world, local, "MAX")
+    res["cold"] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "extract_ms": extract / steps, "chunks": int(st.n_chunks),
+                   "score_launches": int(st.score_launches), "redo": int(st.redo_chunks)}
+    res["launches"] = launches
+    if not do_e2e:
+        return res, None
+
+    # ---- end to end: host buffers in, merged records out, every step --------------------------------------
+    def e2e_loop(step_fn, n_steps, seq0):
+        rec = coll = None
+        for i in range(2):
+            rec, coll = step_fn(seq0 + i + 1)
+        barrier(world, local)
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            rec, coll = step_fn(seq0 + 3 + i)
+        barrier(world, local)
+        return (time.perf_counter() - t0) * 1e3 / n_steps, rec, coll
+
+    stats = {}
+
+    def full_step(seq):
+        h, st2 = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=first, n_words=words, out=hits_buf)
+        stats["st"] = st2
+        if exchange is None:
+            return V.merge_resolved([h], threads=host_threads)
+        exchange.publish(seq, len(h))
+        out = (None, None)
+        if exchange.rank == 0:
+            out = V.merge_resolved(exchange.collect(seq), threads=host_threads)
+            exchange.done(seq)
+        else:
+            exchange.wait_done(seq)
+        return out
+
+    e_ms, rec, coll = e2e_loop(full_step, steps, 0)
+    e_ms = all_reduce(e_ms, world, local, "MAX")
+    st2 = stats["st"]
+    res["e2e"] = {"value": units / (e_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": e_ms,
+                  "h2d_bytes_per_step": int(all_reduce(float(st2.h2d_bytes), world, local, "SUM")),
+                  "d2h_bytes_per_step": int(all_reduce(float(st2.d2h_bytes), world, local, "SUM")),
+                  "rank0_device_ms": float(st2.total_ms), "rank0_upload_ms": float(st2.upload_ms),
+                  "note": "vs_scan_resolved from pinned host buffers (H2D chunked, overlapped with extraction + scoring), hits resolved + sorted on the "
+                          "device, D2H into shared memory, rank 0 merges all ranks' lists into records (vs_merge_resolved, %d threads); wall clock, max over ranks" % host_threads}
+    ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
+    return res, (rec, coll)
 
 
 def main():
@@ -255,10 +437,12 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the text (quick runs only; invalid as a bench number)")
     ap.add_argument("--guides", type=int, default=0, help="override the number of guides")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the contract): one text of the configured size per rank; strong: ONE text sharded over the ranks by vs_shard_bounds")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): ONE text sharded over the ranks by vs_shard_bounds; weak: one text of the configured size per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-target", action="store_true", help="skip the config-4 target block")
+    ap.add_argument("--no-resident-genome", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -266,168 +450,213 @@ def main():
     if args.guides:
         cfg[3] = args.guides
     cfg = tuple(cfg)
-    world, rank, local = dist_setup(args.gpus)
+    world, rank, local = dist_setup()
     all_cpus = os.sched_getaffinity(0)
-    numa_cpus = bind_to_gpu_numa(local) if args.impl == "ours" else 0
     if args.impl == "reference":
         run_reference(args, cfg, world, rank)
         return
+    numa_cpus = bind_to_gpu_numa(local)
 
     import varscot_b200 as V
-    from varscot_b200 import synth
-    desc, gbases, nvar, ng, k, pam = cfg
-    guides = synth.synth_guides(13, ng)
-    strong = args.scaling == "strong" and world > 1
+    from varscot_b200 import _lib, synth
+    desc, gbases, nvar, ng, k, pam, gseed = cfg
+    guides = synth.synth_guides(gseed, ng)
+    strong = args.scaling == "strong" or world == 1
     t_gen = time.perf_counter()
-    text = build_text(cfg, 0 if strong else rank, args.scale)
+    core_text = synth.core.build_workload(gbases, nvar, args.scale, 11 + (0 if strong else 1000 * rank), 12 + (0 if strong else 1000 * rank))
+    text = synth.from_planes(core_text)
     t_gen = time.perf_counter() - t_gen
-    B = text.n_bases
-    nw = text.n_words
-    # strong scaling: every rank holds the same text and owns one shard of its window starts (no collective anywhere)
-    shard_first, shard_words = 0, nw
-    if strong:
+    genome_words = int(core_text.offsets[24] // 32) if nvar else text.n_words
+    B, nw = text.n_bases, text.n_words
+    first, words = 0, nw
+    if strong and world > 1:
         sb = V.shard_bounds(nw, world)
-        shard_first, shard_words = int(sb[rank]), int(sb[rank + 1] - sb[rank])
-    text.pin()                                  # page-locked host buffers: what a caller of the C ABI would hand in
+        first, words = int(sb[rank]), int(sb[rank + 1] - sb[rank])
+    text.pin()                                  # page-locked host buffers: what a caller of the C ABI hands in
     ctx = V.ScanContext(local)
     peak_lop3 = peak_lds = None
     if rank == 0:
         peak_lop3, peak_lds = ctx.measure_int_peaks()
-
-    # ---- resident-text scan ----------------------------------------------------------------------
-    ctx.upload(text, shard_first, shard_words)
-    import ctypes as C
-    from varscot_b200 import _lib
-    pinned = []
-
-    def pinned_hits(n):                          # page-locked result buffer, as a caller expecting many hits would use
-        p = _lib.lib().vs_host_alloc(n * 8)
+    host_threads = max(1, min(16, len(all_cpus) // max(1, world)))
+    cap = 1 << 22
+    exchange = None
+    if world > 1 and strong:
+        exchange = HostExchange(V, world, rank, cap)
+        barrier(world, local)
+        exchange.attach()
+        hits_buf = exchange.mine
+    else:
+        p = _lib.lib().vs_host_alloc(cap * 16)
         if not p:
             raise RuntimeError("vs_host_alloc failed")
-        pinned.append(p)
-        return np.frombuffer((C.c_uint8 * (n * 8)).from_address(p), dtype=V.HIT_DT, count=n)
-
-    cap = 1 << 22
-    hits_buf = pinned_hits(cap)
-    for _ in range(args.warmup):
-        hits, st = ctx.scan(guides, k, pam=pam, out=hits_buf)
-        if len(hits) > cap:
-            cap = int(len(hits) * 1.2); hits_buf = pinned_hits(cap)
+        hits_buf = np.frombuffer((C.c_uint8 * (cap * 16)).from_address(p), dtype=V.LOC_DT, count=cap)
+    total_bases = B if strong else all_reduce(float(B), world, local, "SUM")
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.15)
-    barrier(world, local)
-    t0_wall = time.time(); t0 = time.perf_counter()
-    dev_ms = score_ms = extract_ms = 0.0
-    launches = 0
-    for _ in range(args.steps):
-        hits, st = ctx.scan(guides, k, pam=pam, out=hits_buf)
-        dev_ms += st.total_ms; score_ms += st.score_ms; extract_ms += st.extract_ms
-        launches += st.launches
-    barrier(world, local)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    t1_wall = time.time()
-    n_hits = len(hits)
-    ms_step = all_max(dev_ms / args.steps, world, local)
-    wall_step = all_max(wall_ms / args.steps, world, local)
-    # guide·bp per step over all ranks: the shards of one text (strong) or one whole text per rank (weak)
-    units = float(ng) * B if strong else all_sum(float(ng) * B, world, local)
-    value = units / (ms_step * 1e-3) / 1e9
-
-    # ---- end to end: host buffers in, hits out, every step ------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(2):
-            ctx.scan_text(text, guides, k, pam=pam, out=hits_buf, first_word=shard_first, n_words=shard_words)
-        barrier(world, local)
-        t0 = time.perf_counter()
-        e_dev = 0.0
-        for _ in range(args.steps):
-            h2, st2 = ctx.scan_text(text, guides, k, pam=pam, out=hits_buf, first_word=shard_first, n_words=shard_words)
-            e_dev += st2.total_ms
-        barrier(world, local)
-        e_ms = all_max((time.perf_counter() - t0) * 1e3 / args.steps, world, local)
-        e2e = {"value": units / (e_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": e_ms, "device_ms_per_step": e_dev / args.steps,
-               "h2d_bytes_per_step": int(st2.h2d_bytes), "d2h_bytes_per_step": int(st2.d2h_bytes),
-               "note": "vs_scan_text: pinned host text -> H2D (chunked, overlapped with extract+score) -> hits D2H, wall clock"}
+    t0_wall = time.time()
+    res, merged = measure(V, ctx, text, guides, k, pam, first, words, args.steps, args.warmup, world, local, hits_buf, exchange,
+                          total_bases, ng, host_threads, do_e2e=not args.no_e2e)
     clocks = sampler.stop(t0_wall, time.time()) if sampler else None
 
+    # ---- resident genome: only the variant segments (and the guides) travel per call ---------------------------
+    e2e_rg = None
+    if not args.no_e2e and not args.no_resident_genome and nvar and strong:
+        gw0, gw1 = genome_words * rank // world, genome_words * (rank + 1) // world          # this rank's part of the genome ...
+        sw = nw - genome_words
+        sw0, sw1 = genome_words + sw * rank // world, genome_words + sw * (rank + 1) // world     # ... and of the variant segments
+        gw0, gw1, sw0, sw1 = (x // 256 * 256 if x < nw else x for x in (gw0, gw1, sw0, sw1))
+        if rank == world - 1:
+            sw1 = nw
+        ctx_g = V.ScanContext(local)
+        ctx_g.upload(text, gw0, gw1 - gw0)
+        half = cap // 2
+        ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])                       # builds the genome's index once
+        st_box = {}
+
+        def rg_step(seq):
+            a, sa = ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])
+            b, sb_ = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=sw0, n_words=sw1 - sw0, out=hits_buf[half:])
+            st_box["h2d"] = sa.h2d_bytes + sb_.h2d_bytes; st_box["d2h"] = sa.d2h_bytes + sb_.d2h_bytes
+            if exchange is None:
+                return V.merge_resolved([a, b], threads=host_threads)
+            # the two lists travel as one segment: [0, n_a) and [half, half + n_b); counts packed into one word
+            exchange.publish(seq, len(a) | (len(b) << 32))
+            out = (None, None)
+            if exchange.rank == 0:
+                lists = []
+                for r in range(world):
+                    while exchange.ctl[2 * r] < seq:
+                        pass
+                    c = int(exchange.ctl[2 * r + 1])
+                    lists += [exchange.others[r][: c & 0xFFFFFFFF], exchange.others[r][half: half + (c >> 32)]]
+                out = V.merge_resolved(lists, threads=host_threads)
+                exchange.done(seq)
+            else:
+                exchange.wait_done(seq)
+            return out
+
+        for i in range(2):
+            rg_step(1000 + i)
+        barrier(world, local)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            rec_rg, _ = rg_step(1003 + i)
+        barrier(world, local)
+        rg_ms = all_reduce((time.perf_counter() - t0) * 1e3 / args.steps, world, local, "MAX")
+        e2e_rg = {"value": float(ng) * total_bases / (rg_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": rg_ms,
+                  "h2d_bytes_per_step": int(all_reduce(float(st_box["h2d"]), world, local, "SUM")),
+                  "d2h_bytes_per_step": int(all_reduce(float(st_box["d2h"]), world, local, "SUM")),
+                  "records_equal_full_upload": bool(rank != 0 or merged is None or (len(rec_rg) == len(merged[0]) and (rec_rg == merged[0]).all())),
+                  "note": "per rank: its 1/N of the reference genome resident with its candidate index, its 1/N of the variant segments uploaded "
+                          "and scanned per call (the per-sample call of parallel.py:86-90); records merged on rank 0 as in e2e"}
+        ctx_g.close()
+
+    # ---- config 4 target block (same text, 1000 guides, +AG) ---------------------------------------------------
+    target = None
+    if not args.no_target and args.config == 3 and not args.guides:
+        c4 = CONFIGS[4]
+        g4 = synth.synth_guides(c4[6], c4[3])
+        tsteps = max(3, min(args.steps, 5))
+        r4, merged4 = measure(V, ctx, text, g4, c4[4], c4[5], first, words, tsteps, 3, world, local, hits_buf, exchange, total_bases, c4[3], host_threads,
+                              do_e2e=not args.no_e2e)
+        if rank == 0:
+            (lop_a, lds_a), _ = score_ops(c4[4])
+            ex4 = lop_a * r4["warm"]["blocks"] * c4[3] / (r4["warm"]["score_ms"] * 1e-3)
+            target = {"workload": c4[0], "guides": c4[3], "k": c4[4], "extra_pam": c4[5], "steps": tsteps,
+                      "value": r4["warm"]["value"], "ms_per_step": r4["warm"]["ms"], "value_cold": r4["cold"]["value"], "ms_per_step_cold": r4["cold"]["ms"],
+                      "phase_ms_rank0": {"score": r4["warm"]["score_ms"], "resolve": r4["warm"]["resolve_ms"], "extract_cold": r4["cold"]["extract_ms"]},
+                      "hits_per_step": r4["warm"]["hits"], "frac_executed": ex4 / peak_lop3, "executed_lop3_tlops": ex4 / 1e12,
+                      "e2e": r4.get("e2e"), "redo": r4["cold"]["redo"]}
+            if not args.no_cpu and merged4 is not None:
+                os.sched_setaffinity(0, all_cpus)
+                n4, dt4, rec4, off4, cores4 = cpu_sample(text, g4, c4[4], c4[5], synth, target_s=10.0, max_bases=1 << 28)
+                target["parity"] = parity_on_sample(merged4[0], text.offsets, rec4, off4, n4)
+                target["parity"]["key16_collisions"] = int(merged4[1])
+                target["cpu_baseline"] = {"value": c4[3] * n4 / dt4 / 1e9, "unit": "guide*Gbp/s", "cores": cores4, "kind": "port",
+                                          "sample": f"first {n4} bases, all {c4[3]} guides, one pass ({dt4:.1f} s)"}
+
     if rank != 0:
+        ctx.close()
+        if exchange:
+            barrier(world, local)
+            exchange.close()
         return
     # ---- roofline of the dominant kernel (k_score) -----------------------------------------------------
-    blocks = st.n_blocks_fwd + st.n_blocks_rev
-    score_s = score_ms / args.steps * 1e-3
-    n_score_launch = st.score_launches
-    B_local = min(B - shard_first * 32, shard_words * 32)     # bases whose window starts this rank owns
-    yard = C_ALG * ng * B_local / score_s                 # yardstick LOP3/s of the scoring launches of one step
+    warm, cold = res["warm"], res["cold"]
+    blocks = warm["blocks"]
+    score_s = warm["score_ms"] * 1e-3
+    B_local = min(B - first * 32, words * 32)             # bases whose window starts this rank owns
     (lop_a, lds_a), (lop_b, lds_b) = score_ops(k)
-    executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few warps that pass)
+    executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few iterations that pass)
     lds = lds_a * blocks * ng / score_s
-    # DRAM traffic of one full-chunk k_score launch from the committed ncu capture (dram__bytes_read + dram__bytes_write)
-    traffic = None
-    try:
-        rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r1_score_final_summary.txt")):
-            f = line.split()
-            if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
-                rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
-            if len(f) >= 3 and f[0] == "dram__bytes_write.sum":
-                wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
-        if rd is not None and wr is not None:
-            traffic = rd + wr
-    except Exception:
-        pass
+    yard = C_ALG * ng * B_local / score_s
+    traffic, traffic_src = None, None
+    for name in ("r2_score_summary.txt", "r1_score_final_summary.txt"):
+        try:
+            rd = wr = None
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+                    rd, wr = (v, wr) if f[0].endswith("read.sum") else (rd, v)
+            if rd is not None and wr is not None:
+                traffic, traffic_src = rd + wr, name
+                break
+        except Exception:
+            pass
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    roof = {"bound": "int_alu", "kernel": "k_score", "achieved": yard / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
-            "frac": yard / peak_lop3, "traffic": traffic,
-            "traffic_note": "bytes per full-chunk launch (8 Mi words), ncu capture in profiles/r1_score_final_summary.txt; algorithmic = 192 B x blocks of the chunk",
-            "hbm": {"achieved_gbs": (blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9, "peak_gbs": hbm_peak,
-                    "frac": ((blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9 / hbm_peak) if hbm_peak else None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "MEASURED_PEAKS.json absent"},
+    hbm_alg = blocks * 192.0 / score_s / 1e9
+    roof = {"bound": "int_alu", "kernel": "k_score", "achieved": executed / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
+            "frac": executed / peak_lop3,
+            "frac_note": "executed stage-A LOP3 (34 per 32-candidate block and guide at k = 6: 32 adder + 2 threshold) / measured alu-pipe LOP3 rate; "
+                         "a lower bound of the pipe load (stage B, hit path and loop overhead not counted); ncu pipe_alu of the same kernel: profiles/",
+            "frac_yardstick": yard / peak_lop3,
+            "yardstick_note": "dense-scan yardstick of SURVEY.md 8d: 4.0 LOP3 per guide*bp; the PAM-first index scores ~1/8 of the windows per strand, so this exceeds 1",
+            "traffic": traffic, "traffic_note": f"dram bytes of one k_score launch, ncu capture profiles/{traffic_src}; algorithmic = 192 B per block per launch",
+            "hbm": {"achieved_gbs": hbm_alg, "peak_gbs": hbm_peak, "frac": (hbm_alg / hbm_peak) if hbm_peak else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "MEASURED_PEAKS.json absent"},
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
-            "avg_launch_ms": score_ms / args.steps / max(1, n_score_launch), "launches_per_step": n_score_launch,
-            "executed_lop3_tlops": executed / 1e12, "frac_executed": executed / peak_lop3,
+            "avg_launch_ms": warm["score_ms"] / max(1, warm["score_launches"]), "launches_per_step": warm["score_launches"],
             "ops_per_block_guide": {"stage_a_lop3": lop_a, "stage_a_lds": lds_a, "stage_b_lop3": lop_b, "stage_b_lds": lds_b},
-            "lds_words_per_s_T": lds / 1e12, "lds_peak_T": peak_lds / 1e12, "frac_lds": lds / peak_lds,
-            "hbm_gbs_algorithmic": (blocks * 192.0 * ((ng + 255) // 256)) / score_s / 1e9,
-            "note": "yardstick = 4.0 LOP3 per guide*bp (dense scan, SURVEY.md 8d); PAM-first compaction scores ~1/8 of the windows per strand, so frac may exceed 1; frac_executed is the real alu-pipe load"}
+            "lds_words_per_s_T": lds / 1e12, "lds_peak_T": peak_lds / 1e12, "frac_lds": lds / peak_lds}
+    scaling = "strong" if strong else "weak"
     out = {
-        "metric": "guide_Gbp_per_s", "value": value, "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
-        "data": "synthetic",
-        "config": {"workload": desc + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "guides": ng, "k": k, "extra_pam": pam,
-                   "text_bases_per_gpu": B, "contigs_per_gpu": text.n_contigs, "chunks": int(st.n_chunks),
-                   "l2": "inputs larger than L2 (packed text %.2f GB resident, candidate planes %.2f GB written+read per step)" % ((nw * 16) / 1e9, blocks * 192 / 1e9),
-                   "sharding": ("ONE text cut into %d word ranges by vs_shard_bounds, one per rank" % world) if strong else
-                               "one text shard per rank, no collective; hits merged on the host", "cpus_bound_per_rank": numa_cpus},
-        "wall_ms_per_step": wall_step, "phase_ms": {"extract": extract_ms / args.steps, "score": score_ms / args.steps},
-        "hits_per_step": n_hits, "candidates": int(st.n_cand_fwd + st.n_cand_rev), "gpu_launches": launches,
-        "roofline": roof, "e2e": e2e, "clocks": clocks, "gen_s": t_gen,
+        "metric": "guide_Gbp_per_s", "value": warm["value"], "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": warm["ms"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
+        "data": "synthetic", "config": config_dict(cfg, B, text.n_contigs, scaling if world > 1 else "single", args.scale),
+        "value_note": "packed text AND candidate index resident in HBM (index = PAM-valid windows, built once per text and PAM set: the analogue of "
+                      "the reference's prebuilt FM index); first kernel -> resolved + sorted hits in host memory, CUDA events, max over ranks",
+        "value_cold": cold["value"], "ms_per_step_cold": cold["ms"],
+        "value_cold_note": "the same with the index dropped before every step: extraction of the PAM-valid windows included",
+        "layout": {"text_bases_per_gpu": int(B_local), "shard_words": int(words), "chunks": cold["chunks"], "cpus_bound_per_rank": numa_cpus,
+                   "sharding": ("ONE text cut into %d word ranges by vs_shard_bounds, one per rank; no collective; hit lists merged by rank 0 in host shared memory" % world)
+                               if strong else "one text per rank (weak), no collective",
+                   "host_merge_threads": host_threads},
+        "phase_ms_rank0": {"score": warm["score_ms"], "resolve_sort_d2h": warm["resolve_ms"], "extract_cold": cold["extract_ms"], "score_cold": cold["score_ms"]},
+        "hits_per_step": warm["hits"], "candidates_rank0": warm["cands"], "gpu_launches": res["launches"], "redo": cold["redo"],
+        "roofline": roof, "e2e": res.get("e2e"), "e2e_resident_genome": e2e_rg, "clocks": clocks, "gen_s": t_gen, "host": host_info(),
+        "target_cfg4": target,
     }
-    # ---- CPU baseline + hit-set diff on a bounded sample ------------------------------------------------
-    if not args.no_cpu and world == 1:
+    # ---- CPU baseline + hit-set diff of the MERGED records on a bounded sample -----------------------------
+    if not args.no_cpu:
         os.sched_setaffinity(0, all_cpus)             # the CPU baseline gets every host core back
-        n, dt, rec, off, cores = cpu_sample(text, guides, k, pam)
+        n, dt, rec, off, cores = cpu_sample(text, guides, k, pam, synth)
         out["cpu_baseline"] = {"value": ng * n / dt / 1e9, "unit": "guide*Gbp/s", "cores": cores, "kind": "port",
-                               "sample": f"first {n} bases of the same text, all {ng} guides, one pass ({dt:.1f} s); linear-scan oracle, not SeqAn"}
-        # parity on the sample: windows starting before n-23 (the slice end is an artificial contig end)
-        g_rec, _ = V.resolve_hits(hits, text.offsets)
-        gpos = text.offsets[g_rec["contig"]].astype(np.int64) + g_rec["pos"].astype(np.int64)
-        sel = gpos < n - 23
-        gk = set(zip(g_rec["guide"][sel].tolist(), ((g_rec["flag"][sel] & 16) >> 4).tolist(), gpos[sel].tolist(), g_rec["mm"][sel].tolist()))
-        opos = off[rec.contig].astype(np.int64) + rec.pos.astype(np.int64)
-        osel = opos < n - 23
-        ok = set(zip(rec.guide[osel].tolist(), ((rec.flag[osel] & 16) >> 4).tolist(), opos[osel].tolist(), rec.mm[osel].tolist()))
-        out["parity"] = {"sample_bases": n, "hits_cpu": len(ok), "hits_gpu": len(gk), "diff": len(ok ^ gk)}
+                               "sample": f"first {n} bases of the same text, all {ng} guides, one pass ({dt:.1f} s); linear-scan oracle, not SeqAn", **host_info()}
+        if merged is not None and merged[0] is not None:
+            out["parity"] = parity_on_sample(merged[0], text.offsets, rec, off, n)
+            out["parity"]["key16_collisions"] = int(merged[1])
+            out["parity"]["note"] = "records of the e2e path (all ranks merged on rank 0) vs the oracle; key16_collisions: records the reference's uint16 map key " \
+                                    "(bidir_mapping.cpp:13) would have merged with another one — kept here (declared divergence R7)"
     print(json.dumps(out))
     ctx.close()
-    text.unpin()
-    del hits, hits_buf
-    for p in pinned:
-        _lib.lib().vs_host_free(p)
+    if exchange:
+        barrier(world, local)
+        exchange.close()
 
 
 def _shutdown():

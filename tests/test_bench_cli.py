@@ -31,7 +31,9 @@ def test_gpu_arm_line():
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "parity"} <= set(d)
-    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["scaling"] == "weak" and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["scaling"] == "strong" and d["n_gpus"] == 1
+    assert d["value_cold"] > 0 and d["value"] >= d["value_cold"] * 0.9 and d["redo"] == 0
+    assert d["e2e_resident_genome"]["records_equal_full_upload"] and d["e2e_resident_genome"]["h2d_bytes_per_step"] < d["e2e"]["h2d_bytes_per_step"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
-    assert d["parity"]["diff"] == 0 and d["cpu_baseline"]["value"] > 0
+    assert d["parity"]["diff"] == 0 and d["cpu_baseline"]["value"] > 0 and d["roofline"]["frac"] < 1.2

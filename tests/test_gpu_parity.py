@@ -412,6 +412,186 @@ def test_pipeline_chain_bed_vcf_to_sam(tmp_path):
             assert open(fm_txt).read() == exp_fm
 
 
+def rows_from_records(text, rec, offsets, guides, with_md=True):
+    import varscot_b200 as V
+    rows = []
+    for r in rec:
+        md = V.md_string(text, int(offsets[r["contig"]]) + int(r["pos"]), guides[r["guide"]], (int(r["flag"]) >> 4) & 1) if with_md else ""
+        rows.append((int(r["guide"]), int(r["flag"]), int(r["contig"]), int(r["pos"]), int(r["mm"]), md))
+    return rows
+
+
+def gpu_rows_resolved(case, shards=1, streamed=True, use_source=True, chunk_words=None, hit_capacity=0, use_sink=False, threads=2):
+    """The path of the executables: every shard's hits are resolved to (contig, pos) and sorted ON THE DEVICE
+    (vs_scan_resolved), the host merges the lists (vs_merge_resolved)."""
+    import varscot_b200 as V
+    from varscot_b200 import _lib
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    if not use_source:
+        text.em_code = None
+    nw = text.n_words
+    bounds = [nw * i // shards for i in range(shards + 1)]
+    lists, stats = [], []
+    for i in range(shards):
+        if bounds[i + 1] <= bounds[i]:
+            continue
+        with V.ScanContext(0) as ctx:
+            if chunk_words:
+                ctx.set_chunk_words(chunk_words)
+            if hit_capacity:
+                ctx.set_option(_lib.VS_OPT_HIT_CAPACITY, hit_capacity)
+            got = []
+            sink = (lambda h, lo, hi: got.append(h.copy()) or 0) if use_sink else None
+            if streamed:
+                hits, st = ctx.scan_resolved(case.guides, case.k, pam=case.pam, text=text, first_word=bounds[i], n_words=bounds[i + 1] - bounds[i],
+                                             cap=1 << 12, sink=sink)
+            else:
+                ctx.upload(text, bounds[i], bounds[i + 1] - bounds[i])
+                hits, st = ctx.scan_resolved(case.guides, case.k, pam=case.pam, cap=1 << 12, sink=sink)
+            if use_sink:
+                hits = np.concatenate(got) if got else np.zeros(0, V.LOC_DT)
+            # every list arrives sorted in emission-key order
+            keys = (hits["info"].astype(np.uint64) >> np.uint64(7) << np.uint64(48)) | (hits["key"] & np.uint64((1 << 48) - 1))
+            assert (np.diff(keys.astype(np.int64)) >= 0).all() if len(keys) > 1 and int(keys.max()) < 2 ** 63 else True
+            lists.append(hits.copy())
+            stats.append(st)
+    rec, coll = V.merge_resolved(lists, threads=threads)
+    return rows_from_records(text, rec, case.offsets, case.guides), stats, coll
+
+
+@pytest.mark.parametrize("shards,streamed,use_source", [(1, True, True), (1, False, True), (3, True, True), (4, False, True), (2, True, False)])
+def test_resolved_scan_equals_oracle(shards, streamed, use_source):
+    case = make_case(seed=81, contig_lens=[50000, 45, 45, 45, 23, 22, 46, 20000] + [45] * 300 + [7000], n_guides=9, k=6, pam="AG")
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, case.k, case.pam)
+    got, _, _ = gpu_rows_resolved(case, shards=shards, streamed=streamed, use_source=use_source, chunk_words=700)
+    assert got == exp and len(exp) > 20
+
+
+def test_resolved_scan_with_empty_contigs_uploads_the_offsets():
+    """Empty contigs have no bit in the contig-end plane: the device notices (end-bit count) and the host's offsets are used."""
+    case = make_case(seed=82, contig_lens=[0, 30000, 0, 0, 45, 0, 45, 23, 0, 9000, 0], n_guides=6, k=5)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, case.k, case.pam)
+    for shards, streamed in ((1, True), (1, False), (3, True)):
+        got, _, _ = gpu_rows_resolved(case, shards=shards, streamed=streamed)
+        assert got == exp and len(exp) > 5
+
+
+def test_resolved_scan_over_65536_contigs_orders_ties_by_full_id():
+    rng = np.random.default_rng(19)
+    nct = 70000
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    codes = rng.integers(0, 4, (nct, 45)).astype(np.uint8)
+    guides = rng.integers(0, 4, (3, GLEN)).astype(np.uint8); guides[:, 21:] = 2
+    for c in list(range(0, nct, 1499)) + [5, 65536 + 5]:
+        w = guides[c % 3].copy()
+        w[int(rng.integers(0, 20))] ^= 1
+        codes[c, 7:7 + GLEN] = w
+    codes[65536 + 5] = codes[5]                               # same (id mod 65536, pos), same guide and strand
+    case = type("Case", (), dict(ascii=bytes(lut[codes.reshape(-1)]), offsets=(np.arange(nct + 1) * 45).astype(np.uint64), guides=guides, k=4, pam=None))
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 4)
+    got, _, coll = gpu_rows_resolved(case, shards=2)
+    assert got == exp and coll >= 1
+
+
+def test_resident_index_is_reused_and_rebuilt():
+    """The first scan of a resident text builds the candidate index; scans with the same PAM set score it without
+    extracting again; another -P, vs_index_drop or VS_OPT_KEEP_INDEX 0 rebuild it.  Results never change."""
+    import varscot_b200 as V
+    from varscot_b200 import _lib
+    case = make_case(seed=83, contig_lens=[120000, 45, 45, 60000], n_guides=7, k=5)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 5)
+    exp_ag = oracle_rows(case.ascii, case.offsets, case.guides, 5, "AG")
+
+    def rows(hits):
+        rec, _ = V.resolve_hits(hits, case.offsets)
+        return rows_from_records(text, rec, case.offsets, case.guides)
+
+    with V.ScanContext(0) as ctx:
+        ctx.set_chunk_words(900)
+        ctx.upload(text)
+        a, st_a = ctx.scan(case.guides, 5)
+        b, st_b = ctx.scan(case.guides, 5)
+        assert st_a.index_reused == 0 and st_a.extract_ms > 0
+        assert st_b.index_reused == 1 and st_b.extract_ms == 0 and st_b.score_launches == 1
+        assert (st_b.n_cand_fwd, st_b.n_blocks_fwd) == (st_a.n_cand_fwd, st_a.n_blocks_fwd)
+        assert rows(a) == rows(b) == exp
+        # fewer guides / another k against the same index
+        c, st_c = ctx.scan(case.guides[:3], 3)
+        assert st_c.index_reused == 1
+        exp3 = oracle_rows(case.ascii, case.offsets, case.guides[:3], 3)
+        rec, _ = V.resolve_hits(c, case.offsets)
+        assert rows_from_records(text, rec, case.offsets, case.guides[:3]) == exp3
+        d, st_d = ctx.scan(case.guides, 5, pam="AG")           # another PAM set: extracted again
+        assert st_d.index_reused == 0 and rows(d) == exp_ag
+        e, st_e = ctx.scan(case.guides, 5, pam="AG")
+        assert st_e.index_reused == 1 and rows(e) == exp_ag
+        ctx.drop_index()
+        f, st_f = ctx.scan(case.guides, 5, pam="AG")
+        assert st_f.index_reused == 0 and rows(f) == exp_ag
+        ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 0)
+        for _ in range(2):
+            g, st_g = ctx.scan(case.guides, 5)
+            assert st_g.index_reused == 0 and rows(g) == exp
+        ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
+        ctx.upload(text, 0, text.n_words // 2)                  # a new upload drops the index
+        h, st_h = ctx.scan(case.guides, 5)
+        assert st_h.index_reused == 0 and len(h) < len(a)
+
+
+@pytest.mark.parametrize("use_sink", [False, True])
+def test_guide_super_chunks_with_a_small_hit_buffer(use_sink):
+    """A device hit buffer far smaller than the hit count: the guides are scored in several passes over the resident index
+    (config 5's mode); a sink receives every super-chunk as soon as it is sorted."""
+    case = make_case(seed=84, contig_lens=[150000], n_guides=300, k=8, plant=False)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 8)
+    assert len(exp) > 3000
+    got, stats, _ = gpu_rows_resolved(case, streamed=True, hit_capacity=1500, use_sink=use_sink, chunk_words=2000)
+    assert got == exp
+    assert stats[0].guide_passes > 2
+    got2, stats2, _ = gpu_rows_resolved(case, streamed=False, hit_capacity=40, use_sink=use_sink)      # forces regrowing as well
+    assert got2 == exp and stats2[0].redo_chunks > 0
+
+
+def test_two_contexts_on_one_device_with_different_guides():
+    """Two contexts of the same device scanning at the same time, each with its own > 256 guides: the pattern tables are
+    per context (no shared __constant__ table), so neither sees the other's guides."""
+    import threading
+    import varscot_b200 as V
+    cases = [make_case(seed=90 + i, contig_lens=[60000], n_guides=300, k=3 + i) for i in range(2)]
+    out = [None, None]
+
+    def work(i):
+        text = V.PackedText.from_ascii(cases[i].ascii, cases[i].offsets)
+        with V.ScanContext(0) as ctx:
+            ctx.set_chunk_words(300)
+            rows = None
+            for _ in range(3):
+                hits, _ = ctx.scan_resolved(cases[i].guides, cases[i].k, text=text)
+                rec, _ = V.merge_resolved([hits])
+                r = rows_from_records(text, rec, cases[i].offsets, cases[i].guides)
+                assert rows is None or rows == r
+                rows = r
+            out[i] = rows
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for i in range(2):
+        assert out[i] == oracle_rows(cases[i].ascii, cases[i].offsets, cases[i].guides, cases[i].k) and len(out[i]) > 0
+
+
+def test_map_records_multi_device_equals_oracle():
+    import varscot_b200 as V
+    nd = V.device_count()
+    case = make_case(seed=72, contig_lens=[300000, 45, 45, 200000], n_guides=12, k=6)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 6)
+    for devices in ([0], list(range(nd)) if nd > 1 else [0, 0, 0]):
+        rec, coll, st = V.map_records(text, case.guides, 6, devices=devices, threads=3)
+        assert rows_from_records(text, rec, case.offsets, case.guides) == exp and coll == 0
+
+
 def test_empty_inputs():
     """Empty text, zero guides, text shorter than a window: no hits, no errors."""
     import varscot_b200 as V

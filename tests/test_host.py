@@ -383,3 +383,62 @@ def test_device_code_on_the_host(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "kernel helper units ok" in r.stdout, r.stdout + r.stderr
+
+
+def _loc_lists_from_hits(hits, offsets, n_lists, rng):
+    """What vs_scan_resolved delivers, built on the host: hits -> (key, contig, info), dealt to n_lists shards, each sorted."""
+    off = np.asarray(offsets, dtype=np.uint64)
+    starts = off[:-1]
+    # last contig whose start is <= pos (empty contigs share a start; the non-empty one is the last)
+    contig = np.searchsorted(starts, hits["pos"].astype(np.uint64), side="right") - 1
+    pos = hits["pos"].astype(np.uint64) - starts[contig]
+    info = hits["info"].astype(np.uint64)
+    loc = np.zeros(len(hits), dtype=V.LOC_DT)
+    loc["key"] = ((info >> np.uint64(8)) << np.uint64(49)) | (((info >> np.uint64(7)) & np.uint64(1)) << np.uint64(48)) | \
+                 ((contig.astype(np.uint64) & np.uint64(0xFFFF)) << np.uint64(32)) | pos
+    loc["contig"] = contig
+    loc["info"] = hits["info"]
+    owner = rng.integers(0, n_lists, len(hits))
+    out = []
+    for l in range(n_lists):
+        part = loc[owner == l]
+        out.append(part[np.argsort(part["key"], kind="stable")])
+    return out
+
+
+@pytest.mark.parametrize("n_lists,threads", [(1, 1), (1, 4), (3, 1), (8, 5)])
+def test_merge_resolved_equals_resolve_hits(n_lists, threads):
+    """vs_merge_resolved over device-style sorted shard lists == vs_resolve_hits over the raw hits: same records, same order,
+    same FLAGs, same collision count — incl. > 65536 contigs (ties on the 16-bit key are ordered by the full id)."""
+    rng = np.random.default_rng(100 + n_lists)
+    nct = 70000
+    off = np.concatenate([[0], np.cumsum(rng.integers(0, 60, nct))]).astype(np.uint64)       # incl. empty contigs
+    n = 30000
+    hits = np.zeros(n, dtype=V.HIT_DT)
+    hits["pos"] = rng.integers(0, int(off[-1]), n)
+    # provoke 16-bit key collisions: copies of some hits moved by whole multiples of 65536 contigs are unlikely at random, so
+    # build them: same guide / strand / in-contig position in contig c and c + 65536
+    lens = np.diff(off.astype(np.int64))
+    for c in range(0, 4000, 7):
+        if lens[c] > 5 and lens[c + 65536] > 5:
+            hits["pos"][c] = off[c] + 3
+            hits["pos"][c + 1] = off[c + 65536] + 3
+    guide = rng.integers(0, 40, n).astype(np.uint32)
+    strand = rng.integers(0, 2, n).astype(np.uint32)
+    guide[1:4000:7] = guide[0:3999:7]; strand[1:4000:7] = strand[0:3999:7]
+    hits["info"] = (guide << 8) | (strand << 7) | rng.integers(0, 7, n).astype(np.uint32)
+    hits = np.unique(hits)                                    # a scan never reports a (pos, guide, strand) twice
+    _, first = np.unique(np.stack([hits["pos"], hits["info"] >> 7], axis=1), axis=0, return_index=True)
+    hits = hits[np.sort(first)]
+    want, coll_want = V.resolve_hits(hits, off)
+    lists = _loc_lists_from_hits(hits, off, n_lists, rng)
+    got, coll = V.merge_resolved(lists, threads=threads)
+    assert got.tolist() == want.tolist()
+    assert coll == coll_want and coll > 0
+
+
+def test_merge_resolved_empty_lists():
+    rec, coll = V.merge_resolved([np.zeros(0, V.LOC_DT), np.zeros(0, V.LOC_DT)])
+    assert len(rec) == 0 and coll == 0
+    rec, coll = V.merge_resolved([])
+    assert len(rec) == 0

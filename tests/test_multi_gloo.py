@@ -67,3 +67,64 @@ def test_sharded_hits_merge_to_unpartitioned_result(world):
         assert p.exitcode == 0
     assert ok and n > 10
     assert sum(1 for x in per if x > 0) >= 2        # more than one rank contributed hits
+
+
+def _worker_exchange(rank, world, port, q):
+    """The N > 1 host path of bench.py / the executables: every rank hands its SORTED, resolved hit list (here built from the
+    oracle's hits; on the GPU box vs_scan_resolved delivers it) to rank 0 through shared memory (bench.HostExchange), rank 0
+    merges with vs_merge_resolved."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import varscot_b200 as V
+    import bench
+    from oracle import oracle as O
+    from tests.util import make_case
+    case = make_case(78, [30000] + [45] * 400 + [8211, 0, 23, 9000], 6, 6)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    codes = O.text_codes(case.ascii)
+    whole = O.map_guides(codes, case.offsets, case.guides, case.k)
+    gpos = case.offsets[whole.contig].astype(np.int64) + whole.pos.astype(np.int64)
+    b = V.shard_bounds(text.n_words, world)
+    own = (gpos >= int(b[rank]) * 32) & (gpos < int(b[rank + 1]) * 32)          # the window starts this rank's shard owns
+    loc = np.zeros(int(own.sum()), dtype=V.LOC_DT)
+    strand = ((whole.flag[own] & 16) >> 4).astype(np.uint64)
+    loc["key"] = (whole.guide[own].astype(np.uint64) << np.uint64(49)) | (strand << np.uint64(48)) | \
+                 ((whole.contig[own].astype(np.uint64) & np.uint64(0xFFFF)) << np.uint64(32)) | whole.pos[own].astype(np.uint64)
+    loc["contig"] = whole.contig[own]
+    loc["info"] = (whole.guide[own].astype(np.uint32) << 8) | (strand.astype(np.uint32) << 7) | whole.mm[own]
+    loc = loc[np.argsort(loc["key"], kind="stable")]
+    ex = bench.HostExchange(V, world, rank, 1 << 14, pin=False, tag=f"test_{port}")
+    dist.barrier()
+    ex.attach()
+    for step in (1, 2):                                       # two rounds: the sequence numbers separate them
+        ex.mine[: len(loc)] = loc
+        ex.publish(step, len(loc))
+        if rank == 0:
+            rec, coll = V.merge_resolved(ex.collect(step), threads=2)
+            ex.done(step)
+            got = [(int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"])) for x in rec]
+            if step == 2:
+                q.put((got == [x[:5] for x in whole.rows()], len(got), [int(ex.ctl[2 * r + 1]) for r in range(world)]))
+        else:
+            ex.wait_done(step)
+    dist.barrier()
+    ex.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_memory_exchange_and_merge(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_exchange, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, n, per = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and n > 10
+    assert sum(1 for x in per if x > 0) >= 2

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvarscot_scan.so")
+LIB_PATH = os.environ.get("VARSCOT_LIB") or os.path.join(_HERE, "libvarscot_scan.so")     # VARSCOT_LIB: a tuning build (tools/gpu_variants.sh)
 
 VS_OK, VS_ERR_ARG, VS_ERR_CUDA, VS_ERR_NOMEM, VS_ERR_OVERFLOW, VS_ERR_NODEVICE, VS_ERR_IO = range(7)
 GLEN = 23

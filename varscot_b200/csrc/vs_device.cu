@@ -803,7 +803,8 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
         ctx->ev_pool.push_back(e);
     }
     const unsigned score_threads = std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32);
-    const unsigned score_ctas = (unsigned)ctx->n_sm * 16;   // persistent: a multiple of the SM count, about two waves of resident CTAs
+    unsigned score_ctas = (unsigned)ctx->n_sm * 16;         // persistent: a multiple of the SM count, about two waves of resident CTAs
+    if (const char *e = getenv("VARSCOT_SCORE_CTAS_PER_SM")) score_ctas = (unsigned)ctx->n_sm * (unsigned)std::max(1, atoi(e));   // tuning knob
 
     auto launch_extract = [&](uint32_t c) {
         const uint64_t c0 = plan[c], c1 = plan[c + 1];

@@ -117,7 +117,8 @@ class PackedText:
         return v
 
     def _arrays(self):
-        return ("bases", "masks", "sparse") + (("em_code", "em_dense", "nm_runs", "em_runs") if self.has_source else ())
+        # what an upload reads: with a mask source the window masks never travel (the device computes them)
+        return ("bases", "em_code", "em_dense", "nm_runs", "em_runs") if self.has_source else ("bases", "masks", "sparse")
 
     def pin(self):
         """Move bases, masks, sparse masks and the mask source into page-locked memory (vs_host_alloc) for full-speed H2D."""
