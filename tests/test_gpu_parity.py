@@ -592,6 +592,113 @@ def test_map_records_multi_device_equals_oracle():
         assert rows_from_records(text, rec, case.offsets, case.guides) == exp and coll == 0
 
 
+def test_reference_driver_script_runs_on_the_drop_ins(tmp_path):
+    """The reference's OWN driver (VARSCOT_pipeline/VARSCOT:21-357, made parseable by oracle/ref_hook/build_ref.sh: two stray
+    `then` lines removed, nothing else) runs unchanged on our six executables: a sandbox holds the script, a link to build/
+    and a stand-in for the external TUSCAN tool; the final hit table equals the oracle chain's, with and without a VCF."""
+    import shutil
+    drv = os.path.join(ROOT, "oracle", "_ref", "VARSCOT")
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/VARSCOT absent (built from /root/reference by __graft_entry__.build())")
+    from oracle import merge_oracle as MO, vcf_oracle as VO
+    rng = np.random.default_rng(321)
+    lut = "ACGT"
+    seq = list("".join(rng.choice(list(lut), 50000)))
+    bed_rows, vcf_rows = [], []
+    for gi, p in enumerate((1500, 12000, 30500)):
+        seq[p + 21:p + 23] = "GG"
+        bed_rows.append(("chr1", p, p + 23, f"guide{gi}", 0, "+"))
+        q = p + 4000
+        w = seq[p:p + 23]
+        for off in (2, 9):
+            w[off] = lut[(lut.index(w[off]) + 1) % 4]
+        seq[q:q + 23] = w
+        vcf_rows.append((q + 9, seq[q + 9], seq[p + 9], "0|1"))
+    for p in (700, 720, 25000, 41000):
+        vcf_rows.append((p, seq[p], lut[(lut.index(seq[p]) + 2) % 4], "1|1" if p == 25000 else "0|1"))
+    vcf_rows.sort()
+    sand = tmp_path / "sandbox"
+    (sand / "lib" / "TUSCAN" / "TUSCAN model").mkdir(parents=True)
+    shutil.copy(drv, sand / "VARSCOT")
+    os.symlink(os.path.join(ROOT, "build"), sand / "build")
+    # stand-in for lib/TUSCAN (external tool, out of scope): the activity table bam_merger reads (feature_matrix.h:206-230)
+    (sand / "lib" / "TUSCAN" / "TUSCAN model" / "TUSCAN.py").write_text(
+        "import sys\n"
+        "a = sys.argv\n"
+        "inp, out = a[a.index('-i') + 1], a[a.index('-o') + 1]\n"
+        "ids = [l[1:].strip() for l in open(inp) if l.startswith('>')]\n"
+        "open(out, 'w').write('ID Sequence Score Dir\\n' + ''.join(f'{i} {\"A\" * 30} {1.25 + n} +\\n' for n, i in enumerate(ids)))\n")
+    g, bed, vcf = str(tmp_path / "genome.fa"), str(tmp_path / "t.bed"), str(tmp_path / "v.vcf")
+    s = "".join(seq)
+    open(g, "w").write(">chr1\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+    open(bed, "w").write("".join("\t".join(map(str, r)) + "\n" for r in bed_rows))
+    open(vcf, "w").write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n" +
+                         "".join(f"chr1\t{p + 1}\t.\t{r}\t{a}\t.\t.\t.\tGT\t{gt}\t0|0\n" for p, r, a, gt in vcf_rows))
+    idx = str(tmp_path / "refidx")
+    assert subprocess.run([os.path.join(BIN, "bidir_index"), "-G", g, "-I", idx], capture_output=True).returncode == 0
+    env = dict(os.environ, PATH=os.path.dirname(os.sys.executable) + ":" + os.environ.get("PATH", ""))
+    for with_vcf in (True, False):
+        out = str(tmp_path / f"result_{int(with_vcf)}.txt")
+        tdir = str(tmp_path / f"tmp_{int(with_vcf)}")
+        cmd = ["bash", str(sand / "VARSCOT"), "-b", bed, "-o", out, "-g", g, "-i", idx, "-m", "3", "-t", "2", "-T", tdir, "-v"]
+        if with_vcf:
+            cmd += ["-f", vcf, "-s", "0"]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Analysis finished" in r.stdout
+        # the oracle chain on the same inputs (files the driver left in its temp dir serve as the oracle's inputs where the
+        # producing stage is covered by its own test: guides FASTA, activity table)
+        guides_fa, act = os.path.join(tdir, "t.fa"), os.path.join(tdir, "t_activity.txt")
+        ref_sam = str(tmp_path / f"oracle_ref_{int(with_vcf)}.sam")
+        o = subprocess.run([os.path.join(ROOT, "oracle", "oracle_bidir_mapping"), "-G", g, "-R", guides_fa, "-M", "3", "-O", ref_sam], capture_output=True, text=True)
+        assert o.returncode == 0, o.stderr
+        prefix = os.path.basename(out)[:-4]
+        assert open(os.path.join(tdir, f"{prefix}_reference.sam"), "rb").read() == open(ref_sam, "rb").read()
+        if with_vcf:
+            cut = str(tmp_path / "cut.vcf")
+            open(cut, "w").write("".join("\t".join(l.rstrip("\n").split("\t")[:10]) + "\n" if not l.startswith("##") else l for l in open(vcf)))
+            snp_fa = str(tmp_path / "oracle_snp.fa")
+            VO.write_fasta(snp_fa, VO.vcf_loader(cut, g))
+            assert open(os.path.join(tdir, f"{prefix}.fa")).read() == open(snp_fa).read()
+            snp_sam = str(tmp_path / "oracle_snp.sam")
+            o = subprocess.run([os.path.join(ROOT, "oracle", "oracle_bidir_mapping"), "-G", snp_fa, "-R", guides_fa, "-M", "3", "-O", snp_sam], capture_output=True, text=True)
+            assert o.returncode == 0, o.stderr
+            assert open(os.path.join(tdir, f"{prefix}_snp.sam"), "rb").read() == open(snp_sam, "rb").read()
+            exp_text, _ = MO.bam_merger(ref_sam, snp_sam, bed, g, snp_fa, act, 23, 0)
+        else:
+            exp_text, _ = MO.bam_merger_ref_only(ref_sam, bed, g, act, 23, 0)
+        lines = exp_text.splitlines(keepends=True)
+        # the driver's last step: header, then the rows sorted on column 4 (VARSCOT:355-357, `sort -t$'\\t' -k4,4`)
+        srt = subprocess.run(["sort", "-t", "\t", "-k4,4"], input="".join(lines[1:]), capture_output=True, text=True).stdout
+        assert open(out).read() == lines[0] + srt and len(lines) > 3
+
+
+def test_eight_concurrent_mapper_processes(tmp_path):
+    """parallel.py:17,86-90 runs up to 48 pipelines at once and every pipeline two mappers (VARSCOT:321-323): eight
+    bidir_mapping processes started together spread over the visible devices (pid % n) and write identical SAM files."""
+    case = make_case(seed=56, contig_lens=[200000, 45, 45, 90000], n_guides=20, k=5)
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "guides.fa")
+    write_fasta(gfa, ["chr1", "chr1_10_REF", "chr1_10_ALT_32_A_C", "chr2"], case.ascii, case.offsets)
+    write_guides(rfa, [f"g{i}" for i in range(20)], case.guide_strs)
+    idx = str(tmp_path / "idx")
+    assert subprocess.run([os.path.join(BIN, "bidir_index"), "-G", gfa, "-I", idx], capture_output=True).returncode == 0
+    env = dict(os.environ, VARSCOT_VERBOSE="1")
+    procs = [subprocess.Popen([os.path.join(BIN, "bidir_mapping"), "-G", gfa, "-I", idx, "-R", rfa, "-M", "5", "-T", "1", "-O", str(tmp_path / f"o{i}.sam")],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for i in range(8)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1] for o in outs]
+    ref = str(tmp_path / "ref.sam")
+    o = subprocess.run([os.path.join(ROOT, "oracle", "oracle_bidir_mapping"), "-G", gfa, "-R", rfa, "-M", "5", "-O", ref], capture_output=True, text=True)
+    assert o.returncode == 0, o.stderr
+    want = open(ref, "rb").read()
+    assert len(want) > 0
+    for i in range(8):
+        assert open(str(tmp_path / f"o{i}.sam"), "rb").read() == want
+    import varscot_b200 as V
+    devs = {int(l.split("device ")[1].split()[0]) for _, e in outs for l in e.splitlines() if "scanning on device " in l}
+    assert len(devs) == min(8, V.device_count())
+
+
 def test_empty_inputs():
     """Empty text, zero guides, text shorter than a window: no hits, no errors."""
     import varscot_b200 as V

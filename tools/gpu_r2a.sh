@@ -2,7 +2,7 @@
 cd /root/repo
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -40
 echo "== bench cfg3"
 timeout 900 python bench.py --config 3 --steps 10 --warmup 3 > gpurun_out/r2a_bench_cfg3.json 2> gpurun_out/r2a_bench_cfg3.err; echo "rc=$?"; tail -3 gpurun_out/r2a_bench_cfg3.err
 python - <<'PY'

@@ -17,6 +17,9 @@
 #include <functional>
 #include <string>
 #include <thread>
+#include <fcntl.h>
+#include <sys/file.h>
+#include <unistd.h>
 #include <unistd.h>
 #include <vector>
 
@@ -185,17 +188,39 @@ bool parse_int(const std::string &s, long &v)
 
 Opt *find_opt(std::vector<Opt> &opts, char s) { for (auto &o : opts) if (o.s == s) return &o; return nullptr; }
 
+// Several mapper processes run concurrently (VARSCOT:321-322 runs two, parallel.py:17 up to 48 pipelines).  Each process
+// takes an advisory lock (flock on /tmp/varscot_b200_gpu<i>.lock, held until it exits) on the first free device,
+// starting at pid % n: concurrent processes land on different GPUs as long as there are free ones, and share them
+// evenly afterwards.  VARSCOT_DEVICE pins the choice.
+int first_device()
+{
+    static int chosen = -2;
+    if (chosen != -2) return chosen;
+    int n = vs_device_count();
+    if (n <= 0) return chosen = -1;
+    if (const char *e = getenv("VARSCOT_DEVICE")) { int i = atoi(e); if (i >= 0 && i < n) return chosen = i; }
+    const int start = (int)((unsigned)getpid() % (unsigned)n);
+    for (int j = 0; j < n; ++j) {
+        const int d = (start + j) % n;
+        const std::string path = "/tmp/varscot_b200_gpu" + std::to_string(d) + ".lock";
+        int fd = open(path.c_str(), O_CREAT | O_RDWR, 0666);
+        if (fd < 0) continue;
+        if (flock(fd, LOCK_EX | LOCK_NB) == 0) return chosen = d;      // the descriptor stays open: the lock lives as long as the process
+        close(fd);
+    }
+    return chosen = start;
+}
+
 std::vector<int> choose_devices(uint64_t n_bases)
 {
-    // Several mapper processes run concurrently (VARSCOT:321-322 runs two, parallel.py:17 up to 48 pipelines):
-    // small texts stay on ONE device picked by pid so processes spread out; big texts are sharded.
+    // small texts stay on ONE device so that concurrent processes spread out; big texts are sharded over several
     int n = vs_device_count();
     std::vector<int> d;
     if (n <= 0) return d;
-    if (const char *e = getenv("VARSCOT_DEVICE")) { int i = atoi(e); if (i >= 0 && i < n) { d.push_back(i); return d; } }
+    const int first = first_device();
+    if (getenv("VARSCOT_DEVICE")) { d.push_back(first); return d; }
     int want = (int)std::min<uint64_t>((uint64_t)n, std::max<uint64_t>(1, n_bases / (512ull << 20)));
     if (const char *e = getenv("VARSCOT_GPUS")) { int g = atoi(e); if (g >= 1) want = std::min(g, n); }
-    int first = (int)((unsigned)getpid() % (unsigned)n);
     for (int i = 0; i < want; ++i) d.push_back((first + i) % n);
     return d;
 }
@@ -280,11 +305,8 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
     // CUDA context creation takes 0.3-4 s: start it now, in the background, on the device a small text will use, and
     // read the inputs meanwhile (choose_devices() picks pid % n_gpus first)
     std::thread warm([] {
-        int n = vs_device_count();
-        if (n <= 0) return;
-        int dev = (int)((unsigned)getpid() % (unsigned)n);
-        if (const char *e = getenv("VARSCOT_DEVICE")) { int i = atoi(e); if (i >= 0 && i < n) dev = i; }
-        vs_warmup_device(dev);
+        const int dev = first_device();
+        if (dev >= 0) vs_warmup_device(dev);
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
 
@@ -358,6 +380,8 @@ extern "C" int vs_bidir_mapping_main(int argc, char **argv)
         vs_scan_stats st;
         int rc = vs::scan_text_sharded_resolved(t.v, devices, guides.data(), n_guides, (int)mism, extra_pam, lists, &st, err);
         if (rc != VS_OK) { fprintf(stderr, "%s: scan failed: %s\n", prog, err.c_str()); fclose(out); return 1; }
+        if (getenv("VARSCOT_VERBOSE"))
+            for (int dv : devices) fprintf(stderr, "%s: scanning on device %d\n", prog, dv);
         if (getenv("VARSCOT_VERBOSE"))
             fprintf(stderr, "%s: %zu device(s), %.3f ms upload+scan (extract %.3f, score %.3f, resolve+sort %.3f; %.1f MB H2D), %llu candidates, %llu hits\n", prog,
                     devices.size(), st.total_ms, st.extract_ms, st.score_ms, st.resolve_ms, st.h2d_bytes / 1e6,
