@@ -18,7 +18,7 @@
 #include "cuda_on_host.h"
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
-namespace vs { uint32_t sm[SC_NB * SC_STRIDE + SC_NB] __attribute__((aligned(16))); }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
+namespace vs { uint32_t sm[SC_SMEM_BYTES / 4] __attribute__((aligned(16))); }      // k_score's dynamic shared memory (extern __shared__ in the kernel)
 using namespace vs;
 
 static int failures = 0;

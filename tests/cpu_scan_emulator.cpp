@@ -18,7 +18,7 @@
 #include "cuda_on_host.h"
 #include "../varscot_b200/csrc/vs_kernels.cuh"
 
-namespace vs { uint32_t sm[SC_NB * SC_STRIDE + SC_NB] __attribute__((aligned(16))); }
+namespace vs { uint32_t sm[SC_SMEM_BYTES / 4] __attribute__((aligned(16))); }
 using namespace vs;
 
 template <int K>

@@ -545,11 +545,11 @@ def test_guide_super_chunks_with_a_small_hit_buffer(use_sink):
     (config 5's mode); a sink receives every super-chunk as soon as it is sorted."""
     case = make_case(seed=84, contig_lens=[150000], n_guides=300, k=8, plant=False)
     exp = oracle_rows(case.ascii, case.offsets, case.guides, 8)
-    assert len(exp) > 3000
-    got, stats, _ = gpu_rows_resolved(case, streamed=True, hit_capacity=1500, use_sink=use_sink, chunk_words=2000)
+    assert len(exp) > 2000
+    got, stats, _ = gpu_rows_resolved(case, streamed=True, hit_capacity=600, use_sink=use_sink, chunk_words=2000)
     assert got == exp
     assert stats[0].guide_passes > 2
-    got2, stats2, _ = gpu_rows_resolved(case, streamed=False, hit_capacity=40, use_sink=use_sink)      # forces regrowing as well
+    got2, stats2, _ = gpu_rows_resolved(case, streamed=False, hit_capacity=6, use_sink=use_sink)      # forces regrowing as well
     assert got2 == exp and stats2[0].redo_chunks > 0
 
 

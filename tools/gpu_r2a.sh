@@ -26,8 +26,8 @@ except Exception as e: print('$label cfg$cfg failed', e)"
 }
 q base 3 A=1
 q base 4 A=1
-for v in u4 u2 u16 mb10 mb6 w8 w2 noinl; do
+for v in mb10 w8 exhalf; do
   q $v 3 VARSCOT_LIB=/root/repo/build/variants/lib_$v.so
   q $v 4 VARSCOT_LIB=/root/repo/build/variants/lib_$v.so
 done
-for c in 8 32; do q ctas$c 3 VARSCOT_SCORE_CTAS_PER_SM=$c; q ctas$c 4 VARSCOT_SCORE_CTAS_PER_SM=$c; done
+for c in 32 64; do q ctas$c 3 VARSCOT_SCORE_CTAS_PER_SM=$c; q ctas$c 4 VARSCOT_SCORE_CTAS_PER_SM=$c; done

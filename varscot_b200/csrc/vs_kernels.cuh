@@ -429,7 +429,7 @@ constexpr int SC_THREADS = 32 * SC_WARPS;         // guides per pass of a CTA ov
 constexpr int SC_NB      = BLK_GROUP;             // blocks per batch
 constexpr int SC_STRIDE  = 4 * VS_GLEN;           // words per block in shared memory
 static_assert(SC_STRIDE % 8 == 4, "block stride must be 4 mod 8 words: conflict-free reads of up to 8 blocks at a time");
-constexpr int SC_SMEM_BYTES = (SC_NB * SC_STRIDE + SC_NB) * 4;      // planes + last-window masks
+constexpr int SC_SMEM_BYTES = (SC_NB * SC_STRIDE + SC_NB + BLK_WORDS * SC_NB) * 4;      // planes + last-window masks + raw staging (18 KB)
 constexpr int PAT_STRIDE = 24;                    // uint16 per pattern (23 slot offsets + pad; 48 bytes = 3 x 16)
 
 // position scored by slot j of a strand's slot order: informative positions first, the PAM dinucleotide last
@@ -509,55 +509,89 @@ __global__ void __launch_bounds__(SC_THREADS, score_min_blocks(K))
 k_score(ScoreArgs a)
 {
 #ifndef VS_HOST_UNIT_TEST       // (the host emulation declares vs::sm itself)
-    extern __shared__ __align__(16) uint32_t sm[];     // [SC_NB][SC_STRIDE] planes, then [SC_NB] last-window masks
+    extern __shared__ __align__(16) uint32_t sm[];     // [SC_NB][SC_STRIDE] planes, [SC_NB] last-window masks, [BLK_WORDS][SC_NB] raw staging
 #endif
     constexpr int PA = stage_a_slots(K), PB = VS_GLEN - PA;
+    constexpr uint32_t ROW = SC_STRIDE * 4u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (max(a.rng[2], a.rng[3]) > a.cap) return;          // the candidate store overflowed: the host regrows it and redoes the pass
     // persistent CTAs: batches of the forward range first, then of the reverse range, strided over the grid — the grid does
     // not depend on the block counts, which only the device knows while a pass is in flight
     const unsigned long long nbat_f = (a.rng[2] - a.rng[0] + SC_NB - 1) / SC_NB, nbat = nbat_f + (a.rng[3] - a.rng[1] + SC_NB - 1) / SC_NB;
     uint32_t *lastm_s = sm + SC_NB * SC_STRIDE;
+    uint32_t *raw_s = lastm_s + SC_NB;                      // the batch's 48 raw words per block, as they lie in the store (6 KB)
     const uint32_t zero5[5] = {0u, 0u, 0u, 0u, 0u};
+    auto batch_of = [&](unsigned long long bat, uint32_t &strand, unsigned long long &blk0, uint32_t &nb) {
+        strand = bat >= nbat_f;
+        blk0 = a.rng[strand] + (bat - (strand ? nbat_f : 0ull)) * SC_NB;
+        nb = (uint32_t)min((unsigned long long)SC_NB, a.rng[2 + strand] - blk0);
+    };
+    // stage the raw words of a batch: one layout group = BLK_WORDS * SC_NB contiguous words (ranges start on group boundaries
+    // and the store's capacity is a whole number of groups, so the copy never leaves the allocation); cp.async, so the next
+    // batch's words arrive while this one is scored
+    auto stage = [&](unsigned long long bat) {
+        uint32_t strand, nb; unsigned long long blk0;
+        batch_of(bat, strand, blk0, nb);
+        const uint32_t *src = (strand ? a.planes[1] : a.planes[0]) + plane_index(blk0, 0);
+#ifndef VS_HOST_UNIT_TEST
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw_s);
+        for (uint32_t o = tid * 16u; o < BLK_WORDS * SC_NB * 4u; o += blockDim.x * 16u)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(reinterpret_cast<const char *>(src) + o));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+        for (uint32_t i = tid; i < BLK_WORDS * SC_NB; i += blockDim.x) raw_s[i] = src[i];
+#endif
+    };
+    if ((unsigned long long)blockIdx.x < nbat) stage(blockIdx.x);
+    // a warp whose 32 guides are the same for every batch (the launch has no more guides than the CTA has lanes) keeps the
+    // addresses of its pattern's planes in registers across batches; they change only with the strand
+    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * (uint32_t)wid + 32u <= a.n_guides;
+    const char *adr_keep[PA];
+    int kept_strand = -1;
     for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x) {
-    const uint32_t strand = bat >= nbat_f;
-    const unsigned long long hi = a.rng[2 + strand];
-    const unsigned long long blk0 = a.rng[strand] + (bat - (strand ? nbat_f : 0ull)) * SC_NB;
-    const uint32_t nb = (uint32_t)min((unsigned long long)SC_NB, hi - blk0);
+    uint32_t strand, nb; unsigned long long blk0;
+    batch_of(bat, strand, blk0, nb);
+#ifndef VS_HOST_UNIT_TEST
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    __syncthreads();
     // expand: thread -> (block tid % 32, positions tid / 32, tid / 32 + warps, ...); rows past the range mismatch everywhere
     {
         const uint32_t b = (uint32_t)lane;
-        const uint32_t *gsrc = (strand ? a.planes[1] : a.planes[0]) + plane_index(blk0 + (b < nb ? b : 0), 0);   // word w at gsrc[w * BLK_GROUP]
-        const uint32_t inv = b < nb ? ~__ldg(gsrc + BLK_VALID * BLK_GROUP) : ~0u;
+        const uint32_t inv = b < nb ? ~raw_s[BLK_VALID * SC_NB + b] : ~0u;
         for (int p = wid; p < VS_GLEN; p += (int)(blockDim.x >> 5)) {
-            const uint32_t h = __ldg(gsrc + p * BLK_GROUP), l = __ldg(gsrc + (VS_GLEN + p) * BLK_GROUP);
+            const uint32_t h = raw_s[p * SC_NB + b], l = raw_s[(VS_GLEN + p) * SC_NB + b];
             *reinterpret_cast<uint4 *>(sm + b * SC_STRIDE + 4 * p) =
                 make_uint4((h | l) | inv, (h | ~l) | inv, (~h | l) | inv, (~h | ~l) | inv);     // pattern base A, C, G, T
         }
-        if (wid == 0) lastm_s[b] = b < nb ? __ldg(gsrc + BLK_LAST * BLK_GROUP) : 0u;
+        if (wid == 0) lastm_s[b] = b < nb ? raw_s[BLK_LAST * SC_NB + b] : 0u;
     }
     __syncthreads();
+    if (bat + gridDim.x < nbat) stage(bat + gridDim.x);    // the staging area is free again: fetch the next batch
     const uint16_t *pat0 = a.pat + ((size_t)strand * a.pat_guides + a.guide_base) * PAT_STRIDE;
     const uint32_t *posb = (strand ? a.pos[1] : a.pos[0]) + blk0 * 32;
 
     // one guide segment: GW = 2^L guides [seg, seg + GW) x (32 / GW) blocks per warp iteration.  The walk always covers the
-    // SC_NB rows of the batch (rows past the range mismatch everywhere), so its trip count and the block base are
-    // compile-time / warp-uniform and every LDS is [lane register + uniform register + immediate].
-    auto segment = [&](uint32_t seg, auto gw_log2_c) {
+    // SC_NB rows of the batch (rows past the range mismatch everywhere), so its trip count and the block offsets are
+    // compile-time constants: every LDS is [address register + immediate], no address arithmetic inside a trip.
+    auto segment = [&](uint32_t seg, auto gw_log2_c, auto keep_c) {
         constexpr uint32_t L = decltype(gw_log2_c)::value, GW = 1u << L, STEP = 32u >> L;
+        constexpr bool KEEP = decltype(keep_c)::value;      // walk with the kept address registers (restored after the walk)
         const uint32_t sub = (uint32_t)lane >> L;
         const uint32_t g = seg + ((uint32_t)lane & (GW - 1u));
         const bool real = g < a.n_guides;                  // padding lanes score the segment's first guide; their hits are dropped
         const uint16_t *po = pat0 + (size_t)(real ? g : seg) * PAT_STRIDE;
-        const char *smb = reinterpret_cast<const char *>(sm) + sub * (SC_STRIDE * 4u);     // the lane's first block row
-        const char *adr[PA];                               // the lane's stage-A planes in that row
-        {
+        const char *smb = reinterpret_cast<const char *>(sm) + sub * ROW;     // the lane's first block row
+        const char *adr_local[KEEP ? 1 : PA];
+        const char *(&adr)[KEEP ? PA : (KEEP ? 1 : PA)] = *reinterpret_cast<const char *(*)[PA]>(KEEP ? (void *)adr_keep : (void *)adr_local);   // the lane's stage-A planes in that row
+        if (!KEEP || kept_strand != (int)strand) {
             const uint4 *q = reinterpret_cast<const uint4 *>(po);
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 3; ++i) { const uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
 #pragma unroll
             for (int i = 0; i < PA; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+            if (KEEP) kept_strand = (int)strand;
         }
         // UNR iterations per trip with compile-time offsets; the address registers advance once per trip
         constexpr uint32_t UNR = (uint32_t)SC_UNROLL < (uint32_t)SC_NB / STEP ? (uint32_t)SC_UNROLL : (uint32_t)SC_NB / STEP;
@@ -565,7 +599,6 @@ k_score(ScoreArgs a)
         for (uint32_t j0 = 0; j0 < (uint32_t)SC_NB; j0 += STEP * UNR) {
 #pragma unroll
             for (uint32_t u = 0; u < UNR; ++u) {
-                constexpr uint32_t ROW = SC_STRIDE * 4u;
                 const uint32_t j = j0 + u * STEP;              // first block of the iteration
                 uint32_t m[PA], ca[5];
 #pragma unroll
@@ -590,7 +623,11 @@ k_score(ScoreArgs a)
                 }
             }
 #pragma unroll
-            for (int i = 0; i < PA; ++i) adr[i] += STEP * UNR * SC_STRIDE * 4u;
+            for (int i = 0; i < PA; ++i) adr[i] += STEP * UNR * ROW;
+        }
+        if (KEEP) {
+#pragma unroll
+            for (int i = 0; i < PA; ++i) adr[i] -= SC_NB * ROW;
         }
     };
     const uint32_t warps = blockDim.x >> 5;
@@ -598,15 +635,19 @@ k_score(ScoreArgs a)
         const uint32_t g_w = gc + 32u * (uint32_t)wid;
         if (g_w >= a.n_guides) break;
         const uint32_t n = min(32u, a.n_guides - g_w);
-        if (n == 32u) { segment(g_w, std::integral_constant<uint32_t, 5>{}); continue; }
+        if (n == 32u) {
+            if (fixed_guides) segment(g_w, std::integral_constant<uint32_t, 5>{}, std::true_type{});
+            else segment(g_w, std::integral_constant<uint32_t, 5>{}, std::false_type{});
+            continue;
+        }
         // tail of the guide list: pad to a multiple of 4 and split into 16 / 8 / 4 guides x 2 / 4 / 8 blocks per iteration
         const uint32_t np = (n + 3u) & ~3u;
         uint32_t seg = g_w;
-        if (np & 16u) { segment(seg, std::integral_constant<uint32_t, 4>{}); seg += 16u; }
-        if (np & 8u) { segment(seg, std::integral_constant<uint32_t, 3>{}); seg += 8u; }
-        if (np & 4u) { segment(seg, std::integral_constant<uint32_t, 2>{}); }
+        if (np & 16u) { segment(seg, std::integral_constant<uint32_t, 4>{}, std::false_type{}); seg += 16u; }
+        if (np & 8u) { segment(seg, std::integral_constant<uint32_t, 3>{}, std::false_type{}); seg += 8u; }
+        if (np & 4u) { segment(seg, std::integral_constant<uint32_t, 2>{}, std::false_type{}); }
     }
-    __syncthreads();                                       // the next batch overwrites the planes
+    // (the barrier at the top of the next batch keeps its expansion from overwriting planes that are still being scored)
     }
 }
 
