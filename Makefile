@@ -10,7 +10,7 @@ LIB     := varscot_b200/libvarscot_scan.so
 BINDIR  := build/read_mapping_build
 SRCS    := $(CSRC)/vs_device.cu $(CSRC)/vs_host.cpp $(CSRC)/vs_cli.cpp $(CSRC)/vs_vcf.cpp $(CSRC)/vs_merge.cpp
 VPDIR   := build/variant_processing_build
-HDRS    := $(CSRC)/vs_kernels.cuh $(CSRC)/vs_extract_block.inc $(CSRC)/vs_extract_half_block.inc $(CSRC)/vs_internal.h $(CSRC)/vs_genome.h include/varscot_scan.h
+HDRS    := $(CSRC)/vs_kernels.cuh $(CSRC)/vs_extract_block.inc $(CSRC)/vs_bucket.cuh $(CSRC)/vs_internal.h $(CSRC)/vs_genome.h include/varscot_scan.h
 
 all: $(LIB) $(BINDIR)/bidir_mapping $(BINDIR)/bidir_index $(VPDIR)/vcf_loader $(VPDIR)/fasta_writer $(VPDIR)/bam_merger $(VPDIR)/bam_merger_ref_only
 

@@ -64,6 +64,28 @@ def score_ops(k):
     return a, b
 
 
+def bucketed_ops(guides, k, pam):
+    """Mean (LOP3, LDS) k_score_bucketed executes per (32-candidate block, guide) in stage A on uniform text: a guide meets
+    the buckets of a PAM kind with c = c4 + c_pam mismatches at the six key positions, c4 ~ C(4, j) 3^j / 256 over the 256
+    buckets of the kind (whatever the guide), c_pam = its PAM against the kind's; the budget for the other 17 positions is
+    K' = k - c (nothing is scored when K' < 0) and stage A loads PA = min(17, 7 + 2 K') of them."""
+    from math import comb
+    kinds = [(2, 2), (2, 0)] + ([("ACGT".index(pam[0]), "ACGT".index(pam[1]))] if pam else [])
+    w4 = [comb(4, j) * 3 ** j / 256.0 for j in range(5)]
+    g = np.asarray(guides)
+    lop = lds = 0.0
+    for x, y in kinds:
+        # forward pass: pattern = guide, PAM at 21, 22; reverse pass: pattern = revcomp(guide), PAM at window 0, 1 = (3 - y, 3 - x)
+        cp = (g[:, 21] != x).astype(int) + (g[:, 22] != y).astype(int)       # identical on both strands
+        for j, w in enumerate(w4):
+            kp = k - j - cp
+            pa = np.minimum(17, np.where(kp >= 8, 23, 7 + 2 * kp))
+            ops = np.array([csa_ops(int(a)) + 2 if q >= 0 else 0 for a, q in zip(pa, kp)], dtype=float)
+            lop += w * ops.mean() / len(kinds)
+            lds += w * np.where(kp >= 0, pa, 0).mean() / len(kinds)
+    return lop, lds
+
+
 CONFIGS = {
     # id: (description, genome bases, variants, guides, k, extra PAM, guide seed)
     1: ("cfg1: 10 guides vs 50 Mbp + 10k SNVs, <=4 mm", 50_000_000, 10_000, 10, 4, None, 3),
@@ -355,22 +377,28 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
     units = float(ng) * n_total_bases                     # guide·bp per step over all ranks (strong: ONE text)
     ctx.upload(text, first, words)
     ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
-    # ---- index resident -------------------------------------------------------------------------
-    for _ in range(max(1, warmup)):
-        hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
-    barrier(world, local)
-    dev = score = resolve = 0.0
     launches = 0
-    for _ in range(steps):
-        hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
-        assert st.index_reused == 1
-        dev += st.total_ms; score += st.score_ms; resolve += st.resolve_ms; launches += st.launches
-    barrier(world, local)
-    ms = all_reduce(dev / steps, world, local, "MAX")
-    res["warm"] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "resolve_ms": resolve / steps, "launches": launches,
-                   "score_launches": int(st.score_launches), "blocks": int(st.n_blocks_fwd + st.n_blocks_rev),
-                   "cands": int(st.n_cand_fwd + st.n_cand_rev), "hits": int(all_reduce(float(len(hits)), world, local, "SUM"))}
+    # ---- index resident: its plain form (k_score), then its bucketed form (k_score_bucketed) -------------------------
+    for name, bucket in (("warm_plain", 0), ("warm", 1)):
+        ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, bucket)
+        build_ms = 0.0
+        for _ in range(max(2, warmup)):
+            hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+            build_ms = max(build_ms, st.index_build_ms)
+        barrier(world, local)
+        dev = score = resolve = 0.0
+        for _ in range(steps):
+            hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
+            assert st.index_reused == 1 + bucket
+            dev += st.total_ms; score += st.score_ms; resolve += st.resolve_ms; launches += st.launches
+        barrier(world, local)
+        ms = all_reduce(dev / steps, world, local, "MAX")
+        res[name] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "resolve_ms": resolve / steps, "launches": launches,
+                     "score_launches": int(st.score_launches), "blocks": int(st.n_blocks_fwd + st.n_blocks_rev), "index_build_ms": build_ms,
+                     "cands": int(st.n_cand_fwd + st.n_cand_rev), "hits": int(all_reduce(float(len(hits)), world, local, "SUM"))}
     # ---- cold: the index is extracted again every step ------------------------------------------------
+    res["launches"] = launches
+    launches = 0
     ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 0)
     for _ in range(2):
         ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
@@ -383,7 +411,7 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
     ms = all_reduce(dev / steps, world, local, "MAX")
     res["cold"] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "extract_ms": extract / steps, "chunks": int(st.n_chunks),
                    "score_launches": int(st.score_launches), "redo": int(st.redo_chunks)}
-    res["launches"] = launches
+    res["launches"] += launches
     if not do_e2e:
         return res, None
 
@@ -639,12 +667,16 @@ def main():
         r4, merged4 = measure(V, ctx, text, g4, c4[4], c4[5], first, words, tsteps, 3, world, local, hits_buf, exchange, total_bases, c4[3], host_threads,
                               do_e2e=not args.no_e2e)
         if rank == 0:
-            (lop_a, lds_a), _ = score_ops(c4[4])
+            lop_a, lds_a = bucketed_ops(g4, c4[4], c4[5])
             ex4 = lop_a * r4["warm"]["blocks"] * c4[3] / (r4["warm"]["score_ms"] * 1e-3)
+            (lop_p4, _), _ = score_ops(c4[4])
             target = {"workload": c4[0], "guides": c4[3], "k": c4[4], "extra_pam": c4[5], "steps": tsteps,
                       "value": r4["warm"]["value"], "ms_per_step": r4["warm"]["ms"], "value_cold": r4["cold"]["value"], "ms_per_step_cold": r4["cold"]["ms"],
                       "phase_ms_rank0": {"score": r4["warm"]["score_ms"], "resolve": r4["warm"]["resolve_ms"], "extract_cold": r4["cold"]["extract_ms"]},
                       "hits_per_step": r4["warm"]["hits"], "frac_executed": ex4 / peak_lop3, "executed_lop3_tlops": ex4 / 1e12,
+                      "plain_index": {"value": r4["warm_plain"]["value"], "ms_per_step": r4["warm_plain"]["ms"], "score_ms": r4["warm_plain"]["score_ms"],
+                                      "frac_executed": lop_p4 * r4["warm_plain"]["blocks"] * c4[3] / (r4["warm_plain"]["score_ms"] * 1e-3) / peak_lop3},
+                      "index_build_ms_rank0": r4["warm"]["index_build_ms"],
                       "e2e": r4.get("e2e"), "redo": r4["cold"]["redo"]}
             if not args.no_cpu and merged4 is not None:
                 os.sched_setaffinity(0, all_cpus)
@@ -661,14 +693,16 @@ def main():
             exchange.close()
         return
     # ---- roofline of the dominant kernel (k_score) -----------------------------------------------------
-    warm, cold = res["warm"], res["cold"]
+    warm, cold, plain = res["warm"], res["cold"], res["warm_plain"]
     blocks = warm["blocks"]
     score_s = warm["score_ms"] * 1e-3
     B_local = min(B - first * 32, words * 32)             # bases whose window starts this rank owns
-    (lop_a, lds_a), (lop_b, lds_b) = score_ops(k)
+    (lop_p, lds_p), (lop_b, lds_b) = score_ops(k)
+    lop_a, lds_a = bucketed_ops(guides, k, pam)
     executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few iterations that pass)
     lds = lds_a * blocks * ng / score_s
     yard = C_ALG * ng * B_local / score_s
+    plain_s = plain["score_ms"] * 1e-3
     traffic, traffic_src = None, None
     for name in ("r2_score_summary.txt", "r1_score_final_summary.txt"):
         try:
@@ -689,10 +723,14 @@ def main():
     except Exception:
         pass
     hbm_alg = blocks * 192.0 / score_s / 1e9
-    roof = {"bound": "int_alu", "kernel": "k_score", "achieved": executed / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
+    roof = {"bound": "int_alu", "kernel": "k_score_bucketed", "achieved": executed / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
             "frac": executed / peak_lop3,
-            "frac_note": "executed stage-A LOP3 (34 per 32-candidate block and guide at k = 6: 32 adder + 2 threshold) / measured alu-pipe LOP3 rate; "
-                         "a lower bound of the pipe load (stage B, hit path and loop overhead not counted); ncu pipe_alu of the same kernel: profiles/",
+            "frac_note": "executed stage-A LOP3 of the scoring kernel (adder tree + 2 threshold ops per 32-candidate block and guide; the bucketed index scores "
+                         "%.1f LOP3 / %.1f LDS per pair on average instead of the plain index's %d / %d) / measured alu-pipe LOP3 rate; a lower bound of the pipe load "
+                         "(stage B, hit path, loop and segment overhead not counted); ncu pipe_alu / pipe_lsu of the same kernels: profiles/" % (lop_a, lds_a, lop_p, lds_p),
+            "plain_index": {"kernel": "k_score", "score_ms": plain["score_ms"], "value": plain["value"], "ms_per_step": plain["ms"],
+                            "frac": lop_p * blocks * ng / plain_s / peak_lop3, "frac_lds": lds_p * blocks * ng / plain_s / peak_lds,
+                            "ops_per_block_guide": {"stage_a_lop3": lop_p, "stage_a_lds": lds_p}},
             "frac_yardstick": yard / peak_lop3,
             "yardstick_note": "dense-scan yardstick of SURVEY.md 8d: 4.0 LOP3 per guide*bp; the PAM-first index scores ~1/8 of the windows per strand, so this exceeds 1",
             "traffic": traffic, "traffic_note": f"dram bytes of one k_score launch, ncu capture profiles/{traffic_src}; algorithmic = 192 B per block per launch",
@@ -700,15 +738,17 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "MEASURED_PEAKS.json absent"},
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
             "avg_launch_ms": warm["score_ms"] / max(1, warm["score_launches"]), "launches_per_step": warm["score_launches"],
-            "ops_per_block_guide": {"stage_a_lop3": lop_a, "stage_a_lds": lds_a, "stage_b_lop3": lop_b, "stage_b_lds": lds_b},
+            "ops_per_block_guide": {"stage_a_lop3": lop_a, "stage_a_lds": lds_a},
             "lds_words_per_s_T": lds / 1e12, "lds_peak_T": peak_lds / 1e12, "frac_lds": lds / peak_lds}
     scaling = "strong" if strong else "weak"
     out = {
         "metric": "guide_Gbp_per_s", "value": warm["value"], "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": warm["ms"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
         "data": "synthetic", "config": config_dict(cfg, B, text.n_contigs, scaling if world > 1 else "single", args.scale),
-        "value_note": "packed text AND candidate index resident in HBM (index = PAM-valid windows, built once per text and PAM set: the analogue of "
-                      "the reference's prebuilt FM index); first kernel -> resolved + sorted hits in host memory, CUDA events, max over ranks",
+        "value_note": "packed text AND candidate index resident in HBM (index = the PAM-valid windows of both strands, bucketed by PAM kind + the four bases next to "
+                      "the PAM; built once per text and PAM set: the analogue of the reference's prebuilt FM index); first kernel -> resolved + sorted hits in host memory, "
+                      "CUDA events, max over ranks",
+        "value_plain_index": plain["value"], "ms_per_step_plain_index": plain["ms"], "index_build_ms_rank0": warm["index_build_ms"],
         "value_cold": cold["value"], "ms_per_step_cold": cold["ms"],
         "value_cold_note": "the same with the index dropped before every step: extraction of the PAM-valid windows included",
         "layout": {"text_bases_per_gpu": int(B_local), "shard_words": int(words), "chunks": cold["chunks"], "cpus_bound_per_rank": numa_cpus,

@@ -3,7 +3,7 @@
 //    k_extract_mark, k_resolve_hits, k_pack_loc_hits) run thread by thread from their real source, against naive restatements;
 //    k_score<K> and the contig-start kernels (barriers) run with one OS thread per CUDA thread;
 //  * k_extract (warp shuffles, cp.async) is guarded out; its phase 2 runs through the very text the kernel includes
-//    (vs_extract_block.inc, and the experimental vs_extract_half_block.inc), its phase 1 through cand_masks;
+//    (vs_extract_block.inc), its phase 1 through cand_masks;
 //  * the helpers (register transposes, bit-sliced adders and thresholds, pattern-table encoding, plane layout) have
 //    their own checks.
 // Nothing in the product uses this file.  Built and run by tests/test_host.py::test_device_code_on_the_host.
@@ -82,14 +82,6 @@ static void test_transposes()
         transpose32(a);
         for (int i = 0; i < 32; ++i)
             for (int c = 0; c < 32; ++c) CHECK(((a[i] >> c) & 1) == ((in[c] >> i) & 1));
-        uint32_t in16[16], h[16];
-        for (int i = 0; i < 16; ++i) h[i] = in16[i] = r32();
-        transpose16(h);
-        for (int r = 0; r < 16; ++r)
-            for (int c = 0; c < 16; ++c) {
-                CHECK(((h[r] >> c) & 1) == ((in16[c] >> r) & 1));
-                CHECK(((h[r] >> (16 + c)) & 1) == ((in16[c] >> (16 + r)) & 1));
-            }
     }
 }
 
@@ -167,7 +159,7 @@ static void test_pattern_table()
 }
 
 // ---- phase 2 of k_extract on the host: the very text the kernel includes (vs_extract_block.inc, and the experimental
-// vs_extract_half_block.inc) runs over a random tile and is compared with a naive gather of the tile's candidates.
+// runs over a random tile and is compared with a naive gather of the tile's candidates.
 struct Tile {
     uint32_t nw;
     uint2 s_hl[EX_MAX_WORDS + 2], s_mk[EX_MAX_WORDS + 2];
@@ -203,14 +195,9 @@ static void run_phase2(const Tile &t, bool half, const unsigned long long base[2
     const uint32_t nw = t.nw, nf = t.nf, nr = t.nr, nbf = t.nbf, nbr = t.nbr;
     const uint2 *s_hl = t.s_hl, *s_mk = t.s_mk;
     const uint32_t (*s_m)[EX_MAX_WORDS + 1] = t.s_m, (*s_p)[EX_MAX_WORDS + 1] = t.s_p;
-    if (half) {
-        for (uint32_t j2 = 0; j2 < 2 * (nbf + nbr); ++j2) {
-#include "../varscot_b200/csrc/vs_extract_half_block.inc"
-        }
-    } else {
-        for (uint32_t j = 0; j < nbf + nbr; ++j) {
+    (void)half;
+    for (uint32_t j = 0; j < nbf + nbr; ++j) {
 #include "../varscot_b200/csrc/vs_extract_block.inc"
-        }
     }
 }
 
@@ -228,7 +215,7 @@ static void test_extract_phase2()
         const uint32_t nw = rep % 5 == 0 ? 1 + r32() % 8 : 8 + r32() % (EX_MAX_WORDS - 8);
         make_tile(t, nw, rep % 3, pp);
         const uint32_t gbase = r32() & 0x0FFFFFFFu;
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 1; ++half) {
             std::vector<uint32_t> pl[2], ps[2];
             for (int s = 0; s < 2; ++s) { pl[s].assign(store_words, 0xDEADBEEFu); ps[s].assign(n_store * 32 + 32, 0xDEADBEEFu); }
             run_phase2(t, half != 0, base, n_store, gbase, pl[0].data(), ps[0].data(), pl[1].data(), ps[1].data());

@@ -22,6 +22,18 @@ namespace vs { uint32_t sm[SC_SMEM_BYTES / 4] __attribute__((aligned(16))); }
 using namespace vs;
 
 template <int K>
+static void run_score_bk(const BkScoreArgs &a, unsigned ctas) { launch_cta(ctas, SC_THREADS, [&] { k_score_bucketed<K>(a); }); }
+
+static void dispatch_score_bk(int k, const BkScoreArgs &a, unsigned ctas)
+{
+    switch (k) {
+    case 0: run_score_bk<0>(a, ctas); break; case 1: run_score_bk<1>(a, ctas); break; case 2: run_score_bk<2>(a, ctas); break;
+    case 3: run_score_bk<3>(a, ctas); break; case 4: run_score_bk<4>(a, ctas); break; case 5: run_score_bk<5>(a, ctas); break;
+    case 6: run_score_bk<6>(a, ctas); break; case 7: run_score_bk<7>(a, ctas); break; default: run_score_bk<8>(a, ctas); break;
+    }
+}
+
+template <int K>
 static void run_score(const ScoreArgs &a, unsigned ctas, unsigned threads) { launch_cta(ctas, threads, [&] { k_score<K>(a); }); }
 
 static void dispatch_score(int k, const ScoreArgs &a, unsigned ctas, unsigned threads)
@@ -115,6 +127,59 @@ int main(int argc, char **argv)
         for (unsigned long long i = 0; i < n2; ++i) b.push_back(key(hits2[i]));
         std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
         if (a != b) { fprintf(stderr, "the scan of the whole store (%llu hits) differs from the chunk-by-chunk scan (%llu hits)\n", n2, n_hits); return 4; }
+        // ---- the bucketed index, built from the plain store and the text as build_bucket_index (vs_device.cu) does, then
+        // scored by k_score_bucketed: the same hits once more
+        std::vector<unsigned long long> ctl(2 * BK_N + 2 * BK_N + 2 * (BK_N + 1), 0);
+        unsigned long long *hist = ctl.data(), *cursor = hist + 2 * BK_N, *start = cursor + 2 * BK_N;
+        const uint64_t max_blocks = std::max(all[2], all[3]);
+        const unsigned g = (unsigned)((max_blocks + BKB_THREADS - 1) / BKB_THREADS);
+        launch_cta(g, BKB_THREADS, [&] { k_bucket_hist(planes[0].data(), planes[1].data(), all, pp, hist); }, 2);
+        launch_cta(2, BK_N, [&] { k_bucket_scan(hist, start, cursor); });
+        std::vector<uint32_t> bpl[2], bps[2];
+        uint64_t nbk[2];
+        for (int s = 0; s < 2; ++s) {
+            nbk[s] = start[s * (BK_N + 1) + BK_N];
+            if (nbk[s] % SC_NB) { fprintf(stderr, "bucketed store is not a whole number of batches\n"); return 5; }
+            bpl[s].assign((nbk[s] + SC_NB) * BLK_WORDS, 0xDEADBEEFu);
+            bps[s].assign((nbk[s] + 1) * 32, BK_NOPOS);
+        }
+        launch_cta(g, BKB_THREADS, [&] {
+            k_bucket_scatter(planes[0].data(), planes[1].data(), pos[0].data(), pos[1].data(), all, pp, cursor, bps[0].data(), bps[1].data(), nbk[0] * 32, nbk[1] * 32);
+        }, 2);
+        for (int s = 0; s < 2; ++s)
+            if (nbk[s]) launch((unsigned)((nbk[s] + 63) / 64), 1, 64, [&] { k_bucket_gather(bases.data(), masks.data(), 0, bps[s].data(), nbk[s], bpl[s].data()); });
+        // every candidate of the plain store sits in exactly one bucket slot
+        for (int s = 0; s < 2; ++s) {
+            uint64_t placed = 0;
+            for (uint64_t i = 0; i < nbk[s] * 32; ++i) placed += bps[s][i] != BK_NOPOS;
+            if (placed != cnt[s]) { fprintf(stderr, "strand %d: %llu candidates, %llu bucket slots filled\n", s, cnt[s], (unsigned long long)placed); return 5; }
+        }
+        std::vector<uint16_t> gkey((size_t)2 * n_guides), perm((size_t)2 * BK_N * n_guides, 0xFFFF);
+        std::vector<uint32_t> cls((size_t)2 * BK_N * BK_CLS, 0);
+        for (int s = 0; s < 2; ++s)
+            for (uint32_t gi = 0; gi < n_guides; ++gi) {
+                uint8_t pc[VS_GLEN];
+                for (int i = 0; i < VS_GLEN; ++i) pc[i] = s ? (uint8_t)(3 - guides[(size_t)gi * VS_GLEN + VS_GLEN - 1 - i]) : guides[(size_t)gi * VS_GLEN + i];
+                gkey[(size_t)s * n_guides + gi] = (uint16_t)key_of_codes(s, pc);
+            }
+        launch_cta(BK_N, 128, [&] { k_guide_classes(gkey.data(), n_guides, pp, perm.data(), cls.data()); }, 2);
+        std::vector<vs_hit> hits3(hits.size());
+        unsigned long long n3 = 0;
+        for (;;) {
+            BkScoreArgs q;
+            for (int s = 0; s < 2; ++s) { q.planes[s] = bpl[s].data(); q.pos[s] = bps[s].data(); }
+            q.start = start; q.n_guides = n_guides; q.guide_base = 0; q.pat_guides = n_guides; q.pat = pat16;
+            q.perm = perm.data(); q.cls = cls.data();
+            n3 = 0;
+            q.hits = hits3.data(); q.n_hits = &n3; q.hit_cap = hits3.size();
+            dispatch_score_bk(k, q, 3);
+            if (n3 <= hits3.size()) break;
+            hits3.resize(n3 + n3 / 4);
+        }
+        std::vector<uint64_t> c3;
+        for (unsigned long long i = 0; i < n3; ++i) c3.push_back(key(hits3[i]));
+        std::sort(c3.begin(), c3.end());
+        if (a != c3) { fprintf(stderr, "the scan of the bucketed index (%llu hits) differs from the plain scan (%llu hits)\n", n3, n_hits); return 6; }
     }
     f = fopen(argv[2], "wb");
     if (!f) { perror(argv[2]); return 2; }

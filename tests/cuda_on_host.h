@@ -60,6 +60,8 @@ static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline uint32_t __ldg(const uint32_t *p) { return *p; }
 // (k_score runs under launch_cta: its threads are concurrent OS threads)
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline uint16_t __ldg(const uint16_t *p) { return *p; }
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
@@ -84,19 +86,20 @@ static void launch(unsigned grid_x, unsigned grid_y, unsigned block, F kernel)
 }
 
 template <class F>
-static void launch_cta(unsigned grid_x, unsigned block, F kernel)
+static void launch_cta(unsigned grid_x, unsigned block, F kernel, unsigned grid_y = 1)
 {
-    gridDim = Idx3{grid_x, 1, 1}; blockDim = Idx3{block, 1, 1};
+    gridDim = Idx3{grid_x, grid_y, 1}; blockDim = Idx3{block, 1, 1};
     std::barrier<> bar((std::ptrdiff_t)block);
     g_cta_barrier = &bar;
     std::vector<std::thread> th;
     for (unsigned t = 0; t < block; ++t)
         th.emplace_back([&, t] {
-            for (unsigned bx = 0; bx < grid_x; ++bx) {
-                blockIdx = Idx3{bx, 0, 0}; threadIdx = Idx3{t, 0, 0};
-                kernel();
-                bar.arrive_and_wait();                    // the next CTA reuses the __shared__ statics
-            }
+            for (unsigned by = 0; by < grid_y; ++by)
+                for (unsigned bx = 0; bx < grid_x; ++bx) {
+                    blockIdx = Idx3{bx, by, 0}; threadIdx = Idx3{t, 0, 0};
+                    kernel();
+                    bar.arrive_and_wait();                // the next CTA reuses the __shared__ statics
+                }
         });
     for (auto &x : th) x.join();
     g_cta_barrier = nullptr;

@@ -29,12 +29,6 @@ def emulator(tmp_path_factory):
     return build_emulator(str(tmp_path_factory.mktemp("emu") / "cpu_scan_emulator"))
 
 
-@pytest.fixture(scope="module")
-def emulator_half(tmp_path_factory):
-    """The EXPERIMENTAL k_extract with one thread per half block (-DVS_EX_HALF=1; not the product's default build)."""
-    return build_emulator(str(tmp_path_factory.mktemp("emu_half") / "cpu_scan_emulator"), "-DVS_EX_HALF=1")
-
-
 def emulate(exe, tmp_path, text, guides, k, pam=None, tile_words=0, chunk_words=1 << 20):
     inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     g = np.ascontiguousarray(guides, dtype=np.uint8).reshape(-1, 23)
@@ -86,10 +80,3 @@ def test_emulated_scan_n_runs_and_last_windows(emulator, tmp_path):
     asc[3000:3000 + 9000] = b"N" * 9000
     case.ascii = bytes(asc)
     assert check(emulator, tmp_path, case) > 0
-
-
-@pytest.mark.parametrize("k", [2, 6, 8])
-def test_experimental_half_block_extraction_equals_oracle(emulator_half, tmp_path, k):
-    case = make_case(seed=500 + k, contig_lens=[7000, 45, 45, 23, 0, 46, 2000], n_guides=5, k=k, pam=[None, "AG"][k % 2])
-    assert check(emulator_half, tmp_path, case) > 0
-    assert check(emulator_half, tmp_path, case, chunk_words=57, tile_words=24) > 0

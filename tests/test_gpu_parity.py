@@ -510,6 +510,7 @@ def test_resident_index_is_reused_and_rebuilt():
     with V.ScanContext(0) as ctx:
         ctx.set_chunk_words(900)
         ctx.upload(text)
+        ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, 0)             # the plain index only (its bucketed form has its own test)
         a, st_a = ctx.scan(case.guides, 5)
         b, st_b = ctx.scan(case.guides, 5)
         assert st_a.index_reused == 0 and st_a.extract_ms > 0
@@ -537,6 +538,63 @@ def test_resident_index_is_reused_and_rebuilt():
         ctx.upload(text, 0, text.n_words // 2)                  # a new upload drops the index
         h, st_h = ctx.scan(case.guides, 5)
         assert st_h.index_reused == 0 and len(h) < len(a)
+
+
+@pytest.mark.parametrize("k,pam,n_guides", [(0, None, 5), (1, "AG", 40), (2, None, 7), (3, "TT", 33), (4, None, 130), (5, "AG", 9), (6, None, 100), (7, "CC", 12), (8, None, 36)])
+def test_bucketed_index_equals_oracle(k, pam, n_guides):
+    """The second scan of a resident text regroups the candidate index by PAM kind + the four bases next to the PAM
+    (vs_bucket.cuh) and scores it with per-bucket mismatch budgets: same records as the oracle for every k, with the guide
+    counts exercising full and 4-guide segments of every class, last windows, N runs, several shards."""
+    import varscot_b200 as V
+    case = make_case(seed=700 + k, contig_lens=[60000, 45, 45, 45, 23, 22, 46, 20000] + [45] * 200 + [9000], n_guides=n_guides, k=k, pam=pam,
+                     guide_pam=(pam if pam in ("AG",) else "GG"))
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, k, pam)
+    for shards in (1, 3):
+        lists = []
+        nw = text.n_words
+        for i in range(shards):
+            w0, w1 = nw * i // shards, nw * (i + 1) // shards
+            with V.ScanContext(0) as ctx:
+                ctx.set_chunk_words(500)
+                ctx.upload(text, w0, w1 - w0)
+                h1, st1 = ctx.scan_resolved(case.guides, k, pam=pam)
+                h2, st2 = ctx.scan_resolved(case.guides, k, pam=pam)        # builds and scores the bucketed index
+                h3, st3 = ctx.scan_resolved(case.guides, k, pam=pam)
+                assert (st1.index_reused, st2.index_reused, st3.index_reused) == (0, 2, 2)
+                assert st2.index_build_ms > 0 and st3.index_build_ms == 0
+                assert h1.tolist() == h2.tolist() == h3.tolist()            # sorted lists: identical, not just equal as sets
+                lists.append(h3.copy())
+        rec, _ = V.merge_resolved(lists)
+        assert rows_from_records(text, rec, case.offsets, case.guides) == exp
+    assert len(exp) > 0
+
+
+def test_bucketed_index_many_guides_and_hit_buffer_regrow():
+    import varscot_b200 as V
+    from varscot_b200 import _lib
+    case = make_case(seed=710, contig_lens=[90000], n_guides=1100, k=4, plant=False)
+    rng = np.random.default_rng(5)
+    codes = np.frombuffer(case.ascii, dtype=np.uint8).copy()
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for g in (0, 31, 32, 127, 128, 511, 1023, 1024, 1099):
+        p = int(rng.integers(0, 90000 - GLEN))
+        w = case.guides[g].copy()
+        w[int(rng.integers(0, 23))] ^= 1
+        if g % 2:
+            w = revcomp_codes(w)
+        codes[p:p + GLEN] = lut[w]
+    case.ascii = bytes(codes)
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    exp = oracle_rows(case.ascii, case.offsets, case.guides, 4)
+    with V.ScanContext(0) as ctx:
+        ctx.set_option(_lib.VS_OPT_HIT_CAPACITY, 64)             # several guide passes over the bucketed index + regrowing
+        ctx.upload(text)
+        ctx.scan_resolved(case.guides, 4)
+        hits, st = ctx.scan_resolved(case.guides, 4)
+        assert st.index_reused == 2
+    rec, _ = V.merge_resolved([hits])
+    assert rows_from_records(text, rec, case.offsets, case.guides) == exp and len(exp) >= 9
 
 
 @pytest.mark.parametrize("use_sink", [False, True])

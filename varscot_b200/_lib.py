@@ -36,7 +36,7 @@ class ScanStats(C.Structure):
                 ("n_blocks_fwd", C.c_uint64), ("n_blocks_rev", C.c_uint64),
                 ("n_hits", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint32), ("score_launches", C.c_uint32), ("n_chunks", C.c_uint32), ("redo_chunks", C.c_uint32),
-                ("resolve_ms", C.c_float), ("index_reused", C.c_uint32), ("guide_passes", C.c_uint32), ("reserved", C.c_uint32)]
+                ("resolve_ms", C.c_float), ("index_reused", C.c_uint32), ("guide_passes", C.c_uint32), ("index_build_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -47,7 +47,7 @@ class LocHit(C.Structure):
 
 
 HIT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32)
-VS_OPT_KEEP_INDEX, VS_OPT_HIT_CAPACITY = 1, 2
+VS_OPT_KEEP_INDEX, VS_OPT_HIT_CAPACITY, VS_OPT_BUCKET_INDEX = 1, 2, 3
 
 
 class TextView(C.Structure):

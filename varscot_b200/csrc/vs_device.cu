@@ -58,8 +58,19 @@ struct vs_ctx {
     int idx_pam = -2;
     uint64_t idx_blocks[2] = {0, 0}, idx_cand[2] = {0, 0};
     uint32_t idx_chunks = 0;
+    uint64_t idx_end[2] = {0, 0};       // block claims incl. the padding of every chunk = the whole-store range
     int keep_index = 1;
     uint64_t hit_cap_opt = 0;
+    // bucketed index (vs_bucket.cuh): the candidates regrouped by PAM kind + the four bases next to the PAM
+    int bucket_mode = 1;                 // VS_OPT_BUCKET_INDEX: 0 never, 1 when a resident index is scanned again
+    bool bk_valid = false;
+    uint32_t *d_bk_planes[2] = {nullptr, nullptr}, *d_bk_pos[2] = {nullptr, nullptr};
+    uint64_t bk_cap[2] = {0, 0}, bk_blocks[2] = {0, 0};
+    unsigned long long *d_bk_ctl = nullptr, *h_bk_ctl = nullptr;     // hist [2][BK_N], cursor [2][BK_N], start [2][BK_N + 1]
+    uint16_t *d_perm = nullptr, *d_gkey = nullptr, *h_gkey = nullptr;
+    uint32_t *d_cls = nullptr;
+    uint64_t perm_cap = 0, gkey_cap = 0;
+    float bk_build_ms = 0.f;
     // pattern table [2][n_guides][PAT_STRIDE] of uint16
     uint16_t *d_pat = nullptr, *h_pat = nullptr;
     uint64_t pat_cap = 0;
@@ -171,6 +182,10 @@ extern "C" void vs_ctx_destroy(vs_ctx *ctx)
     cudaFree(ctx->d_pat);
     if (ctx->h_pat) cudaFreeHost(ctx->h_pat);
     cudaFree(ctx->d_hits); cudaFree(ctx->d_loc); cudaFree(ctx->d_sort_tmp);
+    for (int s = 0; s < 2; ++s) { cudaFree(ctx->d_bk_planes[s]); cudaFree(ctx->d_bk_pos[s]); }
+    cudaFree(ctx->d_bk_ctl); cudaFree(ctx->d_perm); cudaFree(ctx->d_gkey); cudaFree(ctx->d_cls);
+    if (ctx->h_bk_ctl) cudaFreeHost(ctx->h_bk_ctl);
+    if (ctx->h_gkey) cudaFreeHost(ctx->h_gkey);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -189,6 +204,7 @@ extern "C" int vs_ctx_set_option(vs_ctx *ctx, int option, int64_t value)
     switch (option) {
     case VS_OPT_KEEP_INDEX: ctx->keep_index = value != 0; if (!ctx->keep_index) ctx->idx_valid = false; return VS_OK;
     case VS_OPT_HIT_CAPACITY: if (value < 0) break; ctx->hit_cap_opt = (uint64_t)value; return VS_OK;
+    case VS_OPT_BUCKET_INDEX: if (value < 0 || value > 1) break; ctx->bucket_mode = (int)value; if (!value) ctx->bk_valid = false; return VS_OK;
     default: break;
     }
     return fail(ctx, VS_ERR_ARG, "vs_ctx_set_option: unknown option or bad value");
@@ -197,7 +213,7 @@ extern "C" int vs_ctx_set_option(vs_ctx *ctx, int option, int64_t value)
 extern "C" int vs_index_drop(vs_ctx *ctx)
 {
     if (!ctx) return fail(nullptr, VS_ERR_ARG, "vs_index_drop: ctx is NULL");
-    ctx->idx_valid = false;
+    ctx->idx_valid = false; ctx->bk_valid = false;
     return VS_OK;
 }
 
@@ -261,6 +277,27 @@ static void dispatch_score(int k, const ScoreArgs &a, unsigned ctas, unsigned th
     case 6: launch_score<6>(a, ctas, threads, st); break;
     case 7: launch_score<7>(a, ctas, threads, st); break;
     default: launch_score<8>(a, ctas, threads, st); break;
+    }
+}
+
+template <int K>
+static void launch_score_bk(const BkScoreArgs &a, unsigned ctas, unsigned threads, cudaStream_t st)
+{
+    k_score_bucketed<K><<<ctas, threads, SC_SMEM_BYTES, st>>>(a);
+}
+
+static void dispatch_score_bk(int k, const BkScoreArgs &a, unsigned ctas, unsigned threads, cudaStream_t st)
+{
+    switch (k) {
+    case 0: launch_score_bk<0>(a, ctas, threads, st); break;
+    case 1: launch_score_bk<1>(a, ctas, threads, st); break;
+    case 2: launch_score_bk<2>(a, ctas, threads, st); break;
+    case 3: launch_score_bk<3>(a, ctas, threads, st); break;
+    case 4: launch_score_bk<4>(a, ctas, threads, st); break;
+    case 5: launch_score_bk<5>(a, ctas, threads, st); break;
+    case 6: launch_score_bk<6>(a, ctas, threads, st); break;
+    case 7: launch_score_bk<7>(a, ctas, threads, st); break;
+    default: launch_score_bk<8>(a, ctas, threads, st); break;
     }
 }
 
@@ -597,7 +634,7 @@ static int abandon_upload(vs_ctx *ctx, int rc)
 {
     cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->prep); cudaStreamSynchronize(ctx->stream);
     (void)cudaGetLastError();
-    ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;
+    ctx->n_words = 0; ctx->idx_valid = false; ctx->bk_valid = false; ctx->cstart_valid = false;
     return rc;
 }
 
@@ -607,7 +644,7 @@ extern "C" int vs_text_upload(vs_ctx *ctx, const vs_text_view *t, uint64_t first
     int r = check_view(ctx, t, first_word, n_words);
     if (r != VS_OK) return r;
     CK(cudaSetDevice(ctx->device));
-    ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;      // nothing is resident until the upload has completed
+    ctx->n_words = 0; ctx->idx_valid = false; ctx->bk_valid = false; ctx->cstart_valid = false;      // nothing is resident until the upload has completed
     if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
     if ((r = ensure_sparse_staging(ctx, t, first_word, n_words)) != VS_OK) return r;
     const StartsPlan sp = plan_contig_starts(t, first_word, n_words);
@@ -642,6 +679,60 @@ static double hit_density(int k, int n_pam)
         c = c * (21 - j) / (j + 1);
     }
     return 2.0 * n_pam / 16.0 * p;
+}
+
+// ---- bucketed index (vs_bucket.cuh) --------------------------------------------------------------------------------
+// Built from the resident plain index and the resident text: bucket histogram -> padded bucket starts -> positions
+// regrouped by bucket -> blocks gathered from the text.  One host synchronisation (the store is sized by the padded total).
+static int build_bucket_index(vs_ctx *ctx, const PamParams &pp, uint32_t &launches)
+{
+    cudaStream_t st = ctx->stream;
+    const size_t ctl_words = 2 * BK_N + 2 * BK_N + 2 * (BK_N + 1);
+    if (!ctx->d_bk_ctl) {
+        CK(cudaMalloc(&ctx->d_bk_ctl, ctl_words * sizeof(unsigned long long)));
+        CK(cudaMallocHost(&ctx->h_bk_ctl, 2 * (BK_N + 1) * sizeof(unsigned long long)));
+    }
+    unsigned long long *d_hist = ctx->d_bk_ctl, *d_cursor = d_hist + 2 * BK_N, *d_start = d_cursor + 2 * BK_N;
+    const unsigned long long *d_all = ctx->d_cnt + 4 + 4 * (ctx->cnt_chunks + 1);
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaMemsetAsync(d_hist, 0, 2 * BK_N * sizeof(unsigned long long), st));
+    const uint64_t max_blocks = std::max(ctx->idx_end[0], ctx->idx_end[1]);
+    const dim3 grid((unsigned)((max_blocks + BKB_THREADS - 1) / BKB_THREADS), 2);
+    if (max_blocks) k_bucket_hist<<<grid, BKB_THREADS, 0, st>>>(ctx->d_planes[0], ctx->d_planes[1], d_all, pp, d_hist);
+    k_bucket_scan<<<2, BK_N, 0, st>>>(d_hist, d_start, d_cursor);
+    launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_bk_ctl, d_start, 2 * (BK_N + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int s = 0; s < 2; ++s) {
+        const uint64_t nb = ctx->h_bk_ctl[s * (BK_N + 1) + BK_N];
+        ctx->bk_blocks[s] = nb;
+        if (nb > ctx->bk_cap[s]) {
+            cudaFree(ctx->d_bk_planes[s]); cudaFree(ctx->d_bk_pos[s]);
+            ctx->d_bk_planes[s] = ctx->d_bk_pos[s] = nullptr; ctx->bk_cap[s] = 0;
+            const uint64_t cap = nb + nb / 64 + SC_NB;
+            CK(cudaMalloc(&ctx->d_bk_planes[s], cap * BLK_WORDS * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->d_bk_pos[s], cap * 32 * sizeof(uint32_t)));
+            ctx->bk_cap[s] = cap;
+        }
+        if (nb) CK(cudaMemsetAsync(ctx->d_bk_pos[s], 0xFF, nb * 32 * sizeof(uint32_t), st));
+    }
+    if (max_blocks) {
+        k_bucket_scatter<<<grid, BKB_THREADS, 0, st>>>(ctx->d_planes[0], ctx->d_planes[1], ctx->d_pos[0], ctx->d_pos[1], d_all, pp, d_cursor,
+                                                        ctx->d_bk_pos[0], ctx->d_bk_pos[1], ctx->bk_blocks[0] * 32, ctx->bk_blocks[1] * 32);
+        launches++;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (ctx->bk_blocks[s]) {
+            k_bucket_gather<<<(unsigned)((ctx->bk_blocks[s] + 63) / 64), 64, 0, st>>>(ctx->d_bases, ctx->d_masks, ctx->first_word * 32, ctx->d_bk_pos[s],
+                                                                                     ctx->bk_blocks[s], ctx->d_bk_planes[s]);
+            launches++;
+        }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->bk_build_ms, ctx->ev[7], ctx->ev[6]));
+    ctx->bk_valid = true;
+    return VS_OK;
 }
 
 struct ScanReq {
@@ -690,7 +781,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     const uint64_t first_word = src ? q.first_word : ctx->first_word;
     StartsPlan sp;
     if (src) {
-        ctx->n_words = 0; ctx->idx_valid = false; ctx->cstart_valid = false;      // nothing is resident until the pass has completed
+        ctx->n_words = 0; ctx->idx_valid = false; ctx->bk_valid = false; ctx->cstart_valid = false;      // nothing is resident until the pass has completed
         if ((r = ensure_text_buffers(ctx, n_words)) != VS_OK) return r;
         if ((r = ensure_sparse_staging(ctx, src, first_word, n_words)) != VS_OK) return r;
         sp = plan_contig_starts(src, first_word, n_words);
@@ -747,7 +838,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
         CK(cudaMalloc(&ctx->d_cnt, (4 + 4 * (nc + 1) + 4 + 4) * sizeof(unsigned long long)));
         CK(cudaMallocHost(&ctx->h_cnt, (4 + 4 * (nc + 1) + 4 + 4) * sizeof(unsigned long long)));
         ctx->cnt_chunks = nc;
-        ctx->idx_valid = false;                              // the whole-store range lived in the old buffer
+        ctx->idx_valid = false; ctx->bk_valid = false;       // the whole-store range lived in the old buffer
     }
     const uint64_t cnt_words = 4 + 4 * (ctx->cnt_chunks + 1) + 4 + 4;
     unsigned long long *d_rng = ctx->d_cnt + 4, *d_all = ctx->d_cnt + 4 + 4 * (ctx->cnt_chunks + 1), *d_hitcnt = d_all + 4;
@@ -760,7 +851,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
             cudaFree(ctx->d_planes[s]); cudaFree(ctx->d_pos[s]);
             ctx->d_planes[s] = ctx->d_pos[s] = nullptr;
         }
-        ctx->blocks_cap = 0; ctx->idx_valid = false;
+        ctx->blocks_cap = 0; ctx->idx_valid = false; ctx->bk_valid = false;
         for (int s = 0; s < 2; ++s) {
             CK(cudaMalloc(&ctx->d_planes[s], need * BLK_WORDS * sizeof(uint32_t)));
             CK(cudaMalloc(&ctx->d_pos[s], need * 32 * sizeof(uint32_t)));
@@ -770,11 +861,40 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     };
     const bool reuse = !src && ctx->idx_valid && ctx->idx_pam == q.extra_pam;
     if (!reuse) {
-        ctx->idx_valid = false;
+        ctx->idx_valid = false; ctx->bk_valid = false;
         const uint64_t tiles = (n_words + tile_words - 1) / tile_words;
         uint64_t est = (uint64_t)((double)n_words * pp.n / 16.0 * 1.15) + tiles + 64ull * n_chunks + 256;
         est = (est + BLK_GROUP - 1) / BLK_GROUP * BLK_GROUP;
         if ((r = ensure_blocks(est)) != VS_OK) return r;
+    }
+    // a resident index that is scanned again gets its bucketed form (built once; this scan pays for it)
+    bool use_bk = false;
+    if (reuse && ctx->bucket_mode) {
+        if (!ctx->bk_valid) {
+            if ((r = build_bucket_index(ctx, pp, S.launches)) != VS_OK) return r;
+            S.index_build_ms = ctx->bk_build_ms;
+        }
+        use_bk = true;
+    }
+    if (use_bk) {
+        // keys of the patterns and, per guide pass, the guides of every bucket sorted by their key mismatches
+        const uint64_t gk = 2ull * n_guides;
+        if (gk > ctx->gkey_cap) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(ctx->d_gkey); if (ctx->h_gkey) cudaFreeHost(ctx->h_gkey);
+            ctx->d_gkey = ctx->h_gkey = nullptr; ctx->gkey_cap = 0;
+            CK(cudaMalloc(&ctx->d_gkey, gk * sizeof(uint16_t)));
+            CK(cudaMallocHost(&ctx->h_gkey, gk * sizeof(uint16_t)));
+            ctx->gkey_cap = gk;
+        }
+        for (int s = 0; s < 2; ++s)
+            for (uint32_t g = 0; g < n_guides; ++g) {
+                uint8_t patc[VS_GLEN];
+                const uint8_t *gd = q.guides + (size_t)g * VS_GLEN;
+                for (int i = 0; i < VS_GLEN; ++i) patc[i] = s ? (uint8_t)(3 - gd[VS_GLEN - 1 - i]) : gd[i];
+                ctx->h_gkey[(size_t)s * n_guides + g] = (uint16_t)key_of_codes(s, patc);
+            }
+        if (!ctx->d_cls) CK(cudaMalloc(&ctx->d_cls, 2ull * BK_N * BK_CLS * sizeof(uint32_t)));
     }
     // hit buffer and guide super-chunks
     const double per_guide = (double)n_words * 32.0 * hit_density(k, pp.n);
@@ -792,7 +912,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     auto guides_per_pass = [&]() -> uint32_t {
         const double fit = per_guide > 0 ? (double)ctx->hits_cap / (per_guide * 1.5) : 1e30;
         uint64_t g = fit >= (double)n_guides ? n_guides : (uint64_t)std::max(1.0, fit);
-        if (g > 32768) g = 32768;                            // the sort key holds 15 bits of guide index per delivery
+        if (g > 32768) g = 32768;                            // the sort key holds 15 bits of guide index per delivery (and k_guide_classes 16)
         if (g < n_guides && g > SC_THREADS) g = g / SC_THREADS * SC_THREADS;
         return (uint32_t)g;
     };
@@ -842,9 +962,32 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
             if (ctx->idx_valid) {
                 // the index is resident: one launch over the whole store
                 CK(cudaEventRecord(ctx->ev[2], st));
-                launch_score(d_all, g0, ng);
+                if (use_bk) {
+                    const uint64_t need = 2ull * BK_N * ng;
+                    if (need > ctx->perm_cap) {
+                        CK(cudaStreamSynchronize(st));
+                        cudaFree(ctx->d_perm); ctx->d_perm = nullptr; ctx->perm_cap = 0;
+                        CK(cudaMalloc(&ctx->d_perm, need * sizeof(uint16_t)));
+                        ctx->perm_cap = need;
+                    }
+                    // the keys of this pass's guides, strand by strand ([2][ng])
+                    for (int s = 0; s < 2; ++s)
+                        CK(cudaMemcpyAsync(ctx->d_gkey + (size_t)s * ng, ctx->h_gkey + (size_t)s * n_guides + g0, (size_t)ng * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+                    S.h2d_bytes += 2ull * ng * sizeof(uint16_t);
+                    k_guide_classes<<<dim3(BK_N, 2), 128, 0, st>>>(ctx->d_gkey, ng, pp, ctx->d_perm, ctx->d_cls);
+                    BkScoreArgs b;
+                    for (int s = 0; s < 2; ++s) { b.planes[s] = ctx->d_bk_planes[s]; b.pos[s] = ctx->d_bk_pos[s]; }
+                    b.start = ctx->d_bk_ctl + 4 * BK_N;
+                    b.n_guides = ng; b.guide_base = g0; b.pat_guides = n_guides; b.pat = ctx->d_pat;
+                    b.perm = ctx->d_perm; b.cls = ctx->d_cls;
+                    b.hits = ctx->d_hits; b.n_hits = d_hitcnt; b.hit_cap = ctx->hits_cap;
+                    dispatch_score_bk(k, b, score_ctas, SC_THREADS, st);
+                    S.launches += 2; S.score_launches++;
+                } else {
+                    launch_score(d_all, g0, ng);
+                }
                 CK(cudaEventRecord(ctx->ev[3], st));
-                S.index_reused = first_pass && reuse ? 1u : S.index_reused;
+                S.index_reused = first_pass && reuse ? (use_bk ? 2u : 1u) : S.index_reused;
             } else {
                 CK(cudaMemsetAsync(ctx->d_cnt, 0, (4 + 4 * (ctx->cnt_chunks + 1) + 4) * sizeof(unsigned long long), st));
                 CK(cudaEventRecord(ctx->ev[1], st));
@@ -896,7 +1039,8 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
                     S.redo_chunks += n_chunks;
                     continue;
                 }
-                ctx->idx_valid = true; ctx->idx_pam = q.extra_pam; ctx->idx_chunks = n_chunks;
+                ctx->idx_valid = true; ctx->bk_valid = false; ctx->idx_pam = q.extra_pam; ctx->idx_chunks = n_chunks;
+                ctx->idx_end[0] = bf; ctx->idx_end[1] = br;
                 ctx->idx_cand[0] = ctx->h_cnt[0]; ctx->idx_cand[1] = ctx->h_cnt[1];
                 ctx->idx_blocks[0] = 0; ctx->idx_blocks[1] = 0;
                 for (uint32_t c = 0; c < n_chunks; ++c) { ctx->idx_blocks[0] += h_rng[4 * c + 2] - h_rng[4 * c]; ctx->idx_blocks[1] += h_rng[4 * c + 3] - h_rng[4 * c + 1]; }
@@ -987,7 +1131,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     S.n_blocks_fwd = ctx->idx_blocks[0]; S.n_blocks_rev = ctx->idx_blocks[1];
     S.n_hits = total_out;
     if (q.n_hits) *q.n_hits = total_out;
-    if (!ctx->keep_index) ctx->idx_valid = false;
+    if (!ctx->keep_index) { ctx->idx_valid = false; ctx->bk_valid = false; }
     if (q.stats) *q.stats = S;
     ctx->err.clear();
     if (out_overflow && !q.sink) {

@@ -297,7 +297,7 @@ extern "C" int vs_pack_text(const char *ascii, uint64_t n_bases, const uint64_t 
 //   * a view WITH a compact mask source (what bidir_index writes): em_code, em_dense, nm_runs, em_runs — the window masks
 //     are not stored; vs_text_load rebuilds them from the source (the file is half the size: 0.27 B per base);
 //   * a view without one: masks, sparse masks.
-// Format 002 (header, offsets, bases, masks, sparse masks) still loads.  All sections are 16-byte aligned.
+// All sections are 16-byte aligned.  (Format 002 of round 1 — no source header — is no longer read: re-run bidir_index.)
 namespace {
 struct IdxHeader {
     char magic[8];
@@ -309,7 +309,6 @@ struct IdxHeader {
 struct IdxSourceHeader {    // 003 only, directly after IdxHeader
     uint64_t n_nm_runs, n_em_runs;
 };
-const char IDX_MAGIC2[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '2'};
 const char IDX_MAGIC3[8] = {'V', 'S', 'I', 'D', 'X', '0', '0', '3'};
 inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
 inline bool has_source(const vs_text_view *t) { return t->em_code && t->em_dense; }
@@ -396,10 +395,10 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
     if (!f) { vs_set_last_error(("cannot open " + path).c_str()); return VS_ERR_IO; }
     IdxHeader h;
     IdxSourceHeader sh{0, 0};
-    if (fread(&h, sizeof(h), 1, f) != 1 || (memcmp(h.magic, IDX_MAGIC2, 8) != 0 && memcmp(h.magic, IDX_MAGIC3, 8) != 0)) {
-        fclose(f); vs_set_last_error((path + " is not a VSIDX002/003 packed text").c_str()); return VS_ERR_IO;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, IDX_MAGIC3, 8) != 0) {
+        fclose(f); vs_set_last_error((path + " is not a VSIDX003 packed text").c_str()); return VS_ERR_IO;
     }
-    const bool v3 = memcmp(h.magic, IDX_MAGIC3, 8) == 0;
+    const bool v3 = true;
     uint64_t data_at = pad16(sizeof(h));
     if (v3) {
         if (fseek(f, (long)data_at, SEEK_SET) != 0 || fread(&sh, sizeof(sh), 1, f) != 1) { fclose(f); vs_set_last_error((path + " is truncated").c_str()); return VS_ERR_IO; }

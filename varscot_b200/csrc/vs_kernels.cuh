@@ -104,28 +104,6 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
     }
 }
 
-// 16 x 32 bit-matrix, both 16 x 16 halves transposed in place: out[r] bits 0..15 = bit r of in[0..15], bits 16..31 =
-// bit 16 + r of in[0..15] (transpose32 without its first stage, on 16 rows).
-__device__ __forceinline__ void transpose16(uint32_t (&a)[16])
-{
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {                        // bytes: odd bytes of a[k] <-> even bytes of a[k+8]
-        const uint32_t x = a[k], y = a[k | 8];
-        a[k] = __byte_perm(x, y, 0x6240);
-        a[k | 8] = __byte_perm(x, y, 0x7351);
-    }
-    uint32_t m = 0x0F0F0F0Fu;
-#pragma unroll
-    for (int j = 4; j; j >>= 1, m ^= m << j) {
-#pragma unroll
-        for (int k = 0; k < 16; k = ((k | j) + 1) & ~j) {
-            const uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
-            a[k | j] ^= t;
-            a[k] ^= t << j;
-        }
-    }
-}
-
 constexpr int EX_THREADS   = 64;                  // threads per extraction CTA
 constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the host picks the tile so that it holds ~60 blocks
 
@@ -138,11 +116,10 @@ constexpr int EX_MAX_WORDS = 256;                 // words per tile (<=); the ho
 // deterministic; hit resolution sorts).  If a claim runs past the capacity nothing is written for that tile; k_score
 // then skips the whole chunk and the host, which reads the counters back, regrows the stores and redoes the chunk.
 // Block layout (48 words): hi_0..hi_22, lo_0..lo_22, last-window mask, valid mask; word w of block b at plane_index(b, w).
-#ifndef VS_EX_HALF
-#define VS_EX_HALF 0                  // 1: EXPERIMENTAL, not yet run on a GPU — one thread per half block (see phase 2 below)
-#endif
+// (Measured on B200 and dropped in round 2: one thread per HALF block — two 16-row transposes, half the registers, twice
+// the resident warps — extracts config 3 in 1.04 ms per 0.25-scale pass against 0.98 ms for this form.)
 #ifndef VS_EX_MINBLOCKS
-#define VS_EX_MINBLOCKS (VS_EX_HALF ? 16 : 10)
+#define VS_EX_MINBLOCKS 10
 #endif
 __global__ void __launch_bounds__(EX_THREADS, VS_EX_MINBLOCKS)
 k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64_t w_begin, uint64_t w_end, uint32_t tile_words,
@@ -235,18 +212,9 @@ k_extract(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, uint64
     }
     __syncthreads();
     const uint32_t gbase = (uint32_t)(global_base + w0 * 32);      // device word 0 sits at global_base
-#if VS_EX_HALF
-    // EXPERIMENTAL (compiled only with -DVS_EX_HALF=1, never run on a GPU so far): one thread per HALF block of 16
-    // candidates.  Half the registers (two 16-row transposes instead of two 32-row ones) let twice as many warps reside,
-    // which is what this latency-bound kernel lacks; the plane words leave as 16-bit halves (lane pairs write one word).
-    for (uint32_t j2 = tid; j2 < 2 * (nbf + nbr); j2 += EX_THREADS) {
-#include "vs_extract_half_block.inc"
-    }
-#else
     for (uint32_t j = tid; j < nbf + nbr; j += EX_THREADS) {
 #include "vs_extract_block.inc"
     }
-#endif
 }
 
 // k_scatter_masks: expand the sparse form of the window masks (only words with a non-zero mask travel over PCIe).
@@ -432,9 +400,10 @@ static_assert(SC_STRIDE % 8 == 4, "block stride must be 4 mod 8 words: conflict-
 constexpr int SC_SMEM_BYTES = (SC_NB * SC_STRIDE + SC_NB + BLK_WORDS * SC_NB) * 4;      // planes + last-window masks + raw staging (18 KB)
 constexpr int PAT_STRIDE = 24;                    // uint16 per pattern (23 slot offsets + pad; 48 bytes = 3 x 16)
 
-// position scored by slot j of a strand's slot order: informative positions first, the PAM dinucleotide last
-// (forward 0..22; reverse 2..22, 0, 1)
-__host__ __device__ constexpr int slot_position(int strand, int j) { return strand ? (j < VS_GLEN - 2 ? j + 2 : j - (VS_GLEN - 2)) : j; }
+// position scored by slot j of a strand's slot order: the PAM dinucleotide last, before it the four bases next to it
+// (forward 0..22; reverse 6..22, 2..5, 0, 1) — so that the first 17 slots are exactly the positions outside the key of
+// the bucketed index (vs_bucket.cuh), and the first PA(K) slots never hold the PAM
+__host__ __device__ constexpr int slot_position(int strand, int j) { return !strand ? j : (j < 17 ? j + 6 : (j < 21 ? j - 15 : j - 21)); }
 // table entry of slot j for pattern base b (0..3): byte offset of plane (4 position + b) inside a block's shared-memory row
 __host__ __device__ constexpr uint16_t pat_slot(int strand, int j, int b) { return (uint16_t)((4 * slot_position(strand, j) + b) * 4); }
 // inverse of pat_slot
@@ -477,16 +446,17 @@ struct ScoreArgs {
 #else
 #define VS_NOINLINE __forceinline__
 #endif
+// `extra` = mismatches already known outside the counted slots (the key positions of a bucket; 0 for the plain index).
 template <int K>
-__device__ VS_NOINLINE void score_hits(const char *row, const uint16_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5],
-                                           uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
-                                           unsigned long long *n_hits, uint64_t hit_cap)
+__device__ __forceinline__ void score_hits_body(const char *row, const uint16_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5], uint32_t extra,
+                                                uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
+                                                unsigned long long *n_hits, uint64_t hit_cap)
 {
     while (le != 0) {
         const int c = __ffs(le) - 1;
         le &= le - 1;
-        const uint32_t mm = ((cnt[0] >> c) & 1u) | (((cnt[1] >> c) & 1u) << 1) | (((cnt[2] >> c) & 1u) << 2) |
-                            (((cnt[3] >> c) & 1u) << 3) | (((cnt[4] >> c) & 1u) << 4);
+        const uint32_t mm = extra + (((cnt[0] >> c) & 1u) | (((cnt[1] >> c) & 1u) << 1) | (((cnt[2] >> c) & 1u) << 2) |
+                                     (((cnt[3] >> c) & 1u) << 3) | (((cnt[4] >> c) & 1u) << 4));
         if ((lastm >> c) & 1u) {                                             // R4: last window of its contig
             uint32_t h2 = 0;
 #pragma unroll 1
@@ -502,6 +472,24 @@ __device__ VS_NOINLINE void score_hits(const char *row, const uint16_t *po, int 
             hits[idx] = hrec;
         }
     }
+}
+template <int K>
+__device__ VS_NOINLINE void score_hits(const char *row, const uint16_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5],
+                                       uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits, unsigned long long *n_hits, uint64_t hit_cap)
+{
+    score_hits_body<K>(row, po, strand, le, cnt, 0u, lastm, pos, info, hits, n_hits, hit_cap);
+}
+// the same out of line (k_score_bucketed instantiates its walk once per class: the rare path must not be copied into each)
+#ifndef VS_HOST_UNIT_TEST
+#define VS_COLD __noinline__
+#else
+#define VS_COLD
+#endif
+template <int K>
+__device__ VS_COLD void score_hits_cold(const char *row, const uint16_t *po, int strand, uint32_t le, const uint32_t (&cnt)[5], uint32_t extra,
+                                        uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits, unsigned long long *n_hits, uint64_t hit_cap)
+{
+    score_hits_body<K>(row, po, strand, le, cnt, extra, lastm, pos, info, hits, n_hits, hit_cap);
 }
 
 template <int K>
@@ -545,7 +533,11 @@ k_score(ScoreArgs a)
     if ((unsigned long long)blockIdx.x < nbat) stage(blockIdx.x);
     // a warp whose 32 guides are the same for every batch (the launch has no more guides than the CTA has lanes) keeps the
     // addresses of its pattern's planes in registers across batches; they change only with the strand
-    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * (uint32_t)wid + 32u <= a.n_guides;
+    // The warps of a CTA sit on different SM sub-partitions (warp id mod 4).  When the guides do not fill every warp (100
+    // guides: three full warps and one that works an eighth of the time) the light role must not always fall on the same
+    // sub-partition: the guide slice of a warp is rotated by the CTA index, so the resident CTAs of an SM spread it evenly.
+    const uint32_t warps = blockDim.x >> 5, role = ((uint32_t)wid + blockIdx.x) % warps;
+    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * role + 32u <= a.n_guides;
     const char *adr_keep[PA];
     int kept_strand = -1;
     for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x) {
@@ -630,9 +622,8 @@ k_score(ScoreArgs a)
             for (int i = 0; i < PA; ++i) adr[i] -= SC_NB * ROW;
         }
     };
-    const uint32_t warps = blockDim.x >> 5;
     for (uint32_t gc = 0; gc < a.n_guides; gc += 32u * warps) {
-        const uint32_t g_w = gc + 32u * (uint32_t)wid;
+        const uint32_t g_w = gc + 32u * role;
         if (g_w >= a.n_guides) break;
         const uint32_t n = min(32u, a.n_guides - g_w);
         if (n == 32u) {
@@ -767,6 +758,8 @@ k_pack_loc_hits(const unsigned long long *__restrict__ keys, const unsigned long
     r.key = keys[i]; r.contig = (uint32_t)(vals[i] >> 32); r.info = (uint32_t)vals[i];
     out[i] = r;
 }
+
+#include "vs_bucket.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Microbenchmarks for the roofline denominators (alu-pipe LOP3 issue rate, shared-memory LDS rate).
