@@ -263,6 +263,20 @@ k_guide_classes(const uint16_t *__restrict__ gkey, uint32_t n_guides, PamParams 
 // slot order of the bucketed walk = the plain one (slot_position): its first BK_REST slots are exactly the positions
 // outside the key on both strands.
 __host__ __device__ constexpr int bk_stage_a(int kp) { return stage_a_slots(kp) < BK_REST ? stage_a_slots(kp) : BK_REST; }
+// The walks are specialised on the number of stage-A slots only — 9, 11, 13, 15 or 17 — not on the budget: budgets that
+// share a slot count (0 and 1; 5 and above) share the code and pick their threshold at run time.  The instruction
+// cache decides this: every batch runs every class, the SM's instruction cache holds 32 KB, and the first version of this
+// kernel (one walk per budget and segment shape, unrolled 4 times: 130 KB) spent 17 of 18 issue cycles waiting for
+// instructions.
+__host__ __device__ constexpr int bk_walk_slots(int kp) { return bk_stage_a(kp) < 9 ? 9 : bk_stage_a(kp); }
+
+// count <= kp for a warp-uniform budget kp in [LO, HI]
+template <int LO, int HI>
+__device__ __forceinline__ uint32_t le_runtime(const uint32_t (&b)[5], int kp)
+{
+    if constexpr (LO == HI) return le_k<LO>(b);
+    else return kp == LO ? le_k<LO>(b) : le_runtime<LO + 1, HI>(b, kp);
+}
 
 struct BkScoreArgs {
     const uint32_t *planes[2];  // bucketed store per strand
@@ -276,6 +290,16 @@ struct BkScoreArgs {
     unsigned long long *n_hits;
     uint64_t hit_cap;
 };
+
+// rare path (inlined: ptxas 12.9 segfaults on several instantiations of this kernel when it is an out-of-line call)
+template <int K>
+__device__ __forceinline__ void bk_hits(const char *row, const uint16_t *po, int strand, uint32_t le, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                uint32_t c4, uint32_t extra, uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
+                                unsigned long long *n_hits, uint64_t hit_cap)
+{
+    const uint32_t cnt[5] = {c0, c1, c2, c3, c4};
+    score_hits_body<K>(row, po, strand, le, cnt, extra, lastm, pos, info, hits, n_hits, hit_cap);
+}
 
 template <int K>
 __global__ void __launch_bounds__(SC_THREADS, score_min_blocks(K))
@@ -338,11 +362,12 @@ k_score_bucketed(BkScoreArgs a)
     const uint16_t *perm = a.perm + ((size_t)strand * BK_N + bucket) * a.n_guides;
     const uint32_t *cls = a.cls + ((size_t)strand * BK_N + bucket) * BK_CLS;
 
-    // one segment of the class with budget KP = K - c: guides perm[at .. at + GW), (32 / GW) blocks per warp iteration
-    auto segment = [&](uint32_t at, uint32_t n_real, uint32_t c, auto kp_c, auto gw_log2_c) {
-        // (K = 0: single stage — ptxas 12.9 segfaults on the two-stage walk of the kernel that has only the class c = 0)
-        constexpr int KP = decltype(kp_c)::value, PA = K == 0 ? BK_REST : bk_stage_a(KP), PB = BK_REST - PA;
+    // one segment of a class: guides perm[at .. at + GW) with c key mismatches (budget kp = K - c for the 17 other positions),
+    // (32 / GW) blocks per warp iteration; PA stage-A slots, the budgets [KLO, KHI] share this code
+    auto segment = [&](uint32_t at, uint32_t n_real, uint32_t c, auto pa_c, auto klo_c, auto khi_c, auto gw_log2_c) {
+        constexpr int PA = decltype(pa_c)::value, PB = BK_REST - PA, KLO = decltype(klo_c)::value, KHI = decltype(khi_c)::value;
         constexpr uint32_t L = decltype(gw_log2_c)::value, GW = 1u << L, STEP = 32u >> L;
+        const int kp = K - (int)c;
         const uint32_t sub = (uint32_t)lane >> L, gl = (uint32_t)lane & (GW - 1u);
         const bool real = gl < n_real;                     // padding lanes score the segment's first guide; their hits are dropped
         const uint32_t g = perm[at + (real ? gl : 0u)];
@@ -357,7 +382,7 @@ k_score_bucketed(BkScoreArgs a)
 #pragma unroll
             for (int i = 0; i < PA; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
         }
-        constexpr uint32_t UNR = 4u < (uint32_t)SC_NB / STEP ? 4u : (uint32_t)SC_NB / STEP;
+        constexpr uint32_t UNR = 2u;
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < (uint32_t)SC_NB; j0 += STEP * UNR) {
 #pragma unroll
@@ -367,21 +392,22 @@ k_score_bucketed(BkScoreArgs a)
 #pragma unroll
                 for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(adr[i] + u * STEP * ROW);
                 popcount_planes<PA, false>(m, zero5, ca);
-                uint32_t le = le_k<KP>(ca);
-                if (PB == 0 ? (le != 0) : __any_sync(0xffffffffu, le != 0)) {
+                uint32_t le = le_runtime<KLO, KHI>(ca, kp);
+                // (always a warp vote, also when there is no stage B: ptxas 12.9 segfaults on a divergent branch around the call)
+                if (__any_sync(0xffffffffu, le != 0)) {
                     const char *row = smb + j * ROW;
                     if constexpr (PB > 0) {
                         uint32_t mb[PB], cb[5];
 #pragma unroll
                         for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(row + po[PA + i]);
                         popcount_planes<PB, true>(mb, ca, cb);
-                        le = le_k<KP>(cb);
+                        le = le_runtime<KLO, KHI>(cb, kp);
 #pragma unroll
                         for (int w = 0; w < 5; ++w) ca[w] = cb[w];
                     }
                     if (le != 0 && real)
-                        score_hits_cold<K>(row, po, (int)strand, le, ca, c, lastm_s[j + sub], posb + (size_t)(j + sub) * 32,
-                                           ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
+                        bk_hits<K>(row, po, (int)strand, le, ca[0], ca[1], ca[2], ca[3], ca[4], c, lastm_s[j + sub], posb + (size_t)(j + sub) * 32,
+                                   ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
                 }
             }
 #pragma unroll
@@ -392,20 +418,22 @@ k_score_bucketed(BkScoreArgs a)
     // walks 8 blocks per iteration, so a class costs 32 * n / 32 iterations however it is cut) — are dealt to the warps
     // round robin; the deal starts at a different warp for every batch and CTA
     uint32_t turn = (uint32_t)(bat + blockIdx.x);
-    auto run_class = [&](uint32_t c, auto kp_c) {
+    auto run_class = [&](uint32_t c, auto pa_c, auto klo_c, auto khi_c) {
         const uint32_t c0 = cls[c], n = cls[c + 1] - c0;
         for (uint32_t i = 0; i + 32u <= n; i += 32u, ++turn)
-            if (turn % warps == (uint32_t)wid) segment(c0 + i, 32u, c, kp_c, std::integral_constant<uint32_t, 5>{});
+            if (turn % warps == (uint32_t)wid) segment(c0 + i, 32u, c, pa_c, klo_c, khi_c, std::integral_constant<uint32_t, 5>{});
         for (uint32_t i = n & ~31u; i < n; i += 4u, ++turn)
-            if (turn % warps == (uint32_t)wid) segment(c0 + i, min(4u, n - i), c, kp_c, std::integral_constant<uint32_t, 2>{});
+            if (turn % warps == (uint32_t)wid) segment(c0 + i, min(4u, n - i), c, pa_c, klo_c, khi_c, std::integral_constant<uint32_t, 2>{});
     };
-    // classes c = 0 .. min(K, VS_KEYLEN): budget K - c for the 17 remaining positions (a guide with c > K cannot hit here)
-    run_class(0u, std::integral_constant<int, K>{});
-    if constexpr (K >= 1) run_class(1u, std::integral_constant<int, (K >= 1 ? K - 1 : 0)>{});
-    if constexpr (K >= 2) run_class(2u, std::integral_constant<int, (K >= 2 ? K - 2 : 0)>{});
-    if constexpr (K >= 3) run_class(3u, std::integral_constant<int, (K >= 3 ? K - 3 : 0)>{});
-    if constexpr (K >= 4) run_class(4u, std::integral_constant<int, (K >= 4 ? K - 4 : 0)>{});
-    if constexpr (K >= 5) run_class(5u, std::integral_constant<int, (K >= 5 ? K - 5 : 0)>{});
-    if constexpr (K >= 6) run_class(6u, std::integral_constant<int, (K >= 6 ? K - 6 : 0)>{});
+    // classes c = 0 .. min(K, VS_KEYLEN), budget kp = K - c (a guide with c > K cannot hit in this bucket), grouped by the
+    // walk that serves them: 17 slots for kp >= 5, 15 / 13 / 11 for kp = 4 / 3 / 2, 9 for kp <= 1
+    for (int c = 0; c <= (K < VS_KEYLEN ? K : VS_KEYLEN); ++c) {
+        const int kp = K - c;
+        if (kp >= 5) run_class((uint32_t)c, std::integral_constant<int, BK_REST>{}, std::integral_constant<int, (K >= 5 ? 5 : K)>{}, std::integral_constant<int, (K >= 5 ? K : K)>{});
+        else if (kp == 4) { if constexpr (K >= 4) run_class((uint32_t)c, std::integral_constant<int, 15>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}); }
+        else if (kp == 3) { if constexpr (K >= 3) run_class((uint32_t)c, std::integral_constant<int, 13>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}); }
+        else if (kp == 2) { if constexpr (K >= 2) run_class((uint32_t)c, std::integral_constant<int, 11>{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
+        else run_class((uint32_t)c, std::integral_constant<int, 9>{}, std::integral_constant<int, 0>{}, std::integral_constant<int, (K >= 1 ? 1 : 0)>{});
+    }
     }
 }

@@ -535,12 +535,14 @@ k_score(ScoreArgs a)
     // addresses of its pattern's planes in registers across batches; they change only with the strand
     // The warps of a CTA sit on different SM sub-partitions (warp id mod 4).  When the guides do not fill every warp (100
     // guides: three full warps and one that works an eighth of the time) the light role must not always fall on the same
-    // sub-partition: the guide slice of a warp is rotated by the CTA index, so the resident CTAs of an SM spread it evenly.
-    const uint32_t warps = blockDim.x >> 5, role = ((uint32_t)wid + blockIdx.x) % warps;
-    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * role + 32u <= a.n_guides;
+    // sub-partition: the guide slice of a warp rotates every 8 batches (and starts at the CTA index).
+    const uint32_t warps = blockDim.x >> 5;
     const char *adr_keep[PA];
-    int kept_strand = -1;
-    for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x) {
+    int kept_strand = -1;                                   // strand and role the kept addresses belong to
+    uint32_t iter = 0;
+    for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x, ++iter) {
+    const uint32_t role = ((uint32_t)wid + blockIdx.x + (iter >> 3)) % warps;
+    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * role + 32u <= a.n_guides;
     uint32_t strand, nb; unsigned long long blk0;
     batch_of(bat, strand, blk0, nb);
 #ifndef VS_HOST_UNIT_TEST
@@ -576,14 +578,14 @@ k_score(ScoreArgs a)
         const char *smb = reinterpret_cast<const char *>(sm) + sub * ROW;     // the lane's first block row
         const char *adr_local[KEEP ? 1 : PA];
         const char *(&adr)[KEEP ? PA : (KEEP ? 1 : PA)] = *reinterpret_cast<const char *(*)[PA]>(KEEP ? (void *)adr_keep : (void *)adr_local);   // the lane's stage-A planes in that row
-        if (!KEEP || kept_strand != (int)strand) {
+        if (!KEEP || kept_strand != (int)(strand * 64u + role)) {
             const uint4 *q = reinterpret_cast<const uint4 *>(po);
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 3; ++i) { const uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
 #pragma unroll
             for (int i = 0; i < PA; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
-            if (KEEP) kept_strand = (int)strand;
+            if (KEEP) kept_strand = (int)(strand * 64u + role);
         }
         // UNR iterations per trip with compile-time offsets; the address registers advance once per trip
         constexpr uint32_t UNR = (uint32_t)SC_UNROLL < (uint32_t)SC_NB / STEP ? (uint32_t)SC_UNROLL : (uint32_t)SC_NB / STEP;
