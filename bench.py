@@ -564,7 +564,7 @@ def main():
     peak_lop3 = peak_lds = None
     if rank == 0:
         peak_lop3, peak_lds = ctx.measure_int_peaks()
-    host_threads = max(1, min(16, len(all_cpus) // max(1, world)))
+    host_threads = max(1, min(16, len(all_cpus) - (world - 1)))      # rank 0 merges; the other ranks wait (one core each)
 
     def expected_hits(n_g, kk, n_pam, bases):
         """uniform-random text: both strands, per PAM (1/16) P[Bin(21, 3/4) <= k]"""

@@ -291,14 +291,38 @@ struct BkScoreArgs {
     uint64_t hit_cap;
 };
 
-// rare path (inlined: ptxas 12.9 segfaults on several instantiations of this kernel when it is an out-of-line call)
+// Rare path, ONE copy per kernel and nothing of the walk's register state: the walk only notes in `pend` which of its
+// iterations had a lane within budget after stage A; afterwards this routine rescans those block rows exactly — every lane
+// counts the 17 slots of its guide with a bit-sliced ripple counter, compares with the budget, and appends its hits
+// (count + c, R4 on last windows).  ~300 instructions per noted iteration, a few percent of the iterations.
 template <int K>
-__device__ __forceinline__ void bk_hits(const char *row, const uint16_t *po, int strand, uint32_t le, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                uint32_t c4, uint32_t extra, uint32_t lastm, const uint32_t *pos, uint32_t info, vs_hit *hits,
+__device__ VS_COLD void bk_cold(const char *row0, uint32_t step_bytes, uint32_t pend, uint32_t step, uint32_t sub, const uint16_t *po, int kp, uint32_t c,
+                                int strand, bool real, const uint32_t *lastm_s, const uint32_t *posb, uint32_t info, vs_hit *hits,
                                 unsigned long long *n_hits, uint64_t hit_cap)
 {
-    const uint32_t cnt[5] = {c0, c1, c2, c3, c4};
-    score_hits_body<K>(row, po, strand, le, cnt, extra, lastm, pos, info, hits, n_hits, hit_cap);
+    while (pend != 0) {
+        const uint32_t it = (uint32_t)__ffs(pend) - 1u;
+        pend &= pend - 1u;
+        const char *row = row0 + it * step_bytes;
+        uint32_t cnt[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int s = 0; s < BK_REST; ++s) {
+            uint32_t carry = *reinterpret_cast<const uint32_t *>(row + po[s]);
+#pragma unroll
+            for (int w = 0; w < 5; ++w) { const uint32_t t = cnt[w] & carry; cnt[w] ^= carry; carry = t; }
+        }
+        // count <= kp, most significant bit first
+        uint32_t gt = 0u, eq = ~0u;
+#pragma unroll
+        for (int w = 4; w >= 0; --w) {
+            const uint32_t kb = ((kp >> w) & 1) ? ~0u : 0u;
+            gt |= eq & cnt[w] & ~kb;
+            eq &= ~(cnt[w] ^ kb);
+        }
+        const uint32_t le = ~gt;
+        const uint32_t j = it * step + sub;
+        if (le != 0 && real) score_hits_body<K>(row, po, strand, le, cnt, c, lastm_s[j], posb + (size_t)j * 32, info, hits, n_hits, hit_cap);
+    }
 }
 
 template <int K>
@@ -362,78 +386,77 @@ k_score_bucketed(BkScoreArgs a)
     const uint16_t *perm = a.perm + ((size_t)strand * BK_N + bucket) * a.n_guides;
     const uint32_t *cls = a.cls + ((size_t)strand * BK_N + bucket) * BK_CLS;
 
-    // one segment of a class: guides perm[at .. at + GW) with c key mismatches (budget kp = K - c for the 17 other positions),
-    // (32 / GW) blocks per warp iteration; PA stage-A slots, the budgets [KLO, KHI] share this code
-    auto segment = [&](uint32_t at, uint32_t n_real, uint32_t c, auto pa_c, auto klo_c, auto khi_c, auto gw_log2_c) {
-        constexpr int PA = decltype(pa_c)::value, PB = BK_REST - PA, KLO = decltype(klo_c)::value, KHI = decltype(khi_c)::value;
-        constexpr uint32_t L = decltype(gw_log2_c)::value, GW = 1u << L, STEP = 32u >> L;
+    // The walk of one segment, stage A only: PA slots per iteration, (32 >> L) blocks per iteration.  Iterations in which some
+    // lane is still within budget are noted in the returned mask and rescanned by bk_cold afterwards.  One copy of this code
+    // per (PA, L) — 5 slot counts x {32-guide, 4-guide} segments — and nothing else inside: the kernel's hot code must fit
+    // the SM's 32 KB instruction cache, every batch runs every variant.
+    auto walk = [&](const char *(&adr)[BK_REST], int kp, auto pa_c, auto klo_c, auto khi_c, auto l_c) -> uint32_t {
+        constexpr int PA = decltype(pa_c)::value, KLO = decltype(klo_c)::value, KHI = decltype(khi_c)::value;
+        constexpr uint32_t L = decltype(l_c)::value, STEP = 32u >> L, UNR = 2u;
+        uint32_t pend = 0u;
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < (uint32_t)SC_NB; j0 += STEP * UNR) {
+#pragma unroll
+            for (uint32_t u = 0; u < UNR; ++u) {
+                uint32_t m[PA], ca[5];
+#pragma unroll
+                for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(adr[i] + u * STEP * ROW);
+                popcount_planes<PA, false>(m, zero5, ca);
+                const uint32_t le = le_runtime<KLO, KHI>(ca, kp);
+                if (__any_sync(0xffffffffu, le != 0)) pend |= 1u << (j0 / STEP + u);
+            }
+#pragma unroll
+            for (int i = 0; i < PA; ++i) adr[i] += STEP * UNR * ROW;
+        }
+        return pend;
+    };
+    // one segment: guides perm[at .. at + GW) (GW = 32 or 4) of the class with c key mismatches, budget kp = K - c for the 17
+    // other positions
+    auto segment = [&](uint32_t at, uint32_t n_real, uint32_t c, uint32_t L) {
         const int kp = K - (int)c;
-        const uint32_t sub = (uint32_t)lane >> L, gl = (uint32_t)lane & (GW - 1u);
+        const uint32_t gw = 1u << L, sub = (uint32_t)lane >> L, gl = (uint32_t)lane & (gw - 1u), step = 32u >> L;
         const bool real = gl < n_real;                     // padding lanes score the segment's first guide; their hits are dropped
         const uint32_t g = perm[at + (real ? gl : 0u)];
         const uint16_t *po = pat0 + (size_t)g * PAT_STRIDE;
         const char *smb = reinterpret_cast<const char *>(sm) + sub * ROW;
-        const char *adr[PA];
+        const char *adr[BK_REST];
         {
             const uint4 *q = reinterpret_cast<const uint4 *>(po);
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 3; ++i) { const uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
 #pragma unroll
-            for (int i = 0; i < PA; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+            for (int i = 0; i < BK_REST; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
         }
-        constexpr uint32_t UNR = 2u;
-#pragma unroll 1
-        for (uint32_t j0 = 0; j0 < (uint32_t)SC_NB; j0 += STEP * UNR) {
-#pragma unroll
-            for (uint32_t u = 0; u < UNR; ++u) {
-                const uint32_t j = j0 + u * STEP;
-                uint32_t m[PA], ca[5];
-#pragma unroll
-                for (int i = 0; i < PA; ++i) m[i] = *reinterpret_cast<const uint32_t *>(adr[i] + u * STEP * ROW);
-                popcount_planes<PA, false>(m, zero5, ca);
-                uint32_t le = le_runtime<KLO, KHI>(ca, kp);
-                // (always a warp vote, also when there is no stage B: ptxas 12.9 segfaults on a divergent branch around the call)
-                if (__any_sync(0xffffffffu, le != 0)) {
-                    const char *row = smb + j * ROW;
-                    if constexpr (PB > 0) {
-                        uint32_t mb[PB], cb[5];
-#pragma unroll
-                        for (int i = 0; i < PB; ++i) mb[i] = *reinterpret_cast<const uint32_t *>(row + po[PA + i]);
-                        popcount_planes<PB, true>(mb, ca, cb);
-                        le = le_runtime<KLO, KHI>(cb, kp);
-#pragma unroll
-                        for (int w = 0; w < 5; ++w) ca[w] = cb[w];
-                    }
-                    if (le != 0 && real)
-                        bk_hits<K>(row, po, (int)strand, le, ca[0], ca[1], ca[2], ca[3], ca[4], c, lastm_s[j + sub], posb + (size_t)(j + sub) * 32,
-                                   ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < PA; ++i) adr[i] += STEP * UNR * ROW;
-        }
+        using I = std::integral_constant<int, 0>;
+        (void)sizeof(I);
+        uint32_t pend = 0u;
+        const int pa = bk_walk_slots(kp);
+        auto go = [&](auto l_c) {
+            // budgets that share a slot count share the walk: 17 slots for kp >= 5, 15 / 13 / 11 for kp = 4 / 3 / 2, 9 for kp <= 1
+            if (pa == BK_REST) pend = walk(adr, kp, std::integral_constant<int, BK_REST>{}, std::integral_constant<int, (K >= 5 ? 5 : K)>{}, std::integral_constant<int, K>{}, l_c);
+            else if (pa == 15) { if constexpr (K >= 4) pend = walk(adr, kp, std::integral_constant<int, 15>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}, l_c); }
+            else if (pa == 13) { if constexpr (K >= 3) pend = walk(adr, kp, std::integral_constant<int, 13>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}, l_c); }
+            else if (pa == 11) { if constexpr (K >= 2) pend = walk(adr, kp, std::integral_constant<int, 11>{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, l_c); }
+            else pend = walk(adr, kp, std::integral_constant<int, 9>{}, std::integral_constant<int, 0>{}, std::integral_constant<int, (K >= 1 ? 1 : 0)>{}, l_c);
+        };
+        if (L == 5u) go(std::integral_constant<uint32_t, 5>{}); else go(std::integral_constant<uint32_t, 2>{});
+        if (pend) bk_cold<K>(smb, step * ROW, pend, step, sub, po, kp, c, (int)strand, real, lastm_s, posb,
+                             ((a.guide_base + g) << 8) | (strand << 7), a.hits, a.n_hits, a.hit_cap);
     };
     // the segments of the batch — per class the full 32-guide segments, then its tail in 4-guide segments (a 4-guide segment
     // walks 8 blocks per iteration, so a class costs 32 * n / 32 iterations however it is cut) — are dealt to the warps
-    // round robin; the deal starts at a different warp for every batch and CTA
-    uint32_t turn = (uint32_t)(bat + blockIdx.x);
-    auto run_class = [&](uint32_t c, auto pa_c, auto klo_c, auto khi_c) {
+    // round robin; the deal starts at a different warp for every batch and CTA.  Classes c = 0 .. min(K, VS_KEYLEN): a
+    // guide with c > K cannot hit in this bucket.
+    uint32_t turn = (uint32_t)(bat + blockIdx.x) % warps;
+    for (uint32_t c = 0; c <= (uint32_t)(K < VS_KEYLEN ? K : VS_KEYLEN); ++c) {
         const uint32_t c0 = cls[c], n = cls[c + 1] - c0;
-        for (uint32_t i = 0; i + 32u <= n; i += 32u, ++turn)
-            if (turn % warps == (uint32_t)wid) segment(c0 + i, 32u, c, pa_c, klo_c, khi_c, std::integral_constant<uint32_t, 5>{});
-        for (uint32_t i = n & ~31u; i < n; i += 4u, ++turn)
-            if (turn % warps == (uint32_t)wid) segment(c0 + i, min(4u, n - i), c, pa_c, klo_c, khi_c, std::integral_constant<uint32_t, 2>{});
-    };
-    // classes c = 0 .. min(K, VS_KEYLEN), budget kp = K - c (a guide with c > K cannot hit in this bucket), grouped by the
-    // walk that serves them: 17 slots for kp >= 5, 15 / 13 / 11 for kp = 4 / 3 / 2, 9 for kp <= 1
-    for (int c = 0; c <= (K < VS_KEYLEN ? K : VS_KEYLEN); ++c) {
-        const int kp = K - c;
-        if (kp >= 5) run_class((uint32_t)c, std::integral_constant<int, BK_REST>{}, std::integral_constant<int, (K >= 5 ? 5 : K)>{}, std::integral_constant<int, (K >= 5 ? K : K)>{});
-        else if (kp == 4) { if constexpr (K >= 4) run_class((uint32_t)c, std::integral_constant<int, 15>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}); }
-        else if (kp == 3) { if constexpr (K >= 3) run_class((uint32_t)c, std::integral_constant<int, 13>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}); }
-        else if (kp == 2) { if constexpr (K >= 2) run_class((uint32_t)c, std::integral_constant<int, 11>{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
-        else run_class((uint32_t)c, std::integral_constant<int, 9>{}, std::integral_constant<int, 0>{}, std::integral_constant<int, (K >= 1 ? 1 : 0)>{});
+        for (uint32_t i = 0; i < n; ) {
+            const bool full = i + 32u <= n;
+            if (turn == (uint32_t)wid) segment(c0 + i, full ? 32u : min(4u, n - i), c, full ? 5u : 2u);
+            i += full ? 32u : 4u;
+            turn = turn + 1u == warps ? 0u : turn + 1u;
+        }
     }
     }
 }

@@ -605,20 +605,18 @@ extern "C" int vs_merge_resolved(const vs_loc_hit *const *lists, const uint64_t 
     std::vector<uint64_t> coll((size_t)n_threads, 0);
     std::vector<int> rc((size_t)n_threads, VS_OK);
     constexpr uint64_t KEY48 = (1ull << 49) - 1;                                                  // strand, contig & 0xFFFF, pos
-    auto less = [&](const vs_loc_hit &a, const vs_loc_hit &b) {
-        const uint64_t pa = pass_of(a), pb = pass_of(b);
-        if (pa != pb) return pa < pb;
-        if ((a.key & KEY48) != (b.key & KEY48)) return (a.key & KEY48) < (b.key & KEY48);
-        return a.contig < b.contig;
-    };
+    // Per thread: a k-way merge of its ranges of the lists (each ascending; ties on the 16-bit key are not ordered inside a
+    // list, so a run of equal keys is collected and ordered by the full contig id before it is emitted), streamed straight
+    // into the running-best walk — no copy of the hits, no sort.
     auto work = [&](int t) {
         const uint64_t o0 = out_at[(size_t)t], o1 = out_at[(size_t)t + 1];
         if (o1 == o0) return;
-        std::vector<vs_loc_hit> v;
-        try { v.reserve(o1 - o0); } catch (...) { rc[(size_t)t] = VS_ERR_NOMEM; return; }
-        for (int l = 0; l < n_lists; ++l)
-            v.insert(v.end(), lists[l] + at[(size_t)t * (size_t)n_lists + (size_t)l], lists[l] + at[(size_t)(t + 1) * (size_t)n_lists + (size_t)l]);
-        if (!std::is_sorted(v.begin(), v.end(), less)) std::sort(v.begin(), v.end(), less);
+        struct Head { const vs_loc_hit *p, *e; };
+        std::vector<Head> heads;
+        for (int l = 0; l < n_lists; ++l) {
+            const vs_loc_hit *b = lists[l] + at[(size_t)t * (size_t)n_lists + (size_t)l], *e = lists[l] + at[(size_t)(t + 1) * (size_t)n_lists + (size_t)l];
+            if (b < e) heads.push_back(Head{b, e});
+        }
         uint64_t w = o0, c = 0;
         auto emit = [&](const vs_loc_hit &h, uint16_t secondary) {
             vs_record &o = out[w++];
@@ -629,19 +627,62 @@ extern "C" int vs_merge_resolved(const vs_loc_hit *const *lists, const uint64_t 
             o.flag = (uint16_t)(secondary | ((h.info & 0x80) ? 16 : 0));
             o.pad = 0;
         };
-        for (uint64_t i = 0; i < v.size();) {
-            uint64_t j = i + 1;
-            while (j < v.size() && pass_of(v[j]) == pass_of(v[i])) ++j;
-            uint64_t best = i;
-            for (uint64_t x = i + 1; x < j; ++x) {
-                if ((v[x].key & KEY48) == (v[x - 1].key & KEY48)) ++c;                        // same (id16, pos): uint16 key collision
-                if ((v[x].info & 0x7F) >= (v[best].info & 0x7F)) emit(v[x], 256);
-                else { emit(v[best], 256); best = x; }
+        // running-best walk (bidir_mapping.cpp:164-187), fed one record at a time in emission-key order
+        bool have_best = false;
+        vs_loc_hit best{};
+        uint64_t cur_pass = ~0ull;
+        auto feed = [&](const vs_loc_hit &h) {
+            const uint64_t p = pass_of(h);
+            if (p != cur_pass) {
+                if (have_best) emit(best, 0);
+                best = h; have_best = true; cur_pass = p;
+                return;
             }
-            emit(v[best], 0);
-            i = j;
+            if ((h.info & 0x7F) >= (best.info & 0x7F)) emit(h, 256);
+            else { emit(best, 256); best = h; }
+        };
+        // records sharing (pass, strand, contig & 0xFFFF, pos) — a uint16 key collision, rare — are ordered by the full contig id:
+        // one record is held back until the next one shows a different key
+        std::vector<vs_loc_hit> ties;
+        bool have_prev = false;
+        vs_loc_hit prev{};
+        uint64_t prev_pass = 0, prev_key = 0;
+        auto flush_ties = [&]() {
+            if (!ties.empty()) {
+                ties.push_back(prev);
+                std::sort(ties.begin(), ties.end(), [](const vs_loc_hit &a, const vs_loc_hit &b) { return a.contig < b.contig; });
+                c += ties.size() - 1;
+                for (const vs_loc_hit &h : ties) feed(h);
+                ties.clear();
+            } else if (have_prev) feed(prev);
+            have_prev = false;
+        };
+        auto take = [&](const vs_loc_hit &h, uint64_t p, uint64_t k) {
+            if (have_prev && p == prev_pass && k == prev_key) { ties.push_back(prev); prev = h; return; }
+            flush_ties();
+            prev = h; prev_pass = p; prev_key = k; have_prev = true;
+        };
+        if (heads.size() == 1) {
+            for (const vs_loc_hit *p = heads[0].p; p < heads[0].e; ++p) take(*p, pass_of(*p), p->key & KEY48);
+        } else {
+            // k-way merge by linear selection over the cached keys of the heads (k = number of shards, a handful)
+            const size_t k = heads.size();
+            std::vector<uint64_t> hp(k), hk(k);
+            for (size_t i = 0; i < k; ++i) { hp[i] = pass_of(*heads[i].p); hk[i] = heads[i].p->key & KEY48; }
+            size_t live = k;
+            while (live) {
+                size_t m = 0;
+                for (size_t i = 1; i < k; ++i)
+                    if (hp[i] < hp[m] || (hp[i] == hp[m] && hk[i] < hk[m])) m = i;
+                take(*heads[m].p, hp[m], hk[m]);
+                if (++heads[m].p < heads[m].e) { hp[m] = pass_of(*heads[m].p); hk[m] = heads[m].p->key & KEY48; }
+                else { hp[m] = ~0ull; hk[m] = ~0ull; --live; }
+            }
         }
+        flush_ties();
+        if (have_best) emit(best, 0);
         coll[(size_t)t] = c;
+        if (w != o1) rc[(size_t)t] = VS_ERR_ARG;             // a list was not ascending
     };
     if (n_threads == 1) work(0);
     else {
