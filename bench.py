@@ -64,22 +64,23 @@ def score_ops(k):
     return a, b
 
 
-def bucketed_ops(guides, k, pam):
+def bucketed_ops(guides, k, pam, keylen=8):
     """Mean (LOP3, LDS) k_score_bucketed executes per (32-candidate block, guide) in stage A on uniform text: a guide meets
-    the buckets of a PAM kind with c = c4 + c_pam mismatches at the six key positions, c4 ~ C(4, j) 3^j / 256 over the 256
-    buckets of the kind (whatever the guide), c_pam = its PAM against the kind's; the budget for the other 17 positions is
-    K' = k - c (nothing is scored when K' < 0) and stage A loads PA = min(17, 7 + 2 K') of them."""
+    the buckets of a PAM kind with c = c_key + c_pam mismatches at the key positions, c_key ~ C(n, j) 3^j / 4^n over the 4^n
+    buckets of the kind (n = keylen - 2 bases next to the PAM, whatever the guide), c_pam = its PAM against the kind's; the
+    budget for the other 23 - keylen positions is K' = k - c (nothing is scored when K' < 0) and stage A loads
+    PA' = min(23 - keylen, 9 + 2 K') of them (vs_bucket.cuh: bk_walk_slots)."""
     from math import comb
     kinds = [(2, 2), (2, 0)] + ([("ACGT".index(pam[0]), "ACGT".index(pam[1]))] if pam else [])
-    w4 = [comb(4, j) * 3 ** j / 256.0 for j in range(5)]
+    n, rest = keylen - 2, 23 - keylen
+    wk = [comb(n, j) * 3 ** j / 4.0 ** n for j in range(n + 1)]
     g = np.asarray(guides)
     lop = lds = 0.0
     for x, y in kinds:
-        # forward pass: pattern = guide, PAM at 21, 22; reverse pass: pattern = revcomp(guide), PAM at window 0, 1 = (3 - y, 3 - x)
         cp = (g[:, 21] != x).astype(int) + (g[:, 22] != y).astype(int)       # identical on both strands
-        for j, w in enumerate(w4):
+        for j, w in enumerate(wk):
             kp = k - j - cp
-            pa = np.minimum(17, np.where(kp >= 8, 23, 7 + 2 * kp))
+            pa = np.minimum(rest, 9 + 2 * np.maximum(kp, 0))
             ops = np.array([csa_ops(int(a)) + 2 if q >= 0 else 0 for a, q in zip(pa, kp)], dtype=float)
             lop += w * ops.mean() / len(kinds)
             lds += w * np.where(kp >= 0, pa, 0).mean() / len(kinds)
@@ -616,7 +617,7 @@ def main():
     while cap < 2.5 * want and cap < (1 << 26):
         cap <<= 1
     exchange = None
-    if world > 1 and strong:
+    if (world > 1 and strong) or os.environ.get("VARSCOT_BENCH_FORCE_EXCHANGE"):     # (the variable lets a one-GPU test exercise the shared-memory hand-over)
         exchange = HostExchange(V, world, rank, cap)
         barrier(world, local)
         exchange.attach()
@@ -657,8 +658,13 @@ def main():
         st_box = {}
 
         def rg_step(seq):
-            a, sa = ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])
+            # the resident genome and the uploaded segments are scanned at the same time (two contexts, two host threads)
+            box = {}
+            th = threading.Thread(target=lambda: box.update(g=ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])))
+            th.start()
             b, sb_ = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=sw0, n_words=sw1 - sw0, out=hits_buf[half:])
+            th.join()
+            a, sa = box["g"]
             st_box["h2d"] = sa.h2d_bytes + sb_.h2d_bytes; st_box["d2h"] = sa.d2h_bytes + sb_.d2h_bytes
             if exchange is None:
                 return V.merge_resolved([a, b], threads=host_threads)

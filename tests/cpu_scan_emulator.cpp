@@ -134,7 +134,7 @@ int main(int argc, char **argv)
         const uint64_t max_blocks = std::max(all[2], all[3]);
         const unsigned g = (unsigned)((max_blocks + BKB_THREADS - 1) / BKB_THREADS);
         launch_cta(g, BKB_THREADS, [&] { k_bucket_hist(planes[0].data(), planes[1].data(), all, pp, hist); }, 2);
-        launch_cta(2, BK_N, [&] { k_bucket_scan(hist, start, cursor); });
+        launch_cta(2, 1024, [&] { k_bucket_scan(hist, start, cursor); });
         std::vector<uint32_t> bpl[2], bps[2];
         uint64_t nbk[2];
         for (int s = 0; s < 2; ++s) {
@@ -162,7 +162,7 @@ int main(int argc, char **argv)
                 for (int i = 0; i < VS_GLEN; ++i) pc[i] = s ? (uint8_t)(3 - guides[(size_t)gi * VS_GLEN + VS_GLEN - 1 - i]) : guides[(size_t)gi * VS_GLEN + i];
                 gkey[(size_t)s * n_guides + gi] = (uint16_t)key_of_codes(s, pc);
             }
-        launch_cta(BK_N, 128, [&] { k_guide_classes(gkey.data(), n_guides, pp, perm.data(), cls.data()); }, 2);
+        launch_cta(BK_N, 32, [&] { k_guide_classes(gkey.data(), n_guides, pp, perm.data(), cls.data()); }, 2);
         std::vector<vs_hit> hits3(hits.size());
         unsigned long long n3 = 0;
         for (;;) {

@@ -37,3 +37,21 @@ def test_gpu_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert d["parity"]["diff"] == 0 and d["cpu_baseline"]["value"] > 0 and d["roofline"]["frac"] < 1.2
+
+
+@pytest.mark.gpu
+def test_gpu_arm_shared_memory_handover_and_dense_mode():
+    """The N > 1 hand-over (hits downloaded straight into a page-locked shared-memory segment, merged by rank 0) exercised on one
+    GPU, and config 5's mode (one end-to-end pass with a hit sink, guide super-chunks) at a small scale."""
+    env = dict(os.environ, VARSCOT_BENCH_FORCE_EXCHANGE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "1", "--steps", "2", "--warmup", "3", "--no-target"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["parity"]["diff"] == 0 and d["e2e"]["value"] > 0 and d["e2e_resident_genome"]["records_equal_full_upload"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5", "--scale", "0.004", "--guides", "600"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["hits_per_step"] > 10000 and d["redo"] == 0 and d["verification"]["per_guide_counts_equal_small_scan"]
+    assert d["parity"]["diff"] == 0 and d["rank0"]["first_delivery_sorted"] and d["e2e"]["value"] > 0

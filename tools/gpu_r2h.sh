@@ -14,7 +14,7 @@ q base 3 0.25 A=1
 q base 4 0.25 A=1
 q base 3 1.0 A=1
 q base 4 1.0 A=1
-for c in 8 32; do q ctas$c 3 0.25 VARSCOT_SCORE_CTAS_PER_SM=$c; q ctas$c 4 0.25 VARSCOT_SCORE_CTAS_PER_SM=$c; done
+q key6 3 0.25 VARSCOT_LIB=/root/repo/build/variants/lib_key6.so; q key6 4 0.25 VARSCOT_LIB=/root/repo/build/variants/lib_key6.so; for c in 32; do q ctas$c 3 0.25 VARSCOT_SCORE_CTAS_PER_SM=$c; q ctas$c 4 0.25 VARSCOT_SCORE_CTAS_PER_SM=$c; done
 CMD="python bench.py --config 4 --scale 0.25 --steps 2 --warmup 3 --no-cpu --no-e2e --no-target"
 ncu --set full --clock-control none --import-source on -k regex:k_score_bucketed -s 2 -c 1 -o gpurun_out/r2_bk_cfg4 $CMD > gpurun_out/ncu_bk4.log 2>&1
 echo "bk cfg4 rc=$?"

@@ -4,12 +4,14 @@
 // 19 LDS per 32-guide x 32-candidate tile at k = 6) and the alu pipe right behind it; the only way to go faster is
 // to score fewer positions.  The candidates of a resident text are therefore regrouped by CONTENT: a bucket holds the
 // candidates of one strand that share the PAM dinucleotide and the four bases next to it (window positions 17..22 on the
-// forward pass, 0..5 on the reverse pass; VS_KEYLEN = 6 positions, 3 PAM kinds x 256 = 768 buckets per strand).  For
-// a (bucket, guide) pair the mismatches c at those six positions are a constant, so
-//   * the six positions are never loaded or counted,
-//   * the remaining 17 positions are scored against the budget K' = K - c (K' < 0: the guide cannot hit in this bucket
-//     at all), and the early-out test needs only PA(K') = min(17, 7 + 2 K') positions instead of PA(K) = 19:
-//     on uniform text E[c] = 3 (+ 1 in the buckets whose PAM differs from the guide's), i.e. 11..13 positions.
+// forward pass, 0..5 on the reverse pass for VS_KEYLEN = 6: 3 PAM kinds x 256 buckets per strand; VS_KEYLEN = 8, the
+// default, takes six bases: positions 15..22 / 0..7, 3 x 4096 buckets).  For a (bucket, guide) pair the mismatches c at
+// those key positions are a constant, so
+//   * the key positions are never loaded or counted,
+//   * the remaining 23 - VS_KEYLEN positions are scored against the budget K' = K - c (K' < 0: the guide cannot hit in this
+//     bucket at all — with six key bases and k = 6 that prunes every fifth pair of the GA buckets outright), and the
+//     early-out test needs only PA'(K') = min(rest, 9 + 2 K') positions instead of PA(K) = 19: on uniform text E[c] = 4.5
+//     (+ 1 in the buckets whose PAM differs from the guide's), i.e. 9..13 positions.
 // The guides of a launch are sorted by c per bucket (k_guide_classes), the CTA that scores a batch of 32 blocks of the
 // bucket walks the classes c = 0..K with the walk specialised on K'.  Everything else — block layout, expanded planes in
 // shared memory, guide per lane, hit path, R4 — is k_score's; the reported mismatch count is count + c.
@@ -18,17 +20,20 @@
 // (bidir_index.cpp:45-47) — and never on the streamed end-to-end path.
 #pragma once
 
-constexpr int VS_KEYLEN   = 6;                          // bucketed window positions: the PAM dinucleotide + 4 bases next to it
 constexpr int BK_KINDS    = 3;                          // PAM kinds: GG, GA, -P XY (forward); their reverse complements (reverse)
-constexpr int BK_PER_KIND = 256;
+constexpr int BK_KEYBITS  = 2 * (VS_KEYLEN - 2);        // key bits of the bases next to the PAM
+constexpr int BK_PER_KIND = 1 << BK_KEYBITS;            // 256 (VS_KEYLEN 6) or 4096 (VS_KEYLEN 8) buckets per PAM kind
 constexpr int BK_N        = BK_KINDS * BK_PER_KIND;     // buckets per strand
-constexpr int BK_REST     = VS_GLEN - VS_KEYLEN;        // 17 positions that are scored
+constexpr int BK_REST     = VS_GLEN - VS_KEYLEN;        // positions that are scored
 constexpr int BK_PAD      = SC_NB * 32;                 // candidates per batch: a bucket is padded to whole batches
 constexpr uint32_t BK_NOPOS = 0xFFFFFFFFu;              // padding slot of a bucket
 
-// window position of key slot t (0..5) of a strand; slots 0..3 are the four bases next to the PAM, 4..5 the PAM itself
-__host__ __device__ constexpr int key_position(int strand, int t) { return strand ? (t < 4 ? 2 + t : t - 4) : 17 + t; }
-// 12-bit key of a window / pattern: 2 bits (Dna code) per key slot, slot t at bits [2t, 2t+2)
+// window position of key slot t of a strand; slots 0 .. VS_KEYLEN-3 are the bases next to the PAM, the last two the PAM itself
+__host__ __device__ constexpr int key_position(int strand, int t)
+{
+    return strand ? (t < VS_KEYLEN - 2 ? 2 + t : t - (VS_KEYLEN - 2)) : VS_GLEN - VS_KEYLEN + t;
+}
+// key of a window / pattern: 2 bits (Dna code) per key slot, slot t at bits [2t, 2t+2)
 __host__ __device__ inline uint32_t key_of_codes(int strand, const uint8_t *codes23)
 {
     uint32_t k = 0;
@@ -38,36 +43,32 @@ __host__ __device__ inline uint32_t key_of_codes(int strand, const uint8_t *code
 // bucket of a candidate key, or -1 if its PAM is none of the strand's kinds (cannot happen for an extracted candidate)
 __host__ __device__ inline int bucket_of_key(int strand, uint32_t key, const PamParams &pp)
 {
-    const int x = (int)((key >> 8) & 3), y = (int)((key >> 10) & 3);         // key slots 4, 5 = the PAM dinucleotide in window order
+    const int x = (int)((key >> BK_KEYBITS) & 3), y = (int)((key >> (BK_KEYBITS + 2)) & 3);      // the PAM dinucleotide in window order
     for (int j = 0; j < pp.n; ++j)
-        if (strand ? (x == pp.rx[j] && y == pp.ry[j]) : (x == pp.fx[j] && y == pp.fy[j])) return j * BK_PER_KIND + (int)(key & 0xFF);
+        if (strand ? (x == pp.rx[j] && y == pp.ry[j]) : (x == pp.fx[j] && y == pp.fy[j])) return j * BK_PER_KIND + (int)(key & (BK_PER_KIND - 1));
     return -1;
 }
-// the 12-bit key every candidate of a bucket has
+// the key every candidate of a bucket has
 __host__ __device__ inline uint32_t key_of_bucket(int strand, int bucket, const PamParams &pp)
 {
     const int j = bucket / BK_PER_KIND;
     const uint32_t x = (uint32_t)(strand ? pp.rx[j] : pp.fx[j]), y = (uint32_t)(strand ? pp.ry[j] : pp.fy[j]);
-    return (uint32_t)(bucket % BK_PER_KIND) | (x << 8) | (y << 10);
+    return (uint32_t)(bucket % BK_PER_KIND) | (x << BK_KEYBITS) | (y << (BK_KEYBITS + 2));
 }
-// mismatches between two 12-bit keys (2 bits per position)
+// mismatches between two keys (2 bits per position)
 __host__ __device__ inline uint32_t key_mismatches(uint32_t a, uint32_t b)
 {
-    const uint32_t x = a ^ b, m = (x | (x >> 1)) & 0x555u;
-#ifdef VS_HOST_UNIT_TEST
-    return (uint32_t)__builtin_popcount(m);
-#else
-#ifdef __CUDA_ARCH__
+    const uint32_t x = a ^ b, m = (x | (x >> 1)) & 0x5555u;
+#if defined(__CUDA_ARCH__) && !defined(VS_HOST_UNIT_TEST)
     return (uint32_t)__popc(m);
 #else
     return (uint32_t)__builtin_popcount(m);
 #endif
-#endif
 }
 
 // ---- index build ---------------------------------------------------------------------------------------------------
-// the 32 candidate keys of one plain block, from its 12 key plane words (bit c of word = candidate c): a 32 x 32 register
-// transpose of which 12 rows are used
+// the 32 candidate keys of one plain block, from its 2 x VS_KEYLEN key plane words (bit c of word = candidate c): a 32 x 32
+// register transpose of which 12 / 16 rows are used
 __device__ __forceinline__ void block_keys(const uint32_t *__restrict__ planes, uint64_t blk, int strand, uint32_t (&key)[32])
 {
     const uint32_t *src = planes + plane_index(blk, 0);
@@ -79,10 +80,16 @@ __device__ __forceinline__ void block_keys(const uint32_t *__restrict__ planes, 
         key[2 * t] = __ldg(src + (VS_GLEN + p) * BLK_GROUP);        // lo plane -> bit 2t
         key[2 * t + 1] = __ldg(src + p * BLK_GROUP);                // hi plane -> bit 2t + 1
     }
-    transpose32(key);                                               // key[c] = the 12-bit key of candidate c
+    transpose32(key);                                               // key[c] = the key of candidate c
 }
 
-constexpr int BKB_THREADS = 128;                 // plain blocks per CTA of the histogram / scatter kernels (4096 candidates)
+#ifndef VS_HOST_UNIT_TEST
+#define VS_BK_SMEM(name) extern __shared__ __align__(16) uint32_t vs_bk_dyn_smem[]; uint32_t *name = vs_bk_dyn_smem
+#else
+#define VS_BK_SMEM(name) static uint32_t name[BK_N]
+#endif
+constexpr int BK_HIST_SMEM = BK_N * 4;           // dynamic shared memory of k_bucket_hist / k_bucket_scatter
+constexpr int BKB_THREADS = 256;                 // plain blocks per CTA of the histogram / scatter kernels (8192 candidates)
 
 // k_bucket_hist: candidates per bucket.  grid.y = strand; one thread per plain block; CTA histogram in shared memory, then
 // one global atomic per non-empty bin.  n_blocks[2] = blocks of the plain store per strand (device).
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(BKB_THREADS)
 k_bucket_hist(const uint32_t *__restrict__ planes_f, const uint32_t *__restrict__ planes_r, const unsigned long long *__restrict__ rng_all,
               PamParams pp, unsigned long long *__restrict__ hist)
 {
-    __shared__ uint32_t h[BK_N];
+    VS_BK_SMEM(h);                                // uint32_t h[BK_N]: dynamic shared memory (48 KB for VS_KEYLEN 8)
     const int strand = blockIdx.y;
     const unsigned long long n_blocks = rng_all[2 + strand];
     const unsigned long long cta0 = (unsigned long long)blockIdx.x * BKB_THREADS;
@@ -117,25 +124,32 @@ k_bucket_hist(const uint32_t *__restrict__ planes_f, const uint32_t *__restrict_
         if (h[i]) atomicAdd(&hist[strand * BK_N + i], (unsigned long long)h[i]);
 }
 
-// k_bucket_scan (one CTA of BK_N threads per strand, grid = 2): pads every bucket to whole batches, turns the counts into
+// k_bucket_scan (one CTA per strand, grid = 2): pads every bucket to whole batches, turns the counts into
 //   start[s][b]  first BLOCK of bucket b in the bucketed store (start[s][BK_N] = total blocks), and
 //   cursor[s][b] next free CANDIDATE slot of the bucket (= 32 * start), advanced by k_bucket_scatter.
-__global__ void __launch_bounds__(BK_N)
+__global__ void __launch_bounds__(1024)
 k_bucket_scan(const unsigned long long *__restrict__ hist, unsigned long long *__restrict__ start, unsigned long long *__restrict__ cursor)
 {
-    __shared__ unsigned long long pre[BK_N];
-    const int s = blockIdx.x, b = threadIdx.x;
-    const unsigned long long n = hist[s * BK_N + b], padded = (n + BK_PAD - 1) / BK_PAD * BK_PAD;
-    pre[b] = padded / 32;
+    __shared__ unsigned long long part[1024];
+    const int s = blockIdx.x;
+    constexpr int PER = (BK_N + 1023) / 1024;
+    const int t0 = (int)threadIdx.x * PER, b0 = t0 < BK_N ? t0 : BK_N, b1 = b0 + PER < BK_N ? b0 + PER : BK_N;
+    unsigned long long sum = 0;
+    for (int b = b0; b < b1; ++b) sum += (hist[s * BK_N + b] + BK_PAD - 1) / BK_PAD * (BK_PAD / 32);
+    part[threadIdx.x] = sum;
     __syncthreads();
-    if (b == 0) {                                                   // 768 additions: not worth a parallel scan
+    if (threadIdx.x == 0) {
         unsigned long long run = 0;
-        for (int i = 0; i < BK_N; ++i) { const unsigned long long v = pre[i]; pre[i] = run; run += v; }
+        for (int i = 0; i < 1024; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
         start[s * (BK_N + 1) + BK_N] = run;
     }
     __syncthreads();
-    start[s * (BK_N + 1) + b] = pre[b];
-    cursor[s * BK_N + b] = pre[b] * 32;
+    unsigned long long run = part[threadIdx.x];
+    for (int b = b0; b < b1; ++b) {
+        start[s * (BK_N + 1) + b] = run;
+        cursor[s * BK_N + b] = run * 32;
+        run += (hist[s * BK_N + b] + BK_PAD - 1) / BK_PAD * (BK_PAD / 32);
+    }
 }
 
 // k_bucket_scatter: the positions of the plain index, regrouped by bucket.  Same traversal as k_bucket_hist; a CTA claims
@@ -146,8 +160,7 @@ k_bucket_scatter(const uint32_t *__restrict__ planes_f, const uint32_t *__restri
                  const uint32_t *__restrict__ pos_r, const unsigned long long *__restrict__ rng_all, PamParams pp,
                  unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out_f, uint32_t *__restrict__ out_r, uint64_t cap_f, uint64_t cap_r)
 {
-    __shared__ uint32_t h[BK_N];
-    __shared__ unsigned long long base[BK_N];
+    VS_BK_SMEM(h);                                // uint32_t h[BK_N]: first the CTA's count per bucket, then the first slot of its range (slots fit 32 bits: <= 4 G bases)
     const int strand = blockIdx.y;
     const unsigned long long n_blocks = rng_all[2 + strand];
     const unsigned long long cta0 = (unsigned long long)blockIdx.x * BKB_THREADS;
@@ -170,7 +183,7 @@ k_bucket_scatter(const uint32_t *__restrict__ planes_f, const uint32_t *__restri
     }
     __syncthreads();
     for (int i = threadIdx.x; i < BK_N; i += BKB_THREADS)
-        if (h[i]) base[i] = atomicAdd(&cursor[strand * BK_N + i], (unsigned long long)h[i]);
+        if (h[i]) h[i] = (uint32_t)atomicAdd(&cursor[strand * BK_N + i], (unsigned long long)h[i]);
     __syncthreads();
     if (valid) {
         const uint32_t *pos = (strand ? pos_r : pos_f) + blk * 32;
@@ -179,7 +192,7 @@ k_bucket_scatter(const uint32_t *__restrict__ planes_f, const uint32_t *__restri
 #pragma unroll
         for (int c = 0; c < 32; ++c)
             if (((valid >> c) & 1u) && key[c] != BK_NOPOS) {
-                const unsigned long long slot = base[key[c] >> 16] + (key[c] & 0xFFFFu);
+                const unsigned long long slot = (unsigned long long)h[key[c] >> 16] + (key[c] & 0xFFFFu);
                 if (slot < out_cap) out[slot] = __ldg(pos + c);
             }
     }
@@ -262,13 +275,13 @@ k_guide_classes(const uint16_t *__restrict__ gkey, uint32_t n_guides, PamParams 
 // ---- scoring -------------------------------------------------------------------------------------------------------
 // slot order of the bucketed walk = the plain one (slot_position): its first BK_REST slots are exactly the positions
 // outside the key on both strands.
-__host__ __device__ constexpr int bk_stage_a(int kp) { return stage_a_slots(kp) < BK_REST ? stage_a_slots(kp) : BK_REST; }
-// The walks are specialised on the number of stage-A slots only — 9, 11, 13, 15 or 17 — not on the budget: budgets that
-// share a slot count (0 and 1; 5 and above) share the code and pick their threshold at run time.  The instruction
-// cache decides this: every batch runs every class, the SM's instruction cache holds 32 KB, and the first version of this
-// kernel (one walk per budget and segment shape, unrolled 4 times: 130 KB) spent 17 of 18 issue cycles waiting for
-// instructions.
-__host__ __device__ constexpr int bk_walk_slots(int kp) { return bk_stage_a(kp) < 9 ? 9 : bk_stage_a(kp); }
+// stage-A slots for the budget kp: two more than k_score's 7 + 2 k — here an iteration that survives stage A is rescanned by a
+// routine of ~100 instructions instead of four more LDS, so it must be ten times rarer (about 1 % of the iterations)
+__host__ __device__ constexpr int bk_walk_slots(int kp) { return 9 + 2 * kp < BK_REST ? 9 + 2 * kp : BK_REST; }
+// The walks are specialised on the number of stage-A slots only — 9, 11, 13, 15 (, 17) — not on the budget: the budgets
+// that share the longest walk share its code and pick their threshold at run time.  The instruction cache decides this: every
+// batch runs every class, the SM's instruction cache holds 32 KB, and the first version of this kernel (one walk per budget
+// and segment shape, unrolled 4 times with the rare path inlined: 130 KB) spent 17 of 18 issue cycles waiting for instructions.
 
 // count <= kp for a warp-uniform budget kp in [LO, HI]
 template <int LO, int HI>
@@ -293,24 +306,25 @@ struct BkScoreArgs {
 
 // Rare path, ONE copy per kernel and nothing of the walk's register state: the walk only notes in `pend` which of its
 // iterations had a lane within budget after stage A; afterwards this routine rescans those block rows exactly — every lane
-// counts the 17 slots of its guide with a bit-sliced ripple counter, compares with the budget, and appends its hits
-// (count + c, R4 on last windows).  ~300 instructions per noted iteration, a few percent of the iterations.
+// counts all scored slots of its guide (carry-save adder tree), compares with the budget, and appends its hits (count + c,
+// R4 on last windows).  ~100 instructions per noted iteration, about 1 % of the iterations.
 template <int K>
 __device__ VS_COLD void bk_cold(const char *row0, uint32_t step_bytes, uint32_t pend, uint32_t step, uint32_t sub, const uint16_t *po, int kp, uint32_t c,
                                 int strand, bool real, const uint32_t *lastm_s, const uint32_t *posb, uint32_t info, vs_hit *hits,
                                 unsigned long long *n_hits, uint64_t hit_cap)
 {
+    const uint32_t zero5[5] = {0u, 0u, 0u, 0u, 0u};
+    uint32_t off[BK_REST];
+#pragma unroll
+    for (int s = 0; s < BK_REST; ++s) off[s] = po[s];
     while (pend != 0) {
         const uint32_t it = (uint32_t)__ffs(pend) - 1u;
         pend &= pend - 1u;
         const char *row = row0 + it * step_bytes;
-        uint32_t cnt[5] = {0u, 0u, 0u, 0u, 0u};
-#pragma unroll 1
-        for (int s = 0; s < BK_REST; ++s) {
-            uint32_t carry = *reinterpret_cast<const uint32_t *>(row + po[s]);
+        uint32_t m[BK_REST], cnt[5];
 #pragma unroll
-            for (int w = 0; w < 5; ++w) { const uint32_t t = cnt[w] & carry; cnt[w] ^= carry; carry = t; }
-        }
+        for (int s = 0; s < BK_REST; ++s) m[s] = *reinterpret_cast<const uint32_t *>(row + off[s]);
+        popcount_planes<BK_REST, false>(m, zero5, cnt);
         // count <= kp, most significant bit first
         uint32_t gt = 0u, eq = ~0u;
 #pragma unroll
@@ -388,8 +402,8 @@ k_score_bucketed(BkScoreArgs a)
 
     // The walk of one segment, stage A only: PA slots per iteration, (32 >> L) blocks per iteration.  Iterations in which some
     // lane is still within budget are noted in the returned mask and rescanned by bk_cold afterwards.  One copy of this code
-    // per (PA, L) — 5 slot counts x {32-guide, 4-guide} segments — and nothing else inside: the kernel's hot code must fit
-    // the SM's 32 KB instruction cache, every batch runs every variant.
+    // per (PA, L) — 4 or 5 slot counts x {32-guide, 4-guide} segments — and nothing else inside: the kernel's hot code must
+    // fit the SM's 32 KB instruction cache, every batch runs every variant.
     auto walk = [&](const char *(&adr)[BK_REST], int kp, auto pa_c, auto klo_c, auto khi_c, auto l_c) -> uint32_t {
         constexpr int PA = decltype(pa_c)::value, KLO = decltype(klo_c)::value, KHI = decltype(khi_c)::value;
         constexpr uint32_t L = decltype(l_c)::value, STEP = 32u >> L, UNR = 2u;
@@ -410,7 +424,7 @@ k_score_bucketed(BkScoreArgs a)
         }
         return pend;
     };
-    // one segment: guides perm[at .. at + GW) (GW = 32 or 4) of the class with c key mismatches, budget kp = K - c for the 17
+    // one segment: guides perm[at .. at + GW) (GW = 32 or 4) of the class with c key mismatches, budget kp = K - c for the
     // other positions
     auto segment = [&](uint32_t at, uint32_t n_real, uint32_t c, uint32_t L) {
         const int kp = K - (int)c;
@@ -428,17 +442,18 @@ k_score_bucketed(BkScoreArgs a)
 #pragma unroll
             for (int i = 0; i < BK_REST; ++i) adr[i] = smb + ((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
         }
-        using I = std::integral_constant<int, 0>;
-        (void)sizeof(I);
         uint32_t pend = 0u;
         const int pa = bk_walk_slots(kp);
         auto go = [&](auto l_c) {
-            // budgets that share a slot count share the walk: 17 slots for kp >= 5, 15 / 13 / 11 for kp = 4 / 3 / 2, 9 for kp <= 1
-            if (pa == BK_REST) pend = walk(adr, kp, std::integral_constant<int, BK_REST>{}, std::integral_constant<int, (K >= 5 ? 5 : K)>{}, std::integral_constant<int, K>{}, l_c);
-            else if (pa == 15) { if constexpr (K >= 4) pend = walk(adr, kp, std::integral_constant<int, 15>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}, l_c); }
-            else if (pa == 13) { if constexpr (K >= 3) pend = walk(adr, kp, std::integral_constant<int, 13>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}, l_c); }
-            else if (pa == 11) { if constexpr (K >= 2) pend = walk(adr, kp, std::integral_constant<int, 11>{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, l_c); }
-            else pend = walk(adr, kp, std::integral_constant<int, 9>{}, std::integral_constant<int, 0>{}, std::integral_constant<int, (K >= 1 ? 1 : 0)>{}, l_c);
+            // 9 / 11 / 13 (/ 15) slots for the budgets 0 / 1 / 2 (/ 3), every scored position (one stage, exact) for the budgets above
+            using I0 = std::integral_constant<int, 0>;
+            if (pa == BK_REST) {
+                constexpr int KLO = (BK_REST - 9) / 2 < K ? (BK_REST - 9) / 2 : K;
+                pend = walk(adr, kp, std::integral_constant<int, BK_REST>{}, std::integral_constant<int, KLO>{}, std::integral_constant<int, K>{}, l_c);
+            } else if (pa == 9) pend = walk(adr, kp, std::integral_constant<int, 9>{}, I0{}, I0{}, l_c);
+            else if (pa == 11) { if constexpr (K >= 1) pend = walk(adr, kp, std::integral_constant<int, 11>{}, std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}, l_c); }
+            else if (pa == 13) { if constexpr (K >= 2) pend = walk(adr, kp, std::integral_constant<int, 13>{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, l_c); }
+            else { if constexpr (K >= 3 && BK_REST > 15) pend = walk(adr, kp, std::integral_constant<int, 15>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}, l_c); }
         };
         if (L == 5u) go(std::integral_constant<uint32_t, 5>{}); else go(std::integral_constant<uint32_t, 2>{});
         if (pend) bk_cold<K>(smb, step * ROW, pend, step, sub, po, kp, c, (int)strand, real, lastm_s, posb,

@@ -698,8 +698,14 @@ static int build_bucket_index(vs_ctx *ctx, const PamParams &pp, uint32_t &launch
     CK(cudaMemsetAsync(d_hist, 0, 2 * BK_N * sizeof(unsigned long long), st));
     const uint64_t max_blocks = std::max(ctx->idx_end[0], ctx->idx_end[1]);
     const dim3 grid((unsigned)((max_blocks + BKB_THREADS - 1) / BKB_THREADS), 2);
-    if (max_blocks) k_bucket_hist<<<grid, BKB_THREADS, 0, st>>>(ctx->d_planes[0], ctx->d_planes[1], d_all, pp, d_hist);
-    k_bucket_scan<<<2, BK_N, 0, st>>>(d_hist, d_start, d_cursor);
+    static bool smem_opt_in = false;                 // 48 KB of dynamic shared memory: at the default limit, opt in anyway
+    if (!smem_opt_in) {
+        CK(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HIST_SMEM));
+        CK(cudaFuncSetAttribute(k_bucket_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HIST_SMEM));
+        smem_opt_in = true;
+    }
+    if (max_blocks) k_bucket_hist<<<grid, BKB_THREADS, BK_HIST_SMEM, st>>>(ctx->d_planes[0], ctx->d_planes[1], d_all, pp, d_hist);
+    k_bucket_scan<<<2, 1024, 0, st>>>(d_hist, d_start, d_cursor);
     launches += 2;
     CK(cudaMemcpyAsync(ctx->h_bk_ctl, d_start, 2 * (BK_N + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -717,7 +723,7 @@ static int build_bucket_index(vs_ctx *ctx, const PamParams &pp, uint32_t &launch
         if (nb) CK(cudaMemsetAsync(ctx->d_bk_pos[s], 0xFF, nb * 32 * sizeof(uint32_t), st));
     }
     if (max_blocks) {
-        k_bucket_scatter<<<grid, BKB_THREADS, 0, st>>>(ctx->d_planes[0], ctx->d_planes[1], ctx->d_pos[0], ctx->d_pos[1], d_all, pp, d_cursor,
+        k_bucket_scatter<<<grid, BKB_THREADS, BK_HIST_SMEM, st>>>(ctx->d_planes[0], ctx->d_planes[1], ctx->d_pos[0], ctx->d_pos[1], d_all, pp, d_cursor,
                                                         ctx->d_bk_pos[0], ctx->d_bk_pos[1], ctx->bk_blocks[0] * 32, ctx->bk_blocks[1] * 32);
         launches++;
     }

@@ -400,10 +400,18 @@ static_assert(SC_STRIDE % 8 == 4, "block stride must be 4 mod 8 words: conflict-
 constexpr int SC_SMEM_BYTES = (SC_NB * SC_STRIDE + SC_NB + BLK_WORDS * SC_NB) * 4;      // planes + last-window masks + raw staging (18 KB)
 constexpr int PAT_STRIDE = 24;                    // uint16 per pattern (23 slot offsets + pad; 48 bytes = 3 x 16)
 
-// position scored by slot j of a strand's slot order: the PAM dinucleotide last, before it the four bases next to it
-// (forward 0..22; reverse 6..22, 2..5, 0, 1) — so that the first 17 slots are exactly the positions outside the key of
-// the bucketed index (vs_bucket.cuh), and the first PA(K) slots never hold the PAM
-__host__ __device__ constexpr int slot_position(int strand, int j) { return !strand ? j : (j < 17 ? j + 6 : (j < 21 ? j - 15 : j - 21)); }
+// key of the bucketed index (vs_bucket.cuh): the PAM dinucleotide + the VS_KEYLEN - 2 bases next to it
+#ifndef VS_KEYLEN
+#define VS_KEYLEN 8
+#endif
+static_assert(VS_KEYLEN == 6 || VS_KEYLEN == 8, "key of 4 or 6 bases + the PAM dinucleotide");
+// position scored by slot j of a strand's slot order: the PAM dinucleotide last, before it the bases next to it
+// (forward 0..22; reverse VS_KEYLEN..22, 2..VS_KEYLEN-1, 0, 1) — so that the first 23 - VS_KEYLEN slots are exactly the positions
+// outside the key of the bucketed index, and the first PA(K) slots never hold the PAM
+__host__ __device__ constexpr int slot_position(int strand, int j)
+{
+    return !strand ? j : (j < VS_GLEN - VS_KEYLEN ? j + VS_KEYLEN : (j < VS_GLEN - 2 ? j - (VS_GLEN - VS_KEYLEN) + 2 : j - (VS_GLEN - 2)));
+}
 // table entry of slot j for pattern base b (0..3): byte offset of plane (4 position + b) inside a block's shared-memory row
 __host__ __device__ constexpr uint16_t pat_slot(int strand, int j, int b) { return (uint16_t)((4 * slot_position(strand, j) + b) * 4); }
 // inverse of pat_slot
