@@ -313,7 +313,7 @@ static void test_mask_kernels()
 // last-window flags, a partial last block and padding blocks with an empty valid mask) against random guides, both
 // strands, a guide count that exercises the 32 / 16 / 8 / 4-guide segments; the hits must be exactly those of a naive count.
 template <int K>
-static void check_k_score(uint32_t n_guides)
+static void check_k_score(uint32_t n_guides, unsigned threads = 0)
 {
     const uint32_t nb[2] = {SC_NB + 7, 2 * SC_NB + 5};                         // blocks per strand (not multiples of the batch)
     const uint32_t lo[2] = {SC_NB, 0};                                         // the forward range starts inside the store
@@ -370,7 +370,7 @@ static void check_k_score(uint32_t n_guides)
     a.rng = rng; a.cap = cap;
     a.n_guides = n_guides; a.guide_base = g_base; a.pat_guides = rows; a.pat = pat;
     a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
-    launch_cta(2, std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32), [&] { k_score<K>(a); });
+    launch_cta(2, threads ? threads : std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32), [&] { k_score<K>(a); });
     std::set<std::pair<uint32_t, uint32_t>> got, want;
     CHECK(n_hits <= hits.size());
     for (unsigned long long i = 0; i < n_hits; ++i) CHECK(got.insert({hits[i].pos, hits[i].info}).second);
@@ -479,6 +479,7 @@ int main()
     test_contig_starts_and_resolve();
     check_k_score<0>(9); check_k_score<1>(33); check_k_score<2>(5); check_k_score<3>(60); check_k_score<4>(128 + 28);
     check_k_score<5>(20); check_k_score<6>(100); check_k_score<7>(12); check_k_score<8>(4);
+    check_k_score<6>(100, 96); check_k_score<4>(40, 32); check_k_score<3>(300, 64);      // CTAs with fewer warps than guide slices (a short tail gets no warp of its own)
     if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
     printf("kernel helper units ok\n");
     return 0;

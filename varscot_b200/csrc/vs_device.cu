@@ -928,7 +928,13 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
         CK(cudaEventCreate(&e));
         ctx->ev_pool.push_back(e);
     }
-    const unsigned score_threads = std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32);
+    // CTA size of k_score: one warp per 32 guides, at most SC_WARPS; a short tail (<= 8 guides) does not get a warp of its own
+    // — it would idle most of the time and hold a warp slot (100 guides: 3 warps; the tail's 4-guide segments rotate over them)
+    const auto score_cta = [](uint32_t ng) {
+        if (ng >= (uint32_t)SC_THREADS) return (unsigned)SC_THREADS;
+        const unsigned full = ng / 32, tail = ng % 32;
+        return 32u * std::max(1u, full + ((tail > 8 || full == 0) ? 1u : 0u));
+    };
     unsigned score_ctas = (unsigned)ctx->n_sm * 16;         // persistent: a multiple of the SM count, about two waves of resident CTAs
     if (const char *e = getenv("VARSCOT_SCORE_CTAS_PER_SM")) score_ctas = (unsigned)ctx->n_sm * (unsigned)std::max(1, atoi(e));   // tuning knob
 
@@ -946,7 +952,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
         a.rng = rng; a.cap = ctx->blocks_cap;
         a.n_guides = ng; a.guide_base = g0; a.pat_guides = n_guides; a.pat = ctx->d_pat;
         a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
-        dispatch_score(k, a, score_ctas, score_threads, st);
+        dispatch_score(k, a, score_ctas, score_cta(ng), st);
         S.launches++; S.score_launches++;
     };
 

@@ -550,7 +550,8 @@ k_score(ScoreArgs a)
     uint32_t iter = 0;
     for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x, ++iter) {
     const uint32_t role = ((uint32_t)wid + blockIdx.x + (iter >> 3)) % warps;
-    const bool fixed_guides = a.n_guides <= blockDim.x && 32u * role + 32u <= a.n_guides;
+    // the role has exactly one full 32-guide segment in the whole guide list: its plane addresses can stay in registers
+    const bool fixed_guides = 32u * role + 32u <= a.n_guides && 32u * warps + 32u * role + 32u > a.n_guides;
     uint32_t strand, nb; unsigned long long blk0;
     batch_of(bat, strand, blk0, nb);
 #ifndef VS_HOST_UNIT_TEST
