@@ -380,7 +380,8 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
     ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
     launches = 0
     # ---- index resident: its plain form (k_score), then its bucketed form (k_score_bucketed) -------------------------
-    for name, bucket in (("warm_plain", 0), ("warm", 1)):
+    use_bucket = 1 if ng >= 64 else 0                    # the library's default policy (VS_OPT_BUCKET_INDEX 1)
+    for name, bucket in (("warm_plain", 0), ("warm", use_bucket)):
         ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, bucket)
         build_ms = 0.0
         for _ in range(max(2, warmup)):
@@ -454,6 +455,7 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
                   "note": "vs_scan_resolved from pinned host buffers (H2D chunked, overlapped with extraction + scoring), hits resolved + sorted on the "
                           "device, D2H into shared memory, rank 0 merges all ranks' lists into records (vs_merge_resolved, %d threads); wall clock, max over ranks" % host_threads}
     ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
+    ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, 1)
     return res, (rec, coll)
 
 
@@ -710,6 +712,7 @@ def main():
                               do_e2e=not args.no_e2e)
         if rank == 0:
             lop_a, lds_a = bucketed_ops(g4, c4[4], c4[5])
+            target_ops = {"stage_a_lop3": lop_a, "stage_a_lds": lds_a}
             ex4 = lop_a * r4["warm"]["blocks"] * c4[3] / (r4["warm"]["score_ms"] * 1e-3)
             (lop_p4, _), _ = score_ops(c4[4])
             target = {"workload": c4[0], "guides": c4[3], "k": c4[4], "extra_pam": c4[5], "steps": tsteps,
@@ -718,7 +721,7 @@ def main():
                       "hits_per_step": r4["warm"]["hits"], "frac_executed": ex4 / peak_lop3, "executed_lop3_tlops": ex4 / 1e12,
                       "plain_index": {"value": r4["warm_plain"]["value"], "ms_per_step": r4["warm_plain"]["ms"], "score_ms": r4["warm_plain"]["score_ms"],
                                       "frac_executed": lop_p4 * r4["warm_plain"]["blocks"] * c4[3] / (r4["warm_plain"]["score_ms"] * 1e-3) / peak_lop3},
-                      "index_build_ms_rank0": r4["warm"]["index_build_ms"],
+                      "index_build_ms_rank0": r4["warm"]["index_build_ms"], "ops_per_block_guide": target_ops,
                       "e2e": r4.get("e2e"), "redo": r4["cold"]["redo"]}
             if not args.no_cpu and merged4 is not None:
                 os.sched_setaffinity(0, all_cpus)
@@ -740,7 +743,8 @@ def main():
     score_s = warm["score_ms"] * 1e-3
     B_local = min(B - first * 32, words * 32)             # bases whose window starts this rank owns
     (lop_p, lds_p), (lop_b, lds_b) = score_ops(k)
-    lop_a, lds_a = bucketed_ops(guides, k, pam)
+    bucketed = ng >= 64                                   # the library's policy: the bucketed index is used from 64 guides on
+    lop_a, lds_a = bucketed_ops(guides, k, pam) if bucketed else (lop_p, lds_p)
     executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few iterations that pass)
     lds = lds_a * blocks * ng / score_s
     yard = C_ALG * ng * B_local / score_s
@@ -765,7 +769,7 @@ def main():
     except Exception:
         pass
     hbm_alg = blocks * 192.0 / score_s / 1e9
-    roof = {"bound": "int_alu", "kernel": "k_score_bucketed", "achieved": executed / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
+    roof = {"bound": "int_alu", "kernel": "k_score_bucketed" if bucketed else "k_score", "achieved": executed / 1e12, "peak": peak_lop3 / 1e12, "unit": "Tlop3/s",
             "frac": executed / peak_lop3,
             "frac_note": "executed stage-A LOP3 of the scoring kernel (adder tree + 2 threshold ops per 32-candidate block and guide; the bucketed index scores "
                          "%.1f LOP3 / %.1f LDS per pair on average instead of the plain index's %d / %d) / measured alu-pipe LOP3 rate; a lower bound of the pipe load "

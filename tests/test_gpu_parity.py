@@ -546,6 +546,7 @@ def test_bucketed_index_equals_oracle(k, pam, n_guides):
     (vs_bucket.cuh) and scores it with per-bucket mismatch budgets: same records as the oracle for every k, with the guide
     counts exercising full and 4-guide segments of every class, last windows, N runs, several shards."""
     import varscot_b200 as V
+    from varscot_b200 import _lib
     case = make_case(seed=700 + k, contig_lens=[60000, 45, 45, 45, 23, 22, 46, 20000] + [45] * 200 + [9000], n_guides=n_guides, k=k, pam=pam,
                      guide_pam=(pam if pam in ("AG",) else "GG"))
     text = V.PackedText.from_ascii(case.ascii, case.offsets)
@@ -557,6 +558,7 @@ def test_bucketed_index_equals_oracle(k, pam, n_guides):
             w0, w1 = nw * i // shards, nw * (i + 1) // shards
             with V.ScanContext(0) as ctx:
                 ctx.set_chunk_words(500)
+                ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, 2)           # whatever the guide count
                 ctx.upload(text, w0, w1 - w0)
                 h1, st1 = ctx.scan_resolved(case.guides, k, pam=pam)
                 h2, st2 = ctx.scan_resolved(case.guides, k, pam=pam)        # builds and scores the bucketed index
