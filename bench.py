@@ -380,8 +380,7 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
     ctx.set_option(_lib.VS_OPT_KEEP_INDEX, 1)
     launches = 0
     # ---- index resident: its plain form (k_score), then its bucketed form (k_score_bucketed) -------------------------
-    use_bucket = 1 if ng >= 64 else 0                    # the library's default policy (VS_OPT_BUCKET_INDEX 1)
-    for name, bucket in (("warm_plain", 0), ("warm", use_bucket)):
+    for name, bucket in (("warm_plain", 0), ("warm", 1)):        # 1 = the library's default policy: bucketed where it pays
         ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, bucket)
         build_ms = 0.0
         for _ in range(max(2, warmup)):
@@ -391,12 +390,13 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
         dev = score = resolve = 0.0
         for _ in range(steps):
             hits, st = ctx.scan_resolved(guides, k, pam=pam, out=hits_buf)
-            assert st.index_reused == 1 + bucket
+            assert st.index_reused >= 1 and (bucket or st.index_reused == 1)
             dev += st.total_ms; score += st.score_ms; resolve += st.resolve_ms; launches += st.launches
         barrier(world, local)
         ms = all_reduce(dev / steps, world, local, "MAX")
         res[name] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "score_ms": score / steps, "resolve_ms": resolve / steps, "launches": launches,
                      "score_launches": int(st.score_launches), "blocks": int(st.n_blocks_fwd + st.n_blocks_rev), "index_build_ms": build_ms,
+                     "bucketed": bool(all_reduce(float(st.index_reused == 2), world, local, "MIN")),
                      "cands": int(st.n_cand_fwd + st.n_cand_rev), "hits": int(all_reduce(float(len(hits)), world, local, "SUM"))}
     # ---- cold: the index is extracted again every step ------------------------------------------------
     res["launches"] = launches
@@ -711,7 +711,7 @@ def main():
         r4, merged4 = measure(V, ctx, text, g4, c4[4], c4[5], first, words, tsteps, 3, world, local, hits_buf, exchange, total_bases, c4[3], host_threads,
                               do_e2e=not args.no_e2e)
         if rank == 0:
-            lop_a, lds_a = bucketed_ops(g4, c4[4], c4[5])
+            lop_a, lds_a = bucketed_ops(g4, c4[4], c4[5]) if r4["warm"]["bucketed"] else score_ops(c4[4])[0]
             target_ops = {"stage_a_lop3": lop_a, "stage_a_lds": lds_a}
             ex4 = lop_a * r4["warm"]["blocks"] * c4[3] / (r4["warm"]["score_ms"] * 1e-3)
             (lop_p4, _), _ = score_ops(c4[4])
@@ -743,7 +743,7 @@ def main():
     score_s = warm["score_ms"] * 1e-3
     B_local = min(B - first * 32, words * 32)             # bases whose window starts this rank owns
     (lop_p, lds_p), (lop_b, lds_b) = score_ops(k)
-    bucketed = ng >= 64                                   # the library's policy: the bucketed index is used from 64 guides on
+    bucketed = warm["bucketed"]                           # the library's policy decided (guide count, shard size)
     lop_a, lds_a = bucketed_ops(guides, k, pam) if bucketed else (lop_p, lds_p)
     executed = lop_a * blocks * ng / score_s             # stage A only: a lower bound (stage B runs for the few iterations that pass)
     lds = lds_a * blocks * ng / score_s
@@ -794,7 +794,7 @@ def main():
         "value_note": "packed text AND candidate index resident in HBM (index = the PAM-valid windows of both strands, bucketed by PAM kind + the four bases next to "
                       "the PAM; built once per text and PAM set: the analogue of the reference's prebuilt FM index); first kernel -> resolved + sorted hits in host memory, "
                       "CUDA events, max over ranks",
-        "value_plain_index": plain["value"], "ms_per_step_plain_index": plain["ms"], "index_build_ms_rank0": warm["index_build_ms"],
+        "index": "bucketed" if bucketed else "plain", "value_plain_index": plain["value"], "ms_per_step_plain_index": plain["ms"], "index_build_ms_rank0": warm["index_build_ms"],
         "value_cold": cold["value"], "ms_per_step_cold": cold["ms"],
         "value_cold_note": "the same with the index dropped before every step: extraction of the PAM-valid windows included",
         "layout": {"text_bases_per_gpu": int(B_local), "shard_words": int(words), "chunks": cold["chunks"], "cpus_bound_per_rank": numa_cpus,

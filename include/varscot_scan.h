@@ -191,7 +191,7 @@ typedef struct {
  * store directly.  It is dropped by a new upload, a different -P, vs_index_drop(), or kept off with VS_OPT_KEEP_INDEX 0. */
 #define VS_OPT_KEEP_INDEX   1     /* 0 / 1 (default 1) */
 #define VS_OPT_HIT_CAPACITY 2     /* entries of the device hit buffer; 0 (default) = sized from k, the PAM set and the shard */
-#define VS_OPT_BUCKET_INDEX 3     /* 0 never / 1 (default) with >= 64 guides / 2 always: when a resident index is scanned a second time,
+#define VS_OPT_BUCKET_INDEX 3     /* 0 never / 1 (default) where it pays (>= 256 guides, or >= 64 guides on a large shard) / 2 always: when a resident index is scanned a second time,
                                    * regroup its candidates by the PAM dinucleotide + the six bases next to it, so that later scans
                                    * score 9-15 instead of 19 positions per window and guide (vs_scan_stats.index_reused == 2) */
 int vs_ctx_set_option(vs_ctx *ctx, int option, int64_t value);

@@ -368,7 +368,7 @@ static void check_k_score(uint32_t n_guides, unsigned threads = 0)
     ScoreArgs a;
     for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
     a.rng = rng; a.cap = cap;
-    a.n_guides = n_guides; a.guide_base = g_base; a.pat_guides = rows; a.pat = pat;
+    a.n_guides = n_guides; a.guide_base = g_base; a.pat_guides = rows; a.pat = pat; a.rot_shift = n_guides % 2 ? 0 : 40;
     a.hits = hits.data(); a.n_hits = &n_hits; a.hit_cap = hits.size();
     launch_cta(2, threads ? threads : std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32), [&] { k_score<K>(a); });
     std::set<std::pair<uint32_t, uint32_t>> got, want;

@@ -98,7 +98,7 @@ int main(int argc, char **argv)
         for (;;) {
             ScoreArgs a;
             for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
-            a.rng = r; a.cap = cap; a.n_guides = n_guides; a.guide_base = 0; a.pat_guides = n_guides; a.pat = pat16;
+            a.rng = r; a.cap = cap; a.n_guides = n_guides; a.guide_base = 0; a.pat_guides = n_guides; a.pat = pat16; a.rot_shift = 1;
             const unsigned long long before = n;
             a.hits = out.data(); a.n_hits = &n; a.hit_cap = out.size();
             dispatch_score(k, a, 3, threads);                  // 3 persistent CTAs stride over the batches

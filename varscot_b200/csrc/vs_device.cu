@@ -62,7 +62,7 @@ struct vs_ctx {
     int keep_index = 1;
     uint64_t hit_cap_opt = 0;
     // bucketed index (vs_bucket.cuh): the candidates regrouped by PAM kind + the four bases next to the PAM
-    int bucket_mode = 1;                 // VS_OPT_BUCKET_INDEX: 0 never, 1 when a resident index is scanned again with >= 64 guides, 2 whatever the guide count
+    int bucket_mode = 1;                 // VS_OPT_BUCKET_INDEX: 0 never, 1 when a resident index is scanned again and it pays (guide count, shard size), 2 always
     bool bk_valid = false;
     uint32_t *d_bk_planes[2] = {nullptr, nullptr}, *d_bk_pos[2] = {nullptr, nullptr};
     uint64_t bk_cap[2] = {0, 0}, bk_blocks[2] = {0, 0};
@@ -875,8 +875,11 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     }
     // a resident index that is scanned again gets its bucketed form (built once; this scan pays for it)
     bool use_bk = false;
-    // (with few guides the classes of a bucket are a handful of 4-guide segments: the plain index is as fast or faster)
-    if (reuse && (ctx->bucket_mode == 2 || (ctx->bucket_mode == 1 && n_guides >= 64))) {
+    // (with few guides the classes of a bucket are a handful of 4-guide segments, and a small shard is scanned in about the
+    // time the per-scan class sort takes: there the plain index is as fast or faster.  Measured on B200: 100 guides x 3.5
+    // Gbases + 8 %, 100 guides x 0.44 Gbases - 9 %, 1000 guides + 58 %)
+    const bool bucket_pays = n_guides >= 256 || (n_guides >= 64 && (double)n_guides * (double)n_words >= 5e9);
+    if (reuse && (ctx->bucket_mode == 2 || (ctx->bucket_mode == 1 && bucket_pays))) {
         if (!ctx->bk_valid) {
             if ((r = build_bucket_index(ctx, pp, S.launches)) != VS_OK) return r;
             S.index_build_ms = ctx->bk_build_ms;
@@ -931,10 +934,12 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
     }
     // CTA size of k_score: one warp per 32 guides, at most SC_WARPS; a short tail (<= 8 guides) does not get a warp of its own
     // — it would idle most of the time and hold a warp slot (100 guides: 3 warps; the tail's 4-guide segments rotate over them)
+    static const int fold_tail = getenv("VARSCOT_SCORE_FOLD_TAIL") ? atoi(getenv("VARSCOT_SCORE_FOLD_TAIL")) : 1;       // tuning knobs
+    static const int rot_shift = getenv("VARSCOT_SCORE_ROT") ? atoi(getenv("VARSCOT_SCORE_ROT")) : 3;
     const auto score_cta = [](uint32_t ng) {
         if (ng >= (uint32_t)SC_THREADS) return (unsigned)SC_THREADS;
         const unsigned full = ng / 32, tail = ng % 32;
-        return 32u * std::max(1u, full + ((tail > 8 || full == 0) ? 1u : 0u));
+        return 32u * std::max(1u, full + ((tail > (fold_tail ? 8u : 0u) || full == 0) ? 1u : 0u));
     };
     unsigned score_ctas = (unsigned)ctx->n_sm * 32;         // persistent: a multiple of the SM count, about four waves of resident CTAs (16 / 32 / 64 per SM measured: 32 is 3 % faster than 16, 64 no better)
     if (const char *e = getenv("VARSCOT_SCORE_CTAS_PER_SM")) score_ctas = (unsigned)ctx->n_sm * (unsigned)std::max(1, atoi(e));   // tuning knob
@@ -952,6 +957,7 @@ static int scan_engine(vs_ctx *ctx, const ScanReq &q)
         for (int s = 0; s < 2; ++s) { a.planes[s] = ctx->d_planes[s]; a.pos[s] = ctx->d_pos[s]; }
         a.rng = rng; a.cap = ctx->blocks_cap;
         a.n_guides = ng; a.guide_base = g0; a.pat_guides = n_guides; a.pat = ctx->d_pat;
+        a.rot_shift = (uint32_t)rot_shift;
         a.hits = ctx->d_hits; a.n_hits = d_hitcnt; a.hit_cap = ctx->hits_cap;
         dispatch_score(k, a, score_ctas, score_cta(ng), st);
         S.launches++; S.score_launches++;

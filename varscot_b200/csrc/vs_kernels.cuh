@@ -437,6 +437,7 @@ struct ScoreArgs {
     uint32_t n_guides;          // guides of this launch: rows [guide_base, guide_base + n_guides) of the table
     uint32_t guide_base;
     uint32_t pat_guides;        // rows per strand of the table
+    uint32_t rot_shift;         // the guide slices of the warps rotate every 2^rot_shift batches (>= 32: never)
     const uint16_t *pat;        // [2][pat_guides][PAT_STRIDE] slot offsets (pat_slot), 16-byte aligned rows
     vs_hit *hits;
     unsigned long long *n_hits;
@@ -549,7 +550,7 @@ k_score(ScoreArgs a)
     int kept_strand = -1;                                   // strand and role the kept addresses belong to
     uint32_t iter = 0;
     for (unsigned long long bat = blockIdx.x; bat < nbat; bat += gridDim.x, ++iter) {
-    const uint32_t role = ((uint32_t)wid + blockIdx.x + (iter >> 3)) % warps;
+    const uint32_t role = ((uint32_t)wid + (a.rot_shift < 32u ? blockIdx.x + (iter >> a.rot_shift) : 0u)) % warps;
     // the role has exactly one full 32-guide segment in the whole guide list: its plane addresses can stay in registers
     const bool fixed_guides = 32u * role + 32u <= a.n_guides && 32u * warps + 32u * role + 32u > a.n_guides;
     uint32_t strand, nb; unsigned long long blk0;
