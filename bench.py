@@ -207,7 +207,7 @@ def dist_setup():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return world, rank, local
 
 
@@ -231,8 +231,9 @@ def all_reduce(x, world, local, op):
 
 class HostExchange:
     """Hand-over of the ranks' sorted hit lists to rank 0 through POSIX shared memory ("merged on the host", north_star):
-    every rank downloads its hits straight into its page-locked segment, publishes the count with a sequence number, rank 0
-    spins on the sequence numbers, merges, and publishes `done`."""
+    every rank downloads its hits straight into its page-locked segment, publishes the counts with a sequence number, rank 0
+    spins on the sequence numbers, merges, and publishes `done`.  The sequence number is one counter per object, advanced by
+    every rank once per step (`begin`): steps of different measurement phases can never be mistaken for one another."""
 
     def __init__(self, V, world, rank, cap, pin=True, tag=None):
         from varscot_b200 import _lib
@@ -242,8 +243,9 @@ class HostExchange:
         base = f"/dev/shm/varscot_bench_{tag}"
         self.paths = [f"{base}_{r}.bin" for r in range(world)]
         self.ctl_path = f"{base}_ctl.bin"
+        self.n_ctl = 3 * world + 1                               # per rank: sequence number, count, second count; then `done`
         if rank == 0:
-            np.zeros(2 * world + 2, dtype=np.int64).tofile(self.ctl_path)
+            np.zeros(self.n_ctl, dtype=np.int64).tofile(self.ctl_path)
         with open(self.paths[rank], "wb") as f:
             f.truncate(cap * 16)
         self.mine = np.memmap(self.paths[rank], dtype=V.LOC_DT, mode="r+", shape=(cap,))
@@ -252,32 +254,47 @@ class HostExchange:
             raise RuntimeError("vs_host_register failed")
         self.ctl = None
         self.others = None
+        self.seq = 0
 
     def attach(self):
         """after a barrier: every segment exists"""
-        self.ctl = np.memmap(self.ctl_path, dtype=np.int64, mode="r+", shape=(2 * self.world + 2,))
+        self.ctl = np.memmap(self.ctl_path, dtype=np.int64, mode="r+", shape=(self.n_ctl,))
         if self.rank == 0:
             self.others = [self.mine if r == 0 else np.memmap(self.paths[r], dtype=self.V.LOC_DT, mode="r", shape=(self.cap,)) for r in range(self.world)]
 
-    def publish(self, step, n):
-        self.ctl[2 * self.rank + 1] = n
-        self.ctl[2 * self.rank] = step                           # x86 keeps the store order; rank 0 reads the count after the sequence number
+    def begin(self):
+        """every rank, once per step, in lockstep"""
+        self.seq += 1
+        return self.seq
 
-    def collect(self, step):
-        """rank 0: wait for every rank's list of this step"""
+    def publish(self, n, n2=0):
+        self.ctl[3 * self.rank + 1] = n
+        self.ctl[3 * self.rank + 2] = n2
+        self.ctl[3 * self.rank] = self.seq                       # x86 keeps the store order; rank 0 reads the counts after the sequence number
+
+    def collect(self, split=0):
+        """rank 0: wait for every rank's list(s) of this step; split > 0: a second list starts at entry `split` of every segment"""
         lists = []
+        deadline = time.time() + 120.0
         for r in range(self.world):
-            while self.ctl[2 * r] < step:
-                pass
-            lists.append(self.others[r][: int(self.ctl[2 * r + 1])])
+            while self.ctl[3 * r] < self.seq:
+                if time.time() > deadline:
+                    raise RuntimeError(f"rank {r} did not publish step {self.seq} within 120 s")
+            if self.ctl[3 * r] != self.seq:
+                raise RuntimeError(f"rank {r} is at step {int(self.ctl[3 * r])}, rank 0 at {self.seq}")
+            lists.append(self.others[r][: int(self.ctl[3 * r + 1])])
+            if split:
+                lists.append(self.others[r][split: split + int(self.ctl[3 * r + 2])])
         return lists
 
-    def done(self, step):
-        self.ctl[2 * self.world] = step
+    def done(self):
+        self.ctl[3 * self.world] = self.seq
 
-    def wait_done(self, step):
-        while self.ctl[2 * self.world] < step:
-            pass
+    def wait_done(self):
+        deadline = time.time() + 120.0
+        while self.ctl[3 * self.world] < self.seq:
+            if time.time() > deadline:
+                raise RuntimeError(f"rank 0 did not finish step {self.seq} within 120 s")
 
     def close(self):
         try:
@@ -418,34 +435,36 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
         return res, None
 
     # ---- end to end: host buffers in, merged records out, every step --------------------------------------
-    def e2e_loop(step_fn, n_steps, seq0):
+    def e2e_loop(step_fn, n_steps):
         rec = coll = None
         for i in range(2):
-            rec, coll = step_fn(seq0 + i + 1)
+            rec, coll = step_fn()
         barrier(world, local)
         t0 = time.perf_counter()
         for i in range(n_steps):
-            rec, coll = step_fn(seq0 + 3 + i)
+            rec, coll = step_fn()
         barrier(world, local)
         return (time.perf_counter() - t0) * 1e3 / n_steps, rec, coll
 
     stats = {}
 
-    def full_step(seq):
+    def full_step():
+        if exchange is not None:
+            exchange.begin()
         h, st2 = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=first, n_words=words, out=hits_buf)
         stats["st"] = st2
         if exchange is None:
             return V.merge_resolved([h], threads=host_threads)
-        exchange.publish(seq, len(h))
+        exchange.publish(len(h))
         out = (None, None)
         if exchange.rank == 0:
-            out = V.merge_resolved(exchange.collect(seq), threads=host_threads)
-            exchange.done(seq)
+            out = V.merge_resolved(exchange.collect(), threads=host_threads)
+            exchange.done()
         else:
-            exchange.wait_done(seq)
+            exchange.wait_done()
         return out
 
-    e_ms, rec, coll = e2e_loop(full_step, steps, 0)
+    e_ms, rec, coll = e2e_loop(full_step, steps)
     e_ms = all_reduce(e_ms, world, local, "MAX")
     st2 = stats["st"]
     res["e2e"] = {"value": units / (e_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": e_ms,
@@ -659,7 +678,9 @@ def main():
         ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])                       # builds the genome's index once
         st_box = {}
 
-        def rg_step(seq):
+        def rg_step():
+            if exchange is not None:
+                exchange.begin()
             # the resident genome and the uploaded segments are scanned at the same time (two contexts, two host threads)
             box = {}
             th = threading.Thread(target=lambda: box.update(g=ctx_g.scan_resolved(guides, k, pam=pam, out=hits_buf[:half])))
@@ -670,28 +691,21 @@ def main():
             st_box["h2d"] = sa.h2d_bytes + sb_.h2d_bytes; st_box["d2h"] = sa.d2h_bytes + sb_.d2h_bytes
             if exchange is None:
                 return V.merge_resolved([a, b], threads=host_threads)
-            # the two lists travel as one segment: [0, n_a) and [half, half + n_b); counts packed into one word
-            exchange.publish(seq, len(a) | (len(b) << 32))
+            exchange.publish(len(a), len(b))                  # the two lists travel in one segment: [0, n_a) and [half, half + n_b)
             out = (None, None)
             if exchange.rank == 0:
-                lists = []
-                for r in range(world):
-                    while exchange.ctl[2 * r] < seq:
-                        pass
-                    c = int(exchange.ctl[2 * r + 1])
-                    lists += [exchange.others[r][: c & 0xFFFFFFFF], exchange.others[r][half: half + (c >> 32)]]
-                out = V.merge_resolved(lists, threads=host_threads)
-                exchange.done(seq)
+                out = V.merge_resolved(exchange.collect(split=half), threads=host_threads)
+                exchange.done()
             else:
-                exchange.wait_done(seq)
+                exchange.wait_done()
             return out
 
         for i in range(2):
-            rg_step(1000 + i)
+            rg_step()
         barrier(world, local)
         t0 = time.perf_counter()
         for i in range(args.steps):
-            rec_rg, _ = rg_step(1003 + i)
+            rec_rg, _ = rg_step()
         barrier(world, local)
         rg_ms = all_reduce((time.perf_counter() - t0) * 1e3 / args.steps, world, local, "MAX")
         e2e_rg = {"value": float(ng) * total_bases / (rg_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": rg_ms,
@@ -840,5 +854,11 @@ def _shutdown():
 if __name__ == "__main__":
     try:
         main()
-    finally:
-        _shutdown()
+    except BaseException:
+        # a rank that fails must take the job down at once: tearing the process group down gracefully would wait for the other
+        # ranks, which are waiting for this one
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)
+    _shutdown()

@@ -98,17 +98,41 @@ def _worker_exchange(rank, world, port, q):
     ex = bench.HostExchange(V, world, rank, 1 << 14, pin=False, tag=f"test_{port}")
     dist.barrier()
     ex.attach()
-    for step in (1, 2):                                       # two rounds: the sequence numbers separate them
-        ex.mine[: len(loc)] = loc
-        ex.publish(step, len(loc))
+    import time
+    results = []
+    half = 1 << 13
+    # several "phases" of steps as bench.py runs them (end to end, resident genome with two lists per rank, the config-4 block):
+    # later steps publish LATE and with fewer hits, so a rank 0 that mistook an old step for the current one would merge stale lists
+    for step in range(1, 8):
+        ex.begin()
+        sub = loc if step % 3 else loc[: len(loc) // 2]          # the list of this step
+        if rank and step >= 3:
+            time.sleep(0.05 * rank)
+        if step % 2:
+            ex.mine[: len(sub)] = sub
+            ex.publish(len(sub))
+        else:                                                    # two lists per rank: even / odd entries
+            a, b2 = sub[0::2], sub[1::2]
+            ex.mine[: len(a)] = a
+            ex.mine[half: half + len(b2)] = b2
+            ex.publish(len(a), len(b2))
         if rank == 0:
-            rec, coll = V.merge_resolved(ex.collect(step), threads=2)
-            ex.done(step)
-            got = [(int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"])) for x in rec]
-            if step == 2:
-                q.put((got == [x[:5] for x in whole.rows()], len(got), [int(ex.ctl[2 * r + 1]) for r in range(world)]))
+            rec, coll = V.merge_resolved(ex.collect(split=0 if step % 2 else half), threads=2)
+            ex.done()
+            results.append((step, len(rec), [(int(x["guide"]), int(x["flag"]), int(x["contig"]), int(x["pos"]), int(x["mm"])) for x in rec]))
         else:
-            ex.wait_done(step)
+            ex.wait_done()
+    counts = [None] * world
+    dist.all_gather_object(counts, (len(loc), len(loc) // 2))
+    if rank == 0:
+        full = [x[:5] for x in whole.rows()]
+        ok = True
+        for step, n, got in results:
+            if step % 3:
+                ok = ok and got == full
+            else:
+                ok = ok and n == sum(c[1] for c in counts) and n < len(full)
+        q.put((ok, len(full), [c[0] for c in counts]))
     dist.barrier()
     ex.close()
     dist.destroy_process_group()
