@@ -763,8 +763,8 @@ def main():
     lds = lds_a * blocks * ng / score_s
     yard = C_ALG * ng * B_local / score_s
     plain_s = plain["score_ms"] * 1e-3
-    traffic, traffic_src = None, None
-    for name in ("r2_score_summary.txt", "r1_score_final_summary.txt"):
+    def dram_bytes(name):
+        """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from a committed ncu --set full summary (profiles/)."""
         try:
             rd = wr = None
             for line in open(os.path.join(ROOT, "profiles", name)):
@@ -772,11 +772,16 @@ def main():
                 if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     v = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
                     rd, wr = (v, wr) if f[0].endswith("read.sum") else (rd, v)
-            if rd is not None and wr is not None:
-                traffic, traffic_src = rd + wr, name
-                break
+            return rd + wr if rd is not None and wr is not None else None
         except Exception:
-            pass
+            return None
+    # captures of round 2 (one launch each; the workload each was taken on is part of the name).  The number is only quoted as THIS run's traffic
+    # when kernel and workload are the ones of this run: the full-size config-3 capture is of the plain-index kernel.
+    captures = {"k_score cfg3 x1.0": dram_bytes("r2_score_cfg3_summary.txt"), "k_score cfg4 x1.0": dram_bytes("r2_score_cfg4_summary.txt"),
+                "k_score_bucketed cfg4 x0.25": dram_bytes("r2_bucketed_cfg4_scale0.25_summary.txt")}
+    same_workload = args.config == 3 and args.scale == 1.0 and world == 1
+    traffic_plain = captures["k_score cfg3 x1.0"] if same_workload else None
+    traffic = None if bucketed else traffic_plain
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -790,10 +795,14 @@ def main():
                          "(stage B, hit path, loop and segment overhead not counted); ncu pipe_alu / pipe_lsu of the same kernels: profiles/" % (lop_a, lds_a, lop_p, lds_p),
             "plain_index": {"kernel": "k_score", "score_ms": plain["score_ms"], "value": plain["value"], "ms_per_step": plain["ms"],
                             "frac": lop_p * blocks * ng / plain_s / peak_lop3, "frac_lds": lds_p * blocks * ng / plain_s / peak_lds,
-                            "ops_per_block_guide": {"stage_a_lop3": lop_p, "stage_a_lds": lds_p}},
+                            "ops_per_block_guide": {"stage_a_lop3": lop_p, "stage_a_lds": lds_p}, "traffic": traffic_plain},
             "frac_yardstick": yard / peak_lop3,
             "yardstick_note": "dense-scan yardstick of SURVEY.md 8d: 4.0 LOP3 per guide*bp; the PAM-first index scores ~1/8 of the windows per strand, so this exceeds 1",
-            "traffic": traffic, "traffic_note": f"dram bytes of one k_score launch, ncu capture profiles/{traffic_src}; algorithmic = 192 B per block per launch",
+            "traffic": traffic, "algorithmic_bytes_per_launch": blocks * 192.0,
+            "traffic_note": "dram bytes of one launch from the committed ncu --set full captures (profiles/r2_*_summary.txt); algorithmic = 192 B per block and launch. "
+                            "The full-size config-3 capture of round 2 is of the plain-index kernel (plain_index.traffic); the bucketed kernel was captured on config 4 "
+                            "at scale 0.25 only (traffic_captures), so its traffic on this workload is null, not guessed",
+            "traffic_captures": captures,
             "hbm": {"achieved_gbs": hbm_alg, "peak_gbs": hbm_peak, "frac": (hbm_alg / hbm_peak) if hbm_peak else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "MEASURED_PEAKS.json absent"},
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
@@ -805,7 +814,7 @@ def main():
         "metric": "guide_Gbp_per_s", "value": warm["value"], "unit": "guide*Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": warm["ms"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)",
         "data": "synthetic", "config": config_dict(cfg, B, text.n_contigs, scaling if world > 1 else "single", args.scale),
-        "value_note": "packed text AND candidate index resident in HBM (index = the PAM-valid windows of both strands, bucketed by PAM kind + the four bases next to "
+        "value_note": "packed text AND candidate index resident in HBM (index = the PAM-valid windows of both strands, bucketed by PAM kind + the six bases next to "
                       "the PAM; built once per text and PAM set: the analogue of the reference's prebuilt FM index); first kernel -> resolved + sorted hits in host memory, "
                       "CUDA events, max over ranks",
         "index": "bucketed" if bucketed else "plain", "value_plain_index": plain["value"], "ms_per_step_plain_index": plain["ms"], "index_build_ms_rank0": warm["index_build_ms"],

@@ -23,7 +23,9 @@ WANT = [
     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
     "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
     "smsp__warp_issue_stalled_membar_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
-]
+] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % x for x in (
+    "selected", "not_selected", "wait", "math_pipe_throttle", "mio_throttle", "short_scoreboard", "long_scoreboard", "barrier",
+    "no_instruction", "branch_resolving", "dispatch_stall", "lg_throttle")]
 
 
 def main():
