@@ -196,7 +196,56 @@ def host_info():
                 break
     except Exception:
         pass
-    return {"cpu_model": model, "cpus": len(os.sched_getaffinity(0))}
+    numa = 0
+    try:
+        numa = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        pass
+    return {"cpu_model": model, "cpus": len(os.sched_getaffinity(0)), "numa_nodes": numa}
+
+
+def gpu_topology(txt=None):
+    """`nvidia-smi topo -m` reduced to one line: link kinds between the GPUs and their CPU / NUMA affinity."""
+    try:
+        import re
+        import subprocess
+        if txt is None:
+            txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        txt = re.sub(r"\x1b\[[0-9;]*m", "", txt)
+        rows = [l.split("\t") for l in txt.splitlines() if l.startswith("GPU")]
+        links, aff = set(), set()
+        for r in rows:
+            cells = [c.strip() for c in r[1:]]
+            n_gpu = len(rows)
+            links.update(c for c in cells[:n_gpu] if c and c != "X")
+            aff.add(tuple(cells[n_gpu:n_gpu + 2]))
+        return {"gpus": len(rows), "links": sorted(links), "cpu_numa_affinity": sorted("/".join(a) for a in aff)}
+    except Exception:
+        return None
+
+
+def ncu_pipes():
+    """ncu's own pipe loads of the scoring kernels from the committed round-2 captures (profiles/r2_*_summary.txt): what `roofline.frac`
+    (executed stage-A LOP3 only) is a lower bound of.  Static evidence of an earlier run of the same kernels, quoted with its source."""
+    out = {}
+    want = {"alu_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "lsu_pct": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "smem_wavefronts_pct": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "issue_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active"}
+    for label, name in (("k_score cfg3 x1.0", "r2_score_cfg3_summary.txt"), ("k_score cfg4 x1.0", "r2_score_cfg4_summary.txt"),
+                        ("k_score_bucketed cfg4 x0.25", "r2_bucketed_cfg4_scale0.25_summary.txt")):
+        try:
+            d = {}
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                f = line.split()
+                for k, m in want.items():
+                    if len(f) >= 2 and f[0] == m:
+                        d[k] = float(f[1])
+            if d:
+                d["source"] = "profiles/" + name
+                out[label] = d
+        except Exception:
+            pass
+    return out or None
 
 
 def dist_setup():
@@ -803,6 +852,7 @@ def main():
                             "The full-size config-3 capture of round 2 is of the plain-index kernel (plain_index.traffic); the bucketed kernel was captured on config 4 "
                             "at scale 0.25 only (traffic_captures), so its traffic on this workload is null, not guessed",
             "traffic_captures": captures,
+            "ncu_pipes": ncu_pipes(),
             "hbm": {"achieved_gbs": hbm_alg, "peak_gbs": hbm_peak, "frac": (hbm_alg / hbm_peak) if hbm_peak else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "MEASURED_PEAKS.json absent"},
             "peak_source": "measured in this run by vs_measure_int_peaks (k_peak_lop3); MEASURED_PEAKS.json has no integer peak",
@@ -826,7 +876,7 @@ def main():
                    "host_merge_threads": host_threads},
         "phase_ms_rank0": {"score": warm["score_ms"], "resolve_sort_d2h": warm["resolve_ms"], "extract_cold": cold["extract_ms"], "score_cold": cold["score_ms"]},
         "hits_per_step": warm["hits"], "candidates_rank0": warm["cands"], "gpu_launches": res["launches"], "redo": cold["redo"],
-        "roofline": roof, "e2e": res.get("e2e"), "e2e_resident_genome": e2e_rg, "clocks": clocks, "gen_s": t_gen, "host": host_info(),
+        "roofline": roof, "e2e": res.get("e2e"), "e2e_resident_genome": e2e_rg, "clocks": clocks, "gen_s": t_gen, "host": {**host_info(), "gpu_topology": gpu_topology()},
         "target_cfg4": target,
     }
     # ---- CPU baseline + hit-set diff of the MERGED records on a bounded sample -----------------------------

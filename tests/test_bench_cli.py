@@ -55,3 +55,17 @@ def test_gpu_arm_shared_memory_handover_and_dense_mode():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["hits_per_step"] > 10000 and d["redo"] == 0 and d["verification"]["per_guide_counts_equal_small_scan"]
     assert d["parity"]["diff"] == 0 and d["rank0"]["first_delivery_sorted"] and d["e2e"]["value"] > 0
+
+
+def test_static_evidence_helpers():
+    """The bench line quotes ncu's pipe loads and DRAM bytes from the committed captures and reduces `nvidia-smi topo -m` to one
+    entry: both parsers against the files under profiles/ (no GPU, no nvidia-smi needed)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    pipes = bench.ncu_pipes()
+    assert set(pipes) == {"k_score cfg3 x1.0", "k_score cfg4 x1.0", "k_score_bucketed cfg4 x0.25"}
+    for d in pipes.values():
+        assert 40 < d["alu_pct"] < 100 and 40 < d["lsu_pct"] < 100 and os.path.exists(os.path.join(ROOT, d["source"]))
+    topo = bench.gpu_topology(open(os.path.join(ROOT, "profiles", "r2_box_8gpu.txt")).read())
+    assert topo == {"gpus": 8, "links": ["NV18"], "cpu_numa_affinity": ["0-31/0"]}
+    assert bench.host_info()["numa_nodes"] >= 0
