@@ -536,12 +536,26 @@ def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank,
     box = {"chunks": 0, "max_chunk": 0, "sorted": True, "host_s": 0.0}
 
     def sink(h, lo, hi):
+        """One delivery = the hits of guides [lo, hi), sorted; its key counts the guide from lo (bits 49..).  Per-guide counts come from
+        the guide boundaries of the sorted list (binary searches on the strided key field: no pass over the 10^7..10^8 entries); every
+        boundary is checked against the guide id stored in the record itself."""
+        try:
+            return sink_body(h, lo, hi)
+        except Exception as e:                                  # (an exception cannot cross the C callback: abort the scan instead)
+            box["error"] = repr(e)
+            return 1
+
+    def sink_body(h, lo, hi):
         t = time.perf_counter()
-        g = (h["info"] >> 8).astype(np.int64)
-        assert g.min() >= lo and g.max() < hi
-        counts[lo:hi] += np.bincount(g - lo, minlength=hi - lo)
-        if box["chunks"] == 0:                                  # order spot check on the first delivery (costs a pass over the array)
-            box["sorted"] = bool((np.diff(h["key"][: 1 << 22].astype(np.int64)) >= 0).all())
+        key, info = h["key"], h["info"]
+        b = np.searchsorted(key, np.arange(hi - lo + 1, dtype=np.uint64) << np.uint64(49))
+        assert b[0] == 0 and b[-1] == len(h), "delivery holds guides outside its range"
+        c = np.diff(b)
+        nz = np.nonzero(c)[0]
+        assert ((info[b[nz]] >> 8) == lo + nz).all() and ((info[b[nz + 1] - 1] >> 8) == lo + nz).all(), "guide boundaries of the delivery are off"
+        counts[lo:hi] += c
+        if box["chunks"] == 0:                                  # order spot check on the first delivery (a pass over its first 4 Mi entries)
+            box["sorted"] = bool((np.diff(key[: 1 << 22].astype(np.int64)) >= 0).all())
         box["chunks"] += 1; box["max_chunk"] = max(box["max_chunk"], len(h))
         box["host_s"] += time.perf_counter() - t
         return 0
@@ -549,7 +563,12 @@ def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank,
     sampler = ClockSampler(local) if rank == 0 else None
     barrier(world, local)
     t0_wall = time.time(); t0 = time.perf_counter()
-    _, st = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=first, n_words=words, sink=sink)
+    try:
+        _, st = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=first, n_words=words, sink=sink)
+    except Exception:
+        if "error" in box:
+            raise RuntimeError("config 5: the sink refused a delivery: " + box["error"])
+        raise
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier(world, local)
     clocks = sampler.stop(t0_wall, time.time()) if sampler else None
@@ -584,6 +603,39 @@ def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank,
         out["cpu_baseline"] = {"value": nv * n / dt / 1e9, "unit": "guide*Gbp/s", "cores": cores, "kind": "port",
                                "sample": f"first {n} bases, {nv} guides, one pass ({dt:.1f} s)", **host_info()}
     print(json.dumps(out))
+
+
+def run_dense_child(args, timeout_s):
+    """The `dense_cfg5` block of the default single-GPU line: config 5 at the same scale (10 000 guides, k <= 8, ~1.9e9 hits at full
+    size) through `bench.py --config 5` in a CHILD process — after this process has released the GPU — so that whatever happens to it
+    (error, time-out) costs the main line nothing but the block.  Returns the child's JSON line (bulky notes dropped) or {"error": ...}."""
+    import signal
+    env = {k_: v for k_, v in os.environ.items()
+           if k_ not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5", "--gpus", "1", "--scale", repr(args.scale)] + (["--no-cpu"] if args.no_cpu else [])
+    t = time.perf_counter()
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True, cwd=ROOT)
+    try:
+        so, se = p.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)                 # exactly the session this call started
+        except OSError:
+            pass
+        p.communicate()
+        return {"error": f"child exceeded {timeout_s:.0f} s", "cmd": " ".join(cmd[1:])}
+    wall = time.perf_counter() - t
+    if p.returncode != 0:
+        return {"error": f"child exit code {p.returncode}", "stderr_tail": se[-400:], "cmd": " ".join(cmd[1:])}
+    try:
+        d = json.loads(so.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": f"child line not parsed: {e!r}", "stdout_tail": so[-200:]}
+    for k_ in ("host", "gen_s", "vs_baseline", "higher_is_better", "data", "dtype", "steps", "warmup"):
+        d.pop(k_, None)
+    d["child_wall_s"] = wall
+    d["cmd"] = " ".join(["python"] + [os.path.basename(c) if c.endswith("bench.py") else c for c in cmd[1:]])
+    return d
 
 
 def run_cli_leg(V, text, guides, k, pam, threads):
@@ -636,6 +688,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-target", action="store_true", help="skip the config-4 target block")
     ap.add_argument("--no-resident-genome", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense_cfg5 block (config 5 in a child process; single-GPU default line only)")
     ap.add_argument("--cli", action="store_true", help="add the cli_e2e leg: the bidir_mapping executable from the .vsidx cache to the SAM file, wall clock")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -891,6 +944,11 @@ def main():
             out["parity"]["note"] = "records of the e2e path (all ranks merged on rank 0) vs the oracle; key16_collisions: records the reference's uint16 map key " \
                                     "(bidir_mapping.cpp:13) would have merged with another one — kept here (declared divergence R7)"
     ctx.close()
+    if world == 1 and args.config == 3 and not args.no_dense:
+        out["dense_cfg5"] = run_dense_child(args, float(os.environ.get("VARSCOT_BENCH_DENSE_TIMEOUT_S", "300")))
+    else:
+        out["dense_cfg5"] = None if args.no_dense or args.config != 3 else \
+            "not run at N > 1 inside this line (it needs the GPUs to itself): python -m torch.distributed.run ... bench.py --gpus N --config 5"
     if args.cli and world == 1:
         text.unpin()
         out["cli_e2e"] = run_cli_leg(V, text, guides, k, pam, min(16, len(all_cpus)))

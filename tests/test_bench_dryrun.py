@@ -187,6 +187,12 @@ def test_bench_orchestration_config3_with_target_block(world):
     t = d["target_cfg4"]
     assert t["guides"] == 1000 and t["parity"]["diff"] == 0 and t["parity"]["hits_gpu"] > 0 and t["e2e"]["value"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "frac_yardstick"} <= set(d["roofline"])
+    # the config-5 block runs in a child process on the single-GPU line only; here (no device) the child must fail WITHOUT taking
+    # the main line with it, and say why
+    if world == 1:
+        assert "error" in d["dense_cfg5"] and "exit code" in d["dense_cfg5"]["error"], d["dense_cfg5"]
+    else:
+        assert isinstance(d["dense_cfg5"], str)
 
 
 @pytest.mark.parametrize("world", [1, 2])
