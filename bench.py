@@ -945,7 +945,7 @@ def main():
                                     "(bidir_mapping.cpp:13) would have merged with another one — kept here (declared divergence R7)"
     ctx.close()
     if world == 1 and args.config == 3 and not args.no_dense:
-        out["dense_cfg5"] = run_dense_child(args, float(os.environ.get("VARSCOT_BENCH_DENSE_TIMEOUT_S", "300")))
+        out["dense_cfg5"] = run_dense_child(args, float(os.environ.get("VARSCOT_BENCH_DENSE_TIMEOUT_S", "180")))
     else:
         out["dense_cfg5"] = None if args.no_dense or args.config != 3 else \
             "not run at N > 1 inside this line (it needs the GPUs to itself): python -m torch.distributed.run ... bench.py --gpus N --config 5"
