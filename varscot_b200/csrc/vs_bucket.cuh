@@ -3,9 +3,9 @@
 // Why: k_score is bound by the shared-memory pipe (one 32-bit word per lane, pattern position and candidate block:
 // 19 LDS per 32-guide x 32-candidate tile at k = 6) and the alu pipe right behind it; the only way to go faster is
 // to score fewer positions.  The candidates of a resident text are therefore regrouped by CONTENT: a bucket holds the
-// candidates of one strand that share the PAM dinucleotide and the four bases next to it (window positions 17..22 on the
-// forward pass, 0..5 on the reverse pass for VS_KEYLEN = 6: 3 PAM kinds x 256 buckets per strand; VS_KEYLEN = 8, the
-// default, takes six bases: positions 15..22 / 0..7, 3 x 4096 buckets).  For a (bucket, guide) pair the mismatches c at
+// candidates of one strand that share the PAM dinucleotide and the VS_KEYLEN - 2 bases next to it (VS_KEYLEN = 8, the default:
+// six bases, window positions 15..22 on the forward pass, 0..7 on the reverse pass, 3 PAM kinds x 4096 buckets per strand;
+// VS_KEYLEN = 6: four bases, positions 17..22 / 0..5, 3 x 256 buckets).  For a (bucket, guide) pair the mismatches c at
 // those key positions are a constant, so
 //   * the key positions are never loaded or counted,
 //   * the remaining 23 - VS_KEYLEN positions are scored against the budget K' = K - c (K' < 0: the guide cannot hit in this

@@ -61,7 +61,7 @@ struct vs_ctx {
     uint64_t idx_end[2] = {0, 0};       // block claims incl. the padding of every chunk = the whole-store range
     int keep_index = 1;
     uint64_t hit_cap_opt = 0;
-    // bucketed index (vs_bucket.cuh): the candidates regrouped by PAM kind + the four bases next to the PAM
+    // bucketed index (vs_bucket.cuh): the candidates regrouped by PAM kind + the VS_KEYLEN - 2 = 6 bases next to the PAM
     int bucket_mode = 1;                 // VS_OPT_BUCKET_INDEX: 0 never, 1 when a resident index is scanned again and it pays (guide count, shard size), 2 always
     bool bk_valid = false;
     uint32_t *d_bk_planes[2] = {nullptr, nullptr}, *d_bk_pos[2] = {nullptr, nullptr};
