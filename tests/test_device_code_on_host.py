@@ -72,6 +72,16 @@ def test_emulated_scan_chunks_tiles_and_guide_chunks(emulator, tmp_path):
     assert check(emulator, tmp_path, many) > 0
 
 
+@pytest.mark.parametrize("n_guides", [27, 28, 29, 30, 31, 32, 33, 61, 63, 95, 127, 157])
+def test_emulated_scan_every_tail_of_a_warp_slice(emulator, tmp_path, n_guides):
+    """A warp's slice of the guide list that holds 29..31 guides pads to a full 32-guide segment (round 2's first form split the
+    tail into 16 + 8 + 4 and scored NOTHING for 29..31: found by tools/fuzz_device_code_on_host.py)."""
+    case = make_case(seed=500 + n_guides, contig_lens=[1500, 45, 45, 23, 800], n_guides=n_guides, k=3, pam=[None, "AG"][n_guides % 2])
+    assert check(emulator, tmp_path, case) > 0
+    exp = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, case.k, pam=case.pam).rows()
+    assert any(r[0] >= (n_guides - 1) // 32 * 32 for r in exp)             # the last slice has hits to lose
+
+
 def test_emulated_scan_n_runs_and_last_windows(emulator, tmp_path):
     # long N stretches (no candidates for many words: blocks span far), contigs ending on last windows (R4)
     rng = np.random.default_rng(9)

@@ -4,7 +4,8 @@ window length, N densities), guides, k, PAMs, tile and chunk sizes run through t
 from their real source, on the host) and compared record by record with the oracle.
 
 usage: tools/fuzz_device_code_on_host.py [SEED] [SECONDS] [-DMACRO ...]      e.g.  ... 7 300 -DVS_EX_HALF=1
-Round 1: 1 329 cases with the default build and 564 with -DVS_EX_HALF=1, 74 k records, no mismatch."""
+Round 1: 1 329 cases with the default build and 564 with -DVS_EX_HALF=1, 74 k records, no mismatch.
+Round 2 (plain, whole-store and bucketed scans; up to 170 guides per case): see tools/README.md."""
 import os
 import pathlib
 import sys
@@ -45,12 +46,34 @@ def main():
         k = int(rng.integers(0, 9))
         pam = [None, "AG", "TT", "CC", "GA", "CT"][int(rng.integers(0, 6))]
         seed = int(rng.integers(0, 1 << 30))
-        case = make_case(seed, lens, int(rng.integers(1, 7)), k, pam=pam, n_frac=float(rng.choice([0, 0.002, 0.02])),
-                         guide_pam=[None, "GG", "GG", "AG"][int(rng.integers(0, 4))])
+        # guide counts: mostly a handful; now and then enough for 32-guide segments, a folded tail, or more than one CTA's worth
+        # (the bucketed kernel deals whole classes of a bucket in 32-guide and 4-guide segments)
+        ng = int(rng.integers(1, 7))
+        r = rng.random()
+        if r < 0.25:
+            ng = int(rng.integers(28, 72))
+        elif r < 0.35:
+            ng = int(rng.integers(120, 170))
+        if ng > 8:                                            # keep the emulation (one OS thread per CUDA thread) short
+            total = 0
+            kept = []
+            for L in lens:
+                if total + L > (6000 if ng > 100 else 12000):
+                    L = max(0, (6000 if ng > 100 else 12000) - total)
+                kept.append(L)
+                total += L
+            lens = kept
+        case_nfrac = float(rng.choice([0, 0.002, 0.02]))
+        case_gpam = [None, "GG", "GG", "AG"][int(rng.integers(0, 4))]
+        case = make_case(seed, lens, ng, k, pam=pam, n_frac=case_nfrac, guide_pam=case_gpam)
         text = V.PackedText.from_ascii(case.ascii, case.offsets)
         tile = int(rng.choice([0, 0, 8, 9, 16, 33, 100, 255, 256]))
         chunk = int(rng.choice([1 << 20, 1 << 20, 7, 64, 65, 1000]))
-        hits = emulate(exe, tmp, text, case.guides, k, pam, tile_words=tile, chunk_words=chunk)
+        try:
+            hits = emulate(exe, tmp, text, case.guides, k, pam, tile_words=tile, chunk_words=chunk)
+        except AssertionError as e:
+            print("EMULATOR FAILED", dict(seed=seed, lens=lens, ng=ng, k=k, pam=pam, tile=tile, chunk=chunk, n_frac=case_nfrac, guide_pam=case_gpam), str(e)[-300:], flush=True)
+            return 1
         exp = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, pam=pam).rows()
         got = rows_of(text, hits, case.offsets, case.guides)
         if got != exp:

@@ -638,13 +638,14 @@ k_score(ScoreArgs a)
         const uint32_t g_w = gc + 32u * role;
         if (g_w >= a.n_guides) break;
         const uint32_t n = min(32u, a.n_guides - g_w);
-        if (n == 32u) {
-            if (fixed_guides) segment(g_w, std::integral_constant<uint32_t, 5>{}, std::true_type{});
+        // tail of the guide list: pad to a multiple of 4 and split into 16 / 8 / 4 guides x 2 / 4 / 8 blocks per iteration; a tail
+        // of 29..31 guides pads to a full segment (its padding lanes score the segment's first guide, their hits are dropped)
+        const uint32_t np = (n + 3u) & ~3u;
+        if (np == 32u) {
+            if (fixed_guides && n == 32u) segment(g_w, std::integral_constant<uint32_t, 5>{}, std::true_type{});
             else segment(g_w, std::integral_constant<uint32_t, 5>{}, std::false_type{});
             continue;
         }
-        // tail of the guide list: pad to a multiple of 4 and split into 16 / 8 / 4 guides x 2 / 4 / 8 blocks per iteration
-        const uint32_t np = (n + 3u) & ~3u;
         uint32_t seg = g_w;
         if (np & 16u) { segment(seg, std::integral_constant<uint32_t, 4>{}, std::false_type{}); seg += 16u; }
         if (np & 8u) { segment(seg, std::integral_constant<uint32_t, 3>{}, std::false_type{}); seg += 8u; }
