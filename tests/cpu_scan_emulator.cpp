@@ -93,15 +93,26 @@ int main(int argc, char **argv)
     unsigned long long *rng = cnt.data() + 4, *all = cnt.data() + 4 + 4 * (n_chunks + 1);
     std::vector<vs_hit> hits(1 << 16), hits2;
     unsigned long long n_hits = 0;
-    const unsigned threads = std::min<unsigned>(SC_THREADS, (n_guides + 31) / 32 * 32);
-    auto score = [&](const unsigned long long *r, std::vector<vs_hit> &out, unsigned long long &n) {
+    // knobs of the emulation (environment): guides per pass of the resident scans (scan_engine's guide super-chunks: guide_base > 0,
+    // a pattern table wider than the launch), persistent CTAs, rotation period of the warp roles
+    const uint32_t guide_pass = getenv("VS_EMU_GUIDE_PASS") ? (uint32_t)atoi(getenv("VS_EMU_GUIDE_PASS")) : 0u;
+    const unsigned ctas = getenv("VS_EMU_CTAS") ? (unsigned)std::max(1, atoi(getenv("VS_EMU_CTAS"))) : 3u;
+    const uint32_t rot = getenv("VS_EMU_ROT") ? (uint32_t)atoi(getenv("VS_EMU_ROT")) : 1u;
+    // CTA size as scan_engine's score_cta: one warp per 32 guides, a tail of <= 8 guides gets no warp of its own
+    auto cta_threads = [](uint32_t ng) {
+        if (ng >= (uint32_t)SC_THREADS) return (unsigned)SC_THREADS;
+        const unsigned full = ng / 32, tail = ng % 32;
+        return 32u * std::max(1u, full + ((tail > 8u || full == 0) ? 1u : 0u));
+    };
+    auto score = [&](const unsigned long long *r, std::vector<vs_hit> &out, unsigned long long &n, uint32_t g0 = 0, uint32_t ng = ~0u) {
+        if (ng == ~0u) ng = n_guides;
         for (;;) {
             ScoreArgs a;
             for (int s = 0; s < 2; ++s) { a.planes[s] = planes[s].data(); a.pos[s] = pos[s].data(); }
-            a.rng = r; a.cap = cap; a.n_guides = n_guides; a.guide_base = 0; a.pat_guides = n_guides; a.pat = pat16; a.rot_shift = 1;
+            a.rng = r; a.cap = cap; a.n_guides = ng; a.guide_base = g0; a.pat_guides = n_guides; a.pat = pat16; a.rot_shift = rot;
             const unsigned long long before = n;
             a.hits = out.data(); a.n_hits = &n; a.hit_cap = out.size();
-            dispatch_score(k, a, 3, threads);                  // 3 persistent CTAs stride over the batches
+            dispatch_score(k, a, ctas, cta_threads(ng));       // persistent CTAs stride over the batches
             if (n <= out.size()) break;
             out.resize(n + n / 4);                             // hit buffer overflow: grow and redo this launch
             n = before;
@@ -120,7 +131,8 @@ int main(int argc, char **argv)
     if (n_guides && n_words) {
         hits2.resize(hits.size());
         unsigned long long n2 = 0;
-        score(all, hits2, n2);
+        if (guide_pass == 0) score(all, hits2, n2);
+        else for (uint32_t g0 = 0; g0 < n_guides; g0 += guide_pass) score(all, hits2, n2, g0, std::min(guide_pass, n_guides - g0));
         auto key = [](const vs_hit &x) { return ((uint64_t)x.pos << 32) | x.info; };
         std::vector<uint64_t> a, b;
         for (unsigned long long i = 0; i < n_hits; ++i) a.push_back(key(hits[i]));
@@ -154,27 +166,36 @@ int main(int argc, char **argv)
             for (uint64_t i = 0; i < nbk[s] * 32; ++i) placed += bps[s][i] != BK_NOPOS;
             if (placed != cnt[s]) { fprintf(stderr, "strand %d: %llu candidates, %llu bucket slots filled\n", s, cnt[s], (unsigned long long)placed); return 5; }
         }
-        std::vector<uint16_t> gkey((size_t)2 * n_guides), perm((size_t)2 * BK_N * n_guides, 0xFFFF);
-        std::vector<uint32_t> cls((size_t)2 * BK_N * BK_CLS, 0);
+        std::vector<uint16_t> gkey_all((size_t)2 * n_guides);
         for (int s = 0; s < 2; ++s)
             for (uint32_t gi = 0; gi < n_guides; ++gi) {
                 uint8_t pc[VS_GLEN];
                 for (int i = 0; i < VS_GLEN; ++i) pc[i] = s ? (uint8_t)(3 - guides[(size_t)gi * VS_GLEN + VS_GLEN - 1 - i]) : guides[(size_t)gi * VS_GLEN + i];
-                gkey[(size_t)s * n_guides + gi] = (uint16_t)key_of_codes(s, pc);
+                gkey_all[(size_t)s * n_guides + gi] = (uint16_t)key_of_codes(s, pc);
             }
-        launch_cta(BK_N, 32, [&] { k_guide_classes(gkey.data(), n_guides, pp, perm.data(), cls.data()); }, 2);
         std::vector<vs_hit> hits3(hits.size());
         unsigned long long n3 = 0;
-        for (;;) {
-            BkScoreArgs q;
-            for (int s = 0; s < 2; ++s) { q.planes[s] = bpl[s].data(); q.pos[s] = bps[s].data(); }
-            q.start = start; q.n_guides = n_guides; q.guide_base = 0; q.pat_guides = n_guides; q.pat = pat16;
-            q.perm = perm.data(); q.cls = cls.data();
-            n3 = 0;
-            q.hits = hits3.data(); q.n_hits = &n3; q.hit_cap = hits3.size();
-            dispatch_score_bk(k, q, 3);
-            if (n3 <= hits3.size()) break;
-            hits3.resize(n3 + n3 / 4);
+        const uint32_t pass = guide_pass ? guide_pass : n_guides;
+        for (uint32_t g0 = 0; g0 < n_guides; g0 += pass) {
+            // per guide pass, as scan_engine: the keys of the pass's guides [2][ng], their order per bucket, one launch
+            const uint32_t ng = std::min(pass, n_guides - g0);
+            std::vector<uint16_t> gkey((size_t)2 * ng), perm((size_t)2 * BK_N * ng, 0xFFFF);
+            std::vector<uint32_t> cls((size_t)2 * BK_N * BK_CLS, 0);
+            for (int s = 0; s < 2; ++s)
+                for (uint32_t gi = 0; gi < ng; ++gi) gkey[(size_t)s * ng + gi] = gkey_all[(size_t)s * n_guides + g0 + gi];
+            launch_cta(BK_N, 32, [&] { k_guide_classes(gkey.data(), ng, pp, perm.data(), cls.data()); }, 2);
+            const unsigned long long before = n3;
+            for (;;) {
+                BkScoreArgs q;
+                for (int s = 0; s < 2; ++s) { q.planes[s] = bpl[s].data(); q.pos[s] = bps[s].data(); }
+                q.start = start; q.n_guides = ng; q.guide_base = g0; q.pat_guides = n_guides; q.pat = pat16;
+                q.perm = perm.data(); q.cls = cls.data();
+                n3 = before;
+                q.hits = hits3.data(); q.n_hits = &n3; q.hit_cap = hits3.size();
+                dispatch_score_bk(k, q, ctas);
+                if (n3 <= hits3.size()) break;
+                hits3.resize(n3 + n3 / 4);
+            }
         }
         std::vector<uint64_t> c3;
         for (unsigned long long i = 0; i < n3; ++i) c3.push_back(key(hits3[i]));

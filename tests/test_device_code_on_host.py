@@ -82,6 +82,15 @@ def test_emulated_scan_every_tail_of_a_warp_slice(emulator, tmp_path, n_guides):
     assert any(r[0] >= (n_guides - 1) // 32 * 32 for r in exp)             # the last slice has hits to lose
 
 
+@pytest.mark.parametrize("n_guides,guide_pass,ctas,rot", [(100, 37, 2, 0), (157, 64, 5, 3), (70, 128, 1, 40), (33, 4, 3, 1), (300, 129, 4, 2)])
+def test_emulated_scan_in_guide_passes(emulator, tmp_path, monkeypatch, n_guides, guide_pass, ctas, rot):
+    """scan_engine's guide super-chunks as the kernels see them: launches with guide_base > 0 over a pattern table wider than the
+    launch (plain and bucketed), different numbers of persistent CTAs, different rotation periods of the warp roles."""
+    monkeypatch.setenv("VS_EMU_GUIDE_PASS", str(guide_pass)); monkeypatch.setenv("VS_EMU_CTAS", str(ctas)); monkeypatch.setenv("VS_EMU_ROT", str(rot))
+    case = make_case(seed=1000 + n_guides, contig_lens=[3000, 45, 45, 23, 900], n_guides=n_guides, k=4, pam="AG")
+    assert check(emulator, tmp_path, case, chunk_words=40) > 0
+
+
 def test_emulated_scan_n_runs_and_last_windows(emulator, tmp_path):
     # long N stretches (no candidates for many words: blocks span far), contigs ending on last windows (R4)
     rng = np.random.default_rng(9)

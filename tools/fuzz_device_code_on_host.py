@@ -69,15 +69,19 @@ def main():
         text = V.PackedText.from_ascii(case.ascii, case.offsets)
         tile = int(rng.choice([0, 0, 8, 9, 16, 33, 100, 255, 256]))
         chunk = int(rng.choice([1 << 20, 1 << 20, 7, 64, 65, 1000]))
+        # knobs of the emulator: guides per pass of the resident scans (guide_base > 0), persistent CTAs, rotation period of the warp roles
+        knobs = dict(VS_EMU_GUIDE_PASS=str(int(rng.choice([0, 0, 4, 32, 37, 64, 128, 129]))), VS_EMU_CTAS=str(int(rng.choice([1, 2, 3, 5, 8]))),
+                     VS_EMU_ROT=str(int(rng.choice([0, 1, 3, 40]))))
+        os.environ.update(knobs)
         try:
             hits = emulate(exe, tmp, text, case.guides, k, pam, tile_words=tile, chunk_words=chunk)
         except AssertionError as e:
-            print("EMULATOR FAILED", dict(seed=seed, lens=lens, ng=ng, k=k, pam=pam, tile=tile, chunk=chunk, n_frac=case_nfrac, guide_pam=case_gpam), str(e)[-300:], flush=True)
+            print("EMULATOR FAILED", dict(seed=seed, lens=lens, ng=ng, k=k, pam=pam, tile=tile, chunk=chunk, n_frac=case_nfrac, guide_pam=case_gpam, **knobs), str(e)[-300:], flush=True)
             return 1
         exp = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, pam=pam).rows()
         got = rows_of(text, hits, case.offsets, case.guides)
         if got != exp:
-            print("MISMATCH", dict(seed=seed, lens=lens, k=k, pam=pam, tile=tile, chunk=chunk, got=len(got), exp=len(exp)), flush=True)
+            print("MISMATCH", dict(seed=seed, lens=lens, ng=ng, k=k, pam=pam, tile=tile, chunk=chunk, n_frac=case_nfrac, guide_pam=case_gpam, got=len(got), exp=len(exp), **knobs), flush=True)
             return 1
         n_cases += 1
         n_rows += len(exp)
