@@ -183,8 +183,9 @@ def test_bench_orchestration_config3_with_target_block(world):
     assert d["n_gpus"] == world and d["scaling"] == "strong" and d["metric"] == "guide_Gbp_per_s"
     assert d["parity"]["diff"] == 0 and d["parity"]["hits_gpu"] == d["parity"]["hits_cpu"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e_resident_genome"]["records_equal_full_upload"]
-    assert d["index"] == "bucketed" and d["value_cold"] > 0 and d["value_plain_index"] > 0
+    assert d["index"] == "bucketed" and d["value_cold"] > 0 and d["value_plain_index"] > 0 and d["index_lists_identical"] is True
     t = d["target_cfg4"]
+    assert t["index_lists_identical"] is True
     assert t["guides"] == 1000 and t["parity"]["diff"] == 0 and t["parity"]["hits_gpu"] > 0 and t["e2e"]["value"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "frac_yardstick"} <= set(d["roofline"])
     # the config-5 block runs in a child process on the single-GPU line only; here (no device) the child must fail WITHOUT taking

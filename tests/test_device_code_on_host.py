@@ -12,7 +12,7 @@ import pytest
 
 import varscot_b200 as V
 from oracle import oracle as O
-from tests.util import make_case
+from tests.util import make_case, make_repeat_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -89,6 +89,14 @@ def test_emulated_scan_in_guide_passes(emulator, tmp_path, monkeypatch, n_guides
     monkeypatch.setenv("VS_EMU_GUIDE_PASS", str(guide_pass)); monkeypatch.setenv("VS_EMU_CTAS", str(ctas)); monkeypatch.setenv("VS_EMU_ROT", str(rot))
     case = make_case(seed=1000 + n_guides, contig_lens=[3000, 45, 45, 23, 900], n_guides=n_guides, k=4, pam="AG")
     assert check(emulator, tmp_path, case, chunk_words=40) > 0
+
+
+@pytest.mark.parametrize("n_bases,n_guides,k,pam", [(150000, 6, 3, None), (90000, 40, 2, "AG"), (60000, 9, 5, None)])
+def test_emulated_scan_low_complexity_text_buckets_of_several_batches(emulator, tmp_path, n_bases, n_guides, k, pam):
+    """Tandem repeats: thousands of candidates in ONE bucket (several batches of the bucketed store, which random text of test size
+    never fills), hits at every repeat (the hit buffer of the emulator regrows)."""
+    case = make_repeat_case(seed=77 + n_guides, n_bases=n_bases, n_guides=n_guides, k=k, pam=pam)
+    assert check(emulator, tmp_path, case, chunk_words=700) > 2000
 
 
 def test_emulated_scan_n_runs_and_last_windows(emulator, tmp_path):

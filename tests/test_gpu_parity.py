@@ -595,6 +595,38 @@ def test_guide_counts_whose_last_warp_slice_holds_29_to_31_guides(n_guides):
     assert any(r[0] >= (n_guides - 1) // 32 * 32 for r in exp)             # the last slice has hits to lose
 
 
+@pytest.mark.parametrize("n_bases,n_guides,k,pam", [(2_000_000, 40, 3, None), (600_000, 130, 4, "AG")])
+def test_low_complexity_text_buckets_of_many_batches(n_bases, n_guides, k, pam):
+    """Tandem repeats (tests/util.py: make_repeat_case): one bucket of the bucketed index holds tens of batches and every repeat is a
+    hit for many guides — what uniform random text only produces at genome size.  Streamed, resident plain and bucketed scans must
+    deliver the same sorted list, and the records must equal the oracle's."""
+    import varscot_b200 as V
+    from varscot_b200 import _lib
+    from tests.util import make_repeat_case
+    case = make_repeat_case(seed=31 + n_guides, n_bases=n_bases, n_guides=n_guides, k=k, pam=pam)
+    from oracle import oracle as O
+    text = V.PackedText.from_ascii(case.ascii, case.offsets)
+    exp = O.map_guides(O.text_codes(case.ascii), case.offsets, case.guides, k, pam=pam)
+    n = len(exp.guide)
+    assert n > 1_000_000
+    with V.ScanContext(0) as ctx:
+        ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, 0)
+        h1, st1 = ctx.scan_resolved(case.guides, k, pam=pam, text=text, cap=1 << 22)
+        h2, st2 = ctx.scan_resolved(case.guides, k, pam=pam, cap=1 << 22)
+        ctx.set_option(_lib.VS_OPT_BUCKET_INDEX, 2)
+        h3, st3 = ctx.scan_resolved(case.guides, k, pam=pam, cap=1 << 22)
+        h4, st4 = ctx.scan_resolved(case.guides, k, pam=pam, cap=1 << 22)
+        assert (st1.index_reused, st2.index_reused, st3.index_reused, st4.index_reused) == (0, 1, 2, 2)
+        assert len(h1) == n and h1.tobytes() == h2.tobytes() == h3.tobytes() == h4.tobytes()
+        rec, _ = V.merge_resolved([h4.copy()], threads=4)
+    # a million records: compared as arrays (order, FLAGs and counts included), the MD strings on a sample
+    for name in ("guide", "flag", "contig", "pos", "mm"):
+        assert np.array_equal(rec[name].astype(np.int64), np.asarray(getattr(exp, name)).astype(np.int64)), name
+    sample = rec[:: max(1, n // 1500)]
+    rows = exp.rows()
+    assert rows_from_records(text, sample, case.offsets, case.guides) == rows[:: max(1, n // 1500)]
+
+
 def test_bucketed_index_many_guides_and_hit_buffer_regrow():
     import varscot_b200 as V
     from varscot_b200 import _lib

@@ -77,6 +77,37 @@ def make_case(seed, contig_lens, n_guides, k, pam=None, plant=True, n_frac=0.002
     return Case(bytes(asc), off, guides, gs, k, pam, names)
 
 
+def make_repeat_case(seed, n_bases, n_guides, k, pam=None, unit_len=37, mut_every=40) -> Case:
+    """A LOW-COMPLEXITY text: tandem repeats of one unit that carries a forward PAM (GG at offset 21, plus `pam` at another phase) and
+    a reverse one (CC), lightly mutated.  Thousands of candidates share their PAM + neighbouring bases — one bucket of the bucketed
+    index spans several batches, which uniform random text never produces below ~10^7 bases — and the guides (windows of the unit with
+    0..3 substitutions, both strands) hit at every repeat: a dense-hit case as well."""
+    rng = np.random.default_rng(seed)
+    unit = rng.integers(0, 4, unit_len).astype(np.uint8)
+    unit[21] = 2; unit[22] = 2
+    unit[30] = 1; unit[31] = 1
+    if pam:
+        unit[26] = "ACGT".index(pam[0]); unit[27] = "ACGT".index(pam[1])      # the window starting at offset 5 ends on the extra PAM
+    codes = np.tile(unit, (n_bases + unit_len - 1) // unit_len)[:n_bases].copy()
+    mut = rng.integers(0, n_bases, max(1, n_bases // mut_every))
+    codes[mut] = rng.integers(0, 4, len(mut))
+    cut = sorted({0, n_bases, n_bases // 3, min(n_bases, n_bases // 3 + 45)})
+    off = np.array(cut, dtype=np.uint64)
+    two = np.tile(unit, 3)
+    guides = np.zeros((n_guides, GLEN), dtype=np.uint8)
+    for g in range(n_guides):
+        start = [0, 5, 30 - 0, 9][g % 4] if pam else [0, 30, 0, 30][g % 4]
+        w = two[start:start + GLEN].copy()
+        if start == 30:
+            w = revcomp_codes(w)                              # the reverse-strand site, written as the guide that finds it
+        idx = rng.choice(GLEN, size=int(rng.integers(0, 4)), replace=False)
+        w[idx] = (w[idx] + rng.integers(1, 4, len(idx))) % 4
+        guides[g] = w
+    asc = _L[codes]
+    gs = ["".join("ACGT"[int(b)] for b in g) for g in guides]
+    return Case(bytes(asc), off, guides, gs, k, pam, [f"ctg{i}" for i in range(len(off) - 1)])
+
+
 def write_fasta(path, names, ascii_bytes, offsets, width=70):
     with open(path, "wb") as f:
         for i, nm in enumerate(names):

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 import varscot_b200 as V                                                      # noqa: E402
 from oracle import oracle as O                                                # noqa: E402
 from tests.test_device_code_on_host import build_emulator, emulate, rows_of  # noqa: E402
-from tests.util import make_case                                              # noqa: E402
+from tests.util import make_case, make_repeat_case                                              # noqa: E402
 
 
 def main():
@@ -65,7 +65,14 @@ def main():
             lens = kept
         case_nfrac = float(rng.choice([0, 0.002, 0.02]))
         case_gpam = [None, "GG", "GG", "AG"][int(rng.integers(0, 4))]
-        case = make_case(seed, lens, ng, k, pam=pam, n_frac=case_nfrac, guide_pam=case_gpam)
+        if rng.random() < 0.12:                               # low-complexity text: buckets of several batches, dense hits
+            lens = ["repeat", int(rng.integers(20000, 120000))]
+            ng = min(ng, 48)
+            k = min(k, 5)
+            case = make_repeat_case(seed, lens[1], ng, k, pam=pam if pam in (None, "AG", "TT") else None)
+            pam = case.pam
+        else:
+            case = make_case(seed, lens, ng, k, pam=pam, n_frac=case_nfrac, guide_pam=case_gpam)
         text = V.PackedText.from_ascii(case.ascii, case.offsets)
         tile = int(rng.choice([0, 0, 8, 9, 16, 33, 100, 255, 256]))
         chunk = int(rng.choice([1 << 20, 1 << 20, 7, 64, 65, 1000]))
