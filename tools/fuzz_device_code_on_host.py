@@ -77,7 +77,7 @@ def main():
         tile = int(rng.choice([0, 0, 8, 9, 16, 33, 100, 255, 256]))
         chunk = int(rng.choice([1 << 20, 1 << 20, 7, 64, 65, 1000]))
         # knobs of the emulator: guides per pass of the resident scans (guide_base > 0), persistent CTAs, rotation period of the warp roles
-        knobs = dict(VS_EMU_GUIDE_PASS=str(int(rng.choice([0, 0, 4, 32, 37, 64, 128, 129]))), VS_EMU_CTAS=str(int(rng.choice([1, 2, 3, 5, 8]))),
+        knobs = dict(VS_EMU_GUIDE_PASS=str(int(rng.choice([0, 0, 4, 32, 37, 64, 128, 129]))), VS_EMU_CTAS=str(int(rng.choice([1, 2, 3, 3, 5, 5, 8, 8, 64, 300]))),
                      VS_EMU_ROT=str(int(rng.choice([0, 1, 3, 40]))))
         os.environ.update(knobs)
         try:
