@@ -532,10 +532,13 @@ def measure(V, ctx, text, guides, k, pam, first, words, steps, warmup, world, lo
     return res, (rec, coll)
 
 
-def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank, local, total_bases, all_cpus, t_gen):
+def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank, local, total_bases, all_cpus, t_gen, as_block=False):
     """Config 5 (10 000 guides, k <= 8: ~1.9e9 hits): ONE pass through the end-to-end call with a sink.  The guides are scored in
     super-chunks sized to the device hit buffer; every super-chunk is resolved + sorted on the device and handed to the host
-    (here: counted per guide, spot-checked for order), so host memory stays O(super-chunk) and no pass is repeated."""
+    (here: counted per guide, spot-checked for order), so host memory stays O(super-chunk) and no pass is repeated.
+    Standalone (`--config 5`) rank 0 prints the line; as_block (the `dense_cfg5` block of a multi-GPU default line) rank 0 returns it.
+    The device part runs without a collective inside and never raises: a rank that fails says so in ONE all-reduce after it, so that
+    no rank is left waiting for another (standalone: every rank then raises; block: the block is {"error": ...})."""
     desc, gbases, nvar, ng, k, pam, gseed = cfg
     counts = np.zeros(ng, dtype=np.int64)
     box = {"chunks": 0, "max_chunk": 0, "sorted": True, "host_s": 0.0}
@@ -567,26 +570,34 @@ def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank,
 
     sampler = ClockSampler(local) if rank == 0 else None
     barrier(world, local)
+    nv = 4
+    err = None
+    st = small = None
+    wall_ms = 0.0
     t0_wall = time.time(); t0 = time.perf_counter()
     try:
         _, st = ctx.scan_resolved(guides, k, pam=pam, text=text, first_word=first, n_words=words, sink=sink)
-    except Exception:
-        if "error" in box:
-            raise RuntimeError("config 5: the sink refused a delivery: " + box["error"])
-        raise
-    wall_ms = (time.perf_counter() - t0) * 1e3
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        # verification scan of the first guides against the now resident index (same per-guide counts; parity with the oracle on a sample below)
+        small, st_s = ctx.scan_resolved(guides[:nv], k, pam=pam, cap=1 << 22)
+    except Exception as e:
+        err = ("the sink refused a delivery: " + box["error"]) if "error" in box else repr(e)
     barrier(world, local)
     clocks = sampler.stop(t0_wall, time.time()) if sampler else None
+    all_ok = all_reduce(0.0 if err else 1.0, world, local, "MIN") == 1.0
+    if not all_ok:
+        msg = f"config 5 failed on rank {rank}: {err}" if err else "config 5 failed on another rank"
+        if not as_block:
+            raise RuntimeError(msg)
+        return {"error": msg} if rank == 0 else None
     ms = all_reduce(float(st.total_ms), world, local, "MAX")
     e_ms = all_reduce(wall_ms, world, local, "MAX")
     hits_total = all_reduce(float(counts.sum()), world, local, "SUM")
-    # verification scan of the first guides against the now resident index: same per-guide counts, and hit-set parity with the oracle on a sample
-    nv = 4
-    small, st_s = ctx.scan_resolved(guides[:nv], k, pam=pam, cap=1 << 22)
     same_counts = bool((np.bincount((small["info"] >> 8).astype(np.int64), minlength=nv) == counts[:nv]).all())
     same_counts = all_reduce(1.0 if same_counts else 0.0, world, local, "MIN") == 1.0
+    redo_total = int(all_reduce(float(st.redo_chunks), world, local, "SUM"))
     if rank != 0:
-        return
+        return None
     units = float(ng) * total_bases
     out = {"metric": "guide_Gbp_per_s", "value": units / (ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "n_gpus": world, "steps": 1, "warmup": 0,
            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-sliced (LOP3)", "data": "synthetic",
@@ -596,18 +607,23 @@ def run_dense(args, cfg, V, synth, text, ctx, guides, first, words, world, rank,
            "rank0": {"guide_passes": int(st.guide_passes), "redo": int(st.redo_chunks), "score_ms": float(st.score_ms), "extract_ms": float(st.extract_ms),
                      "resolve_sort_d2h_ms": float(st.resolve_ms), "sink_host_s": box["host_s"], "deliveries": box["chunks"], "largest_delivery": box["max_chunk"],
                      "first_delivery_sorted": box["sorted"], "hits": int(counts.sum())},
-           "redo": int(st.redo_chunks), "gpu_launches": int(st.launches),
+           "redo": redo_total, "gpu_launches": int(st.launches),
            "e2e": {"value": units / (e_ms * 1e-3) / 1e9, "unit": "guide*Gbp/s", "ms_per_step": e_ms, "h2d_bytes_per_step": int(st.h2d_bytes) * world,
                    "d2h_bytes_per_step": int(hits_total * 16)},
            "verification": {"guides": nv, "per_guide_counts_equal_small_scan": same_counts}, "clocks": clocks, "gen_s": t_gen, "host": host_info()}
     if not args.no_cpu:
         os.sched_setaffinity(0, all_cpus)
-        n, dt, rec, off, cores = cpu_sample(text, guides[:nv], k, pam, synth, target_s=10.0, max_bases=min(1 << 28, words * 32))
+        n, dt, rec, off, cores = cpu_sample(text, guides[:nv], k, pam, synth, target_s=4.0 if as_block else 10.0, max_bases=min(1 << 28, words * 32))
         rec_g, coll = V.merge_resolved([small])
         out["parity"] = parity_on_sample(rec_g, text.offsets, rec, off, n)
         out["cpu_baseline"] = {"value": nv * n / dt / 1e9, "unit": "guide*Gbp/s", "cores": cores, "kind": "port",
                                "sample": f"first {n} bases, {nv} guides, one pass ({dt:.1f} s)", **host_info()}
+    if as_block:
+        for k_ in ("host", "gen_s", "vs_baseline", "higher_is_better", "data", "dtype", "steps", "warmup"):
+            out.pop(k_, None)
+        return out
     print(json.dumps(out))
+    return out
 
 
 def run_dense_child(args, timeout_s):
@@ -852,6 +868,13 @@ def main():
                 target["cpu_baseline"] = {"value": c4[3] * n4 / dt4 / 1e9, "unit": "guide*Gbp/s", "cores": cores4, "kind": "port",
                                           "sample": f"first {n4} bases, all {c4[3]} guides, one pass ({dt4:.1f} s)"}
 
+    # ---- config 5 (10 000 guides, k <= 8, a hit sink) on the same text and ranks: at N > 1 in this process (one pass, no collective inside,
+    # a failing rank reported by one all-reduce); at N = 1 in a child process after the GPU has been released (below) -------------------
+    dense = None
+    if world > 1 and strong and args.config == 3 and not args.no_dense and not args.guides:
+        c5 = CONFIGS[5]
+        dense = run_dense(args, c5, V, synth, text, ctx, synth.synth_guides(c5[6], c5[3]), first, words, world, rank, local, total_bases,
+                          all_cpus, t_gen, as_block=True)
     if rank != 0:
         ctx.close()
         if exchange:
@@ -955,8 +978,7 @@ def main():
     if world == 1 and args.config == 3 and not args.no_dense:
         out["dense_cfg5"] = run_dense_child(args, float(os.environ.get("VARSCOT_BENCH_DENSE_TIMEOUT_S", "180")))
     else:
-        out["dense_cfg5"] = None if args.no_dense or args.config != 3 else \
-            "not run at N > 1 inside this line (it needs the GPUs to itself): python -m torch.distributed.run ... bench.py --gpus N --config 5"
+        out["dense_cfg5"] = dense                             # N > 1: measured in this process, above (None when skipped)
     if args.cli and world == 1:
         text.unpin()
         out["cli_e2e"] = run_cli_leg(V, text, guides, k, pam, min(16, len(all_cpus)))

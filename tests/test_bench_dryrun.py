@@ -95,6 +95,8 @@ def _install_fakes(world, rank, port):
                 st.extract_ms = 0.0
             self.scans = self.scans + 1 if self.keep else 0
             if sink is not None:
+                if os.environ.get("VS_FAKE_FAIL_DENSE_RANK") == str(rank):
+                    raise RuntimeError("injected failure of the dense pass")
                 half = len(g) // 2                            # two deliveries, as two guide super-chunks would arrive
                 gid = loc["info"] >> 8
                 for lo, hi in ((0, half), (half, len(g))):
@@ -193,7 +195,18 @@ def test_bench_orchestration_config3_with_target_block(world):
     if world == 1:
         assert "error" in d["dense_cfg5"] and "exit code" in d["dense_cfg5"]["error"], d["dense_cfg5"]
     else:
-        assert isinstance(d["dense_cfg5"], str)
+        c5 = d["dense_cfg5"]                                  # N > 1: config 5 in the same processes, on the same shards
+        assert c5["n_gpus"] == world and c5["config"]["workload"].startswith("cfg5") and c5["hits_per_step"] > 0 and c5["redo"] == 0
+        assert c5["verification"]["per_guide_counts_equal_small_scan"] and c5["parity"]["diff"] == 0 and c5["rank0"]["first_delivery_sorted"]
+
+
+def test_bench_dense_block_failure_on_one_rank_costs_only_the_block(monkeypatch):
+    """A rank whose config-5 pass fails reports it through one all-reduce: the other ranks do not wait for it, the block says why,
+    and the main line (config 3 + config-4 block) is intact."""
+    monkeypatch.setenv("VS_FAKE_FAIL_DENSE_RANK", "1")
+    d = _spawn(2, ["--gpus", "2", "--config", "3", "--scale", "0.0002", "--steps", "2", "--warmup", "3"])
+    assert "error" in d["dense_cfg5"] and "another rank" in d["dense_cfg5"]["error"]
+    assert d["parity"]["diff"] == 0 and d["e2e"]["value"] > 0 and d["target_cfg4"]["parity"]["diff"] == 0
 
 
 @pytest.mark.parametrize("world", [1, 2])
