@@ -243,9 +243,9 @@ k_bucket_gather(const vs_bases *__restrict__ B, const vs_masks *__restrict__ M, 
 
 // ---- guide classes -----------------------------------------------------------------------------------------------
 // k_guide_classes: for every (strand, bucket) the guides of the launch sorted by c = mismatches between the guide's key and
-// the bucket's (a counting sort: 7 + 1 bins), as perm[strand][bucket][n_guides] (uint16 guide index) and the class starts
+// the bucket's (a counting sort: VS_KEYLEN + 1 bins), as perm[strand][bucket][n_guides] (uint16 guide index) and the class starts
 // cls[strand][bucket][VS_KEYLEN + 2] (cls[c] = first entry with c mismatches; cls[VS_KEYLEN + 1] = n_guides).  gkey[strand][g]
-// = 12-bit key of the pattern the strand's pass scores.  grid = (BK_N, 2), any CTA size; guides beyond 65535 per launch are
+// = 2 * VS_KEYLEN-bit key of the pattern the strand's pass scores.  grid = (BK_N, 2), any CTA size; guides beyond 65535 per launch are
 // not supported (the host splits the launch).
 constexpr int BK_CLS = VS_KEYLEN + 2;
 __global__ void __launch_bounds__(128)
@@ -278,7 +278,7 @@ k_guide_classes(const uint16_t *__restrict__ gkey, uint32_t n_guides, PamParams 
 // stage-A slots for the budget kp: two more than k_score's 7 + 2 k — here an iteration that survives stage A is rescanned by a
 // routine of ~100 instructions instead of four more LDS, so it must be ten times rarer (about 1 % of the iterations)
 __host__ __device__ constexpr int bk_walk_slots(int kp) { return 9 + 2 * kp < BK_REST ? 9 + 2 * kp : BK_REST; }
-// The walks are specialised on the number of stage-A slots only — 9, 11, 13, 15 (, 17) — not on the budget: the budgets
+// The walks are specialised on the number of stage-A slots only — 9, 11, 13, 15 (VS_KEYLEN 6: also 17) — not on the budget: the budgets
 // that share the longest walk share its code and pick their threshold at run time.  The instruction cache decides this: every
 // batch runs every class, the SM's instruction cache holds 32 KB, and the first version of this kernel (one walk per budget
 // and segment shape, unrolled 4 times with the rare path inlined: 130 KB) spent 17 of 18 issue cycles waiting for instructions.
