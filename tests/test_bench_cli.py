@@ -69,3 +69,29 @@ def test_static_evidence_helpers():
     topo = bench.gpu_topology(open(os.path.join(ROOT, "profiles", "r2_box_8gpu.txt")).read())
     assert topo == {"gpus": 8, "links": ["NV18"], "cpu_numa_affinity": ["0-31/0"]}
     assert bench.host_info()["numa_nodes"] >= 0
+
+
+def test_parity_windows_head_and_tail():
+    """bench.py's hit-set diff on a slice of the text: the head sample (artificial END: its last 23 starts are left out) and the tail
+    sample (artificial START: cuts nothing; real end) must both report 0 against records of the whole text, and notice a moved hit."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    from oracle import oracle as O
+    core = bench.load_synth_core()
+    text = core.build_workload(3_100_000_000, 5_000_000, 0.0004)          # ~1.4 Mbases: genome + a swarm of variant segments
+    guides = core.synth_guides(13, 60)
+    full = O.map_guides(core.unpack_codes(text, 0, text.n_bases), text.offsets, guides, 6)
+    rec = np.zeros(len(full.guide), dtype=[("guide", "<u4"), ("contig", "<u4"), ("pos", "<u4"), ("flag", "<u2"), ("mm", "u1")])
+    for f in rec.dtype.names:
+        rec[f] = getattr(full, f)
+    n = text.n_bases // 2 // 32 * 32
+    head = O.map_guides(core.unpack_codes(text, 0, n), core.slice_offsets(text, 0, n), guides, 6)
+    d = bench.parity_on_sample(rec, text.offsets, head, core.slice_offsets(text, 0, n), n)
+    assert d["diff"] == 0 and d["hits_gpu"] > 0
+    t = bench.parity_on_tail(rec, text, guides, 6, None, core, text.n_bases // 3)
+    assert t["diff"] == 0 and t["hits_gpu"] > 0 and t["first_base"] > 0 and t["first_base"] % 32 == 0
+    gpos = text.offsets[rec["contig"]].astype(np.int64) + rec["pos"]
+    i = int(np.nonzero(gpos >= t["first_base"])[0][0])
+    rec["mm"][i] += 1
+    assert bench.parity_on_tail(rec, text, guides, 6, None, core, text.n_bases // 3)["diff"] == 2

@@ -184,6 +184,7 @@ def test_bench_orchestration_config3_with_target_block(world):
     d = _spawn(world, ["--gpus", str(world), "--config", "3", "--scale", "0.0002", "--steps", "2", "--warmup", "3"])
     assert d["n_gpus"] == world and d["scaling"] == "strong" and d["metric"] == "guide_Gbp_per_s"
     assert d["parity"]["diff"] == 0 and d["parity"]["hits_gpu"] == d["parity"]["hits_cpu"] > 0
+    assert d["parity"]["tail"]["diff"] == 0 and d["parity"]["tail"]["hits_gpu"] > 0 and d["target_cfg4"]["parity"]["tail"]["diff"] == 0
     assert d["e2e"]["value"] > 0 and d["e2e_resident_genome"]["records_equal_full_upload"]
     assert d["index"] == "bucketed" and d["value_cold"] > 0 and d["value_plain_index"] > 0 and d["index_lists_identical"] is True
     t = d["target_cfg4"]
