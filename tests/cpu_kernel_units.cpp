@@ -465,6 +465,22 @@ static void test_contig_starts_and_resolve()
     }
 }
 
+// CTA size as scan_engine's score_cta (vs_device.cu): one warp per 32 guides, a tail of <= 8 guides gets no warp of its own
+static unsigned score_cta_threads(uint32_t ng)
+{
+    if (ng >= (uint32_t)SC_THREADS) return (unsigned)SC_THREADS;
+    const unsigned full = ng / 32, tail = ng % 32;
+    return 32u * std::max(1u, full + ((tail > 8u || full == 0) ? 1u : 0u));
+}
+
+// every guide count of a launch, with the CTA size the library would pick: no guide may go unscored (round 2's first k_score split
+// a warp slice's tail into 16 + 8 + 4 guides and scored nothing for slices of 29..31)
+static void sweep_guide_counts()
+{
+    for (uint32_t n = 1; n <= 200; ++n) check_k_score<2>(n, score_cta_threads(n));
+    for (uint32_t n : {253u, 254u, 255u, 256u, 257u, 285u, 286u, 287u, 288u, 383u, 384u, 413u, 415u, 511u, 543u}) check_k_score<1>(n, score_cta_threads(n));
+}
+
 int main()
 {
     test_plane_index();
@@ -480,6 +496,7 @@ int main()
     check_k_score<0>(9); check_k_score<1>(33); check_k_score<2>(5); check_k_score<3>(60); check_k_score<4>(128 + 28);
     check_k_score<5>(20); check_k_score<6>(100); check_k_score<7>(12); check_k_score<8>(4);
     check_k_score<6>(100, 96); check_k_score<4>(40, 32); check_k_score<3>(300, 64);      // CTAs with fewer warps than guide slices (a short tail gets no warp of its own)
+    sweep_guide_counts();
     if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
     printf("kernel helper units ok\n");
     return 0;
