@@ -735,11 +735,12 @@ def main():
     if args.guides:
         cfg[3] = args.guides
     cfg = tuple(cfg)
+    if args.impl == "reference":
+        # the CPU arm needs no process group and no GPU: rank 0 (of the environment torchrun set) measures, the others leave at once
+        run_reference(args, cfg, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
+        return
     world, rank, local = dist_setup()
     all_cpus = os.sched_getaffinity(0)
-    if args.impl == "reference":
-        run_reference(args, cfg, world, rank)
-        return
     numa_cpus = bind_to_gpu_numa(local)
 
     import varscot_b200 as V
