@@ -179,7 +179,7 @@ def _spawn(world, argv):
     return json.loads(line)
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_bench_orchestration_config3_with_target_block(world):
     d = _spawn(world, ["--gpus", str(world), "--config", "3", "--scale", "0.0002", "--steps", "2", "--warmup", "3"])
     assert d["n_gpus"] == world and d["scaling"] == "strong" and d["metric"] == "guide_Gbp_per_s"
