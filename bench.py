@@ -877,6 +877,9 @@ def main():
                       "plain_index": {"value": r4["warm_plain"]["value"], "ms_per_step": r4["warm_plain"]["ms"], "score_ms": r4["warm_plain"]["score_ms"],
                                       "frac_executed": lop_p4 * r4["warm_plain"]["blocks"] * c4[3] / (r4["warm_plain"]["score_ms"] * 1e-3) / peak_lop3},
                       "index_build_ms_rank0": r4["warm"]["index_build_ms"], "ops_per_block_guide": target_ops,
+                      "frac_note": "frac_executed counts the stage-A LOP3 of the adder trees only (a lower bound of the ALU-pipe load: the bucketed walk also "
+                                   "issues one address update per slot and two blocks); ncu's own pipe loads of both kernels on this config: ncu_pipes",
+                      "ncu_pipes": {k_: v for k_, v in (ncu_pipes() or {}).items() if "cfg4" in k_},
                       "e2e": r4.get("e2e"), "redo": r4["cold"]["redo"]}
             if not args.no_cpu and merged4 is not None:
                 os.sched_setaffinity(0, all_cpus)
