@@ -696,7 +696,7 @@ def run_cli_leg(V, text, guides, k, pam, threads):
         runs = []
         for _ in range(2):                                   # first process of the box pays driver initialisation; report both
             t = time.perf_counter()
-            r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, VARSCOT_VERBOSE="1", VARSCOT_GPUS="1"))
+            r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, VARSCOT_VERBOSE="1", VARSCOT_GPUS="1"), timeout=120)
             wall = time.perf_counter() - t
             if r.returncode != 0:
                 return {"error": r.stderr[-300:]}
@@ -727,7 +727,8 @@ def main():
     ap.add_argument("--no-target", action="store_true", help="skip the config-4 target block")
     ap.add_argument("--no-resident-genome", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense_cfg5 block (config 5 in a child process; single-GPU default line only)")
-    ap.add_argument("--cli", action="store_true", help="add the cli_e2e leg: the bidir_mapping executable from the .vsidx cache to the SAM file, wall clock")
+    ap.add_argument("--cli", action="store_true", help="(default on the single-GPU config-3 line) the cli_e2e leg: the bidir_mapping executable from the .vsidx cache to the SAM file, wall clock")
+    ap.add_argument("--no-cli", action="store_true", help="skip the cli_e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -1002,9 +1003,13 @@ def main():
         out["dense_cfg5"] = run_dense_child(args, float(os.environ.get("VARSCOT_BENCH_DENSE_TIMEOUT_S", "180")))
     else:
         out["dense_cfg5"] = dense                             # N > 1: measured in this process, above (None when skipped)
-    if args.cli and world == 1:
-        text.unpin()
-        out["cli_e2e"] = run_cli_leg(V, text, guides, k, pam, min(16, len(all_cpus)))
+    if world == 1 and args.config == 3 and not args.no_cli:
+        # the drop-in executable end to end (a fresh process per run: CUDA context, .vsidx mapped, scan, SAM): an error costs the block only
+        try:
+            text.unpin()
+            out["cli_e2e"] = run_cli_leg(V, text, guides, k, pam, min(16, len(all_cpus)))
+        except Exception as e:
+            out["cli_e2e"] = {"error": repr(e)[:300]}
     print(json.dumps(out))
     if exchange:
         barrier(world, local)

@@ -195,6 +195,7 @@ def test_bench_orchestration_config3_with_target_block(world):
     # the main line with it, and say why
     if world == 1:
         assert "error" in d["dense_cfg5"] and "exit code" in d["dense_cfg5"]["error"], d["dense_cfg5"]
+        assert "error" in d["cli_e2e"]                        # the executable has no device here either: the leg reports it, the line stands
     else:
         c5 = d["dense_cfg5"]                                  # N > 1: config 5 in the same processes, on the same shards
         assert c5["n_gpus"] == world and c5["config"]["workload"].startswith("cfg5") and c5["hits_per_step"] > 0 and c5["redo"] == 0
