@@ -405,7 +405,10 @@ extern "C" int vs_text_load(const char *prefix, vs_text_view *out, void **owner)
         close(fd); vs_set_last_error((path + " is not a VSIDX003 packed text").c_str()); return VS_ERR_IO;
     }
     const uint64_t fsize = (uint64_t)sb.st_size;
-    char *base = (char *)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    // MAP_POPULATE: the page tables are filled here — in the executables while the CUDA context is being created on another thread —
+    // instead of fault by fault inside the driver's staging copies of the upload
+    char *base = (char *)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (base == MAP_FAILED) base = (char *)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (base == MAP_FAILED) { vs_set_last_error(("cannot map " + path).c_str()); return VS_ERR_IO; }
     auto bad = [&](const std::string &why, int code) { munmap(base, fsize); memset(out, 0, sizeof(*out)); vs_set_last_error((path + why).c_str()); return code; };
