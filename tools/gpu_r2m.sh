@@ -1,6 +1,10 @@
 # round 2, GPU session M: A/B of the k_score tuning knobs, then the final ncu evidence (launch list + --set full captures) at full scale
 cd /root/repo
 mkdir -p gpurun_out
+# everything written after the last GPU session first: the whole GPU suite (tests/test_zz_gpu_round2_late.py last), smoke, the default line
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -8
+python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 1200 python bench.py > gpurun_out/r2m_bench_cfg3_1gpu.json 2> gpurun_out/r2m_bench_cfg3_1gpu.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r2m_bench_cfg3_1gpu.json
 q() {  # label, config, scale, env...
   local label="$1" cfg="$2" scale="$3"; shift 3
   env "$@" timeout 900 python bench.py --config $cfg --scale $scale --steps 8 --warmup 3 --no-cpu --no-e2e --no-target 2>/dev/null | python -c "
